@@ -1,0 +1,158 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(oracle/gen_golden.py).  These are the pins that make the oracle trustworthy."""
+import numpy as np
+import pytest
+import torch
+
+import skoots_oracle as orc
+from conftest import load_golden, unpack_mask
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a))
+    return x if dtype is None else x.to(dtype)
+
+
+def test_known_answers_from_reference_main_blocks():
+    fx = load_golden("kat_vec2embed")
+    out = orc.vector_to_embedding(t(fx["scale"]), t(fx["vector"]), N=int(fx["N"]))
+    assert out[0, :, 5, 5, 5].tolist() == [6.0, 6.0, 6.0]  # vector_to_embedding.py:221-232
+    assert np.array_equal(out.numpy(), fx["out"])
+
+
+@pytest.mark.parametrize("tag,dt", [("f16", torch.float16), ("bf16", torch.bfloat16), ("f32", torch.float32)])
+def test_vector_to_embedding_bit_exact(tag, dt):
+    fx = load_golden(f"vec2embed_{tag}")
+    vec = t(fx["vector"]).to(dt)
+    for key in [k for k in fx.files if k.startswith("out_")]:
+        N = int(key.split("_")[1][1:])
+        decay = int(key.split("_")[2][1:]) / 100.0
+        got = orc.vector_to_embedding(t(fx["scale"]), vec, N=N, decay=decay).numpy()
+        assert np.array_equal(got, fx[key]), key
+
+
+def test_vector_to_embedding_2d():
+    fx = load_golden("vec2embed_2d")
+    got = orc.vector_to_embedding(t(fx["scale"]), t(fx["vector"])).numpy()
+    assert np.array_equal(got, fx["out"])
+
+
+def test_index_skeleton_by_embed():
+    fx = load_golden("index_by_embed")
+    got = orc.index_skeleton_by_embed(t(fx["labels"]), t(fx["embed"]))
+    assert got.dtype == torch.int32
+    assert np.array_equal(got.numpy(), fx["out"])
+
+
+@pytest.mark.parametrize("name", ["flood_small", "flood_dense"])
+def test_flood_fill_single_crop(name):
+    fx = load_golden(name)
+    mask = unpack_mask(fx)
+    got = orc.flood_fill_exact(t(mask).to(torch.int16)).numpy()
+    assert got.dtype == np.int16
+    assert np.array_equal(got, fx["out"])  # identical numbering: scipy order + 2
+    assert got[got > 0].min() == 3
+
+
+def test_flood_fill_multicrop_replay_and_exact_agree():
+    fx = load_golden("flood_multicrop")
+    mask = unpack_mask(fx)
+    replay = orc.flood_fill_multicrop(t(mask).to(torch.int16)).numpy()
+    assert np.array_equal(replay, fx["out"])  # bug-compatible replay is bit-identical
+    exact = orc.flood_fill_exact(t(mask).to(torch.int16)).numpy()
+    # on this input the seam heuristic makes no false merge: same partition up to relabelling
+    assert np.array_equal(orc.canonical_relabel(exact), orc.canonical_relabel(fx["out"]))
+
+
+@pytest.mark.parametrize("name", ["morphology", "morphology_binary"])
+def test_morphology(name):
+    fx = load_golden(name)
+    img = t(fx["image"])
+    assert np.array_equal(orc.binary_dilation(img).numpy(), fx["dilation"])
+    assert np.array_equal(orc.binary_dilation_2d(img).numpy(), fx["dilation_2d"])
+    ero = orc.binary_erosion(img).numpy()
+    assert ero.shape == fx["erosion"].shape
+    assert np.array_equal(ero, fx["erosion"])
+
+
+def test_tile_epilogue():
+    fx = load_golden("tile_epilogue")
+    vol_v = torch.zeros(fx["vectors"].shape, dtype=torch.float16)
+    vol_s = torch.zeros(fx["skeleton"].shape, dtype=torch.uint8)
+    orc.tile_epilogue(t(fx["unet"]), vol_v, vol_s, tuple(fx["origin"]), tuple(int(v) for v in fx["overlap"]))
+    assert np.array_equal(vol_v.float().numpy(), fx["vectors"])
+    assert np.array_equal(vol_s.numpy(), fx["skeleton"])
+
+
+def test_assembly_crop_grid_and_whole_volume():
+    fx = load_golden("assembly")
+    labels = t(fx["labels"])
+    vec = t(fx["vectors"]).to(torch.float16)
+    scale = t(fx["scale"])
+    assert np.array_equal(orc.flood_fill_exact(t(unpack_mask(fx, "skeleton")).to(torch.int16)).numpy(), fx["labels"])
+    for key in [k for k in fx.files if k.startswith("cfg_")]:
+        N, d100, cx, cy, cz, ox, oy, oz = (int(v) for v in fx[key])
+        got = orc.assemble_instances(labels, vec, scale, N=N, decay=d100 / 100.0, crop=(cx, cy, cz),
+                                     overlap=(ox, oy, oz))
+        assert np.array_equal(got.numpy(), fx["inst_" + key[4:]]), key
+    for N in (1, 4):
+        emb = orc.vector_to_embedding(scale, vec[None], N=N)
+        got = orc.index_skeleton_by_embed(labels[None, None], emb)[0, 0].numpy()
+        assert np.array_equal(got, fx[f"inst_whole_N{N}"])
+    whole = orc.postprocess(t(unpack_mask(fx, "skeleton")), vec, scale, N=1).numpy()
+    assert np.array_equal(whole, fx["inst_whole_N1"])
+
+
+def test_baked_embed_to_prob():
+    fx = load_golden("embed_prob")
+    got = orc.baked_embed_to_prob(t(fx["embedding"]), t(fx["baked"]), t(fx["sigma"])).numpy()
+    np.testing.assert_allclose(got, fx["out"], rtol=1e-6, atol=0)
+
+
+def _skeleton_dict(fx):
+    out, at = {}, 0
+    for k, n in zip(fx["ids"], fx["lens"]):
+        out[int(k)] = t(fx["points"][at:at + int(n)])
+        at += int(n)
+    return out
+
+
+def test_bake_skeleton_cpu_semantics():
+    fx = load_golden("bake_skeleton")
+    sk = _skeleton_dict(fx)
+    mask = t(fx["mask"])
+    for tag, an in (("iso", (1.0, 1.0, 1.0)), ("aniso", (1.0, 1.0, 3.0))):
+        assert np.array_equal(orc.bake_skeleton(mask, sk, an, average=False).numpy(), fx[f"baked_{tag}"])
+        np.testing.assert_allclose(orc.bake_skeleton(mask, sk, an, average=True).numpy(), fx[f"baked_avg_{tag}"],
+                                   rtol=1e-6, atol=1e-6)
+
+
+def test_average_baked():
+    fx = load_golden("average_baked")
+    np.testing.assert_allclose(orc.average_baked_skeletons(t(fx["baked"])).numpy(), fx["out"], rtol=1e-6, atol=1e-7)
+
+
+def test_skeleton_to_mask_and_offsets():
+    fx = load_golden("skeleton_to_mask")
+    pts = fx["points"]
+    sk = {1: t(pts[:3]), 2: t(pts[3:])}
+    for r, f in ((7, 3), (9, 3), (2, 1)):
+        off = orc.disk_stamp_offsets(r, f)
+        assert np.array_equal(off.T, fx[f"offsets_r{r}_f{f}"])
+        got = orc.skeleton_to_mask(sk, (40, 36, 8), radius=r, flank_radius=f).numpy()
+        assert np.array_equal(got, fx[f"mask_r{r}_f{f}"])
+    assert orc.disk_stamp_offsets(7, 3).shape[0] == 207
+
+
+def test_canonical_relabel():
+    a = np.array([[0, 7, 7], [3, 0, 7], [3, 9, 0]])
+    assert orc.canonical_relabel(a).tolist() == [[0, 1, 1], [2, 0, 1], [2, 3, 0]]
+    assert orc.canonical_relabel(np.zeros((2, 2), dtype=np.int16)).sum() == 0
+
+
+def test_crop_origins_match_reference_quirks():
+    # SURVEY B#16: X=2048 -> origins 0,400,800,1200,1548,1548 ; shifted last crop emitted twice
+    assert orc.crop_origins(2048, 500, 50) == [0, 400, 800, 1200, 1548, 1548]
+    assert orc.crop_origins(512, 50, 5) == [0, 40, 80, 120, 160, 200, 240, 280, 320, 360, 400, 440, 462]
+    with pytest.raises(ValueError):
+        orc.crop_origins(8, 8, 50)

@@ -1,0 +1,121 @@
+/*
+ * skoots_b200 — C-ABI of the B200 (sm_100a) skeleton-embedding instance-assembly path.
+ *
+ * The reference (buswinka/skoots v0.0.5) is pure Python and has no FFI; its "operator API" for
+ * this path is the set of `skoots.lib.*` callables its pipelines bind by name.
+ * Each entry point below replaces the arithmetic of one of those callables; the Python mirror in
+ * `skoots_b200/lib/` keeps their names/signatures and calls these through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller (inputs, outputs and workspace);
+ *     the library never allocates, frees or synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t / CUstream passed as void*; NULL = legacy default stream);
+ *   - volumes are C-contiguous with Z fastest: (X,Y,Z), vector fields (3,X,Y,Z) — the
+ *     reference's layout (skoots/lib/eval.py:61-64);
+ *   - a volume may hold at most 2^31-1 voxels, each axis < 2^24;
+ *   - return value 0 = enqueued; <0 = SKB_E_* (nothing enqueued), text in skb_last_error();
+ *   - asynchronous conditions (workspace overflow) are reported in a caller-provided
+ *     device status word, see skb_ccl_*.
+ */
+#ifndef SKOOTS_B200_H
+#define SKOOTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_VERSION 100
+
+/* element types */
+enum { SKB_U8 = 0, SKB_I16 = 1, SKB_I32 = 2, SKB_F16 = 3, SKB_BF16 = 4, SKB_F32 = 5 };
+
+/* error codes */
+enum {
+    SKB_OK = 0,
+    SKB_E_ARG = -1,       /* bad argument (NULL, size, dtype, alignment) */
+    SKB_E_WORKSPACE = -2, /* workspace too small */
+    SKB_E_CUDA = -3,      /* CUDA launch error */
+    SKB_E_RANGE = -4      /* volume too large for 32-bit voxel indices */
+};
+
+/* bits of the device status word written by the CCL kernels */
+#define SKB_STATUS_ROOT_OVERFLOW 1u  /* more tile-local components than `capacity` */
+
+int skb_version(void);
+const char* skb_last_error(void); /* thread-local, valid until the next failing call */
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  vector_to_embedding            skoots/lib/vector_to_embedding.py:135-174 (_vec2embed3D 79-132)
+ *   out[b,c,x,y,z] = idx_c + vec*scale_c, then N-1 crop-local hops (round, clamp to [0,dim], fp32
+ *   ravel, gather) with decay — bit-exact restatement of the reference's fp32 op sequence.
+ *   vec: (B,3,X,Y,Z) f16|bf16|f32, out: (B,3,X,Y,Z) f32.  B>1 with N>1 reproduces the reference's
+ *   `take` over the flattened batch (all batches index batch 0).
+ * ------------------------------------------------------------------------------------------- */
+int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
+                    const float scale[3], int N, double decay, float* out, void* stream);
+
+/* 2-D form, vector_to_embedding.py:50-76.  vec (B,2,X,Y) -> out (B,2,X,Y) f32 */
+int skb_vec_embed2d(const void* vec, int vec_dtype, int64_t B, int64_t X, int64_t Y,
+                    const float scale[2], float* out, void* stream);
+
+/* backward of the N=1 forms: grad_vec[b,c,...] = grad_out[b,c,...] * scale_c, cast to vec_dtype.
+ * C = 2 or 3 channels of `inner` elements each. */
+int skb_vec_embed_bwd(const float* grad_out, int64_t B, int C, int64_t inner, const float* scale,
+                      void* grad_vec, int vec_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2  index_skeleton_by_embed        skoots/lib/skeleton.py:656-695
+ *   out[i] = labels[clamp(rint(e_x),0,Xs-1), clamp(rint(e_y),..), clamp(rint(e_z),..)] as int32.
+ *   labels (Xs,Ys,Zs) i16|i32|u8 ; embed (3,n) f32 (n = x*y*z of the crop) ; out (n) i32
+ * ------------------------------------------------------------------------------------------- */
+int skb_index_by_embed(const void* labels, int label_dtype, int64_t Xs, int64_t Ys, int64_t Zs,
+                       const float* embed, int64_t n, int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  efficient_flood_fill (connected components of mask>0)   skoots/lib/flood_fill.py:13-140
+ *   6-connectivity in 3-D (scipy.ndimage.label default structure, flood_fill.py:135), or, with
+ *   `planar` != 0, 4-connectivity inside each x-plane with numbering restarting per plane
+ *   (utils/flood_and_stitch.py:63-69 applied to a stack (S,X,Y) passed as (X=S,Y=X,Z=Y)).
+ *   Labels are label_base + 1 + (raster-order rank of the component's first voxel): identical to
+ *   scipy's numbering; the reference's single-crop result is label_base = 2 (flood_fill.py:138).
+ *
+ *   The labelling is produced in a sparse form in `workspace` (skb_ccl_label_sparse); it can then
+ *   be densified (skb_ccl_write_dense) or consumed directly by the fused gather (skb_assemble).
+ *   `capacity` = max number of tile-local components the workspace can hold (worst case V/2+1);
+ *   if exceeded, SKB_STATUS_ROOT_OVERFLOW is OR-ed into *status (device) and labels are invalid.
+ *   ncomp (device int32, may be NULL) receives the number of components.
+ * ------------------------------------------------------------------------------------------- */
+size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity);
+
+int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
+                         int planar, int32_t label_base, int64_t capacity, void* workspace,
+                         size_t workspace_bytes, int32_t* ncomp, uint32_t* status, void* stream);
+
+/* dense labels from the sparse form. out (X,Y,Z) i16|i32, may alias the mask given to
+ * skb_ccl_label_sparse (the reference labels in place, flood_fill.py:50). */
+int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, int64_t Z, void* out,
+                        int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1+a2+a6  fused instance assembly   skoots/lib/eval.py:245-284 (+ cropper.py:58-144)
+ *   For every voxel: find the reference crop that owns it (crop/overlap grid, later crops
+ *   overwrite, outer `overlap` margin never written -> 0), walk N hops in that crop's local
+ *   frame, add the crop origin in fp32 (eval.py:274), round/clamp against the whole volume and
+ *   read the component label there.  crop >= dims and overlap 0 = "whole volume is one crop".
+ *   Labels come either from the sparse CCL workspace (labels_dense == NULL) or from a dense
+ *   label volume (labels_dense != NULL, dtype label_dtype; workspace may then be NULL).
+ *   vec (3,X,Y,Z) f16|bf16|f32 ; out (X,Y,Z) i32|i16.
+ * ------------------------------------------------------------------------------------------- */
+int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z,
+                 const float scale[3], int N, double decay, const int32_t crop[3],
+                 const int32_t overlap[3], const void* workspace, const void* labels_dense,
+                 int label_dtype, void* out, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKOOTS_B200_H */

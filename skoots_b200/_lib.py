@@ -1,0 +1,103 @@
+"""ctypes binding of libskoots_b200.so (include/skoots_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a CUDA tensor is not
+supplied, the call raises.  PyTorch is used only to own device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Sequence
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libskoots_b200.so")
+
+SKB_U8, SKB_I16, SKB_I32, SKB_F16, SKB_BF16, SKB_F32 = range(6)
+STATUS_ROOT_OVERFLOW = 1
+
+_DTYPES = {
+    torch.uint8: SKB_U8, torch.bool: SKB_U8, torch.int16: SKB_I16, torch.int32: SKB_I32,
+    torch.float16: SKB_F16, torch.bfloat16: SKB_BF16, torch.float32: SKB_F32,
+}
+
+_lib = None
+
+_c_i64, _c_int, _c_vp, _c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t
+_c_f3 = ctypes.POINTER(ctypes.c_float)
+_c_i3 = ctypes.POINTER(ctypes.c_int32)
+
+# name -> (restype, argtypes); must list every symbol include/skoots_b200.h declares
+SIGNATURES = {
+    "skb_version": (_c_int, []),
+    "skb_last_error": (ctypes.c_char_p, []),
+    "skb_vec_embed3d": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_vp, _c_vp]),
+    "skb_vec_embed2d": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp]),
+    "skb_vec_embed_bwd": (_c_int, [_c_vp, _c_i64, _c_int, _c_i64, _c_f3, _c_vp, _c_int, _c_vp]),
+    "skb_index_by_embed": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "skb_ccl_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i64, _c_i64]),
+    "skb_ccl_label_sparse": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_int32, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp, _c_vp]),
+    "skb_ccl_write_dense": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp]),
+    "skb_assemble": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
+}
+
+
+class SkootsB200Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SkootsB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m skoots_b200.build` "
+                "(skoots_b200 has no CPU or PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SkootsB200Error(f"libskoots_b200 error {rc}: {load().skb_last_error().decode()}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise SkootsB200Error(f"unsupported dtype {t.dtype}") from None
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise SkootsB200Error("skoots_b200 operates on CUDA tensors only (no CPU fallback)")
+        if dev is not None and t.device != dev:
+            raise SkootsB200Error("all tensors must live on the same CUDA device")
+        dev = t.device
+    return dev
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f3(values: Sequence[float]):
+    vals = [float(v) for v in values]
+    return (ctypes.c_float * len(vals))(*vals)
+
+
+def i3(values: Sequence[int]):
+    vals = [int(v) for v in values]
+    return (ctypes.c_int32 * len(vals))(*vals)
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()

@@ -1,0 +1,430 @@
+// Fused vector -> embedding -> skeleton-label gather (kernel (a) of the north star) and the
+// stand-alone forms of its two halves.
+//
+// Reference arithmetic restated bit-for-bit:
+//   skoots/lib/vector_to_embedding.py:79-132   phi = idx + v*s ; N-1 hops {round, clamp to
+//                                              [0,dim] (sic), fp32 ravel, clamp, gather, add}
+//   skoots/lib/eval.py:258-284                 crop grid, crop-local walk, origin added in fp32
+//   skoots/lib/skeleton.py:678-695             round, clamp to [0,dim-1], gather labels, int32
+// Every fp32 operation is issued with explicit round-to-nearest intrinsics so nvcc cannot
+// contract the reference's separately-rounded multiply and add into an FMA.
+//
+// Memory plan: each thread owns 8 consecutive voxels of the flat (Z-fastest) index, i.e. one
+// 16-byte load per fp16 vector channel and one/two 16-byte stores of labels, all streaming
+// (L1::no_allocate).  The label side is read through the bit-packed mask written by the CCL
+// tile kernel (1/8 B per voxel, L2-resident over the +-scale window) and, only for targets
+// that are foreground, the sparse parent array.  A zero vector (background, ~95 % of a volume)
+// short-cuts to "label of myself", which is decided from one byte of the bit mask.
+#include "skb_common.cuh"
+
+struct AsmParams {
+    const void* vec;        // channel 0 of the field being assembled (batch b)
+    const void* vec_hops;   // field the N>1 hops gather from (batch 0 — reference `take` quirk)
+    long long cstride;      // elements between channels
+    int X, Y, Z;
+    float s[3];
+    int N;
+    double decay;
+    int cs[3];              // crop size clamped to the volume
+    int ov[3];
+    int step[3];
+    int shifted[3];         // the axis has a shifted-back last crop
+    int fast_ok;            // zero-vector voxels provably resolve to themselves
+    int vec_aligned;        // 16-byte loads of the vector channels are legal
+    // label source
+    const ull* bits;
+    const int* parent;
+    int ZW;
+    const void* dense;
+    int dense_dtype;
+};
+
+__device__ __forceinline__ int owner_origin(int g, int dim, int size, int ov, int step, int shifted) {
+    // last crop (in the reference's loop order) whose written interior contains g; -1 if none
+    if (shifted && g >= dim - size + ov && g < dim - ov) return dim - size;
+    if (g >= ov) {
+        int o = ((g - ov) / step) * step;
+        if (o + size <= dim) return o;
+    }
+    return -1;
+}
+
+template <typename VecT>
+__device__ __forceinline__ float load_vec(const void* base, long long idx) {
+    return skb_to_float<VecT>(__ldg(static_cast<const VecT*>(base) + idx));
+}
+template <>
+__device__ __forceinline__ float load_vec<__nv_bfloat16>(const void* base, long long idx) {
+    unsigned short raw = __ldg(static_cast<const unsigned short*>(base) + idx);
+    return __uint_as_float((unsigned)raw << 16);
+}
+
+// crop-local walk: (lx,ly,lz) local integer coords, v* own vector, o* crop origin.
+// returns the embedding in the crop-local frame (before the origin is added).
+template <typename VecT>
+__device__ __forceinline__ void walk(const AsmParams& P, int lx, int ly, int lz, int ox, int oy, int oz, float v0,
+                                     float v1, float v2, float& mx, float& my, float& mz) {
+    mx = __fadd_rn((float)lx, __fmul_rn(v0, P.s[0]));
+    my = __fadd_rn((float)ly, __fmul_rn(v1, P.s[1]));
+    mz = __fadd_rn((float)lz, __fmul_rn(v2, P.s[2]));
+    if (P.N > 1) {
+        const float fy = (float)P.cs[1], fz = (float)P.cs[2];
+        const long long total = (long long)P.cs[0] * P.cs[1] * P.cs[2];
+        const float fmax_index = (float)(total - 1);
+        const unsigned ucz = (unsigned)P.cs[2], ucy = (unsigned)P.cs[1];
+        double k = 1.0;
+        for (int it = 1; it < P.N; ++it) {
+            k *= P.decay;
+            const float kf = (float)k;
+            float ix = fminf(fmaxf(rintf(mx), 0.f), (float)P.cs[0]);
+            float iy = fminf(fmaxf(rintf(my), 0.f), fy);
+            float iz = fminf(fmaxf(rintf(mz), 0.f), fz);
+            float f = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(ix, fy), fz), __fmul_rn(iy, fz)), iz);
+            f = fminf(fmaxf(f, 0.f), fmax_index);
+            long long fi = (long long)f;
+            if (fi > total - 1) fi = total - 1;  // (float)(total-1) may round up; torch would raise here
+            unsigned u = (unsigned)fi;
+            unsigned qz = u / ucz, cz = u - qz * ucz;
+            unsigned cx = qz / ucy, cy = qz - cx * ucy;
+            long long g = ((long long)(ox + (int)cx) * P.Y + (oy + (int)cy)) * P.Z + (oz + (int)cz);
+            float h0 = load_vec<VecT>(P.vec_hops, g);
+            float h1 = load_vec<VecT>(P.vec_hops, g + P.cstride);
+            float h2 = load_vec<VecT>(P.vec_hops, g + 2 * P.cstride);
+            mx = __fadd_rn(mx, __fmul_rn(h0, __fmul_rn(kf, P.s[0])));
+            my = __fadd_rn(my, __fmul_rn(h1, __fmul_rn(kf, P.s[1])));
+            mz = __fadd_rn(mz, __fmul_rn(h2, __fmul_rn(kf, P.s[2])));
+        }
+    }
+}
+
+__device__ __forceinline__ int clamp_index(float e, int dim) {
+    return (int)fminf(fmaxf(rintf(e), 0.f), (float)(dim - 1));
+}
+
+__device__ __forceinline__ int label_at(const AsmParams& P, int tx, int ty, int tz) {
+    long long rowi = (long long)tx * P.Y + ty;
+    if (P.dense) {
+        long long t = rowi * P.Z + tz;
+        if (P.dense_dtype == SKB_I16) return (int)__ldg(static_cast<const short*>(P.dense) + t);
+        if (P.dense_dtype == SKB_I32) return __ldg(static_cast<const int*>(P.dense) + t);
+        return (int)__ldg(static_cast<const unsigned char*>(P.dense) + t);
+    }
+    ull w = __ldg(P.bits + rowi * P.ZW + (tz >> 6));
+    if (!((w >> (tz & 63)) & 1ull)) return 0;
+    return skb_sparse_label(P.parent, (int)(rowi * P.Z + tz));
+}
+
+template <typename VecT>
+__device__ __forceinline__ int assemble_voxel(const AsmParams& P, int x, int y, int z, float v0, float v1, float v2) {
+    int ox = owner_origin(x, P.X, P.cs[0], P.ov[0], P.step[0], P.shifted[0]);
+    int oy = owner_origin(y, P.Y, P.cs[1], P.ov[1], P.step[1], P.shifted[1]);
+    int oz = owner_origin(z, P.Z, P.cs[2], P.ov[2], P.step[2], P.shifted[2]);
+    if ((ox | oy | oz) < 0) return 0;  // outer margin: never written by the reference (eval.py:259-269)
+    float mx, my, mz;
+    walk<VecT>(P, x - ox, y - oy, z - oz, ox, oy, oz, v0, v1, v2, mx, my, mz);
+    float ex = __fadd_rn(mx, (float)ox), ey = __fadd_rn(my, (float)oy), ez = __fadd_rn(mz, (float)oz);
+    return label_at(P, clamp_index(ex, P.X), clamp_index(ey, P.Y), clamp_index(ez, P.Z));
+}
+
+template <typename VecT>
+__device__ __forceinline__ bool load8(const void* base, long long idx, bool aligned, float* out) {
+    // returns true when all 8 raw elements are +0 bit patterns
+    const VecT* p = static_cast<const VecT*>(base) + idx;
+    if (aligned) {
+        if (sizeof(VecT) == 2) {
+            uint4 q = skb_ld_stream16(p);
+            const VecT* e = reinterpret_cast<const VecT*>(&q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j] = skb_to_float<VecT>(e[j]);
+            return (q.x | q.y | q.z | q.w) == 0u;
+        } else {
+            uint4 q0 = skb_ld_stream16(p), q1 = skb_ld_stream16(reinterpret_cast<const char*>(p) + 16);
+            const float* e0 = reinterpret_cast<const float*>(&q0);
+            const float* e1 = reinterpret_cast<const float*>(&q1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { out[j] = e0[j]; out[4 + j] = e1[j]; }
+            return (q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) == 0u;
+        }
+    }
+    bool zero = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        out[j] = skb_to_float<VecT>(p[j]);
+        zero = zero && (out[j] == 0.f) && !signbit(out[j]);
+    }
+    return zero;
+}
+
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(256) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= V) return;
+    const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
+    unsigned q = (unsigned)i0 / uz;
+    int z = (int)((unsigned)i0 - q * uz);
+    int x = (int)(q / uy);
+    int y = (int)(q - (unsigned)x * uy);
+
+    __align__(16) OutT lab[8];
+    if (i0 + 8 <= V) {
+        float v0[8], v1[8], v2[8];
+        const bool al = P.vec_aligned != 0;
+        bool zero = load8<VecT>(P.vec, i0, al, v0);
+        zero = load8<VecT>(P.vec, i0 + P.cstride, al, v1) && zero;
+        zero = load8<VecT>(P.vec, i0 + 2 * P.cstride, al, v2) && zero;
+        bool done = false;
+        if (zero && P.fast_ok && !P.dense && z + 8 <= P.Z) {
+            // all eight voxels point at themselves: their label is their own component (or 0)
+            long long wi = ((long long)x * P.Y + y) * P.ZW + (z >> 6);
+            int sh = z & 63;
+            ull w = __ldg(P.bits + wi) >> sh;
+            if (sh > 56) w |= __ldg(P.bits + wi + 1) << (64 - sh);
+            if ((w & 0xFFull) == 0ull) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) lab[j] = (OutT)0;
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                lab[j] = (OutT)assemble_voxel<VecT>(P, x, y, z, v0[j], v1[j], v2[j]);
+                if (++z == P.Z) { z = 0; if (++y == P.Y) { y = 0; ++x; } }
+            }
+        }
+        if (sizeof(OutT) == 2) {
+            skb_st_stream16(out + i0, *reinterpret_cast<uint4*>(lab));
+        } else {
+            skb_st_stream16(out + i0, reinterpret_cast<uint4*>(lab)[0]);
+            skb_st_stream16(out + i0 + 4, reinterpret_cast<uint4*>(lab)[1]);
+        }
+    } else {
+        for (long long i = i0; i < V; ++i) {
+            float a = load_vec<VecT>(P.vec, i), b = load_vec<VecT>(P.vec, i + P.cstride),
+                  c = load_vec<VecT>(P.vec, i + 2 * P.cstride);
+            out[i] = (OutT)assemble_voxel<VecT>(P, x, y, z, a, b, c);
+            if (++z == P.Z) { z = 0; if (++y == P.Y) { y = 0; ++x; } }
+        }
+    }
+}
+
+// ---- stand-alone a1: materialise the embedding ---------------------------------------------------
+template <typename VecT>
+__global__ void __launch_bounds__(256) vec_embed3d_kernel(AsmParams P, float* __restrict__ out, long long V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
+    unsigned q = (unsigned)i / uz;
+    int z = (int)((unsigned)i - q * uz);
+    int x = (int)(q / uy);
+    int y = (int)(q - (unsigned)x * uy);
+    float v0 = load_vec<VecT>(P.vec, i), v1 = load_vec<VecT>(P.vec, i + P.cstride),
+          v2 = load_vec<VecT>(P.vec, i + 2 * P.cstride);
+    float mx, my, mz;
+    walk<VecT>(P, x, y, z, 0, 0, 0, v0, v1, v2, mx, my, mz);
+    out[i] = mx;
+    out[i + V] = my;
+    out[i + 2 * V] = mz;
+}
+
+template <typename VecT>
+__global__ void __launch_bounds__(256) vec_embed2d_kernel(const VecT* __restrict__ vec, int X, int Y, float s0, float s1,
+                                                         float* __restrict__ out, long long total) {
+    // total = B*X*Y ; vec/out are (B,2,X,Y)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long plane = (long long)X * Y;
+    const long long b = i / plane, r = i - b * plane;
+    const int x = (int)(r / Y), y = (int)(r - (long long)x * Y);
+    const long long at = b * 2 * plane + r;
+    out[at] = __fadd_rn((float)x, __fmul_rn(skb_to_float<VecT>(vec[at]), s0));
+    out[at + plane] = __fadd_rn((float)y, __fmul_rn(skb_to_float<VecT>(vec[at + plane]), s1));
+}
+
+template <typename VecT>
+__global__ void __launch_bounds__(256) vec_embed_bwd_kernel(const float* __restrict__ go, VecT* __restrict__ gv,
+                                                           long long inner, int C, float s0, float s1, float s2,
+                                                           long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)((i / inner) % C);
+    const float s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    gv[i] = skb_from_float<VecT>(__fmul_rn(go[i], s));
+}
+
+// ---- stand-alone a2: gather labels by a materialised embedding -----------------------------------------
+template <typename LabT>
+__global__ void __launch_bounds__(256) index_by_embed_kernel(const LabT* __restrict__ labels, int Xs, int Ys, int Zs,
+                                                            const float* __restrict__ embed, long long n,
+                                                            int* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int tx = clamp_index(embed[i], Xs), ty = clamp_index(embed[i + n], Ys), tz = clamp_index(embed[i + 2 * n], Zs);
+    out[i] = (int)__ldg(labels + ((long long)tx * Ys + ty) * Zs + tz);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int elem_size(int dtype) {
+    switch (dtype) {
+        case SKB_U8: return 1;
+        case SKB_I16: case SKB_F16: case SKB_BF16: return 2;
+        case SKB_I32: case SKB_F32: return 4;
+    }
+    return 0;
+}
+
+static void fill_crop(AsmParams& P, const int32_t crop[3], const int32_t overlap[3]) {
+    const int dims[3] = {P.X, P.Y, P.Z};
+    long long cropvol = 1;
+    for (int a = 0; a < 3; ++a) {
+        P.cs[a] = crop[a] < dims[a] ? crop[a] : dims[a];
+        P.ov[a] = overlap[a];
+        P.step[a] = P.cs[a] - 2 * P.ov[a];
+        int k_last = (dims[a] - 1) / P.step[a];
+        P.shifted[a] = (k_last * P.step[a] + P.cs[a] > dims[a]) ? 1 : 0;
+        cropvol *= P.cs[a];
+    }
+    P.fast_ok = (P.N == 1 || cropvol <= (1LL << 24)) ? 1 : 0;
+}
+
+template <typename VecT>
+static void launch_assemble(const AsmParams& P, void* out, int out_dtype, long long V, cudaStream_t st) {
+    unsigned nb = (unsigned)(((V + 7) / 8 + 255) / 256);
+    if (out_dtype == SKB_I32) assemble_kernel<VecT, int32_t><<<nb, 256, 0, st>>>(P, static_cast<int32_t*>(out), V);
+    else assemble_kernel<VecT, int16_t><<<nb, 256, 0, st>>>(P, static_cast<int16_t*>(out), V);
+}
+
+extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, const float scale[3], int N,
+                            double decay, const int32_t crop[3], const int32_t overlap[3], const void* workspace,
+                            const void* labels_dense, int label_dtype, void* out, int out_dtype, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_assemble");
+    if (rc) return rc;
+    SKB_REQUIRE(vec && out && scale && crop && overlap, "skb_assemble: NULL pointer");
+    SKB_REQUIRE(workspace || labels_dense, "skb_assemble: need a CCL workspace or a dense label volume");
+    SKB_REQUIRE(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32, "skb_assemble: vec dtype");
+    SKB_REQUIRE(out_dtype == SKB_I32 || out_dtype == SKB_I16, "skb_assemble: out dtype must be i32 or i16");
+    SKB_REQUIRE(N >= 1, "skb_assemble: N must be >= 1");
+    SKB_REQUIRE(skb_aligned16(out), "skb_assemble: out must be 16-byte aligned");
+    if (labels_dense)
+        SKB_REQUIRE(label_dtype == SKB_I16 || label_dtype == SKB_I32 || label_dtype == SKB_U8, "skb_assemble: label dtype");
+    const bool any_ov = overlap[0] > 0 || overlap[1] > 0 || overlap[2] > 0;
+    const bool all_ov = overlap[0] > 0 && overlap[1] > 0 && overlap[2] > 0;
+    SKB_REQUIRE(overlap[0] >= 0 && overlap[1] >= 0 && overlap[2] >= 0 && any_ov == all_ov,
+                "skb_assemble: overlap must be all zero or all positive (the reference's destination slicing, eval.py:281-283)");
+    const int64_t dims[3] = {X, Y, Z};
+    for (int a = 0; a < 3; ++a) {
+        int64_t cs = crop[a] < dims[a] ? crop[a] : dims[a];
+        SKB_REQUIRE(crop[a] > 0 && cs - 2 * overlap[a] > 0,
+                    "skb_assemble: crop must exceed twice the overlap on every axis (the reference's crops() would not terminate)");
+    }
+    AsmParams P = {};
+    P.vec = vec; P.vec_hops = vec;
+    P.cstride = X * Y * Z;
+    P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+    P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
+    P.N = N; P.decay = decay;
+    fill_crop(P, crop, overlap);
+    P.vec_aligned = skb_aligned16(vec) && ((P.cstride * elem_size(vec_dtype)) % 16 == 0);
+    if (labels_dense) {
+        P.dense = labels_dense; P.dense_dtype = label_dtype;
+    } else {
+        SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+        const char* base = static_cast<const char*>(workspace);
+        P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
+        P.parent = reinterpret_cast<const int*>(base + L.off_parent);
+        P.ZW = L.ZW;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = X * Y * Z;
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, V, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, V, st);
+    else launch_assemble<float>(P, out, out_dtype, V, st);
+    SKB_LAUNCH_CHECK("assemble_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
+                               const float scale[3], int N, double decay, float* out, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_vec_embed3d");
+    if (rc) return rc;
+    SKB_REQUIRE(vec && out && scale && B >= 1 && N >= 1, "skb_vec_embed3d: bad argument");
+    SKB_REQUIRE(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32, "skb_vec_embed3d: vec dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = X * Y * Z;
+    const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
+    const int es = elem_size(vec_dtype);
+    for (int64_t b = 0; b < B; ++b) {
+        AsmParams P = {};
+        P.vec = static_cast<const char*>(vec) + (size_t)b * 3 * V * es;
+        P.vec_hops = vec;  // reference take() flattens the batch: hops always read batch 0
+        P.cstride = V;
+        P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+        P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
+        P.N = N; P.decay = decay;
+        fill_crop(P, crop, ov);
+        float* o = out + (size_t)b * 3 * V;
+        unsigned nb = (unsigned)((V + 255) / 256);
+        if (vec_dtype == SKB_F16) vec_embed3d_kernel<__half><<<nb, 256, 0, st>>>(P, o, V);
+        else if (vec_dtype == SKB_BF16) vec_embed3d_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(P, o, V);
+        else vec_embed3d_kernel<float><<<nb, 256, 0, st>>>(P, o, V);
+    }
+    SKB_LAUNCH_CHECK("vec_embed3d_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_vec_embed2d(const void* vec, int vec_dtype, int64_t B, int64_t X, int64_t Y, const float scale[2],
+                               float* out, void* stream) {
+    SKB_REQUIRE(vec && out && scale && B >= 1 && X >= 1 && Y >= 1, "skb_vec_embed2d: bad argument");
+    SKB_REQUIRE(X < (1 << 24) && Y < (1 << 24), "skb_vec_embed2d: axis too long for exact fp32 indices");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = B * X * Y;
+    unsigned nb = (unsigned)((total + 255) / 256);
+    if (vec_dtype == SKB_F16)
+        vec_embed2d_kernel<__half><<<nb, 256, 0, st>>>(static_cast<const __half*>(vec), (int)X, (int)Y, scale[0], scale[1], out, total);
+    else if (vec_dtype == SKB_BF16)
+        vec_embed2d_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(vec), (int)X, (int)Y, scale[0], scale[1], out, total);
+    else if (vec_dtype == SKB_F32)
+        vec_embed2d_kernel<float><<<nb, 256, 0, st>>>(static_cast<const float*>(vec), (int)X, (int)Y, scale[0], scale[1], out, total);
+    else SKB_REQUIRE(false, "skb_vec_embed2d: vec dtype");
+    SKB_LAUNCH_CHECK("vec_embed2d_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_vec_embed_bwd(const float* grad_out, int64_t B, int C, int64_t inner, const float* scale,
+                                 void* grad_vec, int vec_dtype, void* stream) {
+    SKB_REQUIRE(grad_out && grad_vec && scale && B >= 1 && (C == 2 || C == 3) && inner >= 1, "skb_vec_embed_bwd: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = B * C * inner;
+    unsigned nb = (unsigned)((total + 255) / 256);
+    const float s2 = C == 3 ? scale[2] : 0.f;
+    if (vec_dtype == SKB_F16)
+        vec_embed_bwd_kernel<__half><<<nb, 256, 0, st>>>(grad_out, static_cast<__half*>(grad_vec), inner, C, scale[0], scale[1], s2, total);
+    else if (vec_dtype == SKB_BF16)
+        vec_embed_bwd_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(grad_out, static_cast<__nv_bfloat16*>(grad_vec), inner, C, scale[0], scale[1], s2, total);
+    else if (vec_dtype == SKB_F32)
+        vec_embed_bwd_kernel<float><<<nb, 256, 0, st>>>(grad_out, static_cast<float*>(grad_vec), inner, C, scale[0], scale[1], s2, total);
+    else SKB_REQUIRE(false, "skb_vec_embed_bwd: vec dtype");
+    SKB_LAUNCH_CHECK("vec_embed_bwd_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_index_by_embed(const void* labels, int label_dtype, int64_t Xs, int64_t Ys, int64_t Zs,
+                                  const float* embed, int64_t n, int32_t* out, void* stream) {
+    int rc = skb_check_volume(Xs, Ys, Zs, "skb_index_by_embed");
+    if (rc) return rc;
+    SKB_REQUIRE(labels && embed && out && n >= 0, "skb_index_by_embed: bad argument");
+    if (n == 0) return SKB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned nb = (unsigned)((n + 255) / 256);
+    if (label_dtype == SKB_I16)
+        index_by_embed_kernel<int16_t><<<nb, 256, 0, st>>>(static_cast<const int16_t*>(labels), (int)Xs, (int)Ys, (int)Zs, embed, n, out);
+    else if (label_dtype == SKB_I32)
+        index_by_embed_kernel<int32_t><<<nb, 256, 0, st>>>(static_cast<const int32_t*>(labels), (int)Xs, (int)Ys, (int)Zs, embed, n, out);
+    else if (label_dtype == SKB_U8)
+        index_by_embed_kernel<uint8_t><<<nb, 256, 0, st>>>(static_cast<const uint8_t*>(labels), (int)Xs, (int)Ys, (int)Zs, embed, n, out);
+    else SKB_REQUIRE(false, "skb_index_by_embed: label dtype must be u8, i16 or i32");
+    SKB_LAUNCH_CHECK("index_by_embed_kernel");
+    return SKB_OK;
+}

@@ -1,0 +1,565 @@
+// Connected-component labelling of the thresholded skeleton mask on B200 (sm_100a).
+//
+// Replaces the arithmetic of skoots/lib/flood_fill.py:13-140 (scipy.ndimage.label per crop +
+// seam merging).  Design:
+//
+//   K1 ccl_tile_kernel      one 4096-voxel tile per CTA.  The mask is read once with 16-byte
+//                           loads (Z is the contiguous axis), turned into one 64-bit word per
+//                           (x,y) row, written out as the bit-packed mask, and labelled inside
+//                           the tile by a shared-memory union-find over z-RUNS (a run's start
+//                           is found with clz on the row word, so z-connectivity costs nothing;
+//                           only y/x neighbour rows need unions).  Every foreground voxel gets
+//                           parent[v] = its tile root; tile roots are appended to a list.
+//   K2 ccl_boundary_kernel  one thread per 64-bit word of the bit-packed mask: unions across
+//                           tile faces with atomicMin on the global parent array.
+//   K3 ccl_flatten_kernel   pointer-jumps every tile root to its global root, marks global
+//                           roots in a bitmap and counts them per 4096-voxel chunk.
+//   K4 ccl_scan_kernel      exclusive scan of the chunk counts (-> raster-order rank bases).
+//   K5 ccl_rank_kernel      rank of each global root = scipy.ndimage.label's numbering.
+//   K6 ccl_publish_kernel   copies the label code into every non-global tile root.
+//
+// After K6:  parent[v] < 0  -> label = -parent[v]      (v is a tile root)
+//            parent[v] >= 0 -> label = -parent[parent[v]]
+// Only foreground entries of `parent` are ever written or read, so the dense 4-byte array is
+// never initialised and never streamed: HBM traffic is 1 B/voxel (mask) + 1/8 B (bit mask)
+// + O(foreground).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "skb_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing shared by every translation unit
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void skb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* skb_last_error(void) { return g_err; }
+extern "C" int skb_version(void) { return SKB_VERSION; }
+
+int skb_check_volume(int64_t X, int64_t Y, int64_t Z, const char* who) {
+    if (X <= 0 || Y <= 0 || Z <= 0) {
+        skb_set_error("%s: dims must be positive (got %lld,%lld,%lld)", who, (long long)X, (long long)Y, (long long)Z);
+        return SKB_E_ARG;
+    }
+    if (X >= (1 << 24) || Y >= (1 << 24) || Z >= (1 << 24) || X * Y * Z > 2147483647LL) {
+        skb_set_error("%s: volume %lldx%lldx%lld exceeds 2^31-1 voxels / 2^24 per axis", who, (long long)X,
+                      (long long)Y, (long long)Z);
+        return SKB_E_RANGE;
+    }
+    return SKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+struct CclView {
+    int X, Y, Z, ZW;
+    int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
+    int capacity;
+    SkbCclHeader* hdr;
+    ull* bits;
+    int* parent;
+    ull* rootbits;
+    int* chunks;
+    int* tile_roots;
+    int* flat;
+    int* groots;
+    unsigned* status;
+    int* ncomp_out;
+    long long n_words, n_chunks;
+};
+
+// start of the z-run containing bit p of row word w (bit p must be set)
+__device__ __forceinline__ int run_start(ull w, int p) {
+    ull below = ~w & ((1ull << p) - 1ull);
+    return below ? 64 - __clzll((long long)below) : 0;
+}
+
+__device__ __forceinline__ int sfind(volatile int* lab, int a) {
+    int p = lab[a];
+    while (p != a) {
+        a = p;
+        p = lab[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void sunion(int* lab, int a, int b) {
+    for (;;) {
+        a = sfind(lab, a);
+        b = sfind(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__device__ __forceinline__ int gload(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ __forceinline__ int gfind(const int* parent, int a) {
+    int p = gload(parent + a);
+    while (p != a) {
+        a = p;
+        p = gload(parent + a);
+    }
+    return a;
+}
+
+__device__ __forceinline__ void gunion(int* parent, int a, int b) {
+    for (;;) {
+        a = gfind(parent, a);
+        b = gfind(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// foreground bits of up to 16 consecutive mask elements starting at p (n valid)
+template <typename MaskT>
+__device__ __forceinline__ unsigned fg16(const MaskT* p, int n, bool vec_ok);
+
+template <>
+__device__ __forceinline__ unsigned fg16<uint8_t>(const uint8_t* p, int n, bool vec_ok) {
+    unsigned bits = 0;
+    if (vec_ok && n == 16) {
+        uint4 q = skb_ld_stream16(p);
+        unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // non-zero byte -> bit: (b | -b) has its top bit set iff b != 0, per byte via SIMD
+            unsigned nz = __vcmpne4(w[i], 0u);  // 0xFF per non-zero byte
+            unsigned m = nz & 0x08040201u;      // byte k keeps bit k
+            m |= m >> 16;
+            m |= m >> 8;
+            bits |= (m & 0xFu) << (4 * i);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) bits |= (unsigned)(p[i] != 0) << i;
+    }
+    return bits;
+}
+
+template <>
+__device__ __forceinline__ unsigned fg16<int16_t>(const int16_t* p, int n, bool vec_ok) {
+    unsigned bits = 0;
+    if (vec_ok && n == 16) {
+        uint4 q0 = skb_ld_stream16(p), q1 = skb_ld_stream16(p + 8);
+        unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            unsigned gt = __vcmpgts2(w[i], 0u);  // 0xFFFF per halfword > 0 (signed)
+            bits |= ((gt & 1u) | ((gt >> 15) & 2u)) << (2 * i);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) bits |= (unsigned)(p[i] > 0) << i;
+    }
+    return bits;
+}
+
+__global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
+    if (threadIdx.x == 0) {
+        *v.hdr = h;
+        *v.status = 0u;
+        if (v.ncomp_out) *v.ncomp_out = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: tile-local run-based union-find
+// ------------------------------------------------------------------------------------------
+template <typename MaskT, int TZ>
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
+    constexpr int SZ = TZ / 16;           // 16-voxel segments per row
+    constexpr int ROWS = 256 / SZ;        // rows per tile
+    constexpr int TY = (TZ == 64) ? 8 : 16;
+    constexpr int TX = ROWS / TY;
+    __shared__ ull srow[ROWS];
+    __shared__ int slab[ROWS * TZ];
+    __shared__ int s_count, s_base;
+
+    const int tid = threadIdx.x;
+    const int seg = tid % SZ, row = tid / SZ;
+    const int ly = row % TY, lx = row / TY;
+    const int x0 = blockIdx.z * TX, y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
+    const int x = x0 + lx, y = y0 + ly, z = z0 + seg * 16;
+    const bool in_row = (x < v.X) && (y < v.Y);
+    const long long rowi = (long long)x * v.Y + y;
+
+    if (tid == 0) s_count = 0;
+    unsigned b16 = 0;
+    if (in_row && z < v.Z) b16 = fg16<MaskT>(mask + rowi * v.Z + z, min(16, v.Z - z), vec_ok != 0);
+
+    ull w = (ull)b16 << (16 * seg);
+#pragma unroll
+    for (int o = 1; o < SZ; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+    if (seg == 0) {
+        srow[row] = w;
+        if (in_row) v.bits[rowi * v.ZW + blockIdx.x] = w;
+    }
+    if (!__syncthreads_or(b16 != 0)) return;  // empty tile: nothing to label
+
+    const ull segmask = 0xFFFFull << (16 * seg);
+    const ull starts = w & ~(w << 1) & segmask;  // run starts inside my segment
+    for (ull s = starts; s; s &= s - 1) {
+        int p = __ffsll((long long)s) - 1;
+        slab[row * TZ + p] = row * TZ + p;
+    }
+    __syncthreads();
+
+    // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
+    if (w & segmask) {
+        if (ly > 0) {
+            ull wn = srow[row - 1], a = w & wn;
+            for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
+                int p = __ffsll((long long)s) - 1;
+                sunion(slab, row * TZ + run_start(w, p), (row - 1) * TZ + run_start(wn, p));
+            }
+        }
+        if (lx > 0 && v.connect_x) {
+            ull wn = srow[row - TY], a = w & wn;
+            for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
+                int p = __ffsll((long long)s) - 1;
+                sunion(slab, row * TZ + run_start(w, p), (row - TY) * TZ + run_start(wn, p));
+            }
+        }
+    }
+    __syncthreads();
+
+    // resolve every run starting in my segment; write parent for all its voxels
+    unsigned rootmask = 0;  // bit (p - 16*seg) set when the run starting at p is a tile root
+    const int gbase = (int)(rowi * v.Z) + z0;  // voxel index of bit 0 of this row word
+    for (ull s = starts; s; s &= s - 1) {
+        int p = __ffsll((long long)s) - 1;
+        int l = row * TZ + p;
+        int r = sfind(slab, l);
+        int groot;
+        if (r == l) {
+            rootmask |= 1u << (p - 16 * seg);
+            groot = gbase + p;
+        } else {
+            int rrow = r / TZ, rp = r % TZ;
+            groot = (int)(((long long)(x0 + rrow / TY) * v.Y + (y0 + rrow % TY)) * v.Z) + z0 + rp;
+        }
+        ull t = ~(w >> p);
+        int len = t ? __ffsll((long long)t) - 1 : 64 - p;
+        for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+    }
+    int mine = __popc(rootmask);
+    int off = mine ? atomicAdd(&s_count, mine) : 0;
+    __syncthreads();
+    if (tid == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
+    __syncthreads();
+    if (mine) {
+        int at = s_base + off;
+        for (unsigned m = rootmask; m; m &= m - 1) {
+            int p = 16 * seg + __ffs((int)m) - 1;
+            if (at < v.capacity) v.tile_roots[at] = gbase + p;
+            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            ++at;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: unions across tile faces, driven by the bit-packed mask
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY) {
+    long long widx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (widx >= v.n_words) return;
+    ull w = v.bits[widx];
+    if (!w) return;
+    int k = (int)(widx % v.ZW);
+    long long rowi = widx / v.ZW;
+    int y = (int)(rowi % v.Y), x = (int)(rowi / v.Y);
+    int gbase = (int)(rowi * v.Z) + 64 * k;
+    if (k > 0 && (w & 1ull)) {
+        if (v.bits[widx - 1] >> 63) gunion(v.parent, gbase, gbase - 1);
+    }
+    if (y > 0 && (y % TY) == 0) {
+        ull a = w & v.bits[widx - v.ZW];
+        for (ull s = a & ~(a << 1); s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            gunion(v.parent, gbase + p, gbase + p - v.Z);
+        }
+    }
+    if (v.connect_x && x > 0 && (x % TX) == 0) {
+        ull a = w & v.bits[widx - (long long)v.Y * v.ZW];
+        int plane = v.Y * v.Z;
+        for (ull s = a & ~(a << 1); s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            gunion(v.parent, gbase + p, gbase + p - plane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: pointer jumping of tile roots; global roots -> bitmap + chunk histogram + list
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long word_of_voxel(const CclView& v, int vox, int* bit) {
+    int zrow = vox % v.Z;
+    long long rowi = vox / v.Z;
+    *bit = zrow & 63;
+    return rowi * v.ZW + (zrow >> 6);
+}
+
+__global__ void __launch_bounds__(256) ccl_flatten_kernel(CclView v) {
+    unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int r = v.tile_roots[i];
+        int g = gfind(v.parent, r);
+        v.flat[i] = g;
+        if (g == r) {
+            int bit;
+            long long wi = word_of_voxel(v, r, &bit);
+            atomicOr(&v.rootbits[wi], 1ull << bit);
+            atomicAdd(&v.chunks[wi >> 6], 1);
+            // warp-aggregated append: one atomic per warp, slots handed out by ballot rank
+            unsigned m = __activemask();
+            int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&v.hdr->n_global_roots, (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            v.groots[base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: exclusive scan of the chunk histogram (single CTA, 1024 threads, sequential tiles)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ccl_scan_kernel(CclView v) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    constexpr int PER = 8;
+    for (long long base = 0; base < v.n_chunks; base += 1024 * PER) {
+        int vals[PER], sum = 0;
+        long long at = base + (long long)tid * PER;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            vals[j] = (at + j < v.n_chunks) ? v.chunks[at + j] : 0;
+            sum += vals[j];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive
+        }
+        __syncthreads();
+        int run = carry + warp_sums[wid] + incl - sum;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (at + j < v.n_chunks) v.chunks[at + j] = run;
+            run += vals[j];
+        }
+        __syncthreads();
+        if (tid == 1023) carry = run;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        v.chunks[v.n_chunks] = carry;
+        v.hdr->n_components = carry;
+        if (v.ncomp_out) *v.ncomp_out = carry;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: raster-order rank of each global root -> label code
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int roots_before_word(const CclView& v, long long wi) {
+    long long c = wi >> 6;
+    int r = v.chunks[c];
+    for (long long j = c << 6; j < wi; ++j) r += __popcll(v.rootbits[j]);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) ccl_rank_kernel(CclView v) {
+    unsigned n = v.hdr->n_global_roots;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int r = v.groots[i];
+        int bit;
+        long long wi = word_of_voxel(v, r, &bit);
+        int rank = roots_before_word(v, wi) + __popcll(v.rootbits[wi] & ((1ull << bit) - 1ull));
+        if (!v.connect_x) {  // planar: numbering restarts in every x-plane
+            long long plane_words = (long long)v.Y * v.ZW;
+            rank -= roots_before_word(v, (wi / plane_words) * plane_words);
+        }
+        v.parent[r] = -(v.hdr->label_base + 1 + rank);
+    }
+}
+
+// K6: tile roots that are not global roots take the code of their global root
+__global__ void __launch_bounds__(256) ccl_publish_kernel(CclView v) {
+    unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int r = v.tile_roots[i], g = v.flat[i];
+        if (g != r) v.parent[r] = v.parent[g];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dense writer: 8 voxels (one byte of the bit mask) per thread
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256) ccl_dense_kernel(const ull* __restrict__ bits, const int* __restrict__ parent,
+                                                       int Z, int ZW, int Z8, long long n_groups,
+                                                       OutT* __restrict__ out, int vec_ok) {
+    long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    long long rowi = gi / Z8;
+    int z = (int)(gi % Z8) * 8;
+    unsigned byte = (unsigned)(bits[rowi * ZW + (z >> 6)] >> (z & 63)) & 0xFFu;
+    long long vox = rowi * Z + z;
+    __align__(16) OutT lab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lab[j] = (byte >> j) & 1u ? (OutT)skb_sparse_label(parent, (int)(vox + j)) : (OutT)0;
+    if (vec_ok) {
+        if (sizeof(OutT) == 2) {
+            *reinterpret_cast<uint4*>(out + vox) = *reinterpret_cast<uint4*>(lab);
+        } else {
+            reinterpret_cast<uint4*>(out + vox)[0] = reinterpret_cast<uint4*>(lab)[0];
+            reinterpret_cast<uint4*>(out + vox)[1] = reinterpret_cast<uint4*>(lab)[1];
+        }
+    } else {
+        for (int j = 0; j < 8 && z + j < Z; ++j) out[vox + j] = lab[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t capacity, uint32_t* status,
+                         int32_t* ncomp) {
+    char* base = static_cast<char*>(ws);
+    CclView v;
+    v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
+    v.connect_x = planar ? 0 : 1;
+    v.capacity = (int)capacity;
+    v.hdr = reinterpret_cast<SkbCclHeader*>(base);
+    v.bits = reinterpret_cast<ull*>(base + L.off_bits);
+    v.parent = reinterpret_cast<int*>(base + L.off_parent);
+    v.rootbits = reinterpret_cast<ull*>(base + L.off_rootbits);
+    v.chunks = reinterpret_cast<int*>(base + L.off_chunks);
+    v.tile_roots = reinterpret_cast<int*>(base + L.off_tile_roots);
+    v.flat = reinterpret_cast<int*>(base + L.off_flat);
+    v.groots = reinterpret_cast<int*>(base + L.off_groots);
+    v.status = status;
+    v.ncomp_out = ncomp;
+    v.n_words = L.n_words;
+    v.n_chunks = L.n_chunks;
+    return v;
+}
+
+extern "C" size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity) {
+    if (X <= 0 || Y <= 0 || Z <= 0 || capacity <= 0) return 0;
+    return skb_ccl_layout(X, Y, Z, capacity).total;
+}
+
+template <typename MaskT>
+static void launch_tile(const void* mask, const CclView& v, int tz, int vec_ok, cudaStream_t st) {
+    const MaskT* m = static_cast<const MaskT*>(mask);
+    if (tz == 64) {
+        dim3 grid((v.Z + 63) / 64, (v.Y + 7) / 8, (v.X + 7) / 8);
+        ccl_tile_kernel<MaskT, 64><<<grid, 256, 0, st>>>(m, v, vec_ok);
+    } else if (tz == 32) {
+        dim3 grid(1, (v.Y + 15) / 16, (v.X + 7) / 8);
+        ccl_tile_kernel<MaskT, 32><<<grid, 256, 0, st>>>(m, v, vec_ok);
+    } else {
+        dim3 grid(1, (v.Y + 15) / 16, (v.X + 15) / 16);
+        ccl_tile_kernel<MaskT, 16><<<grid, 256, 0, st>>>(m, v, vec_ok);
+    }
+}
+
+extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int planar,
+                                    int32_t label_base, int64_t capacity, void* workspace, size_t workspace_bytes,
+                                    int32_t* ncomp, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_ccl_label_sparse");
+    if (rc) return rc;
+    SKB_REQUIRE(mask && workspace && status, "skb_ccl_label_sparse: NULL pointer");
+    SKB_REQUIRE(mask_dtype == SKB_U8 || mask_dtype == SKB_I16, "skb_ccl_label_sparse: mask dtype must be u8 or i16");
+    SKB_REQUIRE(label_base >= 0, "skb_ccl_label_sparse: label_base must be >= 0");
+    SKB_REQUIRE(capacity > 0 && capacity <= 0x7fffffff, "skb_ccl_label_sparse: bad capacity");
+    SKB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "skb_ccl_label_sparse: workspace must be 256-byte aligned");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
+    if (workspace_bytes < L.total) {
+        skb_set_error("skb_ccl_label_sparse: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+        return SKB_E_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CclView v = make_view(L, workspace, planar, capacity, status, ncomp);
+
+    SkbCclHeader h = {};
+    h.label_base = label_base; h.planar = planar; h.capacity = (int)capacity;
+    h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
+    char* base = static_cast<char*>(workspace);
+    ccl_init_kernel<<<1, 32, 0, st>>>(v, h);  // header by value: no host->device copy on the path
+    cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
+    cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
+
+    const int tz = Z > 32 ? 64 : (Z > 16 ? 32 : 16);
+    const int elem = mask_dtype == SKB_U8 ? 1 : 2;
+    const int vec_ok = ((Z * elem) % 16 == 0) && skb_aligned16(mask) ? 1 : 0;
+    if (mask_dtype == SKB_U8) launch_tile<uint8_t>(mask, v, tz, vec_ok, st);
+    else launch_tile<int16_t>(mask, v, tz, vec_ok, st);
+    SKB_LAUNCH_CHECK("ccl_tile_kernel");
+
+    const int TY = tz == 64 ? 8 : 16, TX = tz == 16 ? 16 : 8;
+    unsigned nb = (unsigned)((L.n_words + 255) / 256);
+    ccl_boundary_kernel<<<nb, 256, 0, st>>>(v, TX, TY);
+    const int list_grid = 148 * 4;
+    ccl_flatten_kernel<<<list_grid, 256, 0, st>>>(v);
+    ccl_scan_kernel<<<1, 1024, 0, st>>>(v);
+    ccl_rank_kernel<<<list_grid, 256, 0, st>>>(v);
+    ccl_publish_kernel<<<list_grid, 256, 0, st>>>(v);
+    SKB_LAUNCH_CHECK("ccl merge kernels");
+    return SKB_OK;
+}
+
+extern "C" int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, int64_t Z, void* out, int out_dtype,
+                                   void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_ccl_write_dense");
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && out, "skb_ccl_write_dense: NULL pointer");
+    SKB_REQUIRE(out_dtype == SKB_I16 || out_dtype == SKB_I32, "skb_ccl_write_dense: out dtype must be i16 or i32");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    const char* base = static_cast<const char*>(workspace);
+    const ull* bits = reinterpret_cast<const ull*>(base + L.off_bits);
+    const int* parent = reinterpret_cast<const int*>(base + L.off_parent);
+    int Z8 = (int)((Z + 7) / 8);
+    long long groups = (long long)X * Y * Z8;
+    unsigned nb = (unsigned)((groups + 255) / 256);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int vec_ok = (Z % 8 == 0) && skb_aligned16(out) ? 1 : 0;
+    if (out_dtype == SKB_I16)
+        ccl_dense_kernel<int16_t><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
+    else
+        ccl_dense_kernel<int32_t><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
+    SKB_LAUNCH_CHECK("ccl_dense_kernel");
+    return SKB_OK;
+}

@@ -1,0 +1,105 @@
+// Shared device/host helpers for the skoots_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "skoots_b200.h"
+
+typedef unsigned long long ull;
+
+void skb_set_error(const char* fmt, ...);
+
+#define SKB_REQUIRE(cond, ...)        \
+    do {                              \
+        if (!(cond)) {                \
+            skb_set_error(__VA_ARGS__); \
+            return SKB_E_ARG;         \
+        }                             \
+    } while (0)
+
+#define SKB_LAUNCH_CHECK(what)                                                   \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            skb_set_error("%s: CUDA error %s", what, cudaGetErrorString(e__));   \
+            return SKB_E_CUDA;                                                   \
+        }                                                                        \
+    } while (0)
+
+static inline size_t skb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline bool skb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// volume limits shared by every entry point (see include/skoots_b200.h)
+int skb_check_volume(int64_t X, int64_t Y, int64_t Z, const char* who);
+
+// ---- element conversion -------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float skb_to_float(T v);
+template <> __device__ __forceinline__ float skb_to_float<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float skb_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float skb_to_float<float>(float v) { return v; }
+
+template <typename T> __device__ __forceinline__ T skb_from_float(float v);
+template <> __device__ __forceinline__ __half skb_from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 skb_from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float skb_from_float<float>(float v) { return v; }
+
+// ---- streaming loads/stores: bypass L1 for data touched once ---------------------------------
+__device__ __forceinline__ uint4 skb_ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void skb_st_stream16(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// ---- sparse CCL workspace layout (skb_ccl.cu writes it, skb_assemble.cu reads it) ---------------
+struct SkbCclHeader {
+    unsigned n_tile_roots;    // appended by the tile kernel
+    unsigned n_global_roots;  // appended by the flatten kernel
+    int n_components;         // written by the scan kernel
+    int label_base;
+    int planar;
+    int capacity;
+    int dims[3];
+    int reserved[7];
+};
+
+struct SkbCclLayout {
+    int X, Y, Z, ZW;      // ZW = 64-bit words per (x,y) row of the bit-packed mask
+    int64_t V, n_words, n_chunks;
+    size_t off_bits, off_parent, off_rootbits, off_chunks, off_tile_roots, off_flat, off_groots, total;
+};
+
+static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64_t capacity) {
+    SkbCclLayout L;
+    L.X = (int)X; L.Y = (int)Y; L.Z = (int)Z;
+    L.ZW = (int)((Z + 63) / 64);
+    L.V = X * Y * Z;
+    L.n_words = X * Y * (int64_t)L.ZW;
+    L.n_chunks = (L.n_words + 63) / 64;
+    size_t at = 256;  // header
+    L.off_bits = at;       at = skb_align_up(at + (size_t)L.n_words * 8, 256);
+    L.off_parent = at;     at = skb_align_up(at + (size_t)L.V * 4, 256);
+    L.off_rootbits = at;   at = skb_align_up(at + (size_t)L.n_words * 8, 256);
+    L.off_chunks = at;     at = skb_align_up(at + (size_t)(L.n_chunks + 1) * 4, 256);
+    L.off_tile_roots = at; at = skb_align_up(at + (size_t)capacity * 4, 256);
+    L.off_flat = at;       at = skb_align_up(at + (size_t)capacity * 4, 256);
+    L.off_groots = at;     at = skb_align_up(at + (size_t)capacity * 4, 256);
+    L.total = at;
+    return L;
+}
+
+// label of a foreground voxel `t` from the sparse form: parent[t] is either the (negative) label
+// code or the index of the voxel's tile root, whose entry is the code.
+__device__ __forceinline__ int skb_sparse_label(const int* __restrict__ parent, int t) {
+    int p = __ldg(parent + t);
+    if (p >= 0) p = __ldg(parent + p);
+    return -p;
+}

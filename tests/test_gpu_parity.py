@@ -1,0 +1,152 @@
+"""GPU: CUDA path vs the CPU oracle on seeded synthetic inputs (sizes the oracle finishes in
+seconds), edge cases, and size-independent properties on large volumes."""
+import numpy as np
+import pytest
+import torch
+
+import skoots_oracle as orc
+from skoots_b200.synthetic import make_tube_volume
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ccl(mask_np, planar=False, dtype=torch.uint8):
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    m = torch.from_numpy(mask_np.astype(np.uint8)).to(DEV).to(dtype)
+    sp = label_components(m, planar=planar, label_base=0)
+    out = torch.empty(m.shape, dtype=torch.int32, device=DEV)
+    write_dense(sp, out)
+    return out.cpu().numpy(), sp.num_components
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 5, 7), (9, 17, 16), (16, 16, 33), (8, 8, 64), (20, 33, 65),
+                                   (17, 9, 130), (40, 40, 20), (33, 70, 96)])
+@pytest.mark.parametrize("density", [0.0, 0.02, 0.3, 0.6, 1.0])
+def test_ccl_matches_scipy_numbering(shape, density):
+    rng = np.random.default_rng(hash((shape, density)) % (2**32))
+    mask = rng.random(shape) < density
+    got, n = _ccl(mask)
+    want, n_want = orc.label_components(mask)
+    assert n == n_want
+    assert np.array_equal(got, want)
+
+
+def test_ccl_int16_input_uses_gt_zero():
+    rng = np.random.default_rng(5)
+    vol = rng.integers(-3, 4, size=(12, 20, 48)).astype(np.int16)
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    sp = label_components(torch.from_numpy(vol).to(DEV), label_base=0)
+    out = torch.empty(vol.shape, dtype=torch.int32, device=DEV)
+    write_dense(sp, out)
+    want, _ = orc.label_components(vol > 0)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_ccl_long_snake_across_tiles():
+    # one component winding through many tiles: worst case for pointer jumping
+    mask = np.zeros((24, 40, 200), dtype=bool)
+    for x in range(0, 24, 2):
+        mask[x, :, :] = False
+        for y in range(0, 40, 2):
+            mask[x, y, :] = True
+            mask[x, min(y + 1, 39), 199 if (y // 2) % 2 == 0 else 0] = True
+        if x + 1 < 24:
+            mask[x + 1, 38 if (x // 2) % 2 == 0 else 0, 0 if (x // 2) % 2 == 0 else 199] = True
+    got, n = _ccl(mask)
+    want, n_want = orc.label_components(mask)
+    assert n == n_want and np.array_equal(got, want)
+
+
+def test_ccl_planar_is_per_slice_4_connectivity():
+    rng = np.random.default_rng(9)
+    stack = rng.random((5, 70, 130)) < 0.4
+    got, _ = _ccl(stack, planar=True)
+    for s in range(stack.shape[0]):
+        want, _ = orc.label_components(stack[s])  # 2-D scipy label = 4-connectivity
+        assert np.array_equal(got[s], want), s
+
+
+def test_ccl_overflow_retry():
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    rng = np.random.default_rng(1)
+    mask = rng.random((32, 32, 64)) < 0.5
+    sp = label_components(torch.from_numpy(mask).to(DEV), label_base=0, capacity=16)
+    out = torch.empty(mask.shape, dtype=torch.int32, device=DEV)
+    write_dense(sp, out)
+    want, _ = orc.label_components(mask)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("N,decay", [(1, 1.0), (10, 1.0), (10, 0.95)])
+def test_c1_whole_volume_path(N, decay):
+    """config 1: 128x128x32, 20 tubes, lib functions applied to the whole volume."""
+    from skoots_b200.pipeline import assemble_instances
+    tv = make_tube_volume((128, 128, 32), 20, seed=0)
+    scale = torch.tensor((60, 60, 12))
+    want = orc.postprocess(tv.skeleton, tv.vectors, scale, N=N, decay=decay)
+    got = assemble_instances(tv.skeleton.to(DEV), tv.vectors.to(DEV), scale, N=N, decay=decay)
+    assert np.array_equal(got.cpu().numpy(), want.numpy())
+    assert int(want.max()) > 2
+
+
+def test_eval_crop_grid_matches_oracle_loop():
+    """eval()'s 500/500/50 grid with 50/50/5 overlap on a volume that needs several crops in z and
+    a shifted last crop in every axis."""
+    from skoots_b200.pipeline import EVAL_CROP, EVAL_OVERLAP, assemble_instances
+    tv = make_tube_volume((520, 130, 72), 60, seed=2)
+    scale = torch.tensor((60, 60, 12))
+    labels = orc.flood_fill_exact(tv.skeleton.to(torch.int16))
+    want = orc.assemble_instances(labels, tv.vectors, scale, N=3, crop=EVAL_CROP, overlap=EVAL_OVERLAP)
+    got = assemble_instances(tv.skeleton.to(DEV), tv.vectors.to(DEV), scale, N=3, crop=EVAL_CROP,
+                             overlap=EVAL_OVERLAP, out_dtype=torch.int16)
+    assert np.array_equal(got.cpu().numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("shape", [(7, 5, 3), (16, 16, 20), (31, 9, 13)])
+def test_ragged_shapes_unaligned_paths(shape):
+    from skoots_b200.pipeline import assemble_instances
+    g = torch.Generator().manual_seed(sum(shape))
+    mask = (torch.rand(shape, generator=g) < 0.2).to(torch.uint8)
+    vec = ((torch.rand((3,) + shape, generator=g) * 2 - 1) * (torch.rand(shape, generator=g) < 0.5)).half()
+    scale = torch.tensor((4.0, 3.0, 2.0))
+    for N in (1, 3):
+        want = orc.postprocess(mask, vec, scale, N=N)
+        got = assemble_instances(mask.to(DEV), vec.to(DEV), scale, N=N)
+        assert np.array_equal(got.cpu().numpy(), want.numpy()), N
+
+
+def test_autograd_vector_to_embedding():
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    v = (torch.rand((2, 3, 6, 5, 4), device=DEV) * 2 - 1).requires_grad_(True)
+    scale = torch.tensor((60.0, 60.0, 12.0), device=DEV)
+    out = vector_to_embedding(scale, v)
+    w = torch.rand_like(out)
+    (out * w).sum().backward()
+    want = w * scale.view(1, 3, 1, 1, 1)
+    assert torch.allclose(v.grad, want, rtol=0, atol=0)
+
+
+def test_large_volume_properties():
+    """Size-independent checks at a size the CPU oracle would need minutes for: zero vectors give
+    label-of-self; labelling is idempotent under relabel; components of a known tiling are counted."""
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    from skoots_b200.pipeline import gather_instances
+    X, Y, Z = 512, 512, 256
+    mask = torch.zeros((X, Y, Z), dtype=torch.uint8, device=DEV)
+    mask[4::16, 4::16, :] = 1          # (X/16)*(Y/16) separate z-columns spanning all z tiles
+    mask[4::16, 4:10, 100] = 1          # widen each column a little inside its own cell
+    sp = label_components(mask, label_base=2)
+    assert sp.num_components == (X // 16) * (Y // 16)
+    lab = torch.empty((X, Y, Z), dtype=torch.int32, device=DEV)
+    write_dense(sp, lab)
+    assert int(lab.max()) == sp.num_components + 2 and int(lab[mask == 0].abs().max()) == 0
+    cols = lab[4::16, 4::16, :]
+    assert bool((cols == cols[:, :, :1]).all())                       # one label per column
+    assert torch.equal(cols[:, :, 0].flatten(), torch.arange(3, sp.num_components + 3, device=DEV, dtype=torch.int32))
+    vec = torch.zeros((3, X, Y, Z), dtype=torch.float16, device=DEV)
+    inst = gather_instances(vec, (60, 60, 12), sp)
+    assert torch.equal(inst, lab)                                      # zero field -> label of self
+    vec[2] = 1.0 / 12.0                                                # every voxel points one plane up
+    inst = gather_instances(vec, (60, 60, 12), sp)
+    assert torch.equal(inst[:, :, :-1], lab[:, :, 1:])

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — post-processing throughput of the skeleton-embedding instance-assembly path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path (connected-component labelling of the u8 skeleton mask +
+fused vector->embedding->label gather) over the synthetic analytic-tube volume named in
+`config.workload`.  `value` is voxels/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` is the same pass through the public host-buffer API with the host<->device copies
+inside the timed region.  See DESIGN.md §Measurement for the byte accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SCALE = (60, 60, 12)           # SKOOTS.VECTOR_SCALING default, skoots/config.py:144
+ALGO_BYTES_PATH = 11.0         # u8 mask + 3 x fp16 vectors in, int32 label out
+ALGO_BYTES_GATHER = 10.0       # dominant kernel: 6 B vectors in + 4 B labels out (label side is the 1/8 B bit mask)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default=os.environ.get("SKB_BENCH_SHAPE", "2048,2048,512"))
+    ap.add_argument("--tubes", type=int, default=0, help="0 = 16384 scaled by volume")
+    ap.add_argument("--hops", type=int, default=1, help="N of vector_to_embedding (eval() uses 10)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def n_tubes_for(shape, requested):
+    if requested:
+        return requested
+    vox = shape[0] * shape[1] * shape[2]
+    return max(8, int(round(16384 * vox / (2048 * 2048 * 512))))
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_shape(budget_s: float):
+    """largest sample of the workload whose oracle pass fits the budget (~12 Mvox/s at N=1)."""
+    for shape in ((1024, 1024, 128), (768, 768, 128), (512, 512, 128), (384, 384, 128), (256, 256, 128), (128, 128, 64)):
+        if shape[0] * shape[1] * shape[2] / 12e6 <= budget_s:
+            return shape
+    return (128, 128, 32)
+
+
+def cpu_pass(mask, vec, hops):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import skoots_oracle as orc
+    t0 = time.perf_counter()
+    out = orc.postprocess(mask, vec, torch.tensor(SCALE), N=hops)
+    return time.perf_counter() - t0, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from skoots_b200.synthetic import make_tube_volume
+    torch.set_num_threads(os.cpu_count() or 1)
+    total_steps = max(1, args.steps + args.warmup)
+    shape = cpu_sample_shape(150.0 / total_steps)
+    full = tuple(int(v) for v in args.shape.split(","))
+    tv = make_tube_volume(shape, n_tubes_for(shape, 0), seed=0, want_mask=False, want_skeleton_dict=False)
+    for _ in range(args.warmup):
+        cpu_pass(tv.skeleton, tv.vectors, args.hops)
+    times = [cpu_pass(tv.skeleton, tv.vectors, args.hops)[0] for _ in range(args.steps)]
+    vox = shape[0] * shape[1] * shape[2]
+    value = vox * len(times) / sum(times)
+    sample = f"{shape[0]}x{shape[1]}x{shape[2]} sub-volume of the workload, same tube density, whole pass per step"
+    line = {
+        "impl": "reference", "metric": "post-proc voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(full, args.hops), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(shape, hops):
+    return (f"synthetic analytic tubes {shape[0]}x{shape[1]}x{shape[2]} (BASELINE.json configs[2]), whole-volume "
+            f"flood fill + vector_to_embedding(N={hops}) + index_skeleton_by_embed")
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from skoots_b200.lib.flood_fill import label_components
+    from skoots_b200.pipeline import HostAssembler, gather_instances
+    from skoots_b200.synthetic import make_tube_volume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shape = tuple(int(v) for v in args.shape.split(","))
+    X, Y, Z = shape
+    V = X * Y * Z
+    scale = torch.tensor(SCALE)
+    hbm_peak, peak_src = peaks()
+
+    if world > 1:
+        from skoots_b200.sharded import ShardedAssembler
+        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops)
+        z0, z1 = runner.z_range
+        tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, z_range=(z0, z1),
+                              want_mask=False, want_skeleton_dict=False)
+        runner.load(tv.skeleton, tv.vectors)
+        del tv
+
+        def step(timers=None):
+            return runner.step(timers)
+        launches_per_step = runner.launches_per_step
+    else:
+        tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, want_mask=False,
+                              want_skeleton_dict=False)
+        mask, vec = tv.skeleton, tv.vectors
+        out = torch.empty(shape, dtype=torch.int32, device=dev)
+        state = {"ws": None, "sparse": None}
+
+        def step(timers=None):
+            sp = label_components(mask, label_base=2, workspace=state["ws"], check=False)
+            state["ws"], state["sparse"] = sp.workspace, sp
+            if timers is not None:
+                timers[0].record()
+            gather_instances(vec, scale, sp, N=args.hops, out=out)
+            if timers is not None:
+                timers[1].record()
+            return out
+        launches_per_step = 8  # init, tile, boundary, flatten, scan, rank, publish, gather (+2 memsets)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if world == 1:
+        state["sparse"].check()
+        n_components = state["sparse"].num_components
+        labelled = int((out > 0).sum().item())
+    else:
+        n_components, labelled = runner.check()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for k in range(args.steps):
+        step(timers[k])
+    t_end.record()
+    barrier()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    gather_ms = sum(a.elapsed_time(b) for a, b in timers) / args.steps
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms, gather_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, gather_ms = t.tolist()
+    ms_per_step = elapsed_ms / args.steps
+    value = V / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the public API ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            host_mask = torch.empty(shape, dtype=torch.uint8).pin_memory()
+            host_vec = torch.empty((3,) + shape, dtype=torch.float16).pin_memory()
+            host_out = torch.empty(shape, dtype=torch.int32).pin_memory()
+            host_mask.copy_(mask)
+            host_vec.copy_(vec)
+            del out
+            state["ws"] = state["sparse"] = None
+            del mask, vec
+            torch.cuda.empty_cache()
+            runner_h = HostAssembler(shape, dev)
+            e2e_steps = max(1, min(args.steps, 5))
+            runner_h(host_mask, host_vec, scale, host_out, N=args.hops)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                runner_h(host_mask, host_vec, scale, host_out, N=args.hops)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / e2e_steps
+            e2e = {"value": V / dt, "unit": "voxels/s", "h2d_bytes_per_step": host_mask.numel() + host_vec.numel() * 2,
+                   "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "api": "skoots_b200.pipeline.HostAssembler"}
+            assert int((host_out > 0).sum().item()) == labelled, "e2e result differs from the device-resident run"
+        else:
+            e2e = runner.e2e(max(1, min(args.steps, 5)))
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample + parity of that sample ----------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sshape = cpu_sample_shape(20.0)
+        sshape = tuple(min(a, b) for a, b in zip(sshape, shape))
+        torch.set_num_threads(os.cpu_count() or 1)
+        if e2e is not None:
+            smask = host_mask[:sshape[0], :sshape[1], :sshape[2]].contiguous()
+            svec = host_vec[:, :sshape[0], :sshape[1], :sshape[2]].contiguous()
+        else:
+            smask = mask[:sshape[0], :sshape[1], :sshape[2]].contiguous().cpu()
+            svec = vec[:, :sshape[0], :sshape[1], :sshape[2]].contiguous().cpu()
+        cpu_pass(smask[:64, :64, :32].contiguous(), svec[:, :64, :64, :32].contiguous(), args.hops)  # warm the thread pool
+        dt, want = cpu_pass(smask, svec, args.hops)
+        from skoots_b200.pipeline import assemble_instances
+        got = assemble_instances(smask.to(dev), svec.to(dev), scale, N=args.hops).cpu()
+        parity = bool(torch.equal(got, want))
+        svox = sshape[0] * sshape[1] * sshape[2]
+        cpu = {"value": svox / dt, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"first {sshape[0]}x{sshape[1]}x{sshape[2]} voxels of the workload volume, one whole pass "
+                         f"({dt:.1f} s); GPU result on the same sample bit-exact: {parity}"}
+        assert parity, "GPU instance mask differs from the oracle on the CPU-baseline sample"
+
+    if rank == 0:
+        gather_bytes = ALGO_BYTES_GATHER * V / world
+        achieved = gather_bytes / (gather_ms * 1e-3) / 1e9
+        line = {
+            "metric": "post-proc voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(shape, args.hops), "tubes": n_tubes_for(shape, args.tubes),
+                       "components": n_components, "labelled_voxels": labelled,
+                       "l2": f"inputs larger than L2 ({ALGO_BYTES_PATH * V / world / 1e9:.1f} GB per GPU per step vs 126 MB)",
+                       "sharding": "none" if world == 1 else f"Z-slabs x{world}, NCCL halo-run exchange + root all-gather"},
+            "path_roofline": {"bytes_per_voxel": ALGO_BYTES_PATH, "achieved": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9,
+                              "peak": hbm_peak, "unit": "GB/s",
+                              "frac": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+            "roofline": {"kernel": "assemble_kernel<half,int>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_voxel": ALGO_BYTES_GATHER, "ms_per_launch": gather_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback; use --impl reference)")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

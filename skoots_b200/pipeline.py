@@ -66,3 +66,47 @@ def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1
     sparse = label_components(mask, planar=False, label_base=2, workspace=workspace, check=check)
     return gather_instances(vectors, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=out,
                             out_dtype=out_dtype)
+
+
+class HostAssembler:
+    """End-to-end form of `assemble_instances` for volumes that live in HOST memory (the reference
+    keeps them in zarr / numpy, skoots/lib/eval.py:102-103,223,245): copies the u8 skeleton mask
+    and the fp16 vectors host->device, labels + gathers on the GPU, and copies the instance mask
+    back.  Device buffers and the CCL workspace are allocated once and reused across calls.
+
+    Uploads run on a copy stream: the CCL starts as soon as the mask has landed and overlaps the
+    (6x larger) vector upload; the gather waits for the vectors.
+    """
+
+    def __init__(self, shape: Tuple[int, int, int], device="cuda:0", vec_dtype=torch.float16,
+                 out_dtype=torch.int32):
+        X, Y, Z = shape
+        self.shape, self.dev = (X, Y, Z), torch.device(device)
+        self.mask = torch.empty((X, Y, Z), dtype=torch.uint8, device=self.dev)
+        self.vec = torch.empty((3, X, Y, Z), dtype=vec_dtype, device=self.dev)
+        self.out = torch.empty((X, Y, Z), dtype=out_dtype, device=self.dev)
+        self.workspace = None
+        self.copy_stream = torch.cuda.Stream(self.dev)
+
+    def __call__(self, mask_host: Tensor, vec_host: Tensor, scale, out_host: Tensor, N: int = 1, decay: float = 1.0,
+                 crop=None, overlap=(0, 0, 0)) -> Tensor:
+        X, Y, Z = self.shape
+        main = torch.cuda.current_stream(self.dev)
+        cs = self.copy_stream
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            self.mask.copy_(mask_host.reshape(X, Y, Z), non_blocking=True)
+            mask_ready = torch.cuda.Event()
+            mask_ready.record(cs)
+            self.vec.copy_(vec_host.reshape(3, X, Y, Z), non_blocking=True)
+            vec_ready = torch.cuda.Event()
+            vec_ready.record(cs)
+        main.wait_event(mask_ready)
+        sparse = label_components(self.mask, label_base=2, workspace=self.workspace, check=False)
+        self.workspace = sparse.workspace
+        main.wait_event(vec_ready)
+        gather_instances(self.vec, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=self.out)
+        out_host.reshape(X, Y, Z).copy_(self.out, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+        sparse.check()
+        return out_host

@@ -13,7 +13,7 @@
  *     (a cudaStream_t / CUstream passed as void*; NULL = legacy default stream);
  *   - volumes are C-contiguous with Z fastest: (X,Y,Z), vector fields (3,X,Y,Z) — the
  *     reference's layout (skoots/lib/eval.py:61-64);
- *   - a volume may hold at most 2^31-1 voxels, each axis < 2^24;
+ *   - a volume may hold at most 2^31 voxels (voxel indices are non-negative int32), each axis < 2^24;
  *   - return value 0 = enqueued; <0 = SKB_E_* (nothing enqueued), text in skb_last_error();
  *   - asynchronous conditions (workspace overflow) are reported in a caller-provided
  *     device status word, see skb_ccl_*.

@@ -155,43 +155,115 @@ __device__ __forceinline__ bool load8(const void* base, long long idx, bool alig
     return zero;
 }
 
-template <typename VecT, typename OutT>
-__global__ void __launch_bounds__(256) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
-    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (i0 >= V) return;
-    const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
-    unsigned q = (unsigned)i0 / uz;
-    int z = (int)((unsigned)i0 - q * uz);
-    int x = (int)(q / uy);
-    int y = (int)(q - (unsigned)x * uy);
+// One warp owns 256 consecutive voxels (8 per lane).  Voxels that need real work — a non-zero
+// vector, or a zero vector sitting on a foreground voxel — are compacted into a per-warp queue in
+// shared memory and processed one per lane, so the divergent part (walk + dependent label reads)
+// always runs with full warps and 32 independent load chains in flight.  Everything else is a
+// pure stream: 3 x 16-byte loads, one byte of the bit mask, 2 x 16-byte stores.
+constexpr int ASM_WARPS = 8;
 
-    __align__(16) OutT lab[8];
-    if (i0 + 8 <= V) {
-        float v0[8], v1[8], v2[8];
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+    __shared__ float s_vec[ASM_WARPS][3][256];
+    __shared__ int s_res[ASM_WARPS][256];
+    __shared__ unsigned char s_queue[ASM_WARPS][256];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp_base = ((long long)blockIdx.x * ASM_WARPS + warp) * 256;
+    if (warp_base >= V) return;
+    const long long i0 = warp_base + lane * 8;
+    const long long left = V - i0;
+    const int nvalid = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
+    const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
+
+    float v0[8], v1[8], v2[8];
+    if (nvalid == 8) {
         const bool al = P.vec_aligned != 0;
-        bool zero = load8<VecT>(P.vec, i0, al, v0);
-        zero = load8<VecT>(P.vec, i0 + P.cstride, al, v1) && zero;
-        zero = load8<VecT>(P.vec, i0 + 2 * P.cstride, al, v2) && zero;
-        bool done = false;
-        if (zero && P.fast_ok && !P.dense && z + 8 <= P.Z) {
-            // all eight voxels point at themselves: their label is their own component (or 0)
-            long long wi = ((long long)x * P.Y + y) * P.ZW + (z >> 6);
-            int sh = z & 63;
-            ull w = __ldg(P.bits + wi) >> sh;
-            if (sh > 56) w |= __ldg(P.bits + wi + 1) << (64 - sh);
-            if ((w & 0xFFull) == 0ull) {
+        load8<VecT>(P.vec, i0, al, v0);
+        load8<VecT>(P.vec, i0 + P.cstride, al, v1);
+        load8<VecT>(P.vec, i0 + 2 * P.cstride, al, v2);
+    } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) lab[j] = (OutT)0;
-                done = true;
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = j < nvalid;
+            v0[j] = ok ? load_vec<VecT>(P.vec, i0 + j) : 0.f;
+            v1[j] = ok ? load_vec<VecT>(P.vec, i0 + j + P.cstride) : 0.f;
+            v2[j] = ok ? load_vec<VecT>(P.vec, i0 + j + 2 * P.cstride) : 0.f;
+        }
+    }
+
+    // which of my voxels need the slow path
+    unsigned work = 0;
+    if (nvalid > 0) {
+        if (!P.fast_ok) {
+            work = (1u << nvalid) - 1u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) work |= (unsigned)((v0[j] != 0.f) | (v1[j] != 0.f) | (v2[j] != 0.f)) << j;
+            // a zero vector resolves to the voxel itself: only foreground voxels need a label read
+            const unsigned q = (unsigned)i0 / uz;
+            const int z = (int)((unsigned)i0 - q * uz);
+            if (P.dense) {
+                work = (1u << nvalid) - 1u;  // dense label volumes are the compatibility path: no bit mask to consult
+            } else if (z + 8 <= P.Z) {
+                const long long wi = (long long)q * P.ZW + (z >> 6);
+                const int sh = z & 63;
+                ull w = __ldg(P.bits + wi) >> sh;
+                if (sh > 56) w |= __ldg(P.bits + wi + 1) << (64 - sh);
+                work |= (unsigned)(w & 0xFFull);
+            } else {
+                unsigned qq = q;
+                int zz = z;
+                for (int j = 0; j < nvalid; ++j) {
+                    ull w = __ldg(P.bits + (long long)qq * P.ZW + (zz >> 6));
+                    work |= (unsigned)((w >> (zz & 63)) & 1ull) << j;
+                    if (++zz == P.Z) { zz = 0; ++qq; }
+                }
+            }
+            work &= (1u << nvalid) - 1u;
+        }
+    }
+
+    // warp-wide compaction of the work items
+    const int cnt = __popc(work);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total > 0) {
+        int at = incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if ((work >> j) & 1u) {
+                const int code = j * 32 + lane;
+                s_queue[warp][at++] = (unsigned char)code;
+                s_vec[warp][0][code] = v0[j];
+                s_vec[warp][1][code] = v1[j];
+                s_vec[warp][2][code] = v2[j];
             }
         }
-        if (!done) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                lab[j] = (OutT)assemble_voxel<VecT>(P, x, y, z, v0[j], v1[j], v2[j]);
-                if (++z == P.Z) { z = 0; if (++y == P.Y) { y = 0; ++x; } }
-            }
+        __syncwarp();
+        for (int qi = lane; qi < total; qi += 32) {
+            const int code = s_queue[warp][qi];
+            const unsigned vi = (unsigned)(warp_base + (code & 31) * 8 + (code >> 5));
+            const unsigned q = vi / uz;
+            const int z = (int)(vi - q * uz);
+            const int x = (int)(q / uy);
+            const int y = (int)(q - (unsigned)x * uy);
+            s_res[warp][code] = assemble_voxel<VecT>(P, x, y, z, s_vec[warp][0][code], s_vec[warp][1][code],
+                                                     s_vec[warp][2][code]);
         }
+        __syncwarp();
+    }
+
+    if (nvalid == 0) return;
+    __align__(16) OutT lab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lab[j] = ((work >> j) & 1u) ? (OutT)s_res[warp][j * 32 + lane] : (OutT)0;
+    if (nvalid == 8) {
         if (sizeof(OutT) == 2) {
             skb_st_stream16(out + i0, *reinterpret_cast<uint4*>(lab));
         } else {
@@ -199,12 +271,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(AsmParams P, OutT* __rest
             skb_st_stream16(out + i0 + 4, reinterpret_cast<uint4*>(lab)[1]);
         }
     } else {
-        for (long long i = i0; i < V; ++i) {
-            float a = load_vec<VecT>(P.vec, i), b = load_vec<VecT>(P.vec, i + P.cstride),
-                  c = load_vec<VecT>(P.vec, i + 2 * P.cstride);
-            out[i] = (OutT)assemble_voxel<VecT>(P, x, y, z, a, b, c);
-            if (++z == P.Z) { z = 0; if (++y == P.Y) { y = 0; ++x; } }
-        }
+        for (int j = 0; j < nvalid; ++j) out[i0 + j] = lab[j];
     }
 }
 
@@ -291,7 +358,7 @@ static void fill_crop(AsmParams& P, const int32_t crop[3], const int32_t overlap
 
 template <typename VecT>
 static void launch_assemble(const AsmParams& P, void* out, int out_dtype, long long V, cudaStream_t st) {
-    unsigned nb = (unsigned)(((V + 7) / 8 + 255) / 256);
+    unsigned nb = (unsigned)((V + 256 * ASM_WARPS - 1) / (256 * ASM_WARPS));
     if (out_dtype == SKB_I32) assemble_kernel<VecT, int32_t><<<nb, 256, 0, st>>>(P, static_cast<int32_t*>(out), V);
     else assemble_kernel<VecT, int16_t><<<nb, 256, 0, st>>>(P, static_cast<int16_t*>(out), V);
 }

@@ -14,7 +14,7 @@
 //                           tile faces with atomicMin on the global parent array.
 //   K3 ccl_flatten_kernel   pointer-jumps every tile root to its global root, marks global
 //                           roots in a bitmap and counts them per 4096-voxel chunk.
-//   K4 ccl_scan_kernel      exclusive scan of the chunk counts (-> raster-order rank bases).
+//   K4 ccl_scan_*_kernel    two-level exclusive scan of the chunk counts (-> raster-order rank bases).
 //   K5 ccl_rank_kernel      rank of each global root = scipy.ndimage.label's numbering.
 //   K6 ccl_publish_kernel   copies the label code into every non-global tile root.
 //
@@ -48,8 +48,8 @@ int skb_check_volume(int64_t X, int64_t Y, int64_t Z, const char* who) {
         skb_set_error("%s: dims must be positive (got %lld,%lld,%lld)", who, (long long)X, (long long)Y, (long long)Z);
         return SKB_E_ARG;
     }
-    if (X >= (1 << 24) || Y >= (1 << 24) || Z >= (1 << 24) || X * Y * Z > 2147483647LL) {
-        skb_set_error("%s: volume %lldx%lldx%lld exceeds 2^31-1 voxels / 2^24 per axis", who, (long long)X,
+    if (X >= (1 << 24) || Y >= (1 << 24) || Z >= (1 << 24) || X * Y * Z > 2147483648LL) {
+        skb_set_error("%s: volume %lldx%lldx%lld exceeds 2^31 voxels / 2^24 per axis", who, (long long)X,
                       (long long)Y, (long long)Z);
         return SKB_E_RANGE;
     }
@@ -68,12 +68,13 @@ struct CclView {
     int* parent;
     ull* rootbits;
     int* chunks;
+    int* scan_tiles;
     int* tile_roots;
     int* flat;
     int* groots;
     unsigned* status;
     int* ncomp_out;
-    long long n_words, n_chunks;
+    long long n_words, n_chunks, n_scan_tiles;
 };
 
 // start of the z-run containing bit p of row word w (bit p must be set)
@@ -179,6 +180,8 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
 // ------------------------------------------------------------------------------------------
 // K1: tile-local run-based union-find
 // ------------------------------------------------------------------------------------------
+constexpr int CCL_NT = 4;  // tiles (stacked along y) per CTA: 4 independent 16-byte loads in flight per thread
+
 template <typename MaskT, int TZ>
 __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
     constexpr int SZ = TZ / 16;           // 16-voxel segments per row
@@ -192,83 +195,99 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__
     const int tid = threadIdx.x;
     const int seg = tid % SZ, row = tid / SZ;
     const int ly = row % TY, lx = row / TY;
-    const int x0 = blockIdx.z * TX, y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
-    const int x = x0 + lx, y = y0 + ly, z = z0 + seg * 16;
-    const bool in_row = (x < v.X) && (y < v.Y);
-    const long long rowi = (long long)x * v.Y + y;
+    const int x0 = blockIdx.z * TX, z0 = blockIdx.x * TZ;
+    const int x = x0 + lx, z = z0 + seg * 16;
 
-    if (tid == 0) s_count = 0;
-    unsigned b16 = 0;
-    if (in_row && z < v.Z) b16 = fg16<MaskT>(mask + rowi * v.Z + z, min(16, v.Z - z), vec_ok != 0);
-
-    ull w = (ull)b16 << (16 * seg);
+    // issue every tile's load before touching any of them
+    unsigned b16s[CCL_NT];
 #pragma unroll
-    for (int o = 1; o < SZ; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
-    if (seg == 0) {
-        srow[row] = w;
-        if (in_row) v.bits[rowi * v.ZW + blockIdx.x] = w;
+    for (int t = 0; t < CCL_NT; ++t) {
+        const int y = (blockIdx.y * CCL_NT + t) * TY + ly;
+        b16s[t] = 0;
+        if (x < v.X && y < v.Y && z < v.Z)
+            b16s[t] = fg16<MaskT>(mask + ((long long)x * v.Y + y) * v.Z + z, min(16, v.Z - z), vec_ok != 0);
     }
-    if (!__syncthreads_or(b16 != 0)) return;  // empty tile: nothing to label
 
-    const ull segmask = 0xFFFFull << (16 * seg);
-    const ull starts = w & ~(w << 1) & segmask;  // run starts inside my segment
-    for (ull s = starts; s; s &= s - 1) {
-        int p = __ffsll((long long)s) - 1;
-        slab[row * TZ + p] = row * TZ + p;
-    }
-    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CCL_NT; ++t) {
+        const int y0 = (blockIdx.y * CCL_NT + t) * TY;
+        if (y0 >= v.Y) continue;  // uniform across the CTA
+        const int y = y0 + ly;
+        const bool in_row = (x < v.X) && (y < v.Y);
+        const long long rowi = (long long)x * v.Y + y;
+        const unsigned b16 = b16s[t];
 
-    // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
-    if (w & segmask) {
-        if (ly > 0) {
-            ull wn = srow[row - 1], a = w & wn;
-            for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
-                int p = __ffsll((long long)s) - 1;
-                sunion(slab, row * TZ + run_start(w, p), (row - 1) * TZ + run_start(wn, p));
+        if (tid == 0) s_count = 0;
+        ull w = (ull)b16 << (16 * seg);
+#pragma unroll
+        for (int o = 1; o < SZ; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+        if (seg == 0) {
+            srow[row] = w;
+            if (in_row) v.bits[rowi * v.ZW + blockIdx.x] = w;
+        }
+        if (!__syncthreads_or(b16 != 0)) continue;  // empty tile: nothing to label
+
+        const ull segmask = 0xFFFFull << (16 * seg);
+        const ull starts = w & ~(w << 1) & segmask;  // run starts inside my segment
+        for (ull s = starts; s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            slab[row * TZ + p] = row * TZ + p;
+        }
+        __syncthreads();
+
+        // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
+        if (w & segmask) {
+            if (ly > 0) {
+                ull wn = srow[row - 1], a = w & wn;
+                for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
+                    int p = __ffsll((long long)s) - 1;
+                    sunion(slab, row * TZ + run_start(w, p), (row - 1) * TZ + run_start(wn, p));
+                }
+            }
+            if (lx > 0 && v.connect_x) {
+                ull wn = srow[row - TY], a = w & wn;
+                for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
+                    int p = __ffsll((long long)s) - 1;
+                    sunion(slab, row * TZ + run_start(w, p), (row - TY) * TZ + run_start(wn, p));
+                }
             }
         }
-        if (lx > 0 && v.connect_x) {
-            ull wn = srow[row - TY], a = w & wn;
-            for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
-                int p = __ffsll((long long)s) - 1;
-                sunion(slab, row * TZ + run_start(w, p), (row - TY) * TZ + run_start(wn, p));
+        __syncthreads();
+
+        // resolve every run starting in my segment; write parent for all its voxels
+        unsigned rootmask = 0;  // bit (p - 16*seg) set when the run starting at p is a tile root
+        const int gbase = (int)(rowi * v.Z) + z0;  // voxel index of bit 0 of this row word
+        for (ull s = starts; s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            int l = row * TZ + p;
+            int r = sfind(slab, l);
+            int groot;
+            if (r == l) {
+                rootmask |= 1u << (p - 16 * seg);
+                groot = gbase + p;
+            } else {
+                int rrow = r / TZ, rp = r % TZ;
+                groot = (int)(((long long)(x0 + rrow / TY) * v.Y + (y0 + rrow % TY)) * v.Z) + z0 + rp;
+            }
+            ull tt = ~(w >> p);
+            int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+            for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+        }
+        int mine = __popc(rootmask);
+        int off = mine ? atomicAdd(&s_count, mine) : 0;
+        __syncthreads();
+        if (tid == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
+        __syncthreads();
+        if (mine) {
+            int at = s_base + off;
+            for (unsigned m = rootmask; m; m &= m - 1) {
+                int p = 16 * seg + __ffs((int)m) - 1;
+                if (at < v.capacity) v.tile_roots[at] = gbase + p;
+                else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+                ++at;
             }
         }
-    }
-    __syncthreads();
-
-    // resolve every run starting in my segment; write parent for all its voxels
-    unsigned rootmask = 0;  // bit (p - 16*seg) set when the run starting at p is a tile root
-    const int gbase = (int)(rowi * v.Z) + z0;  // voxel index of bit 0 of this row word
-    for (ull s = starts; s; s &= s - 1) {
-        int p = __ffsll((long long)s) - 1;
-        int l = row * TZ + p;
-        int r = sfind(slab, l);
-        int groot;
-        if (r == l) {
-            rootmask |= 1u << (p - 16 * seg);
-            groot = gbase + p;
-        } else {
-            int rrow = r / TZ, rp = r % TZ;
-            groot = (int)(((long long)(x0 + rrow / TY) * v.Y + (y0 + rrow % TY)) * v.Z) + z0 + rp;
-        }
-        ull t = ~(w >> p);
-        int len = t ? __ffsll((long long)t) - 1 : 64 - p;
-        for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
-    }
-    int mine = __popc(rootmask);
-    int off = mine ? atomicAdd(&s_count, mine) : 0;
-    __syncthreads();
-    if (tid == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
-    __syncthreads();
-    if (mine) {
-        int at = s_base + off;
-        for (unsigned m = rootmask; m; m &= m - 1) {
-            int p = 16 * seg + __ffs((int)m) - 1;
-            if (at < v.capacity) v.tile_roots[at] = gbase + p;
-            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
-            ++at;
-        }
+        __syncthreads();  // smem is reused by the next tile
     }
 }
 
@@ -337,55 +356,73 @@ __global__ void __launch_bounds__(256) ccl_flatten_kernel(CclView v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: exclusive scan of the chunk histogram (single CTA, 1024 threads, sequential tiles)
+// K4: exclusive scan of the chunk histogram — one CTA per 8192-entry tile, then one CTA over the
+// (<= 4096) tile totals.  The rank kernel adds the two levels, so there is no third pass.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) ccl_scan_kernel(CclView v) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry;
+__device__ __forceinline__ int block_exclusive_scan_1024(int sum, int* warp_sums, int* total) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    constexpr int PER = 8;
-    for (long long base = 0; base < v.n_chunks; base += 1024 * PER) {
-        int vals[PER], sum = 0;
-        long long at = base + (long long)tid * PER;
+    int incl = sum;
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            vals[j] = (at + j < v.n_chunks) ? v.chunks[at + j] : 0;
-            sum += vals[j];
-        }
-        int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = warp_sums[lane], wi = ws;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
         }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int ws = warp_sums[lane], wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - ws;  // exclusive
-        }
-        __syncthreads();
-        int run = carry + warp_sums[wid] + incl - sum;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            if (at + j < v.n_chunks) v.chunks[at + j] = run;
-            run += vals[j];
-        }
-        __syncthreads();
-        if (tid == 1023) carry = run;
-        __syncthreads();
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) *total = wi;
     }
-    if (tid == 0) {
-        v.chunks[v.n_chunks] = carry;
-        v.hdr->n_components = carry;
-        if (v.ncomp_out) *v.ncomp_out = carry;
+    __syncthreads();
+    return warp_sums[wid] + incl - sum;
+}
+
+__global__ void __launch_bounds__(1024) ccl_scan_tiles_kernel(CclView v) {
+    __shared__ int warp_sums[32];
+    __shared__ int total;
+    constexpr int PER = SKB_SCAN_TILE / 1024;
+    const long long at = (long long)blockIdx.x * SKB_SCAN_TILE + (long long)threadIdx.x * PER;
+    int vals[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        vals[j] = (at + j < v.n_chunks) ? v.chunks[at + j] : 0;
+        sum += vals[j];
+    }
+    int run = block_exclusive_scan_1024(sum, warp_sums, &total);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (at + j < v.n_chunks) v.chunks[at + j] = run;
+        run += vals[j];
+    }
+    if (threadIdx.x == 0) v.scan_tiles[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) ccl_scan_top_kernel(CclView v) {
+    __shared__ int warp_sums[32];
+    __shared__ int total;
+    constexpr int PER = 4;  // n_scan_tiles <= 4096 for any volume the library accepts
+    const long long at = (long long)threadIdx.x * PER;
+    int vals[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        vals[j] = (at + j < v.n_scan_tiles) ? v.scan_tiles[at + j] : 0;
+        sum += vals[j];
+    }
+    int run = block_exclusive_scan_1024(sum, warp_sums, &total);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        if (at + j < v.n_scan_tiles) v.scan_tiles[at + j] = run;
+        run += vals[j];
+    }
+    if (threadIdx.x == 0) {
+        v.hdr->n_components = total;
+        if (v.ncomp_out) *v.ncomp_out = total;
     }
 }
 
@@ -394,7 +431,7 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(CclView v) {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int roots_before_word(const CclView& v, long long wi) {
     long long c = wi >> 6;
-    int r = v.chunks[c];
+    int r = v.chunks[c] + v.scan_tiles[c / SKB_SCAN_TILE];
     for (long long j = c << 6; j < wi; ++j) r += __popcll(v.rootbits[j]);
     return r;
 }
@@ -466,6 +503,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.parent = reinterpret_cast<int*>(base + L.off_parent);
     v.rootbits = reinterpret_cast<ull*>(base + L.off_rootbits);
     v.chunks = reinterpret_cast<int*>(base + L.off_chunks);
+    v.scan_tiles = reinterpret_cast<int*>(base + L.off_scan_tiles);
     v.tile_roots = reinterpret_cast<int*>(base + L.off_tile_roots);
     v.flat = reinterpret_cast<int*>(base + L.off_flat);
     v.groots = reinterpret_cast<int*>(base + L.off_groots);
@@ -473,6 +511,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.ncomp_out = ncomp;
     v.n_words = L.n_words;
     v.n_chunks = L.n_chunks;
+    v.n_scan_tiles = L.n_scan_tiles;
     return v;
 }
 
@@ -485,13 +524,13 @@ template <typename MaskT>
 static void launch_tile(const void* mask, const CclView& v, int tz, int vec_ok, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
     if (tz == 64) {
-        dim3 grid((v.Z + 63) / 64, (v.Y + 7) / 8, (v.X + 7) / 8);
+        dim3 grid((v.Z + 63) / 64, ((v.Y + 7) / 8 + CCL_NT - 1) / CCL_NT, (v.X + 7) / 8);
         ccl_tile_kernel<MaskT, 64><<<grid, 256, 0, st>>>(m, v, vec_ok);
     } else if (tz == 32) {
-        dim3 grid(1, (v.Y + 15) / 16, (v.X + 7) / 8);
+        dim3 grid(1, ((v.Y + 15) / 16 + CCL_NT - 1) / CCL_NT, (v.X + 7) / 8);
         ccl_tile_kernel<MaskT, 32><<<grid, 256, 0, st>>>(m, v, vec_ok);
     } else {
-        dim3 grid(1, (v.Y + 15) / 16, (v.X + 15) / 16);
+        dim3 grid(1, ((v.Y + 15) / 16 + CCL_NT - 1) / CCL_NT, (v.X + 15) / 16);
         ccl_tile_kernel<MaskT, 16><<<grid, 256, 0, st>>>(m, v, vec_ok);
     }
 }
@@ -534,7 +573,8 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     ccl_boundary_kernel<<<nb, 256, 0, st>>>(v, TX, TY);
     const int list_grid = 148 * 4;
     ccl_flatten_kernel<<<list_grid, 256, 0, st>>>(v);
-    ccl_scan_kernel<<<1, 1024, 0, st>>>(v);
+    ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
+    ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
     ccl_rank_kernel<<<list_grid, 256, 0, st>>>(v);
     ccl_publish_kernel<<<list_grid, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("ccl merge kernels");

@@ -115,6 +115,72 @@ int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z
                  const int32_t overlap[3], const void* workspace, const void* labels_dense,
                  int label_dtype, void* out, int out_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a4  binary_dilation / binary_dilation_2d / binary_erosion     skoots/lib/morphology.py:130-199
+ *   zero-padded 3x3x3 max (op 0), 3x3x1 max (op 1), 3x3x3 min (op 2) over n_volumes = B*C
+ *   volumes of (X,Y,Z) fp32.  Out of place.
+ * ------------------------------------------------------------------------------------------- */
+int skb_stencil3(const float* in, float* out, int64_t n_volumes, int64_t X, int64_t Y, int64_t Z,
+                 int op, void* stream);
+
+/* average_baked_skeletons, skoots/lib/skeleton.py:18-48: sum(3x3x3 window)/max(1,count(window>0)) */
+int skb_masked_mean27(const float* in, float* out, int64_t n_volumes, int64_t X, int64_t Y,
+                      int64_t Z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5  tile epilogue                                              skoots/lib/eval.py:145-176
+ *   unet: one tile of network output (C>=5, tx,ty,tz) f32|f16|bf16: channels 0..2 vectors,
+ *   C-2 skeleton, C-1 probability.  Writes the tile interior (tile minus `overlap` on each side)
+ *   at `origin` into vectors_f16 (3,X,Y,Z) and skeleton_u8 (X,Y,Z).
+ *   tile/origin/overlap are HOST arrays.
+ * ------------------------------------------------------------------------------------------- */
+int skb_tile_epilogue(const void* unet, int in_dtype, int C, const int32_t tile[3],
+                      const int32_t origin[3], const int32_t overlap[3], float threshold,
+                      void* vectors_f16, uint8_t* skeleton_u8, int64_t X, int64_t Y, int64_t Z,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7  baked_embed_to_prob                                skoots/lib/embedding_to_prob.py:5-51
+ *   embedding (B,C,inner) f32, baked (B,C,inner) f32|f16|bf16, sigma: HOST array of C floats,
+ *   out (B,1,inner) f32.  C = 2 or 3.  _bwd writes grad_embedding (f32) and/or grad_baked
+ *   (baked dtype); either may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int skb_embed_prob_fwd(const float* embedding, const void* baked, int baked_dtype, int64_t B, int C,
+                       int64_t inner, const float* sigma, float eps, float* out, void* stream);
+int skb_embed_prob_bwd(const float* embedding, const void* baked, int baked_dtype,
+                       const float* prob, const float* grad_out, int64_t B, int C, int64_t inner,
+                       const float* sigma, float eps, float* grad_embedding, void* grad_baked,
+                       void* stream);
+
+/* fused vector_to_embedding(N=1) + baked_embed_to_prob (train/engine.py:465-466): vec (B,C,X,Y[,Z]).
+ * grad_out == NULL -> forward, writes prob (B,1,...) ; else backward, writes grad_vec (vec dtype). */
+int skb_vec_prob(const void* vec, int vec_dtype, const void* baked, int baked_dtype, int64_t B, int C,
+                 int64_t X, int64_t Y, int64_t Z, const float* scale, const float* sigma, float eps,
+                 float* prob, const float* grad_out, void* grad_vec, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8  bake_skeleton (CPU/torch semantics)                     skoots/lib/skeleton.py:370-445
+ *   mask (X,Y,Z) u8|i16|i32 object ids; ids: sorted object ids (device, n_ids); offsets: device
+ *   prefix (n_ids+1) into points_xyzw (device, n_points x 4 floats, 16-byte rows);
+ *   anisotropy: HOST array.  baked (3,X,Y,Z) f32 = nearest point of the voxel's own skeleton
+ *   (first minimum), 0 on background; distance (X,Y,Z) f32 optional.  *status |= 2 when a mask
+ *   id has no skeleton (the reference raises KeyError, skeleton.py:422).
+ * ------------------------------------------------------------------------------------------- */
+#define SKB_STATUS_MISSING_ID 2u
+int skb_bake_skeleton(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
+                      const int32_t* ids, const int32_t* offsets, int n_ids,
+                      const float* points_xyzw, int n_points, const float anisotropy[3],
+                      float* baked, float* distance, uint32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9  skeleton_to_mask                                         skoots/lib/skeleton.py:531-593
+ *   points (n_points,3) f32 device; offsets (n_offsets,3) i32 device (the disk stamp of
+ *   lib/utils.py:421-438); out (X,Y,Z) f32 must be zeroed by the caller; sets 1.0 at
+ *   trunc(point + offset) where inside the volume.
+ * ------------------------------------------------------------------------------------------- */
+int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offsets_xyz, int n_offsets,
+                    int64_t X, int64_t Y, int64_t Z, float* out_zeroed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

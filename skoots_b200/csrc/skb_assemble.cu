@@ -31,6 +31,8 @@ struct AsmParams {
     int shifted[3];         // the axis has a shifted-back last crop
     int fast_ok;            // zero-vector voxels provably resolve to themselves
     int vec_aligned;        // 16-byte loads of the vector channels are legal
+    int flat_bits;          // Z % 64 == 0: the bit mask has no row padding, bit index == voxel index
+    int single_crop;        // the whole volume is one crop with no overlap: owner origin is 0 everywhere
     // label source
     const ull* bits;
     const int* parent;
@@ -116,55 +118,60 @@ __device__ __forceinline__ int label_at(const AsmParams& P, int tx, int ty, int 
 
 template <typename VecT>
 __device__ __forceinline__ int assemble_voxel(const AsmParams& P, int x, int y, int z, float v0, float v1, float v2) {
-    int ox = owner_origin(x, P.X, P.cs[0], P.ov[0], P.step[0], P.shifted[0]);
-    int oy = owner_origin(y, P.Y, P.cs[1], P.ov[1], P.step[1], P.shifted[1]);
-    int oz = owner_origin(z, P.Z, P.cs[2], P.ov[2], P.step[2], P.shifted[2]);
-    if ((ox | oy | oz) < 0) return 0;  // outer margin: never written by the reference (eval.py:259-269)
+    int ox = 0, oy = 0, oz = 0;
+    if (!P.single_crop) {
+        ox = owner_origin(x, P.X, P.cs[0], P.ov[0], P.step[0], P.shifted[0]);
+        oy = owner_origin(y, P.Y, P.cs[1], P.ov[1], P.step[1], P.shifted[1]);
+        oz = owner_origin(z, P.Z, P.cs[2], P.ov[2], P.step[2], P.shifted[2]);
+        if ((ox | oy | oz) < 0) return 0;  // outer margin: never written by the reference (eval.py:259-269)
+    }
     float mx, my, mz;
     walk<VecT>(P, x - ox, y - oy, z - oz, ox, oy, oz, v0, v1, v2, mx, my, mz);
     float ex = __fadd_rn(mx, (float)ox), ey = __fadd_rn(my, (float)oy), ez = __fadd_rn(mz, (float)oz);
     return label_at(P, clamp_index(ex, P.X), clamp_index(ey, P.Y), clamp_index(ez, P.Z));
 }
 
-template <typename VecT>
-__device__ __forceinline__ bool load8(const void* base, long long idx, bool aligned, float* out) {
-    // returns true when all 8 raw elements are +0 bit patterns
-    const VecT* p = static_cast<const VecT*>(base) + idx;
-    if (aligned) {
-        if (sizeof(VecT) == 2) {
-            uint4 q = skb_ld_stream16(p);
-            const VecT* e = reinterpret_cast<const VecT*>(&q);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) out[j] = skb_to_float<VecT>(e[j]);
-            return (q.x | q.y | q.z | q.w) == 0u;
-        } else {
-            uint4 q0 = skb_ld_stream16(p), q1 = skb_ld_stream16(reinterpret_cast<const char*>(p) + 16);
-            const float* e0 = reinterpret_cast<const float*>(&q0);
-            const float* e1 = reinterpret_cast<const float*>(&q1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { out[j] = e0[j]; out[4 + j] = e1[j]; }
-            return (q0.x | q0.y | q0.z | q0.w | q1.x | q1.y | q1.z | q1.w) == 0u;
-        }
-    }
-    bool zero = true;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        out[j] = skb_to_float<VecT>(p[j]);
-        zero = zero && (out[j] == 0.f) && !signbit(out[j]);
-    }
-    return zero;
-}
-
 // One warp owns 256 consecutive voxels (8 per lane).  Voxels that need real work — a non-zero
 // vector, or a zero vector sitting on a foreground voxel — are compacted into a per-warp queue in
 // shared memory and processed one per lane, so the divergent part (walk + dependent label reads)
 // always runs with full warps and 32 independent load chains in flight.  Everything else is a
-// pure stream: 3 x 16-byte loads, one byte of the bit mask, 2 x 16-byte stores.
+// pure stream: 3 x 16-byte loads, one byte of the bit mask, 2 x 16-byte stores, ~40 instructions
+// per warp (the zero test works on the raw bit patterns; nothing is converted to float).
 constexpr int ASM_WARPS = 8;
 
+template <typename VecT> struct RawOf { typedef unsigned short type; };
+template <> struct RawOf<float> { typedef unsigned type; };
+
+template <typename VecT>
+__device__ __forceinline__ float raw_to_float(typename RawOf<VecT>::type r);
+template <> __device__ __forceinline__ float raw_to_float<__half>(unsigned short r) { return __half2float(__ushort_as_half(r)); }
+template <> __device__ __forceinline__ float raw_to_float<__nv_bfloat16>(unsigned short r) { return __uint_as_float((unsigned)r << 16); }
+template <> __device__ __forceinline__ float raw_to_float<float>(unsigned r) { return __uint_as_float(r); }
+
+// 8 consecutive raw elements of one channel; `aligned` selects 16-byte streaming loads
+template <typename VecT>
+__device__ __forceinline__ void load8_raw(const void* base, long long idx, bool aligned, int nvalid,
+                                          typename RawOf<VecT>::type* r) {
+    typedef typename RawOf<VecT>::type raw_t;
+    const raw_t* p = static_cast<const raw_t*>(base) + idx;
+    if (aligned && nvalid == 8) {
+        if (sizeof(raw_t) == 2) {
+            uint4 q = skb_ld_stream16(p);
+            *reinterpret_cast<uint4*>(r) = q;
+        } else {
+            reinterpret_cast<uint4*>(r)[0] = skb_ld_stream16(p);
+            reinterpret_cast<uint4*>(r)[1] = skb_ld_stream16(p + 4);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = j < nvalid ? __ldg(p + j) : (raw_t)0;
+    }
+}
+
 template <typename VecT, typename OutT>
-__global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
-    __shared__ float s_vec[ASM_WARPS][3][256];
+__global__ void __launch_bounds__(32 * ASM_WARPS, 6) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+    typedef typename RawOf<VecT>::type raw_t;
+    __shared__ raw_t s_raw[ASM_WARPS][3][256];
     __shared__ int s_res[ASM_WARPS][256];
     __shared__ unsigned char s_queue[ASM_WARPS][256];
 
@@ -176,36 +183,42 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, O
     const int nvalid = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
     const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
 
-    float v0[8], v1[8], v2[8];
-    if (nvalid == 8) {
+    __align__(16) raw_t r0[8], r1[8], r2[8];
+    {
         const bool al = P.vec_aligned != 0;
-        load8<VecT>(P.vec, i0, al, v0);
-        load8<VecT>(P.vec, i0 + P.cstride, al, v1);
-        load8<VecT>(P.vec, i0 + 2 * P.cstride, al, v2);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool ok = j < nvalid;
-            v0[j] = ok ? load_vec<VecT>(P.vec, i0 + j) : 0.f;
-            v1[j] = ok ? load_vec<VecT>(P.vec, i0 + j + P.cstride) : 0.f;
-            v2[j] = ok ? load_vec<VecT>(P.vec, i0 + j + 2 * P.cstride) : 0.f;
-        }
+        load8_raw<VecT>(P.vec, i0, al, nvalid, r0);
+        load8_raw<VecT>(P.vec, i0 + P.cstride, al, nvalid, r1);
+        load8_raw<VecT>(P.vec, i0 + 2 * P.cstride, al, nvalid, r2);
     }
 
     // which of my voxels need the slow path
     unsigned work = 0;
-    if (nvalid > 0) {
-        if (!P.fast_ok) {
-            work = (1u << nvalid) - 1u;
+    const unsigned valid_mask = (1u << nvalid) - 1u;
+    if (!P.fast_ok || P.dense) {
+        work = valid_mask;  // N>1 over a >2^24-voxel crop, or a dense label volume (compatibility path)
+    } else if (nvalid > 0) {
+        // non-zero vector (sign bit ignored: -0 * s adds nothing) -> work
+        if (sizeof(raw_t) == 2) {
+            const uint4 a = *reinterpret_cast<uint4*>(r0), b = *reinterpret_cast<uint4*>(r1), c = *reinterpret_cast<uint4*>(r2);
+            const unsigned o[4] = {(a.x | b.x | c.x) & 0x7fff7fffu, (a.y | b.y | c.y) & 0x7fff7fffu,
+                                   (a.z | b.z | c.z) & 0x7fff7fffu, (a.w | b.w | c.w) & 0x7fff7fffu};
+            if ((o[0] | o[1] | o[2] | o[3]) != 0u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    work |= ((unsigned)((o[k] & 0xffffu) != 0u) << (2 * k)) | ((unsigned)((o[k] >> 16) != 0u) << (2 * k + 1));
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) work |= (unsigned)((v0[j] != 0.f) | (v1[j] != 0.f) | (v2[j] != 0.f)) << j;
-            // a zero vector resolves to the voxel itself: only foreground voxels need a label read
+            for (int j = 0; j < 8; ++j)
+                work |= (unsigned)((((unsigned)r0[j] | (unsigned)r1[j] | (unsigned)r2[j]) & 0x7fffffffu) != 0u) << j;
+        }
+        // a zero vector resolves to the voxel itself: only foreground voxels need a label read
+        if (P.flat_bits) {
+            work |= (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (i0 >> 3));
+        } else {
             const unsigned q = (unsigned)i0 / uz;
             const int z = (int)((unsigned)i0 - q * uz);
-            if (P.dense) {
-                work = (1u << nvalid) - 1u;  // dense label volumes are the compatibility path: no bit mask to consult
-            } else if (z + 8 <= P.Z) {
+            if (z + 8 <= P.Z) {
                 const long long wi = (long long)q * P.ZW + (z >> 6);
                 const int sh = z & 63;
                 ull w = __ldg(P.bits + wi) >> sh;
@@ -220,29 +233,32 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, O
                     if (++zz == P.Z) { zz = 0; ++qq; }
                 }
             }
-            work &= (1u << nvalid) - 1u;
         }
+        work &= valid_mask;
     }
 
-    // warp-wide compaction of the work items
-    const int cnt = __popc(work);
-    int incl = cnt;
+    if (__ballot_sync(0xffffffffu, work != 0u) != 0u) {
+        // warp-wide compaction of the work items
+        const int cnt = __popc(work);
+        int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total > 0) {
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
         int at = incl - cnt;
+        for (unsigned m = work; m; m &= m - 1) {
+            const int j = __ffs((int)m) - 1;
+            const int code = j * 32 + lane;
+            s_queue[warp][at++] = (unsigned char)code;
+        }
+        if (work) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if ((work >> j) & 1u) {
-                const int code = j * 32 + lane;
-                s_queue[warp][at++] = (unsigned char)code;
-                s_vec[warp][0][code] = v0[j];
-                s_vec[warp][1][code] = v1[j];
-                s_vec[warp][2][code] = v2[j];
+            for (int j = 0; j < 8; ++j) {  // unconditional, conflict-free; cheaper than predicating 24 stores
+                s_raw[warp][0][j * 32 + lane] = r0[j];
+                s_raw[warp][1][j * 32 + lane] = r1[j];
+                s_raw[warp][2][j * 32 + lane] = r2[j];
             }
         }
         __syncwarp();
@@ -253,8 +269,9 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, O
             const int z = (int)(vi - q * uz);
             const int x = (int)(q / uy);
             const int y = (int)(q - (unsigned)x * uy);
-            s_res[warp][code] = assemble_voxel<VecT>(P, x, y, z, s_vec[warp][0][code], s_vec[warp][1][code],
-                                                     s_vec[warp][2][code]);
+            s_res[warp][code] = assemble_voxel<VecT>(P, x, y, z, raw_to_float<VecT>(s_raw[warp][0][code]),
+                                                     raw_to_float<VecT>(s_raw[warp][1][code]),
+                                                     raw_to_float<VecT>(s_raw[warp][2][code]));
         }
         __syncwarp();
     }
@@ -262,7 +279,12 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_kernel(AsmParams P, O
     if (nvalid == 0) return;
     __align__(16) OutT lab[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lab[j] = ((work >> j) & 1u) ? (OutT)s_res[warp][j * 32 + lane] : (OutT)0;
+    for (int j = 0; j < 8; ++j) lab[j] = (OutT)0;
+    if (work) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if ((work >> j) & 1u) lab[j] = (OutT)s_res[warp][j * 32 + lane];
+    }
     if (nvalid == 8) {
         if (sizeof(OutT) == 2) {
             skb_st_stream16(out + i0, *reinterpret_cast<uint4*>(lab));
@@ -354,6 +376,7 @@ static void fill_crop(AsmParams& P, const int32_t crop[3], const int32_t overlap
         cropvol *= P.cs[a];
     }
     P.fast_ok = (P.N == 1 || cropvol <= (1LL << 24)) ? 1 : 0;
+    P.single_crop = (P.cs[0] == P.X && P.cs[1] == P.Y && P.cs[2] == P.Z && !P.ov[0] && !P.ov[1] && !P.ov[2]) ? 1 : 0;
 }
 
 template <typename VecT>
@@ -402,6 +425,7 @@ extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y
         P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
         P.parent = reinterpret_cast<const int*>(base + L.off_parent);
         P.ZW = L.ZW;
+        P.flat_bits = (Z % 64 == 0) ? 1 : 0;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = X * Y * Z;

@@ -3,13 +3,14 @@
 // Replaces the arithmetic of skoots/lib/flood_fill.py:13-140 (scipy.ndimage.label per crop +
 // seam merging).  Design:
 //
-//   K1 ccl_tile_kernel      one 4096-voxel tile per CTA.  The mask is read once with 16-byte
-//                           loads (Z is the contiguous axis), turned into one 64-bit word per
-//                           (x,y) row, written out as the bit-packed mask, and labelled inside
-//                           the tile by a shared-memory union-find over z-RUNS (a run's start
-//                           is found with clz on the row word, so z-connectivity costs nothing;
-//                           only y/x neighbour rows need unions).  Every foreground voxel gets
-//                           parent[v] = its tile root; tile roots are appended to a list.
+//   K1 ccl_tile_kernel      one 8x8x64 tile per 64-thread CTA, one (x,y) row per thread.  The mask
+//                           is read once with 16-byte loads (Z is the contiguous axis), packed
+//                           into one 64-bit word per row, written out as the bit-packed mask,
+//                           and labelled inside the tile by a shared-memory union-find over
+//                           z-RUNS (a run's start is found with clz on the row word, so
+//                           z-connectivity costs nothing; only y/x neighbour rows need unions).
+//                           Every foreground voxel gets parent[v] = its tile root; tile roots
+//                           are appended to a list.
 //   K2 ccl_boundary_kernel  one thread per 64-bit word of the bit-packed mask: unions across
 //                           tile faces with atomicMin on the global parent array.
 //   K3 ccl_flatten_kernel   pointer-jumps every tile root to its global root, marks global
@@ -62,6 +63,7 @@ int skb_check_volume(int64_t X, int64_t Y, int64_t Z, const char* who) {
 struct CclView {
     int X, Y, Z, ZW;
     int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
+    int ZW_tiles;   // z tiles per row in the tile kernel
     int capacity;
     SkbCclHeader* hdr;
     ull* bits;
@@ -127,47 +129,70 @@ __device__ __forceinline__ void gunion(int* parent, int a, int b) {
     }
 }
 
-// foreground bits of up to 16 consecutive mask elements starting at p (n valid)
-template <typename MaskT>
-__device__ __forceinline__ unsigned fg16(const MaskT* p, int n, bool vec_ok);
-
-template <>
-__device__ __forceinline__ unsigned fg16<uint8_t>(const uint8_t* p, int n, bool vec_ok) {
-    unsigned bits = 0;
-    if (vec_ok && n == 16) {
-        uint4 q = skb_ld_stream16(p);
-        unsigned w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // non-zero byte -> bit: (b | -b) has its top bit set iff b != 0, per byte via SIMD
-            unsigned nz = __vcmpne4(w[i], 0u);  // 0xFF per non-zero byte
-            unsigned m = nz & 0x08040201u;      // byte k keeps bit k
-            m |= m >> 16;
-            m |= m >> 8;
-            bits |= (m & 0xFu) << (4 * i);
-        }
-    } else {
-        for (int i = 0; i < n; ++i) bits |= (unsigned)(p[i] != 0) << i;
-    }
-    return bits;
+// ---- mask elements -> foreground bits ---------------------------------------------------------
+// 4 bytes -> 4 bits (byte != 0).  High bit of every non-zero byte, then a multiply gathers the four
+// flags into one nibble (the partial products land on distinct bit positions, so no carries).
+__device__ __forceinline__ unsigned nz4(unsigned w) {
+    unsigned t = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+    return (((t >> 7) * 0x01020408u) >> 24) & 0xFu;
+}
+// 2 int16 -> 2 bits (element > 0): non-zero and sign bit clear
+__device__ __forceinline__ unsigned gt2(unsigned w) {
+    unsigned t = (((w & 0x7fff7fffu) + 0x7fff7fffu) | w) & ~w & 0x80008000u;
+    return ((t >> 15) | (t >> 30)) & 3u;
 }
 
-template <>
-__device__ __forceinline__ unsigned fg16<int16_t>(const int16_t* p, int n, bool vec_ok) {
-    unsigned bits = 0;
-    if (vec_ok && n == 16) {
-        uint4 q0 = skb_ld_stream16(p), q1 = skb_ld_stream16(p + 8);
-        unsigned w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            unsigned gt = __vcmpgts2(w[i], 0u);  // 0xFFFF per halfword > 0 (signed)
-            bits |= ((gt & 1u) | ((gt >> 15) & 2u)) << (2 * i);
-        }
-    } else {
-        for (int i = 0; i < n; ++i) bits |= (unsigned)(p[i] > 0) << i;
-    }
-    return bits;
+// foreground bits of the n (<= TZ) mask elements of one row segment
+template <typename MaskT, int TZ>
+__device__ __forceinline__ ull row_bits(const MaskT* p, int n, bool vec_ok);
+
+template <typename MaskT, int TZ>
+__device__ __forceinline__ ull row_bits_scalar(const MaskT* p, int n) {
+    ull w = 0;
+    for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
+    return w;
 }
+
+template <int TZ>
+__device__ __forceinline__ ull row_bits_u8(const uint8_t* p, int n, bool vec_ok) {
+    if (!vec_ok) return row_bits_scalar<uint8_t, TZ>(p, n);
+    ull w = 0;
+    uint4 q[TZ / 16];
+#pragma unroll
+    for (int k = 0; k < TZ / 16; ++k)  // all loads first; groups past the end of the row read nothing
+        q[k] = (16 * (k + 1) <= n) ? __ldg(reinterpret_cast<const uint4*>(p) + k) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < TZ / 16; ++k) {
+        unsigned h = nz4(q[k].x) | (nz4(q[k].y) << 4) | (nz4(q[k].z) << 8) | (nz4(q[k].w) << 12);
+        w |= (ull)h << (16 * k);
+    }
+    for (int i = n & ~15; i < n; ++i) w |= (ull)(p[i] != 0) << i;
+    return w;
+}
+
+template <int TZ>
+__device__ __forceinline__ ull row_bits_i16(const int16_t* p, int n, bool vec_ok) {
+    if (!vec_ok) return row_bits_scalar<int16_t, TZ>(p, n);
+    ull w = 0;
+#pragma unroll
+    for (int k = 0; k < TZ / 8; ++k) {
+        if (8 * (k + 1) <= n) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + k);
+            unsigned h = gt2(q.x) | (gt2(q.y) << 2) | (gt2(q.z) << 4) | (gt2(q.w) << 6);
+            w |= (ull)h << (8 * k);
+        }
+    }
+    for (int i = n & ~7; i < n; ++i) w |= (ull)(p[i] > 0) << i;
+    return w;
+}
+
+template <typename MaskT, int TZ> struct RowBits;
+template <int TZ> struct RowBits<uint8_t, TZ> {
+    static __device__ __forceinline__ ull get(const uint8_t* p, int n, bool v) { return row_bits_u8<TZ>(p, n, v); }
+};
+template <int TZ> struct RowBits<int16_t, TZ> {
+    static __device__ __forceinline__ ull get(const int16_t* p, int n, bool v) { return row_bits_i16<TZ>(p, n, v); }
+};
 
 __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
     if (threadIdx.x == 0) {
@@ -180,114 +205,97 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
 // ------------------------------------------------------------------------------------------
 // K1: tile-local run-based union-find
 // ------------------------------------------------------------------------------------------
-constexpr int CCL_NT = 4;  // tiles (stacked along y) per CTA: 4 independent 16-byte loads in flight per thread
-
+// One CTA = one 8 x 8 x TZ tile, one THREAD = one (x,y) row of it: the thread loads its whole
+// TZ-element row segment (4 independent 16-byte loads for u8, TZ = 64), packs it into a 64-bit
+// word, and does every union of that row with its y-1 / x-1 neighbour rows.  A run start can only
+// sit at every other bit, so the union-find array needs 32 slots per row: slot = row*32 + (p>>1).
 template <typename MaskT, int TZ>
-__global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
-    constexpr int SZ = TZ / 16;           // 16-voxel segments per row
-    constexpr int ROWS = 256 / SZ;        // rows per tile
-    constexpr int TY = (TZ == 64) ? 8 : 16;
-    constexpr int TX = ROWS / TY;
-    __shared__ ull srow[ROWS];
-    __shared__ int slab[ROWS * TZ];
+__global__ void __launch_bounds__(64) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
+    constexpr int TY = 8;
+    __shared__ ull srow[64];
+    __shared__ int slab[64 * 32];
     __shared__ int s_count, s_base;
 
-    const int tid = threadIdx.x;
-    const int seg = tid % SZ, row = tid / SZ;
-    const int ly = row % TY, lx = row / TY;
-    const int x0 = blockIdx.z * TX, z0 = blockIdx.x * TZ;
-    const int x = x0 + lx, z = z0 + seg * 16;
+    const int row = threadIdx.x;
+    const int ly = row & 7, lx = row >> 3;
+    // linear CTA index -> (z tile fastest, then y, then x); avoids the 65535 limit of grid.y/z
+    const unsigned nzt = (unsigned)v.ZW_tiles, nyt = (unsigned)((v.Y + 7) >> 3);
+    const unsigned bq = blockIdx.x / nzt, zt = blockIdx.x - bq * nzt;
+    const unsigned xt = bq / nyt, yt = bq - xt * nyt;
+    const int x0 = (int)xt * 8, y0 = (int)yt * 8, z0 = (int)zt * TZ;
+    const int x = x0 + lx, y = y0 + ly;
+    const bool in_row = (x < v.X) && (y < v.Y);
+    const unsigned rowi = (unsigned)x * (unsigned)v.Y + (unsigned)y;
 
-    // issue every tile's load before touching any of them
-    unsigned b16s[CCL_NT];
-#pragma unroll
-    for (int t = 0; t < CCL_NT; ++t) {
-        const int y = (blockIdx.y * CCL_NT + t) * TY + ly;
-        b16s[t] = 0;
-        if (x < v.X && y < v.Y && z < v.Z)
-            b16s[t] = fg16<MaskT>(mask + ((long long)x * v.Y + y) * v.Z + z, min(16, v.Z - z), vec_ok != 0);
+    if (row == 0) s_count = 0;
+    ull w = 0;
+    if (in_row) {
+        w = RowBits<MaskT, TZ>::get(mask + (size_t)rowi * v.Z + z0, min(TZ, v.Z - z0), vec_ok != 0);
+        v.bits[(size_t)rowi * v.ZW + zt] = w;
     }
+    srow[row] = w;
+    if (!__syncthreads_or(w != 0ull)) return;  // empty tile: nothing to label
 
-#pragma unroll
-    for (int t = 0; t < CCL_NT; ++t) {
-        const int y0 = (blockIdx.y * CCL_NT + t) * TY;
-        if (y0 >= v.Y) continue;  // uniform across the CTA
-        const int y = y0 + ly;
-        const bool in_row = (x < v.X) && (y < v.Y);
-        const long long rowi = (long long)x * v.Y + y;
-        const unsigned b16 = b16s[t];
+    const ull starts = w & ~(w << 1);
+    for (ull s = starts; s; s &= s - 1) {
+        int p = __ffsll((long long)s) - 1;
+        slab[row * 32 + (p >> 1)] = row * 32 + (p >> 1);
+    }
+    __syncthreads();
 
-        if (tid == 0) s_count = 0;
-        ull w = (ull)b16 << (16 * seg);
-#pragma unroll
-        for (int o = 1; o < SZ; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
-        if (seg == 0) {
-            srow[row] = w;
-            if (in_row) v.bits[rowi * v.ZW + blockIdx.x] = w;
-        }
-        if (!__syncthreads_or(b16 != 0)) continue;  // empty tile: nothing to label
-
-        const ull segmask = 0xFFFFull << (16 * seg);
-        const ull starts = w & ~(w << 1) & segmask;  // run starts inside my segment
-        for (ull s = starts; s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            slab[row * TZ + p] = row * TZ + p;
-        }
-        __syncthreads();
-
-        // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
-        if (w & segmask) {
-            if (ly > 0) {
-                ull wn = srow[row - 1], a = w & wn;
-                for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
-                    int p = __ffsll((long long)s) - 1;
-                    sunion(slab, row * TZ + run_start(w, p), (row - 1) * TZ + run_start(wn, p));
-                }
-            }
-            if (lx > 0 && v.connect_x) {
-                ull wn = srow[row - TY], a = w & wn;
-                for (ull s = a & ~(a << 1) & segmask; s; s &= s - 1) {
-                    int p = __ffsll((long long)s) - 1;
-                    sunion(slab, row * TZ + run_start(w, p), (row - TY) * TZ + run_start(wn, p));
-                }
+    // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
+    if (w) {
+        if (ly > 0) {
+            ull wn = srow[row - 1], a = w & wn;
+            for (ull s = a & ~(a << 1); s; s &= s - 1) {
+                int p = __ffsll((long long)s) - 1;
+                sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - 1) * 32 + (run_start(wn, p) >> 1));
             }
         }
-        __syncthreads();
+        if (lx > 0 && v.connect_x) {
+            ull wn = srow[row - TY], a = w & wn;
+            for (ull s = a & ~(a << 1); s; s &= s - 1) {
+                int p = __ffsll((long long)s) - 1;
+                sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - TY) * 32 + (run_start(wn, p) >> 1));
+            }
+        }
+    }
+    __syncthreads();
 
-        // resolve every run starting in my segment; write parent for all its voxels
-        unsigned rootmask = 0;  // bit (p - 16*seg) set when the run starting at p is a tile root
-        const int gbase = (int)(rowi * v.Z) + z0;  // voxel index of bit 0 of this row word
-        for (ull s = starts; s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            int l = row * TZ + p;
-            int r = sfind(slab, l);
-            int groot;
-            if (r == l) {
-                rootmask |= 1u << (p - 16 * seg);
-                groot = gbase + p;
-            } else {
-                int rrow = r / TZ, rp = r % TZ;
-                groot = (int)(((long long)(x0 + rrow / TY) * v.Y + (y0 + rrow % TY)) * v.Z) + z0 + rp;
-            }
-            ull tt = ~(w >> p);
-            int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
-            for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+    // resolve every run of my row; write parent for all its voxels
+    ull rootmask = 0;  // bit p set when the run starting at p is a tile root
+    const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
+    for (ull s = starts; s; s &= s - 1) {
+        int p = __ffsll((long long)s) - 1;
+        int l = row * 32 + (p >> 1);
+        int r = sfind(slab, l);
+        int groot;
+        if (r == l) {
+            rootmask |= 1ull << p;
+            groot = gbase + p;
+        } else {
+            const int rrow = r >> 5, rh = r & 31;
+            const ull rs = srow[rrow] & ~(srow[rrow] << 1);
+            const int rp = 2 * rh + (int)((rs >> (2 * rh + 1)) & 1ull);
+            groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + rp;
         }
-        int mine = __popc(rootmask);
-        int off = mine ? atomicAdd(&s_count, mine) : 0;
-        __syncthreads();
-        if (tid == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
-        __syncthreads();
-        if (mine) {
-            int at = s_base + off;
-            for (unsigned m = rootmask; m; m &= m - 1) {
-                int p = 16 * seg + __ffs((int)m) - 1;
-                if (at < v.capacity) v.tile_roots[at] = gbase + p;
-                else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
-                ++at;
-            }
+        ull tt = ~(w >> p);
+        int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+        for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+    }
+    int mine = __popcll(rootmask);
+    int off = mine ? atomicAdd(&s_count, mine) : 0;
+    __syncthreads();
+    if (row == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
+    __syncthreads();
+    if (mine) {
+        int at = s_base + off;
+        for (ull m = rootmask; m; m &= m - 1) {
+            int p = __ffsll((long long)m) - 1;
+            if (at < v.capacity) v.tile_roots[at] = gbase + p;
+            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            ++at;
         }
-        __syncthreads();  // smem is reused by the next tile
     }
 }
 
@@ -295,26 +303,27 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__
 // K2: unions across tile faces, driven by the bit-packed mask
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY) {
-    long long widx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (widx >= v.n_words) return;
-    ull w = v.bits[widx];
+    // n_words <= 2^31: all index math in 32 bits (64-bit div/mod costs ~100 instructions each)
+    const unsigned widx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (widx >= (unsigned)v.n_words) return;
+    const ull w = v.bits[widx];
     if (!w) return;
-    int k = (int)(widx % v.ZW);
-    long long rowi = widx / v.ZW;
-    int y = (int)(rowi % v.Y), x = (int)(rowi / v.Y);
-    int gbase = (int)(rowi * v.Z) + 64 * k;
+    const unsigned uzw = (unsigned)v.ZW, uyy = (unsigned)v.Y;
+    const unsigned rowi = widx / uzw, k = widx - rowi * uzw;
+    const unsigned x = rowi / uyy, y = rowi - x * uyy;
+    const int gbase = (int)(rowi * (unsigned)v.Z + 64u * k);
     if (k > 0 && (w & 1ull)) {
         if (v.bits[widx - 1] >> 63) gunion(v.parent, gbase, gbase - 1);
     }
-    if (y > 0 && (y % TY) == 0) {
-        ull a = w & v.bits[widx - v.ZW];
+    if (y > 0 && (y % (unsigned)TY) == 0) {
+        ull a = w & v.bits[widx - uzw];
         for (ull s = a & ~(a << 1); s; s &= s - 1) {
             int p = __ffsll((long long)s) - 1;
             gunion(v.parent, gbase + p, gbase + p - v.Z);
         }
     }
-    if (v.connect_x && x > 0 && (x % TX) == 0) {
-        ull a = w & v.bits[widx - (long long)v.Y * v.ZW];
+    if (v.connect_x && x > 0 && (x % (unsigned)TX) == 0) {
+        ull a = w & v.bits[widx - uyy * uzw];
         int plane = v.Y * v.Z;
         for (ull s = a & ~(a << 1); s; s &= s - 1) {
             int p = __ffsll((long long)s) - 1;
@@ -497,6 +506,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     CclView v;
     v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
     v.connect_x = planar ? 0 : 1;
+    v.ZW_tiles = 1;
     v.capacity = (int)capacity;
     v.hdr = reinterpret_cast<SkbCclHeader*>(base);
     v.bits = reinterpret_cast<ull*>(base + L.off_bits);
@@ -523,16 +533,12 @@ extern "C" size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64
 template <typename MaskT>
 static void launch_tile(const void* mask, const CclView& v, int tz, int vec_ok, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
-    if (tz == 64) {
-        dim3 grid((v.Z + 63) / 64, ((v.Y + 7) / 8 + CCL_NT - 1) / CCL_NT, (v.X + 7) / 8);
-        ccl_tile_kernel<MaskT, 64><<<grid, 256, 0, st>>>(m, v, vec_ok);
-    } else if (tz == 32) {
-        dim3 grid(1, ((v.Y + 15) / 16 + CCL_NT - 1) / CCL_NT, (v.X + 7) / 8);
-        ccl_tile_kernel<MaskT, 32><<<grid, 256, 0, st>>>(m, v, vec_ok);
-    } else {
-        dim3 grid(1, ((v.Y + 15) / 16 + CCL_NT - 1) / CCL_NT, (v.X + 15) / 16);
-        ccl_tile_kernel<MaskT, 16><<<grid, 256, 0, st>>>(m, v, vec_ok);
-    }
+    CclView vv = v;
+    vv.ZW_tiles = (v.Z + tz - 1) / tz;
+    const unsigned grid = (unsigned)((long long)vv.ZW_tiles * ((v.Y + 7) / 8) * ((v.X + 7) / 8));
+    if (tz == 64) ccl_tile_kernel<MaskT, 64><<<grid, 64, 0, st>>>(m, vv, vec_ok);
+    else if (tz == 32) ccl_tile_kernel<MaskT, 32><<<grid, 64, 0, st>>>(m, vv, vec_ok);
+    else ccl_tile_kernel<MaskT, 16><<<grid, 64, 0, st>>>(m, vv, vec_ok);
 }
 
 extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int planar,
@@ -568,7 +574,7 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     else launch_tile<int16_t>(mask, v, tz, vec_ok, st);
     SKB_LAUNCH_CHECK("ccl_tile_kernel");
 
-    const int TY = tz == 64 ? 8 : 16, TX = tz == 16 ? 16 : 8;
+    const int TY = 8, TX = 8;
     unsigned nb = (unsigned)((L.n_words + 255) / 256);
     ccl_boundary_kernel<<<nb, 256, 0, st>>>(v, TX, TY);
     const int list_grid = 148 * 4;

@@ -1,0 +1,75 @@
+"""Rebinds the reference's by-name imports to the B200 implementations.
+
+    import skoots_b200.patch; skoots_b200.patch.patch_skoots()
+
+Only modules that are importable are touched; `from x import y` copies are rebound in every already-
+imported caller module listed in SURVEY.md §8b.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+from typing import List, Tuple
+
+# (defining module, attribute) -> replacement (module path, attribute)
+_TARGETS = {
+    ("skoots.lib.vector_to_embedding", "vector_to_embedding"): ("skoots_b200.lib.vector_to_embedding", "vector_to_embedding"),
+    ("skoots.lib.skeleton", "index_skeleton_by_embed"): ("skoots_b200.lib.skeleton", "index_skeleton_by_embed"),
+    ("skoots.lib.skeleton", "bake_skeleton"): ("skoots_b200.lib.skeleton", "bake_skeleton"),
+    ("skoots.lib.skeleton", "skeleton_to_mask"): ("skoots_b200.lib.skeleton", "skeleton_to_mask"),
+    ("skoots.lib.skeleton", "average_baked_skeletons"): ("skoots_b200.lib.skeleton", "average_baked_skeletons"),
+    ("skoots.lib.flood_fill", "efficient_flood_fill"): ("skoots_b200.lib.flood_fill", "efficient_flood_fill"),
+    ("skoots.lib.morphology", "binary_dilation"): ("skoots_b200.lib.morphology", "binary_dilation"),
+    ("skoots.lib.morphology", "binary_dilation_2d"): ("skoots_b200.lib.morphology", "binary_dilation_2d"),
+    ("skoots.lib.morphology", "binary_erosion"): ("skoots_b200.lib.morphology", "binary_erosion"),
+    ("skoots.lib.embedding_to_prob", "baked_embed_to_prob"): ("skoots_b200.lib.embedding_to_prob", "baked_embed_to_prob"),
+}
+
+# modules holding `from ... import name` copies (SURVEY.md §8b "bound at")
+_CALLERS = (
+    "skoots.lib.eval", "skoots.train.engine", "skoots.train.merged_transform", "skoots.train.loss",
+    "skoots.experimental.sparse_engine", "skoots.experimental.eval", "skoots.experimental.sparse_loss",
+    "skoots.experimental.sparse_transforms", "skoots.experimental.modifiers",
+)
+
+
+_SAVED: dict = {}
+
+
+def unpatch_skoots() -> None:
+    """Restores every attribute patch_skoots() rebound."""
+    for (mod_name, attr), old in list(_SAVED.items()):
+        mod = sys.modules.get(mod_name)
+        if mod is not None:
+            setattr(mod, attr, old)
+    _SAVED.clear()
+
+
+def patch_skoots() -> List[Tuple[str, str]]:
+    """Returns the (module, attribute) pairs that were rebound. Idempotent."""
+    done: List[Tuple[str, str]] = []
+    originals = {}
+    for (mod_name, attr), (new_mod, new_attr) in _TARGETS.items():
+        try:
+            mod = importlib.import_module(mod_name)
+        except Exception:
+            continue
+        new = getattr(importlib.import_module(new_mod), new_attr)
+        old = getattr(mod, attr, None)
+        if old is not None and old is not new:
+            originals[id(old)] = new
+            _SAVED.setdefault((mod_name, attr), old)
+        setattr(mod, attr, new)
+        done.append((mod_name, attr))
+    by_name = {attr: getattr(importlib.import_module(nm), na) for (_, attr), (nm, na) in _TARGETS.items()}
+    for caller in _CALLERS:
+        mod = sys.modules.get(caller)
+        if mod is None:
+            continue
+        for attr, new in by_name.items():
+            cur = getattr(mod, attr, None)
+            if cur is not None and cur is not new and (id(cur) in originals or getattr(cur, "__module__", "").startswith("skoots.lib")):
+                _SAVED.setdefault((caller, attr), cur)
+                setattr(mod, attr, new)
+                done.append((caller, attr))
+    return done

@@ -110,3 +110,25 @@ class HostAssembler:
         torch.cuda.synchronize(self.dev)
         sparse.check()
         return out_host
+
+
+def tile_epilogue(unet_out: Tensor, vectors: Tensor, skeleton: Tensor, origin: Sequence[int],
+                  overlap: Sequence[int] = (50, 50, 5), threshold: float = 0.8) -> None:
+    """skoots/lib/eval.py:145-176 in one kernel: unet_out (1,C>=5,x,y,z) -> masked fp16 vectors and the
+    dilated, thresholded u8 skeleton, written into the interior of the tile's slot of the device-
+    resident whole-volume arrays `vectors` (3,X,Y,Z) fp16 and `skeleton` (1,X,Y,Z) or (X,Y,Z) uint8."""
+    dev = L.require_cuda(unet_out, vectors, skeleton)
+    if unet_out.ndim != 5 or unet_out.shape[0] != 1 or unet_out.shape[1] < 5:
+        raise RuntimeError(f"unet_out must be (1,C>=5,x,y,z), got {tuple(unet_out.shape)}")
+    if unet_out.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        unet_out = unet_out.float()
+    unet_out = unet_out.contiguous()
+    assert vectors.dtype == torch.float16 and vectors.is_contiguous() and vectors.shape[0] == 3
+    assert skeleton.dtype == torch.uint8 and skeleton.is_contiguous()
+    X, Y, Z = vectors.shape[1:]
+    assert skeleton.numel() == X * Y * Z
+    _, C, tx, ty, tz = unet_out.shape
+    with torch.cuda.device(dev):
+        L.check(L.load().skb_tile_epilogue(unet_out.data_ptr(), L.dtype_code(unet_out), C, L.i3((tx, ty, tz)),
+                                           L.i3(origin), L.i3(overlap), float(threshold), vectors.data_ptr(),
+                                           skeleton.data_ptr(), X, Y, Z, L.stream_ptr(dev)))

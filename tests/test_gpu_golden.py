@@ -101,3 +101,72 @@ def test_assembly_against_reference_loop():
         got = assemble_instances(mask, vec, scale, N=N)
         assert got.dtype == torch.int32
         assert np.array_equal(got.cpu().numpy(), fx[f"inst_whole_N{N}"])
+
+
+@pytest.mark.parametrize("name", ["morphology", "morphology_binary"])
+def test_morphology(name):
+    from skoots_b200.lib.morphology import binary_dilation, binary_dilation_2d, binary_erosion
+    fx = load_golden(name)
+    img = cu(fx["image"])
+    assert np.array_equal(binary_dilation(img).cpu().numpy(), fx["dilation"])
+    assert np.array_equal(binary_dilation_2d(img).cpu().numpy(), fx["dilation_2d"])
+    ero = binary_erosion(img).cpu().numpy()
+    assert ero.shape == fx["erosion"].shape and np.array_equal(ero, fx["erosion"])
+
+
+def test_tile_epilogue():
+    from skoots_b200.pipeline import tile_epilogue
+    fx = load_golden("tile_epilogue")
+    vol_v = torch.zeros(fx["vectors"].shape, dtype=torch.float16, device=DEV)
+    vol_s = torch.zeros(fx["skeleton"].shape, dtype=torch.uint8, device=DEV)
+    tile_epilogue(cu(fx["unet"]), vol_v, vol_s, tuple(int(v) for v in fx["origin"]), tuple(int(v) for v in fx["overlap"]))
+    assert np.array_equal(vol_v.float().cpu().numpy(), fx["vectors"])
+    assert np.array_equal(vol_s.cpu().numpy(), fx["skeleton"])
+
+
+def test_baked_embed_to_prob():
+    from skoots_b200.lib.embedding_to_prob import baked_embed_to_prob
+    fx = load_golden("embed_prob")
+    got = baked_embed_to_prob(cu(fx["embedding"]), cu(fx["baked"]), cu(fx["sigma"]))
+    assert got.shape == fx["out"].shape
+    np.testing.assert_allclose(got.cpu().numpy(), fx["out"], rtol=1e-5, atol=0)  # north star: 1e-5 relative in fp32
+
+
+def _skeleton_dict(fx):
+    out, at = {}, 0
+    for k, n in zip(fx["ids"], fx["lens"]):
+        out[int(k)] = cu(fx["points"][at:at + int(n)])
+        at += int(n)
+    return out
+
+
+def test_bake_skeleton():
+    from skoots_b200.lib.skeleton import bake_skeleton
+    fx = load_golden("bake_skeleton")
+    sk = _skeleton_dict(fx)
+    mask = cu(fx["mask"])
+    for tag, an in (("iso", (1.0, 1.0, 1.0)), ("aniso", (1.0, 1.0, 3.0))):
+        got = bake_skeleton(mask, sk, anisotropy=an, average=False)
+        assert np.array_equal(got.cpu().numpy(), fx[f"baked_{tag}"]), tag
+        got = bake_skeleton(mask.unsqueeze(0), sk, anisotropy=an, average=True)
+        np.testing.assert_allclose(got.cpu().numpy(), fx[f"baked_avg_{tag}"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(KeyError):
+        bake_skeleton(mask, {k: v for k, v in list(sk.items())[1:]})
+    assert bake_skeleton(mask, {-1: sk[next(iter(sk))]}).dtype == torch.float16
+
+
+def test_average_baked():
+    from skoots_b200.lib.skeleton import average_baked_skeletons
+    fx = load_golden("average_baked")
+    np.testing.assert_allclose(average_baked_skeletons(cu(fx["baked"])).cpu().numpy(), fx["out"], rtol=1e-5, atol=1e-7)
+
+
+def test_skeleton_to_mask():
+    from skoots_b200.lib.skeleton import get_cached_disk_coords, skeleton_to_mask
+    fx = load_golden("skeleton_to_mask")
+    pts = fx["points"]
+    sk = {1: cu(pts[:3]), 2: cu(pts[3:])}
+    for r, f in ((7, 3), (9, 3), (2, 1)):
+        assert np.array_equal(get_cached_disk_coords(DEV, r, f).cpu().numpy(), fx[f"offsets_r{r}_f{f}"])
+        got = skeleton_to_mask(sk, (40, 36, 8), radius=r, flank_radius=f)
+        assert np.array_equal(got.cpu().numpy(), fx[f"mask_r{r}_f{f}"])

@@ -150,3 +150,93 @@ def test_large_volume_properties():
     vec[2] = 1.0 / 12.0                                                # every voxel points one plane up
     inst = gather_instances(vec, (60, 60, 12), sp)
     assert torch.equal(inst[:, :, :-1], lab[:, :, 1:])
+
+
+def test_training_step_c4_ops_match_oracle():
+    """config 4 shape: crops of 300x300x20; bake + prob (fwd) vs the oracle, fused op == two-step op,
+    and gradients vs torch autograd through the oracle formula."""
+    from skoots_b200.lib.embedding_to_prob import baked_embed_to_prob, vector_to_prob
+    from skoots_b200.lib.skeleton import bake_skeleton, skeleton_to_mask
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    tv = make_tube_volume((300, 300, 20), 20, seed=1)
+    present = {int(k): tv.skeletons[int(k)] for k in torch.unique(tv.mask).tolist() if k != 0}
+    want_baked = orc.bake_skeleton(tv.mask, present, (1.0, 1.0, 3.0), average=True)
+    got_baked = bake_skeleton(tv.mask.to(DEV), {k: v.to(DEV) for k, v in present.items()}, (1.0, 1.0, 3.0), average=True)
+    np.testing.assert_allclose(got_baked.cpu().numpy(), want_baked.numpy(), rtol=1e-5, atol=1e-5)
+    want_mask = orc.skeleton_to_mask(present, (300, 300, 20), radius=9, flank_radius=3)
+    got_mask = skeleton_to_mask({k: v.to(DEV) for k, v in present.items()}, (300, 300, 20), radius=9, flank_radius=3)
+    assert np.array_equal(got_mask.cpu().numpy(), want_mask.numpy())
+
+    scale = torch.tensor((60.0, 60.0, 12.0))
+    sigma = torch.tensor((20.0, 20.0, 20.0))
+    vec = tv.vectors.float()[None].to(torch.bfloat16)
+    baked = want_baked[None].to(torch.bfloat16)
+    want = orc.baked_embed_to_prob(orc.vector_to_embedding(scale, vec), baked, sigma)
+    v_cu = vec.to(DEV).requires_grad_(True)
+    emb = vector_to_embedding(scale, v_cu)
+    got = baked_embed_to_prob(emb, baked.to(DEV), sigma)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-30)
+    fused = vector_to_prob(scale, v_cu, baked.to(DEV), sigma)
+    assert torch.equal(fused, got)
+
+    w = torch.rand(want.shape)
+    v_ref = vec.float().requires_grad_(True)
+    p_ref = orc.baked_embed_to_prob(orc.vector_to_embedding(scale, v_ref), baked.float(), sigma)
+    (p_ref * w).sum().backward()
+    (got * w.to(DEV)).sum().backward()
+    g_two_step = v_cu.grad.float().cpu()
+    v_cu.grad = None
+    (fused * w.to(DEV)).sum().backward()
+    g_fused = v_cu.grad.float().cpu()
+    # bf16 gradients: compare at bf16 resolution
+    np.testing.assert_allclose(g_two_step.numpy(), v_ref.grad.numpy(), rtol=1.6e-2, atol=1e-6)
+    np.testing.assert_allclose(g_fused.numpy(), v_ref.grad.numpy(), rtol=1.6e-2, atol=1e-6)
+
+
+def test_embed_prob_2d_and_grad_fp32():
+    from skoots_b200.lib.embedding_to_prob import baked_embed_to_prob
+    g = torch.Generator().manual_seed(3)
+    E = (torch.rand((2, 2, 17, 9), generator=g) * 20).requires_grad_(True)
+    S = torch.rand((2, 2, 17, 9), generator=g) * 20
+    sig = torch.tensor((5.0, 7.0))
+    want = orc.baked_embed_to_prob(E, S, sig)
+    Ec = E.detach().to(DEV).requires_grad_(True)
+    got = baked_embed_to_prob(Ec, S.to(DEV), sig)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-5)
+    want.sum().backward()
+    got.sum().backward()
+    np.testing.assert_allclose(Ec.grad.cpu().numpy(), E.grad.numpy(), rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 9, 7, 5), (2, 3, 16, 16, 20), (1, 2, 33, 12, 64)])
+def test_morphology_random_vs_oracle(shape):
+    from skoots_b200.lib.morphology import binary_dilation, binary_dilation_2d, binary_erosion
+    g = torch.Generator().manual_seed(sum(shape))
+    img = torch.randn(shape, generator=g)
+    assert torch.equal(binary_dilation(img.to(DEV)).cpu(), orc.binary_dilation(img))
+    assert torch.equal(binary_dilation_2d(img.to(DEV)).cpu(), orc.binary_dilation_2d(img))
+    assert torch.equal(binary_erosion(img.to(DEV)).cpu(), orc.binary_erosion(img))
+
+
+def test_c2_tile_then_assembly():
+    """config 2: one 300x300x20 tile of stand-in network output -> epilogue -> flood fill -> assembly,
+    every stage against the oracle."""
+    from skoots_b200.pipeline import assemble_instances, tile_epilogue
+    tv = make_tube_volume((300, 300, 20), 20, seed=0)
+    g = torch.Generator().manual_seed(1)
+    unet = torch.zeros((1, 5, 300, 300, 20))
+    unet[0, 0:3] = tv.vectors.float() + 0.05 * torch.randn((3, 300, 300, 20), generator=g)
+    unet[0, 3] = tv.skeleton.float() * 0.9 + 0.05 * torch.rand((300, 300, 20), generator=g)
+    unet[0, 4] = (tv.mask > 0).float() * 0.95 + 0.04 * torch.rand((300, 300, 20), generator=g)
+    want_v = torch.zeros((3, 300, 300, 20), dtype=torch.float16)
+    want_s = torch.zeros((1, 300, 300, 20), dtype=torch.uint8)
+    orc.tile_epilogue(unet, want_v, want_s, (0, 0, 0), (50, 50, 5))
+    got_v = torch.zeros((3, 300, 300, 20), dtype=torch.float16, device=DEV)
+    got_s = torch.zeros((1, 300, 300, 20), dtype=torch.uint8, device=DEV)
+    tile_epilogue(unet.to(DEV), got_v, got_s, (0, 0, 0), (50, 50, 5))
+    assert torch.equal(got_v.cpu(), want_v) and torch.equal(got_s.cpu(), want_s)
+    assert int(want_s.sum()) > 0
+    scale = torch.tensor((60, 60, 12))
+    want = orc.postprocess(want_s[0], want_v, scale, N=1)
+    got = assemble_instances(got_s, got_v, scale, N=1)
+    assert torch.equal(got.cpu(), want)

@@ -1,0 +1,89 @@
+"""CPU: host-side logic — the C-ABI library loads and exports every declared symbol, the cropper
+mirror reproduces the reference's grid, patch_skoots rebinds the by-name imports, the product fails
+loudly without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import skoots_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import skoots_b200._lib as L
+    from skoots_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "skoots_b200.h")).read()
+    declared = set(re.findall(r"\b(skb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/skoots_b200.h but not exported"
+    assert declared == set(L.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert L.load().skb_version() == 100
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    import skoots_b200._lib as L
+    lib = L.load()
+    assert lib.skb_ccl_workspace_bytes(0, 4, 4, 16) == 0
+    rc = lib.skb_ccl_label_sparse(None, 0, 4, 4, 4, 0, 2, 16, None, 0, None, None, None)
+    assert rc == -1 and b"NULL" in lib.skb_last_error()
+    rc = lib.skb_assemble(None, 3, 1 << 20, 1 << 20, 4, L.f3((1, 1, 1)), 1, 1.0, L.i3((1, 1, 1)), L.i3((0, 0, 0)),
+                          None, None, 0, None, 2, None)
+    assert rc == -4  # SKB_E_RANGE: more than 2^31 voxels
+
+
+def test_no_cpu_fallback():
+    import skoots_b200._lib as L
+    from skoots_b200.lib.flood_fill import efficient_flood_fill
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    with pytest.raises(L.SkootsB200Error):
+        vector_to_embedding(torch.tensor((1, 1, 1)), torch.zeros((1, 3, 4, 4, 4)))
+    with pytest.raises(L.SkootsB200Error):
+        efficient_flood_fill(torch.zeros((4, 4, 4), dtype=torch.int16))
+
+
+@pytest.mark.parametrize("dims,crop,ov", [((1, 70, 60, 24), [40, 40, 16], (5, 5, 2)), ((3, 2048, 300, 64), [500, 500, 50], (50, 50, 5)),
+                                          ((1, 128, 128, 32), [500, 500, 50], (50, 50, 5)), ((1, 1100, 40, 24), [1000, 1000, 200], (0, 0, 0))])
+def test_cropper_mirror_matches_oracle_grid(dims, crop, ov):
+    from skoots_b200.lib.cropper import crops, get_total_num_crops
+    img = torch.zeros(dims, dtype=torch.uint8)
+    mine = list(crop)
+    got = [tuple(o) for _, o in crops(img, mine, ov)]
+    want = list(orc.crop_grid(dims[1:], crop, ov))
+    assert got == want
+    assert mine == orc.clamp_crop(dims[1:], crop)  # the caller's list is clamped in place, like the reference
+    assert get_total_num_crops(img.shape, list(crop), ov) == len(want)
+    first = next(iter(crops(img, list(crop), ov)))[0]
+    assert first.shape == (1, dims[0]) + tuple(mine)
+
+
+def test_cropper_guards_the_reference_hang():
+    from skoots_b200.lib.cropper import crops
+    with pytest.raises(ValueError):
+        list(crops(torch.zeros((1, 64, 8, 64)), [500, 500, 50], (50, 50, 5)))
+
+
+def test_patch_skoots_rebinds_reference_modules():
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present")
+    ref_shim.install()
+    import skoots.lib.flood_fill
+    import skoots.lib.vector_to_embedding
+    import skoots_b200.lib.flood_fill as ff
+    import skoots_b200.patch
+    before = skoots.lib.flood_fill.efficient_flood_fill
+    try:
+        done = skoots_b200.patch.patch_skoots()
+        assert ("skoots.lib.flood_fill", "efficient_flood_fill") in done
+        assert skoots.lib.flood_fill.efficient_flood_fill is ff.efficient_flood_fill
+        assert skoots.lib.vector_to_embedding.vector_to_embedding.__module__ == "skoots_b200.lib.vector_to_embedding"
+    finally:
+        skoots_b200.patch.unpatch_skoots()
+    assert skoots.lib.flood_fill.efficient_flood_fill is before

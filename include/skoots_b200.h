@@ -181,6 +181,39 @@ int skb_bake_skeleton(const void* mask, int mask_dtype, int64_t X, int64_t Y, in
 int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offsets_xyz, int n_offsets,
                     int64_t X, int64_t Y, int64_t Z, float* out_zeroed, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (e)  Z-sharded post-processing: one rank per GPU owns the slab z in [z_off, z_off+Zl) of the
+ *   mask and of the vector field (Z, z_off, Zl multiples of 64).  New design — the reference has no
+ *   collective on this path (skoots/lib/eval.py:223-284 is single-process).  Each rank's union-find
+ *   lives in the GLOBAL voxel index space of a full-size workspace, so component ids agree across
+ *   ranks.  Call order per rank (the two exchanges are NCCL send/recv and all-gather, driven by the
+ *   caller — skoots_b200/sharded.py):
+ *     skb_shard_label_local -> skb_shard_emit_runs (low / high H planes) -> [send/recv with the
+ *     Z-neighbours] -> skb_shard_ingest_runs (into zeroed per-row halo words) ->
+ *     skb_shard_boundary_pairs (packs [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]]) ->
+ *     [all-gather] -> skb_shard_merge -> skb_assemble_slab.
+ *   Numbering after the merge is the single-GPU numbering (label_base + 1 + raster rank).
+ *   runs buffers hold 3*(cap+1) int32: [count,_,_] then (start voxel, length, root id) triples.
+ * ------------------------------------------------------------------------------------------- */
+int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
+                          int64_t z_off, int64_t Zl, int64_t capacity, void* workspace,
+                          size_t workspace_bytes, uint32_t* status, void* stream);
+int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_lo, int64_t z_hi,
+                        int32_t* runs, int64_t cap, uint32_t* status, void* stream);
+int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs,
+                          int64_t cap, uint64_t* halo_words_zeroed, void* stream);
+int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
+                             int64_t Zl, int64_t capacity, const uint64_t* halo_hi, int32_t* exchange,
+                             int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream);
+int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity,
+                    const int32_t* gathered, int world, int rank, int64_t cap_roots, int64_t cap_pairs,
+                    int32_t label_base, int32_t* ncomp, uint32_t* status, void* stream);
+/* fused gather on a slab (N = 1, whole volume as one crop): vec (3,X,Y,Zl), out (X,Y,Zl);
+ * halo_lo / halo_hi (X*Y words each, NULL at the volume's ends) come from skb_shard_ingest_runs */
+int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
+                      int64_t Zl, const float scale[3], const void* workspace, const uint64_t* halo_lo,
+                      const uint64_t* halo_hi, void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,10 @@ struct AsmParams {
     const void* vec;        // channel 0 of the field being assembled (batch b)
     const void* vec_hops;   // field the N>1 hops gather from (batch 0 — reference `take` quirk)
     long long cstride;      // elements between channels
-    int X, Y, Z;
+    int X, Y, Z;            // global volume
+    int Zl, z_off;          // this call covers z in [z_off, z_off+Zl): vec/out are (.,X,Y,Zl) slabs (whole volume: Z, 0)
+    const ull* halo_lo;     // slab mode: bits of global word k0-1 / k1 per row (the Z-neighbours' boundary planes)
+    const ull* halo_hi;
     float s[3];
     int N;
     double decay;
@@ -111,7 +114,10 @@ __device__ __forceinline__ int label_at(const AsmParams& P, int tx, int ty, int 
         if (P.dense_dtype == SKB_I32) return __ldg(static_cast<const int*>(P.dense) + t);
         return (int)__ldg(static_cast<const unsigned char*>(P.dense) + t);
     }
-    ull w = __ldg(P.bits + rowi * P.ZW + (tz >> 6));
+    ull w;
+    if (tz < P.z_off) w = P.halo_lo ? __ldg(P.halo_lo + rowi) : 0ull;
+    else if (tz >= P.z_off + P.Zl) w = P.halo_hi ? __ldg(P.halo_hi + rowi) : 0ull;
+    else w = __ldg(P.bits + rowi * P.ZW + (tz >> 6));
     if (!((w >> (tz & 63)) & 1ull)) return 0;
     return skb_sparse_label(P.parent, (int)(rowi * P.Z + tz));
 }
@@ -148,94 +154,119 @@ template <> __device__ __forceinline__ float raw_to_float<__half>(unsigned short
 template <> __device__ __forceinline__ float raw_to_float<__nv_bfloat16>(unsigned short r) { return __uint_as_float((unsigned)r << 16); }
 template <> __device__ __forceinline__ float raw_to_float<float>(unsigned r) { return __uint_as_float(r); }
 
-// 8 consecutive raw elements of one channel; `aligned` selects 16-byte streaming loads
-template <typename VecT>
-__device__ __forceinline__ void load8_raw(const void* base, long long idx, bool aligned, int nvalid,
-                                          typename RawOf<VecT>::type* r) {
+// Raw bits of 8 consecutive elements of one channel, kept as 32-bit words (4 for 16-bit types, 8 for fp32).
+template <typename VecT> struct Raw8 {
+    static constexpr int NW = sizeof(typename RawOf<VecT>::type) * 2;  // words
+    unsigned w[NW];
+};
+
+template <typename VecT, bool FULL>
+__device__ __forceinline__ Raw8<VecT> load_raw8(const void* base, long long idx, int nvalid) {
     typedef typename RawOf<VecT>::type raw_t;
+    Raw8<VecT> r;
     const raw_t* p = static_cast<const raw_t*>(base) + idx;
-    if (aligned && nvalid == 8) {
-        if (sizeof(raw_t) == 2) {
-            uint4 q = skb_ld_stream16(p);
-            *reinterpret_cast<uint4*>(r) = q;
-        } else {
-            reinterpret_cast<uint4*>(r)[0] = skb_ld_stream16(p);
-            reinterpret_cast<uint4*>(r)[1] = skb_ld_stream16(p + 4);
+    if (FULL) {
+        uint4 q = skb_ld_stream16(p);
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+        if (Raw8<VecT>::NW == 8) {
+            uint4 q1 = skb_ld_stream16(reinterpret_cast<const char*>(p) + 16);
+            r.w[4] = q1.x; r.w[5] = q1.y; r.w[6] = q1.z; r.w[7] = q1.w;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = j < nvalid ? __ldg(p + j) : (raw_t)0;
+        for (int k = 0; k < Raw8<VecT>::NW; ++k) r.w[k] = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nvalid) {
+                const unsigned e = (unsigned)__ldg(p + j);
+                if (sizeof(raw_t) == 2) r.w[j >> 1] |= e << (16 * (j & 1));
+                else r.w[j] = e;
+            }
+        }
     }
+    return r;
 }
 
-template <typename VecT, typename OutT>
-__global__ void __launch_bounds__(32 * ASM_WARPS, 6) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+template <typename VecT>
+__device__ __forceinline__ typename RawOf<VecT>::type raw_elem(const unsigned* words, int j) {
     typedef typename RawOf<VecT>::type raw_t;
-    __shared__ raw_t s_raw[ASM_WARPS][3][256];
-    __shared__ int s_res[ASM_WARPS][256];
-    __shared__ unsigned char s_queue[ASM_WARPS][256];
+    if (sizeof(raw_t) == 2) return (raw_t)(words[j >> 1] >> (16 * (j & 1)));
+    return (raw_t)words[j];
+}
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long warp_base = ((long long)blockIdx.x * ASM_WARPS + warp) * 256;
-    if (warp_base >= V) return;
+// per-voxel "vector is non-zero" bits (sign ignored: -0 * s adds nothing)
+template <typename VecT>
+__device__ __forceinline__ unsigned nonzero_bits(const Raw8<VecT>& a, const Raw8<VecT>& b, const Raw8<VecT>& c) {
+    unsigned work = 0;
+    if (Raw8<VecT>::NW == 4) {
+        unsigned o[4], any = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[k] = (a.w[k] | b.w[k] | c.w[k]) & 0x7fff7fffu; any |= o[k]; }
+        if (any) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                work |= ((unsigned)((o[k] & 0xffffu) != 0u) << (2 * k)) | ((unsigned)((o[k] >> 16) != 0u) << (2 * k + 1));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) work |= (unsigned)(((a.w[j] | b.w[j] | c.w[j]) & 0x7fffffffu) != 0u) << j;
+    }
+    return work;
+}
+
+// FULL = all 32 lanes own 8 valid voxels and 16-byte loads are legal: no per-element guards at all.
+template <typename VecT, typename OutT, bool FULL>
+__device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restrict__ out, long long V, long long warp_base,
+                                              unsigned (*s_raw)[32][Raw8<VecT>::NW], int* s_res, unsigned char* s_queue) {
+    typedef typename RawOf<VecT>::type raw_t;
+    const int lane = threadIdx.x & 31;
     const long long i0 = warp_base + lane * 8;
     const long long left = V - i0;
-    const int nvalid = left >= 8 ? 8 : (left > 0 ? (int)left : 0);
-    const unsigned uz = (unsigned)P.Z, uy = (unsigned)P.Y;
+    const int nvalid = FULL ? 8 : (left >= 8 ? 8 : (left > 0 ? (int)left : 0));
+    const unsigned uz = (unsigned)P.Zl, uy = (unsigned)P.Y;  // index decomposition runs over the slab
 
-    __align__(16) raw_t r0[8], r1[8], r2[8];
-    {
-        const bool al = P.vec_aligned != 0;
-        load8_raw<VecT>(P.vec, i0, al, nvalid, r0);
-        load8_raw<VecT>(P.vec, i0 + P.cstride, al, nvalid, r1);
-        load8_raw<VecT>(P.vec, i0 + 2 * P.cstride, al, nvalid, r2);
-    }
-
-    // which of my voxels need the slow path
-    unsigned work = 0;
-    const unsigned valid_mask = (1u << nvalid) - 1u;
-    if (!P.fast_ok || P.dense) {
-        work = valid_mask;  // N>1 over a >2^24-voxel crop, or a dense label volume (compatibility path)
-    } else if (nvalid > 0) {
-        // non-zero vector (sign bit ignored: -0 * s adds nothing) -> work
-        if (sizeof(raw_t) == 2) {
-            const uint4 a = *reinterpret_cast<uint4*>(r0), b = *reinterpret_cast<uint4*>(r1), c = *reinterpret_cast<uint4*>(r2);
-            const unsigned o[4] = {(a.x | b.x | c.x) & 0x7fff7fffu, (a.y | b.y | c.y) & 0x7fff7fffu,
-                                   (a.z | b.z | c.z) & 0x7fff7fffu, (a.w | b.w | c.w) & 0x7fff7fffu};
-            if ((o[0] | o[1] | o[2] | o[3]) != 0u) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    work |= ((unsigned)((o[k] & 0xffffu) != 0u) << (2 * k)) | ((unsigned)((o[k] >> 16) != 0u) << (2 * k + 1));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                work |= (unsigned)((((unsigned)r0[j] | (unsigned)r1[j] | (unsigned)r2[j]) & 0x7fffffffu) != 0u) << j;
-        }
+    // every independent load is issued before anything waits on one of them
+    const Raw8<VecT> r0 = load_raw8<VecT, FULL>(P.vec, i0, nvalid);
+    const Raw8<VecT> r1 = load_raw8<VecT, FULL>(P.vec, i0 + P.cstride, nvalid);
+    const Raw8<VecT> r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
+    const bool lookup_self = P.fast_ok && !P.dense;
+    unsigned self = 0;
+    if (lookup_self && nvalid > 0) {
         // a zero vector resolves to the voxel itself: only foreground voxels need a label read
         if (P.flat_bits) {
-            work |= (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (i0 >> 3));
+            size_t gv = (size_t)i0;  // global voxel index of my first voxel
+            if (P.Zl != P.Z) {
+                const unsigned q = (unsigned)i0 / uz;
+                gv = (size_t)q * P.Z + ((unsigned)i0 - q * uz) + (unsigned)P.z_off;
+            }
+            self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (gv >> 3));
         } else {
-            const unsigned q = (unsigned)i0 / uz;
-            const int z = (int)((unsigned)i0 - q * uz);
+            unsigned q = (unsigned)i0 / uz;
+            int z = (int)((unsigned)i0 - q * uz);
             if (z + 8 <= P.Z) {
                 const long long wi = (long long)q * P.ZW + (z >> 6);
                 const int sh = z & 63;
                 ull w = __ldg(P.bits + wi) >> sh;
                 if (sh > 56) w |= __ldg(P.bits + wi + 1) << (64 - sh);
-                work |= (unsigned)(w & 0xFFull);
+                self = (unsigned)(w & 0xFFull);
             } else {
-                unsigned qq = q;
-                int zz = z;
                 for (int j = 0; j < nvalid; ++j) {
-                    ull w = __ldg(P.bits + (long long)qq * P.ZW + (zz >> 6));
-                    work |= (unsigned)((w >> (zz & 63)) & 1ull) << j;
-                    if (++zz == P.Z) { zz = 0; ++qq; }
+                    ull w = __ldg(P.bits + (long long)q * P.ZW + (z >> 6));
+                    self |= (unsigned)((w >> (z & 63)) & 1ull) << j;
+                    if (++z == P.Z) { z = 0; ++q; }
                 }
             }
         }
-        work &= valid_mask;
     }
+
+    const unsigned valid_mask = FULL ? 0xFFu : ((1u << nvalid) - 1u);
+    unsigned work;
+    if (lookup_self) work = (nonzero_bits<VecT>(r0, r1, r2) | self) & valid_mask;
+    else work = valid_mask;  // N>1 over a >2^24-voxel crop, or a dense label volume (compatibility path)
+
+    unsigned lab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lab[j] = 0u;
 
     if (__ballot_sync(0xffffffffu, work != 0u) != 0u) {
         // warp-wide compaction of the work items
@@ -247,54 +278,66 @@ __global__ void __launch_bounds__(32 * ASM_WARPS, 6) assemble_kernel(AsmParams P
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int at = incl - cnt;
-        for (unsigned m = work; m; m &= m - 1) {
-            const int j = __ffs((int)m) - 1;
-            const int code = j * 32 + lane;
-            s_queue[warp][at++] = (unsigned char)code;
-        }
         if (work) {
+            int at = incl - cnt;
+            for (unsigned m = work; m; m &= m - 1) s_queue[at++] = (unsigned char)((__ffs((int)m) - 1) * 32 + lane);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {  // unconditional, conflict-free; cheaper than predicating 24 stores
-                s_raw[warp][0][j * 32 + lane] = r0[j];
-                s_raw[warp][1][j * 32 + lane] = r1[j];
-                s_raw[warp][2][j * 32 + lane] = r2[j];
+            for (int k = 0; k < Raw8<VecT>::NW; ++k) {
+                s_raw[0][lane][k] = r0.w[k];
+                s_raw[1][lane][k] = r1.w[k];
+                s_raw[2][lane][k] = r2.w[k];
             }
         }
         __syncwarp();
         for (int qi = lane; qi < total; qi += 32) {
-            const int code = s_queue[warp][qi];
-            const unsigned vi = (unsigned)(warp_base + (code & 31) * 8 + (code >> 5));
+            const int code = s_queue[qi];
+            const int src = code & 31, j = code >> 5;
+            const unsigned vi = (unsigned)(warp_base + src * 8 + j);
             const unsigned q = vi / uz;
-            const int z = (int)(vi - q * uz);
+            const int z = (int)(vi - q * uz) + P.z_off;
             const int x = (int)(q / uy);
             const int y = (int)(q - (unsigned)x * uy);
-            s_res[warp][code] = assemble_voxel<VecT>(P, x, y, z, raw_to_float<VecT>(s_raw[warp][0][code]),
-                                                     raw_to_float<VecT>(s_raw[warp][1][code]),
-                                                     raw_to_float<VecT>(s_raw[warp][2][code]));
+            s_res[code] = assemble_voxel<VecT>(P, x, y, z, raw_to_float<VecT>(raw_elem<VecT>(s_raw[0][src], j)),
+                                               raw_to_float<VecT>(raw_elem<VecT>(s_raw[1][src], j)),
+                                               raw_to_float<VecT>(raw_elem<VecT>(s_raw[2][src], j)));
         }
         __syncwarp();
+        if (work) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int v = s_res[j * 32 + lane];  // unconditional read, selected below: keeps lab[] in registers
+                lab[j] = ((work >> j) & 1u) ? (unsigned)v : 0u;
+            }
+        }
     }
 
-    if (nvalid == 0) return;
-    __align__(16) OutT lab[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) lab[j] = (OutT)0;
-    if (work) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if ((work >> j) & 1u) lab[j] = (OutT)s_res[warp][j * 32 + lane];
-    }
-    if (nvalid == 8) {
+    if (FULL || nvalid == 8) {
         if (sizeof(OutT) == 2) {
-            skb_st_stream16(out + i0, *reinterpret_cast<uint4*>(lab));
+            skb_st_stream16(out + i0, make_uint4((lab[0] & 0xffffu) | (lab[1] << 16), (lab[2] & 0xffffu) | (lab[3] << 16),
+                                                 (lab[4] & 0xffffu) | (lab[5] << 16), (lab[6] & 0xffffu) | (lab[7] << 16)));
         } else {
-            skb_st_stream16(out + i0, reinterpret_cast<uint4*>(lab)[0]);
-            skb_st_stream16(out + i0 + 4, reinterpret_cast<uint4*>(lab)[1]);
+            skb_st_stream16(out + i0, make_uint4(lab[0], lab[1], lab[2], lab[3]));
+            skb_st_stream16(out + i0 + 4, make_uint4(lab[4], lab[5], lab[6], lab[7]));
         }
     } else {
-        for (int j = 0; j < nvalid; ++j) out[i0 + j] = lab[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nvalid) out[i0 + j] = (OutT)lab[j];
     }
+}
+
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(32 * ASM_WARPS, 5) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+    __shared__ unsigned s_raw[ASM_WARPS][3][32][Raw8<VecT>::NW];
+    __shared__ int s_res[ASM_WARPS][256];
+    __shared__ unsigned char s_queue[ASM_WARPS][256];
+    const int warp = threadIdx.x >> 5;
+    const long long warp_base = ((long long)blockIdx.x * ASM_WARPS + warp) * 256;
+    if (warp_base >= V) return;
+    if (warp_base + 256 <= V && P.vec_aligned)
+        assemble_warp<VecT, OutT, true>(P, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
+    else
+        assemble_warp<VecT, OutT, false>(P, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
 }
 
 // ---- stand-alone a1: materialise the embedding ---------------------------------------------------
@@ -413,6 +456,7 @@ extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y
     P.vec = vec; P.vec_hops = vec;
     P.cstride = X * Y * Z;
     P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+    P.Zl = (int)Z; P.z_off = 0;
     P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
     P.N = N; P.decay = decay;
     fill_crop(P, crop, overlap);
@@ -436,6 +480,46 @@ extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y
     return SKB_OK;
 }
 
+// Z-slab form (N = 1, whole volume as one crop): vec/out hold only z in [z_off, z_off+Zl); targets that
+// leave the slab are answered from the neighbours' boundary planes ingested by skb_shard_ingest_runs.
+extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                 const float scale[3], const void* workspace, const uint64_t* halo_lo,
+                                 const uint64_t* halo_hi, void* out, int out_dtype, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_assemble_slab");
+    if (rc) return rc;
+    SKB_REQUIRE(vec && out && scale && workspace, "skb_assemble_slab: NULL pointer");
+    SKB_REQUIRE(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32, "skb_assemble_slab: vec dtype");
+    SKB_REQUIRE(out_dtype == SKB_I32 || out_dtype == SKB_I16, "skb_assemble_slab: out dtype must be i32 or i16");
+    SKB_REQUIRE(Z % 64 == 0 && z_off % 64 == 0 && Zl % 64 == 0 && Zl > 0 && z_off >= 0 && z_off + Zl <= Z,
+                "skb_assemble_slab: Z, z_off and Zl must be multiples of 64 with the slab inside the volume");
+    SKB_REQUIRE(skb_aligned16(out), "skb_assemble_slab: out must be 16-byte aligned");
+    AsmParams P = {};
+    P.vec = vec; P.vec_hops = vec;
+    P.cstride = X * Y * Zl;
+    P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+    P.Zl = (int)Zl; P.z_off = (int)z_off;
+    P.halo_lo = reinterpret_cast<const ull*>(halo_lo);
+    P.halo_hi = reinterpret_cast<const ull*>(halo_hi);
+    P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
+    P.N = 1; P.decay = 1.0;
+    const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
+    fill_crop(P, crop, ov);
+    P.vec_aligned = skb_aligned16(vec) && ((P.cstride * elem_size(vec_dtype)) % 16 == 0);
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    const char* base = static_cast<const char*>(workspace);
+    P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
+    P.parent = reinterpret_cast<const int*>(base + L.off_parent);
+    P.ZW = L.ZW;
+    P.flat_bits = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = X * Y * Zl;
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, V, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, V, st);
+    else launch_assemble<float>(P, out, out_dtype, V, st);
+    SKB_LAUNCH_CHECK("assemble_kernel (slab)");
+    return SKB_OK;
+}
+
 extern "C" int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
                                const float scale[3], int N, double decay, float* out, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_vec_embed3d");
@@ -452,6 +536,7 @@ extern "C" int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_
         P.vec_hops = vec;  // reference take() flattens the batch: hops always read batch 0
         P.cstride = V;
         P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+        P.Zl = (int)Z; P.z_off = 0;
         P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
         P.N = N; P.decay = decay;
         fill_crop(P, crop, ov);

@@ -64,6 +64,8 @@ struct CclView {
     int X, Y, Z, ZW;
     int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
     int ZW_tiles;   // z tiles per row in the tile kernel
+    int z_off, Zl;  // the slab [z_off, z_off+Zl) of the global volume held by `mask` (whole volume: 0, Z)
+    int k0, nk;     // word range of the slab inside each row of the bit mask
     int capacity;
     SkbCclHeader* hdr;
     ull* bits;
@@ -142,57 +144,41 @@ __device__ __forceinline__ unsigned gt2(unsigned w) {
     return ((t >> 15) | (t >> 30)) & 3u;
 }
 
-// foreground bits of the n (<= TZ) mask elements of one row segment
-template <typename MaskT, int TZ>
-__device__ __forceinline__ ull row_bits(const MaskT* p, int n, bool vec_ok);
-
-template <typename MaskT, int TZ>
-__device__ __forceinline__ ull row_bits_scalar(const MaskT* p, int n) {
-    ull w = 0;
-    for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
-    return w;
-}
-
-template <int TZ>
-__device__ __forceinline__ ull row_bits_u8(const uint8_t* p, int n, bool vec_ok) {
-    if (!vec_ok) return row_bits_scalar<uint8_t, TZ>(p, n);
-    ull w = 0;
-    uint4 q[TZ / 16];
+// foreground bits of one lane's segment of SEG (= TZ/4) consecutive mask elements; n of them exist.
+// Vector path: one 4/8/16/32-byte load, an all-zero early-out (the common case in a sparse mask),
+// then 4 (u8) or 2 (i16) elements per 32-bit word through nz4 / gt2.
+template <typename MaskT, int SEG>
+__device__ __forceinline__ unsigned seg_bits(const MaskT* p, int n, bool vec_ok) {
+    constexpr int BYTES = SEG * (int)sizeof(MaskT);
+    constexpr int NWORD = BYTES / 4;
+    constexpr int PER = 4 / (int)sizeof(MaskT);  // elements per 32-bit word
+    unsigned bits = 0;
+    if (vec_ok && n == SEG) {
+        unsigned w[NWORD];
+        if (BYTES == 4) {
+            w[0] = __ldg(reinterpret_cast<const unsigned*>(p));
+        } else if (BYTES == 8) {
+            uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = q.x; w[1] = q.y;
+        } else {
 #pragma unroll
-    for (int k = 0; k < TZ / 16; ++k)  // all loads first; groups past the end of the row read nothing
-        q[k] = (16 * (k + 1) <= n) ? __ldg(reinterpret_cast<const uint4*>(p) + k) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < TZ / 16; ++k) {
-        unsigned h = nz4(q[k].x) | (nz4(q[k].y) << 4) | (nz4(q[k].z) << 8) | (nz4(q[k].w) << 12);
-        w |= (ull)h << (16 * k);
-    }
-    for (int i = n & ~15; i < n; ++i) w |= (ull)(p[i] != 0) << i;
-    return w;
-}
-
-template <int TZ>
-__device__ __forceinline__ ull row_bits_i16(const int16_t* p, int n, bool vec_ok) {
-    if (!vec_ok) return row_bits_scalar<int16_t, TZ>(p, n);
-    ull w = 0;
-#pragma unroll
-    for (int k = 0; k < TZ / 8; ++k) {
-        if (8 * (k + 1) <= n) {
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + k);
-            unsigned h = gt2(q.x) | (gt2(q.y) << 2) | (gt2(q.z) << 4) | (gt2(q.w) << 6);
-            w |= (ull)h << (8 * k);
+            for (int k = 0; k < BYTES / 16; ++k) {
+                uint4 q = skb_ld_stream16(reinterpret_cast<const uint4*>(p) + k);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+            }
         }
+        unsigned any = 0;
+#pragma unroll
+        for (int k = 0; k < NWORD; ++k) any |= w[k];
+        if (any) {
+#pragma unroll
+            for (int k = 0; k < NWORD; ++k) bits |= (sizeof(MaskT) == 1 ? nz4(w[k]) : gt2(w[k])) << (PER * k);
+        }
+    } else {
+        for (int i = 0; i < n; ++i) bits |= (unsigned)(p[i] > 0) << i;
     }
-    for (int i = n & ~7; i < n; ++i) w |= (ull)(p[i] > 0) << i;
-    return w;
+    return bits;
 }
-
-template <typename MaskT, int TZ> struct RowBits;
-template <int TZ> struct RowBits<uint8_t, TZ> {
-    static __device__ __forceinline__ ull get(const uint8_t* p, int n, bool v) { return row_bits_u8<TZ>(p, n, v); }
-};
-template <int TZ> struct RowBits<int16_t, TZ> {
-    static __device__ __forceinline__ ull get(const int16_t* p, int n, bool v) { return row_bits_i16<TZ>(p, n, v); }
-};
 
 __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
     if (threadIdx.x == 0) {
@@ -205,115 +191,137 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
 // ------------------------------------------------------------------------------------------
 // K1: tile-local run-based union-find
 // ------------------------------------------------------------------------------------------
-// One CTA = one 8 x 8 x TZ tile, one THREAD = one (x,y) row of it: the thread loads its whole
-// TZ-element row segment (4 independent 16-byte loads for u8, TZ = 64), packs it into a 64-bit
-// word, and does every union of that row with its y-1 / x-1 neighbour rows.  A run start can only
-// sit at every other bit, so the union-find array needs 32 slots per row: slot = row*32 + (p>>1).
+// One CTA = CCL_NT 8 x 8 x TZ tiles stacked along y.  Loading is fully coalesced: 4 adjacent lanes
+// read the 4 segments of one row (64 contiguous bytes for u8, TZ = 64), turn them into bits and
+// combine them into the row's 64-bit word with two shuffles.  All CCL_NT loads are issued before
+// anything is consumed.  Lane 0 of each 4-lane group then owns the row: it does every union of the
+// row with its y-1 / x-1 neighbour rows (only non-empty tiles get that far).  A run start can
+// only sit at every other bit, so the union-find array needs 32 slots per row:
+// slot = row*32 + (p>>1).
+constexpr int CCL_NT = 2;
+
 template <typename MaskT, int TZ>
-__global__ void __launch_bounds__(64) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
-    constexpr int TY = 8;
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
+    constexpr int TY = 8, SEG = TZ / 4;
     __shared__ ull srow[64];
     __shared__ int slab[64 * 32];
     __shared__ int s_count, s_base;
 
-    const int row = threadIdx.x;
+    const int seg = threadIdx.x & 3, row = threadIdx.x >> 2;
     const int ly = row & 7, lx = row >> 3;
-    // linear CTA index -> (z tile fastest, then y, then x); avoids the 65535 limit of grid.y/z
-    const unsigned nzt = (unsigned)v.ZW_tiles, nyt = (unsigned)((v.Y + 7) >> 3);
+    // linear CTA index -> (z tile fastest, then y group, then x); avoids the 65535 limit of grid.y/z
+    const unsigned nzt = (unsigned)v.ZW_tiles, nyt = (unsigned)(((v.Y + 7) >> 3) + CCL_NT - 1) / CCL_NT;
     const unsigned bq = blockIdx.x / nzt, zt = blockIdx.x - bq * nzt;
-    const unsigned xt = bq / nyt, yt = bq - xt * nyt;
-    const int x0 = (int)xt * 8, y0 = (int)yt * 8, z0 = (int)zt * TZ;
-    const int x = x0 + lx, y = y0 + ly;
-    const bool in_row = (x < v.X) && (y < v.Y);
-    const unsigned rowi = (unsigned)x * (unsigned)v.Y + (unsigned)y;
+    const unsigned xt = bq / nyt, yg = bq - xt * nyt;
+    const int x0 = (int)xt * 8, zl0 = (int)zt * TZ, z0 = v.z_off + zl0;
+    const int x = x0 + lx;
+    const int zs = zl0 + seg * SEG;  // slab-local z of my segment
 
-    if (row == 0) s_count = 0;
-    ull w = 0;
-    if (in_row) {
-        w = RowBits<MaskT, TZ>::get(mask + (size_t)rowi * v.Z + z0, min(TZ, v.Z - z0), vec_ok != 0);
-        v.bits[(size_t)rowi * v.ZW + zt] = w;
+    unsigned b[CCL_NT];
+#pragma unroll
+    for (int t = 0; t < CCL_NT; ++t) {
+        const int y = ((int)yg * CCL_NT + t) * 8 + ly;
+        b[t] = 0;
+        if (x < v.X && y < v.Y && zs < v.Zl)
+            b[t] = seg_bits<MaskT, SEG>(mask + ((size_t)x * v.Y + y) * v.Zl + zs, min(SEG, v.Zl - zs), vec_ok != 0);
     }
-    srow[row] = w;
-    if (!__syncthreads_or(w != 0ull)) return;  // empty tile: nothing to label
 
-    const ull starts = w & ~(w << 1);
-    for (ull s = starts; s; s &= s - 1) {
-        int p = __ffsll((long long)s) - 1;
-        slab[row * 32 + (p >> 1)] = row * 32 + (p >> 1);
-    }
-    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CCL_NT; ++t) {
+        const int y0 = ((int)yg * CCL_NT + t) * 8;
+        if (y0 >= v.Y) continue;  // uniform across the CTA
+        const int y = y0 + ly;
+        const bool in_row = (x < v.X) && (y < v.Y);
+        const unsigned rowi = (unsigned)x * (unsigned)v.Y + (unsigned)y;
 
-    // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
-    if (w) {
-        if (ly > 0) {
-            ull wn = srow[row - 1], a = w & wn;
-            for (ull s = a & ~(a << 1); s; s &= s - 1) {
-                int p = __ffsll((long long)s) - 1;
-                sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - 1) * 32 + (run_start(wn, p) >> 1));
+        ull w = (ull)b[t] << (SEG * seg);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        const bool owner = seg == 0;
+        if (threadIdx.x == 0) s_count = 0;
+        if (owner) {
+            srow[row] = w;
+            if (in_row) v.bits[(size_t)rowi * v.ZW + (z0 >> 6)] = w;
+        }
+        if (!__syncthreads_or(b[t] != 0u)) continue;  // empty tile: nothing to label
+
+        const ull starts = owner ? (w & ~(w << 1)) : 0ull;
+        for (ull s = starts; s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            slab[row * 32 + (p >> 1)] = row * 32 + (p >> 1);
+        }
+        __syncthreads();
+
+        // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
+        if (owner && w) {
+            if (ly > 0) {
+                ull wn = srow[row - 1], a = w & wn;
+                for (ull s = a & ~(a << 1); s; s &= s - 1) {
+                    int p = __ffsll((long long)s) - 1;
+                    sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - 1) * 32 + (run_start(wn, p) >> 1));
+                }
+            }
+            if (lx > 0 && v.connect_x) {
+                ull wn = srow[row - TY], a = w & wn;
+                for (ull s = a & ~(a << 1); s; s &= s - 1) {
+                    int p = __ffsll((long long)s) - 1;
+                    sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - TY) * 32 + (run_start(wn, p) >> 1));
+                }
             }
         }
-        if (lx > 0 && v.connect_x) {
-            ull wn = srow[row - TY], a = w & wn;
-            for (ull s = a & ~(a << 1); s; s &= s - 1) {
-                int p = __ffsll((long long)s) - 1;
-                sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - TY) * 32 + (run_start(wn, p) >> 1));
+        __syncthreads();
+
+        // resolve every run of my row; write parent for all its voxels
+        ull rootmask = 0;  // bit p set when the run starting at p is a tile root
+        const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
+        for (ull s = starts; s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            int l = row * 32 + (p >> 1);
+            int r = sfind(slab, l);
+            int groot;
+            if (r == l) {
+                rootmask |= 1ull << p;
+                groot = gbase + p;
+            } else {
+                const int rrow = r >> 5, rh = r & 31;
+                const ull rs = srow[rrow] & ~(srow[rrow] << 1);
+                const int rp = 2 * rh + (int)((rs >> (2 * rh + 1)) & 1ull);
+                groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + rp;
+            }
+            ull tt = ~(w >> p);
+            int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+            for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+        }
+        int mine = __popcll(rootmask);
+        int off = mine ? atomicAdd(&s_count, mine) : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
+        __syncthreads();
+        if (mine) {
+            int at = s_base + off;
+            for (ull m = rootmask; m; m &= m - 1) {
+                int p = __ffsll((long long)m) - 1;
+                if (at < v.capacity) v.tile_roots[at] = gbase + p;
+                else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+                ++at;
             }
         }
-    }
-    __syncthreads();
-
-    // resolve every run of my row; write parent for all its voxels
-    ull rootmask = 0;  // bit p set when the run starting at p is a tile root
-    const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
-    for (ull s = starts; s; s &= s - 1) {
-        int p = __ffsll((long long)s) - 1;
-        int l = row * 32 + (p >> 1);
-        int r = sfind(slab, l);
-        int groot;
-        if (r == l) {
-            rootmask |= 1ull << p;
-            groot = gbase + p;
-        } else {
-            const int rrow = r >> 5, rh = r & 31;
-            const ull rs = srow[rrow] & ~(srow[rrow] << 1);
-            const int rp = 2 * rh + (int)((rs >> (2 * rh + 1)) & 1ull);
-            groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + rp;
-        }
-        ull tt = ~(w >> p);
-        int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
-        for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
-    }
-    int mine = __popcll(rootmask);
-    int off = mine ? atomicAdd(&s_count, mine) : 0;
-    __syncthreads();
-    if (row == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
-    __syncthreads();
-    if (mine) {
-        int at = s_base + off;
-        for (ull m = rootmask; m; m &= m - 1) {
-            int p = __ffsll((long long)m) - 1;
-            if (at < v.capacity) v.tile_roots[at] = gbase + p;
-            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
-            ++at;
-        }
+        __syncthreads();  // smem is reused by the next tile
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: unions across tile faces, driven by the bit-packed mask
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY) {
-    // n_words <= 2^31: all index math in 32 bits (64-bit div/mod costs ~100 instructions each)
-    const unsigned widx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (widx >= (unsigned)v.n_words) return;
-    const ull w = v.bits[widx];
-    if (!w) return;
+__device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, ull w, bool have_prev, ull prev, int TX, int TY) {
+    // slow path: only words that contain foreground get here.  n_words <= 2^31: 32-bit index math.
     const unsigned uzw = (unsigned)v.ZW, uyy = (unsigned)v.Y;
     const unsigned rowi = widx / uzw, k = widx - rowi * uzw;
     const unsigned x = rowi / uyy, y = rowi - x * uyy;
     const int gbase = (int)(rowi * (unsigned)v.Z + 64u * k);
-    if (k > 0 && (w & 1ull)) {
-        if (v.bits[widx - 1] >> 63) gunion(v.parent, gbase, gbase - 1);
+    if ((int)k > v.k0 && (w & 1ull)) {
+        if (!have_prev) prev = v.bits[widx - 1];
+        if (prev >> 63) gunion(v.parent, gbase, gbase - 1);
     }
     if (y > 0 && (y % (unsigned)TY) == 0) {
         ull a = w & v.bits[widx - uzw];
@@ -329,6 +337,29 @@ __global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, in
             int p = __ffsll((long long)s) - 1;
             gunion(v.parent, gbase + p, gbase + p - plane);
         }
+    }
+}
+
+// pair_mode: the slab is the whole row and rows hold an even number of words -> every thread streams
+// two adjacent words with one 16-byte load and returns at once when both are empty (no divisions
+// on that path).  Otherwise one word per thread, (row, k) by division.
+__global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY, int pair_mode) {
+    const unsigned tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair_mode) {
+        const unsigned widx = 2u * tix;
+        if (widx >= (unsigned)v.n_words) return;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(v.bits + widx));
+        if ((q.x | q.y | q.z | q.w) == 0u) return;
+        const ull w0 = ((ull)q.y << 32) | q.x, w1 = ((ull)q.w << 32) | q.z;
+        if (w0) boundary_word(v, widx, w0, false, 0ull, TX, TY);
+        if (w1) boundary_word(v, widx + 1, w1, true, w0, TX, TY);
+    } else {
+        const unsigned unk = (unsigned)v.nk;
+        const unsigned rowi = tix / unk, kl = tix - rowi * unk;
+        if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
+        const unsigned widx = rowi * (unsigned)v.ZW + (unsigned)v.k0 + kl;
+        const ull w = v.bits[widx];
+        if (w) boundary_word(v, widx, w, false, 0ull, TX, TY);
     }
 }
 
@@ -507,6 +538,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
     v.connect_x = planar ? 0 : 1;
     v.ZW_tiles = 1;
+    v.z_off = 0; v.Zl = L.Z; v.k0 = 0; v.nk = L.ZW;
     v.capacity = (int)capacity;
     v.hdr = reinterpret_cast<SkbCclHeader*>(base);
     v.bits = reinterpret_cast<ull*>(base + L.off_bits);
@@ -534,11 +566,18 @@ template <typename MaskT>
 static void launch_tile(const void* mask, const CclView& v, int tz, int vec_ok, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
     CclView vv = v;
-    vv.ZW_tiles = (v.Z + tz - 1) / tz;
-    const unsigned grid = (unsigned)((long long)vv.ZW_tiles * ((v.Y + 7) / 8) * ((v.X + 7) / 8));
-    if (tz == 64) ccl_tile_kernel<MaskT, 64><<<grid, 64, 0, st>>>(m, vv, vec_ok);
-    else if (tz == 32) ccl_tile_kernel<MaskT, 32><<<grid, 64, 0, st>>>(m, vv, vec_ok);
-    else ccl_tile_kernel<MaskT, 16><<<grid, 64, 0, st>>>(m, vv, vec_ok);
+    vv.ZW_tiles = (v.Zl + tz - 1) / tz;
+    const long long ygroups = ((v.Y + 7) / 8 + CCL_NT - 1) / CCL_NT;
+    const unsigned grid = (unsigned)((long long)vv.ZW_tiles * ygroups * ((v.X + 7) / 8));
+    if (tz == 64) ccl_tile_kernel<MaskT, 64><<<grid, 256, 0, st>>>(m, vv, vec_ok);
+    else if (tz == 32) ccl_tile_kernel<MaskT, 32><<<grid, 256, 0, st>>>(m, vv, vec_ok);
+    else ccl_tile_kernel<MaskT, 16><<<grid, 256, 0, st>>>(m, vv, vec_ok);
+}
+
+static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int TY, cudaStream_t st) {
+    const int pair_mode = (v.nk == L.ZW && L.ZW % 2 == 0) ? 1 : 0;
+    const long long threads = pair_mode ? L.n_words / 2 : (long long)L.X * L.Y * v.nk;
+    ccl_boundary_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(v, TX, TY, pair_mode);
 }
 
 extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int planar,
@@ -575,8 +614,7 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     SKB_LAUNCH_CHECK("ccl_tile_kernel");
 
     const int TY = 8, TX = 8;
-    unsigned nb = (unsigned)((L.n_words + 255) / 256);
-    ccl_boundary_kernel<<<nb, 256, 0, st>>>(v, TX, TY);
+    launch_boundary(v, L, TX, TY, st);
     const int list_grid = 148 * 4;
     ccl_flatten_kernel<<<list_grid, 256, 0, st>>>(v);
     ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
@@ -607,5 +645,314 @@ extern "C" int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, 
     else
         ccl_dense_kernel<int32_t><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
     SKB_LAUNCH_CHECK("ccl_dense_kernel");
+    return SKB_OK;
+}
+
+// ==========================================================================================
+// Z-sharded labelling.
+//
+// Every rank owns the slab z in [z_off, z_off+Zl) (z_off, Zl multiples of 64) of the mask, but its
+// union-find lives in the GLOBAL voxel index space, so component ids (= the smallest global voxel
+// index of the component) mean the same thing on every rank and no id translation is ever needed.
+//
+//   local   : init + tile kernel + boundary kernel on the slab, pointer-jump the tile roots,
+//             list the slab's roots                                    (skb_shard_label_local)
+//   runs    : the z-runs inside the H boundary planes of the slab, each with its root id
+//             -> sent to the Z-neighbour (NCCL send/recv)               (skb_shard_emit_runs)
+//   ingest  : the neighbour's runs become my halo: one 64-bit word per row (bits) and
+//             parent[halo voxel] = the neighbour's root id             (skb_shard_ingest_runs)
+//   pairs   : (my root, neighbour root) wherever my last plane touches the halo's first plane;
+//             packed behind my root list -> all-gathered (NCCL)        (skb_shard_boundary_pairs)
+//   merge   : every rank applies every pair to its own union-find, ranks all global roots in
+//             raster order (identical numbering on every rank = the single-GPU numbering) and
+//             publishes the label codes                                 (skb_shard_merge)
+// ==========================================================================================
+__global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
+    unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int r = v.tile_roots[i];
+        int g = gfind(v.parent, r);
+        v.flat[i] = g;
+        if (g == r) {
+            unsigned m = __activemask();
+            int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&v.hdr->n_global_roots, (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            v.groots[base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
+    }
+}
+
+// runs[0] = count, then (start voxel, length, root id) triples from index 3
+__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, int z_lo, int z_hi, int* __restrict__ runs,
+                                                             int cap, unsigned* status) {
+    const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
+    const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
+    const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
+    const ull w = v.bits[(size_t)rowi * v.ZW + k] & range;
+    if (!w) return;
+    const int gbase = (int)(rowi * (unsigned)v.Z) + 64 * k;
+    for (ull s = w & ~(w << 1); s; s &= s - 1) {
+        const int p = __ffsll((long long)s) - 1;
+        const ull tt = ~(w >> p);
+        const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+        const int root = gfind(v.parent, gbase + p);
+        const int slot = atomicAdd(runs, 1);
+        if (slot < cap) {
+            runs[3 + 3 * slot] = gbase + p;
+            runs[4 + 3 * slot] = len;
+            runs[5 + 3 * slot] = root;
+        } else {
+            atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) shard_ingest_runs_kernel(CclView v, const int* __restrict__ runs, int cap,
+                                                               ull* __restrict__ halo) {
+    const int n = min(runs[0], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = runs[3 + 3 * i], len = runs[4 + 3 * i], root = runs[5 + 3 * i];
+        const unsigned rowi = (unsigned)s / (unsigned)v.Z;
+        const int z = (int)((unsigned)s - rowi * (unsigned)v.Z);
+        const ull m = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << (z & 63);
+        atomicOr(&halo[rowi], m);
+        for (int j = 0; j < len; ++j) v.parent[s + j] = root;
+        v.parent[root] = root;  // the neighbour's root becomes a node of my union-find (idempotent)
+    }
+}
+
+// exch = [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]]
+__global__ void __launch_bounds__(256) shard_pack_roots_kernel(CclView v, int* __restrict__ exch, int cap_roots,
+                                                              unsigned* status) {
+    const unsigned n = v.hdr->n_global_roots;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        exch[0] = (int)min(n, (unsigned)cap_roots);
+        if (n > (unsigned)cap_roots) atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < (unsigned)cap_roots; i += gridDim.x * blockDim.x)
+        exch[2 + i] = v.groots[i];
+}
+
+__global__ void __launch_bounds__(256) shard_boundary_pairs_kernel(CclView v, const ull* __restrict__ halo_hi,
+                                                                  int* __restrict__ exch, int cap_roots, int cap_pairs,
+                                                                  unsigned* status) {
+    const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
+    const int z1 = v.z_off + v.Zl;  // first plane of the upper neighbour
+    if (!(halo_hi[rowi] & 1ull)) return;
+    if (!(v.bits[(size_t)rowi * v.ZW + ((z1 - 1) >> 6)] >> 63)) return;
+    const int mine = (int)(rowi * (unsigned)v.Z) + z1 - 1;
+    const int a = gfind(v.parent, mine), b = v.parent[mine + 1];
+    const int slot = atomicAdd(exch + 1, 1);
+    if (slot < cap_pairs) {
+        exch[2 + cap_roots + 2 * slot] = a;
+        exch[3 + cap_roots + 2 * slot] = b;
+    } else {
+        atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+    }
+}
+
+struct MergeView {
+    const int* gathered;  // world x stride ints
+    int world, rank, stride, cap_roots, cap_pairs;
+};
+
+__device__ __forceinline__ bool merge_item(const MergeView& m, unsigned i, bool pairs, int& a, int& b) {
+    // flattened index over (rank, slot); returns false for slots past that rank's count
+    const unsigned cap = pairs ? (unsigned)m.cap_pairs : (unsigned)m.cap_roots;
+    const unsigned r = i / cap, s = i - r * cap;
+    const int* e = m.gathered + (size_t)r * m.stride;
+    const int n = min(pairs ? e[1] : e[0], (int)cap);
+    if ((int)s >= n) return false;
+    if (pairs) { a = e[2 + m.cap_roots + 2 * s]; b = e[3 + m.cap_roots + 2 * s]; }
+    else { a = e[2 + s]; b = (int)r; }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeView m) {
+    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int root, r;
+        if (!merge_item(m, i, false, root, r)) continue;
+        if (r != m.rank) v.parent[root] = root;  // foreign roots join my union-find as singletons
+    }
+}
+
+__global__ void __launch_bounds__(256) shard_merge_union_kernel(CclView v, MergeView m) {
+    const unsigned total = (unsigned)m.world * (unsigned)m.cap_pairs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int a, b;
+        if (merge_item(m, i, true, a, b)) gunion(v.parent, a, b);
+    }
+}
+
+// global roots among all ranks' roots -> bitmap + chunk histogram + list (reuses groots: the local list
+// has already been shipped in the exchange buffer)
+__global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeView m) {
+    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int root, r;
+        if (!merge_item(m, i, false, root, r)) continue;
+        if (gfind(v.parent, root) != root) continue;
+        int bit;
+        long long wi = word_of_voxel(v, root, &bit);
+        atomicOr(&v.rootbits[wi], 1ull << bit);
+        atomicAdd(&v.chunks[wi >> 6], 1);
+        unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
+        if (slot < (unsigned)v.capacity) v.groots[slot] = root;
+        else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+    }
+}
+
+__global__ void shard_set_label_base_kernel(CclView v, int label_base) {
+    if (threadIdx.x == 0) v.hdr->label_base = label_base;
+}
+
+__global__ void shard_reset_groots_kernel(CclView v) {
+    if (threadIdx.x == 0) v.hdr->n_global_roots = 0u;
+}
+
+// every listed root takes the label code of its global root (codes are negative, indices are not)
+__global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, MergeView m) {
+    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int root, r;
+        if (!merge_item(m, i, false, root, r)) continue;
+        int a = root, p = gload(v.parent + a);
+        while (p >= 0 && p != a) { a = p; p = gload(v.parent + a); }
+        if (p < 0 && a != root) v.parent[root] = p;
+    }
+}
+
+static int shard_common(const char* who, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl) {
+    int rc = skb_check_volume(X, Y, Z, who);
+    if (rc) return rc;
+    if (Z % 64 != 0 || z_off % 64 != 0 || Zl % 64 != 0 || Zl <= 0 || z_off < 0 || z_off + Zl > Z) {
+        skb_set_error("%s: Z, z_off and Zl must be multiples of 64 with the slab inside the volume", who);
+        return SKB_E_ARG;
+    }
+    return SKB_OK;
+}
+
+static CclView slab_view(const SkbCclLayout& L, void* ws, int64_t capacity, int64_t z_off, int64_t Zl, uint32_t* status) {
+    CclView v = make_view(L, ws, 0, capacity, status, nullptr);
+    v.z_off = (int)z_off; v.Zl = (int)Zl;
+    v.k0 = (int)(z_off / 64); v.nk = (int)(Zl / 64);
+    return v;
+}
+
+extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
+                                     int64_t Zl, int64_t capacity, void* workspace, size_t workspace_bytes,
+                                     uint32_t* status, void* stream) {
+    int rc = shard_common("skb_shard_label_local", X, Y, Z, z_off, Zl);
+    if (rc) return rc;
+    SKB_REQUIRE(mask && workspace && status, "skb_shard_label_local: NULL pointer");
+    SKB_REQUIRE(mask_dtype == SKB_U8 || mask_dtype == SKB_I16, "skb_shard_label_local: mask dtype must be u8 or i16");
+    SKB_REQUIRE(capacity > 0 && capacity <= 0x7fffffff, "skb_shard_label_local: bad capacity");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
+    if (workspace_bytes < L.total) {
+        skb_set_error("skb_shard_label_local: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+        return SKB_E_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CclView v = slab_view(L, workspace, capacity, z_off, Zl, status);
+    SkbCclHeader h = {};
+    h.capacity = (int)capacity;
+    h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
+    char* base = static_cast<char*>(workspace);
+    ccl_init_kernel<<<1, 32, 0, st>>>(v, h);
+    cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
+    cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
+    const int elem = mask_dtype == SKB_U8 ? 1 : 2;
+    const int vec_ok = skb_aligned16(mask) && ((Zl * elem) % 16 == 0) ? 1 : 0;
+    if (mask_dtype == SKB_U8) launch_tile<uint8_t>(mask, v, 64, vec_ok, st);
+    else launch_tile<int16_t>(mask, v, 64, vec_ok, st);
+    launch_boundary(v, L, 8, 8, st);
+    shard_local_roots_kernel<<<148 * 4, 256, 0, st>>>(v);
+    SKB_LAUNCH_CHECK("skb_shard_label_local");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_lo, int64_t z_hi,
+                                   int32_t* runs, int64_t cap, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_emit_runs");
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && runs && status && cap > 0, "skb_shard_emit_runs: bad argument");
+    SKB_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= Z && (z_lo >> 6) == ((z_hi - 1) >> 6),
+                "skb_shard_emit_runs: [z_lo,z_hi) must lie inside one 64-plane word");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    CclView v = make_view(L, workspace, 0, 1, status, nullptr);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(runs, 0, 3 * sizeof(int32_t), st);
+    unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
+    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, (int)z_lo, (int)z_hi, runs, (int)cap, status);
+    SKB_LAUNCH_CHECK("shard_emit_runs_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs, int64_t cap,
+                                     uint64_t* halo_words_zeroed, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_ingest_runs");
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && runs && halo_words_zeroed && cap > 0, "skb_shard_ingest_runs: bad argument");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    CclView v = make_view(L, workspace, 0, 1, nullptr, nullptr);
+    shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, runs, (int)cap,
+                                                                                   reinterpret_cast<ull*>(halo_words_zeroed));
+    SKB_LAUNCH_CHECK("shard_ingest_runs_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                        int64_t capacity, const uint64_t* halo_hi, int32_t* exchange, int64_t cap_roots,
+                                        int64_t cap_pairs, uint32_t* status, void* stream) {
+    int rc = shard_common("skb_shard_boundary_pairs", X, Y, Z, z_off, Zl);
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && exchange && status && cap_roots > 0 && cap_pairs > 0, "skb_shard_boundary_pairs: bad argument");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
+    CclView v = slab_view(L, workspace, capacity, z_off, Zl, status);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(exchange, 0, 2 * sizeof(int32_t), st);
+    shard_pack_roots_kernel<<<148, 256, 0, st>>>(v, exchange, (int)cap_roots, status);
+    if (halo_hi && z_off + Zl < Z) {
+        unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
+        shard_boundary_pairs_kernel<<<nb, 256, 0, st>>>(v, reinterpret_cast<const ull*>(halo_hi), exchange, (int)cap_roots,
+                                                       (int)cap_pairs, status);
+    }
+    SKB_LAUNCH_CHECK("skb_shard_boundary_pairs");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, const int32_t* gathered,
+                               int world, int rank, int64_t cap_roots, int64_t cap_pairs, int32_t label_base,
+                               int32_t* ncomp, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_merge");
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && gathered && status && world >= 1 && rank >= 0 && rank < world && label_base >= 0,
+                "skb_shard_merge: bad argument");
+    SKB_REQUIRE((long long)world * cap_roots < (1LL << 31) && (long long)world * cap_pairs < (1LL << 31), "skb_shard_merge: capacities too large");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
+    CclView v = make_view(L, workspace, 0, capacity, status, ncomp);
+    MergeView m;
+    m.gathered = gathered; m.world = world; m.rank = rank;
+    m.cap_roots = (int)cap_roots; m.cap_pairs = (int)cap_pairs;
+    m.stride = 2 + (int)cap_roots + 2 * (int)cap_pairs;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int g = 148 * 4;
+    shard_merge_init_kernel<<<g, 256, 0, st>>>(v, m);
+    shard_merge_union_kernel<<<g, 256, 0, st>>>(v, m);
+    shard_reset_groots_kernel<<<1, 32, 0, st>>>(v);
+    shard_merge_mark_kernel<<<g, 256, 0, st>>>(v, m);
+    ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
+    ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
+    // the header's label_base is what the rank kernel reads
+    shard_set_label_base_kernel<<<1, 32, 0, st>>>(v, label_base);
+    ccl_rank_kernel<<<g, 256, 0, st>>>(v);
+    shard_publish_roots_kernel<<<g, 256, 0, st>>>(v, m);
+    ccl_publish_kernel<<<g, 256, 0, st>>>(v);
+    SKB_LAUNCH_CHECK("skb_shard_merge");
     return SKB_OK;
 }

@@ -1,0 +1,253 @@
+"""Z-sharded post-processing across the GPUs of one box.
+
+One process per GPU; rank r owns the slab z in [z0, z1) of the u8 skeleton mask and of the fp16 vector
+field.  A pass has two exchange steps, both tiny compared with the slab itself:
+
+  1. neighbour send/recv (NCCL P2P): the z-runs in my first / last H planes with their component ids
+     -> the neighbour's halo (H = ceil(scale_z), the farthest a vector can point along z);
+  2. all-gather: every rank's component roots and the (my root, neighbour root) pairs found on the
+     slab faces -> every rank solves the same union-find and numbers all components identically
+     (the single-GPU numbering).
+
+Everything else is the single-GPU kernels restricted to the slab.  `ShardedAssembler.step` is split
+into phases so that the collectives can be swapped: `TorchDistComm` (NCCL / gloo) for real runs and
+`LocalGroup` to run all ranks inside one process on one GPU (used by the GPU parity test, which
+checks the sharded result is bit-identical to the unsharded one).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+
+def slab_bounds(Z: int, world: int) -> List[Tuple[int, int]]:
+    """contiguous z ranges, multiples of 64 planes (the bit-mask word), as even as possible."""
+    if Z % 64 != 0:
+        raise ValueError("sharded post-processing needs Z to be a multiple of 64")
+    words = Z // 64
+    if words < world:
+        raise ValueError(f"Z={Z} has only {words} 64-plane words: cannot shard over {world} ranks")
+    cuts = [(words * r) // world * 64 for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def exchange_layout(cap_roots: int, cap_pairs: int) -> int:
+    """int32 elements of one rank's all-gather payload: [n_roots, n_pairs, roots, pairs]."""
+    return 2 + cap_roots + 2 * cap_pairs
+
+
+class TorchDistComm:
+    """collectives over torch.distributed (NCCL on GPUs; gloo in the CPU tests of the plumbing)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def neighbour_exchange(self, send_lo: Tensor, send_hi: Tensor, recv_lo: Tensor, recv_hi: Tensor) -> None:
+        """send_lo -> rank-1 (arrives in its recv_hi); send_hi -> rank+1 (arrives in its recv_lo)."""
+        d, ops = self.dist, []
+        if self.rank > 0:
+            ops.append(d.P2POp(d.isend, send_lo, self.rank - 1, self.group))
+            ops.append(d.P2POp(d.irecv, recv_lo, self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(d.P2POp(d.isend, send_hi, self.rank + 1, self.group))
+            ops.append(d.P2POp(d.irecv, recv_hi, self.rank + 1, self.group))
+        if ops:
+            for req in d.batch_isend_irecv(ops):
+                req.wait()
+
+    def all_gather(self, out: Tensor, src: Tensor) -> None:
+        self.dist.all_gather_into_tensor(out, src, group=self.group)
+
+    def barrier(self) -> None:
+        self.dist.barrier(self.group)
+
+
+class ShardedAssembler:
+    """Per-rank state + the phases of one pass.  N = 1 (the headline mode): with N > 1 the reference's
+    walks are confined to its 500x500x50 crops and need vector halos as well."""
+
+    def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
+                 comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, out_dtype=torch.int32):
+        if hops != 1:
+            raise NotImplementedError("the Z-sharded path implements N = 1")
+        X, Y, Z = (int(v) for v in shape)
+        self.shape, self.world, self.rank, self.dev = (X, Y, Z), world, rank, torch.device(device)
+        self.scale = [float(s) for s in scale]
+        self.z_range = slab_bounds(Z, world)[rank]
+        self.Zl = self.z_range[1] - self.z_range[0]
+        self.halo = int(math.ceil(abs(self.scale[2])))  # |v| <= 1 -> a target is at most this many planes away
+        if self.halo > 64 or self.halo > self.Zl:
+            raise ValueError("halo deeper than one 64-plane word / than the slab is not supported")
+        self.comm = comm
+        self.lib = L.load()
+        V = X * Y * Z
+        self.capacity = max(1 << 16, (X * Y * self.Zl) // 8)
+        need = self.lib.skb_ccl_workspace_bytes(X, Y, Z, self.capacity)
+        self.workspace = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        self.cap_runs = max(1 << 12, (X * Y * self.halo) // 32)
+        self.cap_roots, self.cap_pairs = cap_roots, cap_pairs
+        mk = lambda n, dt=torch.int32: torch.zeros(n, dtype=dt, device=self.dev)
+        self.send_lo, self.send_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
+        self.recv_lo, self.recv_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
+        self.halo_lo = mk(X * Y, torch.int64) if rank > 0 else None
+        self.halo_hi = mk(X * Y, torch.int64) if rank < world - 1 else None
+        self.exch = mk(exchange_layout(cap_roots, cap_pairs))
+        self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
+        self.meta = mk(2)  # [n_components, status]
+        self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
+        self.mask: Optional[Tensor] = None
+        self.vec: Optional[Tensor] = None
+        # kernels of one pass: local(init,tile,boundary,roots)=4, emit<=2, ingest<=2, pack+pairs<=2,
+        # merge(init,union,reset,mark,scan x2,base,rank,publish x2)=10, gather=1
+        self.launches_per_step = 4 + 2 * (rank > 0) + 2 * (rank < world - 1) + 2 + 10 + 1
+
+    # ---- data ------------------------------------------------------------------------------------
+    def load(self, mask_slab: Tensor, vec_slab: Tensor) -> None:
+        X, Y, _ = self.shape
+        assert tuple(mask_slab.shape) == (X, Y, self.Zl) and tuple(vec_slab.shape) == (3, X, Y, self.Zl)
+        L.require_cuda(mask_slab, vec_slab)
+        self.mask = (mask_slab.view(torch.uint8) if mask_slab.dtype == torch.bool else mask_slab).contiguous()
+        self.vec = vec_slab.contiguous()
+
+    def _s(self):
+        return L.stream_ptr(self.dev)
+
+    # ---- phases ------------------------------------------------------------------------------------
+    def phase_local(self) -> None:
+        X, Y, Z = self.shape
+        z0, z1 = self.z_range
+        with torch.cuda.device(self.dev):
+            L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, z0, self.Zl,
+                                                   self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
+                                                   self.meta[1:2].data_ptr(), self._s()))
+            if self.rank > 0:
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z0, z0 + self.halo,
+                                                     self.send_lo.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
+            if self.rank < self.world - 1:
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z1 - self.halo, z1,
+                                                     self.send_hi.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
+
+    def phase_ingest(self) -> None:
+        """after the neighbour exchange: recv_lo / recv_hi hold the neighbours' boundary runs."""
+        X, Y, Z = self.shape
+        z0, z1 = self.z_range
+        with torch.cuda.device(self.dev):
+            if self.halo_lo is not None:
+                self.halo_lo.zero_()
+                L.check(self.lib.skb_shard_ingest_runs(self.workspace.data_ptr(), X, Y, Z, self.recv_lo.data_ptr(),
+                                                       self.cap_runs, self.halo_lo.data_ptr(), self._s()))
+            if self.halo_hi is not None:
+                self.halo_hi.zero_()
+                L.check(self.lib.skb_shard_ingest_runs(self.workspace.data_ptr(), X, Y, Z, self.recv_hi.data_ptr(),
+                                                       self.cap_runs, self.halo_hi.data_ptr(), self._s()))
+            L.check(self.lib.skb_shard_boundary_pairs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, self.capacity,
+                                                      L.ptr(self.halo_hi), self.exch.data_ptr(), self.cap_roots,
+                                                      self.cap_pairs, self.meta[1:2].data_ptr(), self._s()))
+
+    def phase_merge_and_gather(self, timers=None) -> Tensor:
+        """after the all-gather: `gathered` holds every rank's roots and pairs."""
+        X, Y, Z = self.shape
+        z0, _ = self.z_range
+        with torch.cuda.device(self.dev):
+            L.check(self.lib.skb_shard_merge(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.gathered.data_ptr(),
+                                             self.world, self.rank, self.cap_roots, self.cap_pairs, 2,
+                                             self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
+            if timers is not None:
+                timers[0].record()
+            L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
+                                               L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
+                                               L.ptr(self.halo_hi), self.out.data_ptr(), L.dtype_code(self.out), self._s()))
+            if timers is not None:
+                timers[1].record()
+        return self.out
+
+    # ---- one pass over torch.distributed ----------------------------------------------------------
+    def step(self, timers=None) -> Tensor:
+        self.phase_local()
+        self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
+        self.phase_ingest()
+        self.comm.all_gather(self.gathered, self.exch)
+        return self.phase_merge_and_gather(timers)
+
+    def check(self) -> Tuple[int, int]:
+        """(n_components, labelled voxels over all ranks); raises on a capacity overflow."""
+        ncomp, status = (int(v) for v in self.meta.tolist())
+        if status & L.STATUS_ROOT_OVERFLOW:
+            raise L.SkootsB200Error("sharded CCL: a list capacity (roots / runs / pairs) overflowed")
+        labelled = (self.out > 0).sum().to(torch.int64)
+        if self.comm is not None and self.world > 1:
+            self.comm.dist.all_reduce(labelled, group=self.comm.group)
+        return ncomp, int(labelled.item())
+
+    def e2e(self, steps: int, mask_host: Optional[Tensor] = None, vec_host: Optional[Tensor] = None,
+            out_host: Optional[Tensor] = None) -> dict:
+        """the same pass with this rank's slab in pinned HOST memory: H2D + pass + D2H per step."""
+        import time
+        X, Y, Z = self.shape
+        if mask_host is None:
+            mask_host = self.mask.cpu().pin_memory()
+            vec_host = self.vec.cpu().pin_memory()
+            out_host = torch.empty(self.out.shape, dtype=self.out.dtype).pin_memory()
+
+        def once():
+            self.mask.copy_(mask_host, non_blocking=True)
+            self.vec.copy_(vec_host, non_blocking=True)
+            self.step()
+            out_host.copy_(self.out, non_blocking=True)
+            torch.cuda.synchronize(self.dev)
+        once()
+        self.comm.barrier()
+        torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            once()
+        self.comm.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=self.dev)
+        self.comm.dist.all_reduce(dt, op=self.comm.dist.ReduceOp.MAX, group=self.comm.group)
+        dt = float(dt.item())
+        return {"value": X * Y * Z / dt, "unit": "voxels/s",
+                "h2d_bytes_per_step": (mask_host.numel() + vec_host.numel() * 2) * self.world,
+                "d2h_bytes_per_step": out_host.numel() * out_host.element_size() * self.world,
+                "ms_per_step": dt * 1e3, "steps": steps, "api": "skoots_b200.sharded.ShardedAssembler.e2e"}
+
+
+class LocalGroup:
+    """All ranks of a sharded pass inside ONE process on ONE GPU: the collectives become plain copies.
+    For tests (and for a box with fewer GPUs than ranks — kernels of different ranks never wait on each
+    other, so running them back to back is safe)."""
+
+    def __init__(self, shape, world: int, device, scale=(60, 60, 12), **kw):
+        self.ranks = [ShardedAssembler(shape, world, r, device, scale=scale, **kw) for r in range(world)]
+        self.world = world
+
+    def load_volume(self, mask: Tensor, vec: Tensor) -> None:
+        for r in self.ranks:
+            z0, z1 = r.z_range
+            r.load(mask[:, :, z0:z1].contiguous(), vec[:, :, :, z0:z1].contiguous())
+
+    def step(self) -> Tensor:
+        for r in self.ranks:
+            r.phase_local()
+        for i, r in enumerate(self.ranks):
+            if i > 0:
+                r.recv_lo.copy_(self.ranks[i - 1].send_hi)
+            if i < self.world - 1:
+                r.recv_hi.copy_(self.ranks[i + 1].send_lo)
+        for r in self.ranks:
+            r.phase_ingest()
+        allg = torch.cat([r.exch for r in self.ranks])
+        for r in self.ranks:
+            r.gathered.copy_(allg)
+        outs = [r.phase_merge_and_gather() for r in self.ranks]
+        for r in self.ranks:
+            ncomp, status = (int(v) for v in r.meta.tolist())
+            if status & L.STATUS_ROOT_OVERFLOW:
+                raise L.SkootsB200Error("sharded CCL: a list capacity overflowed")
+        return torch.cat(outs, dim=2)

@@ -1,0 +1,62 @@
+"""CPU, world_size 2 over gloo: the host-side plumbing of the sharded pass — slab partition, exchange
+buffer layout, and that TorchDistComm routes boundary runs to the right neighbour and all-gathers
+payloads in rank order.  (The kernels themselves need a GPU: tests/test_gpu_sharded.py.)"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from skoots_b200.sharded import TorchDistComm, exchange_layout, slab_bounds
+
+
+def test_slab_bounds():
+    assert slab_bounds(512, 8) == [(64 * r, 64 * (r + 1)) for r in range(8)]
+    assert slab_bounds(512, 2) == [(0, 256), (256, 512)]
+    assert slab_bounds(192, 2) == [(0, 64), (64, 192)]
+    with pytest.raises(ValueError):
+        slab_bounds(500, 2)
+    with pytest.raises(ValueError):
+        slab_bounds(128, 4)
+    assert exchange_layout(8, 4) == 2 + 8 + 8
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = TorchDistComm()
+        n = 12
+        send_lo = torch.full((n,), 10 * rank + 1, dtype=torch.int32)
+        send_hi = torch.full((n,), 10 * rank + 2, dtype=torch.int32)
+        recv_lo = torch.full((n,), -1, dtype=torch.int32)
+        recv_hi = torch.full((n,), -1, dtype=torch.int32)
+        comm.neighbour_exchange(send_lo, send_hi, recv_lo, recv_hi)
+        payload = torch.arange(5, dtype=torch.int32) + 100 * rank
+        gathered = torch.empty(5 * world, dtype=torch.int32)
+        comm.all_gather(gathered, payload)
+        comm.barrier()
+        results[rank] = (recv_lo.tolist(), recv_hi.tolist(), gathered.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_comm_routing_gloo(world):
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+        for r in range(world):
+            lo, hi, gathered = results[r]
+            assert lo == ([10 * (r - 1) + 2] * 12 if r > 0 else [-1] * 12)        # lower neighbour's send_hi
+            assert hi == ([10 * (r + 1) + 1] * 12 if r < world - 1 else [-1] * 12)  # upper neighbour's send_lo
+            assert gathered == [v + 100 * q for q in range(world) for v in range(5)]

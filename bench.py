@@ -189,8 +189,8 @@ def run_b200(args):
     hbm_peak, peak_src = peaks()
 
     if world > 1:
-        from skoots_b200.sharded import ShardedAssembler
-        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops)
+        from skoots_b200.sharded import ShardedAssembler, TorchDistComm
+        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops, comm=TorchDistComm())
         z0, z1 = runner.z_range
         tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, z_range=(z0, z1),
                               want_mask=False, want_skeleton_dict=False)

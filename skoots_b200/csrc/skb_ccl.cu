@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__
     constexpr int TY = 8, SEG = TZ / 4;
     __shared__ ull srow[64];
     __shared__ int slab[64 * 32];
-    __shared__ int s_count, s_base;
 
     const int seg = threadIdx.x & 3, row = threadIdx.x >> 2;
     const int ly = row & 7, lx = row >> 3;
@@ -238,7 +237,6 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
         const bool owner = seg == 0;
-        if (threadIdx.x == 0) s_count = 0;
         if (owner) {
             srow[row] = w;
             if (in_row) v.bits[(size_t)rowi * v.ZW + (z0 >> 6)] = w;
@@ -292,13 +290,9 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__
             int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
             for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
         }
-        int mine = __popcll(rootmask);
-        int off = mine ? atomicAdd(&s_count, mine) : 0;
-        __syncthreads();
-        if (threadIdx.x == 0) s_base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)s_count);
-        __syncthreads();
-        if (mine) {
-            int at = s_base + off;
+        // append my tile roots: one global atomic per row that has any (no CTA-wide round trip)
+        if (rootmask) {
+            int at = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)__popcll(rootmask));
             for (ull m = rootmask; m; m &= m - 1) {
                 int p = __ffsll((long long)m) - 1;
                 if (at < v.capacity) v.tile_roots[at] = gbase + p;

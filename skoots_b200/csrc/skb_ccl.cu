@@ -3,10 +3,10 @@
 // Replaces the arithmetic of skoots/lib/flood_fill.py:13-140 (scipy.ndimage.label per crop +
 // seam merging).  Design:
 //
-//   K1 ccl_tile_kernel      one 8x8x64 tile per 64-thread CTA, one (x,y) row per thread.  The mask
-//                           is read once with 16-byte loads (Z is the contiguous axis), packed
-//                           into one 64-bit word per row, written out as the bit-packed mask,
-//                           and labelled inside the tile by a shared-memory union-find over
+//   K1a ccl_pack_kernel     streams the mask once (16-byte loads, Z is the contiguous axis) into the
+//                           bit-packed mask: one 64-bit word per 64 z of an (x,y) row.
+//   K1b ccl_tile_kernel     one WARP per 8x8x64 tile of the bit mask: empty tiles cost two loads and
+//                           a vote; otherwise a warp-synchronous shared-memory union-find over
 //                           z-RUNS (a run's start is found with clz on the row word, so
 //                           z-connectivity costs nothing; only y/x neighbour rows need unions).
 //                           Every foreground voxel gets parent[v] = its tile root; tile roots
@@ -63,7 +63,6 @@ int skb_check_volume(int64_t X, int64_t Y, int64_t Z, const char* who) {
 struct CclView {
     int X, Y, Z, ZW;
     int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
-    int ZW_tiles;   // z tiles per row in the tile kernel
     int z_off, Zl;  // the slab [z_off, z_off+Zl) of the global volume held by `mask` (whole volume: 0, Z)
     int k0, nk;     // word range of the slab inside each row of the bit mask
     int capacity;
@@ -191,117 +190,177 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
 // ------------------------------------------------------------------------------------------
 // K1: tile-local run-based union-find
 // ------------------------------------------------------------------------------------------
-// One CTA = CCL_NT 8 x 8 x TZ tiles stacked along y.  Loading is fully coalesced: 4 adjacent lanes
-// read the 4 segments of one row (64 contiguous bytes for u8, TZ = 64), turn them into bits and
-// combine them into the row's 64-bit word with two shuffles.  All CCL_NT loads are issued before
-// anything is consumed.  Lane 0 of each 4-lane group then owns the row: it does every union of the
-// row with its y-1 / x-1 neighbour rows (only non-empty tiles get that far).  A run start can
-// only sit at every other bit, so the union-find array needs 32 slots per row:
-// slot = row*32 + (p>>1).
-constexpr int CCL_NT = 2;
-
-template <typename MaskT, int TZ>
-__global__ void __launch_bounds__(256) ccl_tile_kernel(const MaskT* __restrict__ mask, CclView v, int vec_ok) {
-    constexpr int TY = 8, SEG = TZ / 4;
-    __shared__ ull srow[64];
-    __shared__ int slab[64 * 32];
-
-    const int seg = threadIdx.x & 3, row = threadIdx.x >> 2;
-    const int ly = row & 7, lx = row >> 3;
-    // linear CTA index -> (z tile fastest, then y group, then x); avoids the 65535 limit of grid.y/z
-    const unsigned nzt = (unsigned)v.ZW_tiles, nyt = (unsigned)(((v.Y + 7) >> 3) + CCL_NT - 1) / CCL_NT;
-    const unsigned bq = blockIdx.x / nzt, zt = blockIdx.x - bq * nzt;
-    const unsigned xt = bq / nyt, yg = bq - xt * nyt;
-    const int x0 = (int)xt * 8, zl0 = (int)zt * TZ, z0 = v.z_off + zl0;
-    const int x = x0 + lx;
-    const int zs = zl0 + seg * SEG;  // slab-local z of my segment
-
-    unsigned b[CCL_NT];
-#pragma unroll
-    for (int t = 0; t < CCL_NT; ++t) {
-        const int y = ((int)yg * CCL_NT + t) * 8 + ly;
-        b[t] = 0;
-        if (x < v.X && y < v.Y && zs < v.Zl)
-            b[t] = seg_bits<MaskT, SEG>(mask + ((size_t)x * v.Y + y) * v.Zl + zs, min(SEG, v.Zl - zs), vec_ok != 0);
+// K1a  mask -> bit-packed mask: a pure stream.  Every lane reads 16 consecutive mask elements with
+// one (u8) or two (i16) 16-byte loads, turns them into 16 bits (all-zero early-out), four lanes
+// combine their bits into one 64-bit word with two shuffles and lane 0 of the group stores it:
+// a warp reads 512 contiguous bytes and writes 64 contiguous bytes.
+template <typename MaskT>
+__global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__ mask, CclView v, unsigned n_seg,
+                                                      int nk_shift) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // 16-element segment of the slab, flat order
+    unsigned b = 0;
+    if (t < n_seg) b = seg_bits<MaskT, 16>(mask + (size_t)t * 16, 16, true);
+    ull w = (ull)b << (16 * (t & 3u));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    if ((t & 3u) == 0u && t < n_seg) {
+        const unsigned wl = t >> 2;  // word of the slab, flat order = (row, k local)
+        size_t widx = wl;
+        if (v.nk != v.ZW) {
+            const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
+            widx = (size_t)rowi * v.ZW + v.k0 + (wl - rowi * (unsigned)v.nk);
+        }
+        v.bits[widx] = w;
     }
+}
 
-#pragma unroll
-    for (int t = 0; t < CCL_NT; ++t) {
-        const int y0 = ((int)yg * CCL_NT + t) * 8;
-        if (y0 >= v.Y) continue;  // uniform across the CTA
-        const int y = y0 + ly;
-        const bool in_row = (x < v.X) && (y < v.Y);
-        const unsigned rowi = (unsigned)x * (unsigned)v.Y + (unsigned)y;
+// any Z / unaligned masks: one thread per word, element-wise
+template <typename MaskT>
+__global__ void __launch_bounds__(256) ccl_pack_generic_kernel(const MaskT* __restrict__ mask, CclView v) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned rows = (unsigned)v.X * (unsigned)v.Y;
+    const unsigned rowi = t / (unsigned)v.nk, kl = t - rowi * (unsigned)v.nk;
+    if (rowi >= rows) return;
+    const int zl0 = (int)kl * 64, n = min(64, v.Zl - zl0);
+    const MaskT* p = mask + (size_t)rowi * v.Zl + zl0;
+    ull w = 0;
+    for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
+    v.bits[(size_t)rowi * v.ZW + v.k0 + kl] = w;
+}
 
-        ull w = (ull)b[t] << (SEG * seg);
-        w |= __shfl_xor_sync(0xffffffffu, w, 1);
-        w |= __shfl_xor_sync(0xffffffffu, w, 2);
-        const bool owner = seg == 0;
-        if (owner) {
-            srow[row] = w;
-            if (in_row) v.bits[(size_t)rowi * v.ZW + (z0 >> 6)] = w;
-        }
-        if (!__syncthreads_or(b[t] != 0u)) continue;  // empty tile: nothing to label
-
-        const ull starts = owner ? (w & ~(w << 1)) : 0ull;
-        for (ull s = starts; s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            slab[row * 32 + (p >> 1)] = row * 32 + (p >> 1);
-        }
-        __syncthreads();
-
-        // unions with the y-1 and x-1 rows of the same tile: one per maximal joint run
-        if (owner && w) {
-            if (ly > 0) {
-                ull wn = srow[row - 1], a = w & wn;
-                for (ull s = a & ~(a << 1); s; s &= s - 1) {
-                    int p = __ffsll((long long)s) - 1;
-                    sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - 1) * 32 + (run_start(wn, p) >> 1));
-                }
-            }
-            if (lx > 0 && v.connect_x) {
-                ull wn = srow[row - TY], a = w & wn;
-                for (ull s = a & ~(a << 1); s; s &= s - 1) {
-                    int p = __ffsll((long long)s) - 1;
-                    sunion(slab, row * 32 + (run_start(w, p) >> 1), (row - TY) * 32 + (run_start(wn, p) >> 1));
-                }
-            }
-        }
-        __syncthreads();
-
-        // resolve every run of my row; write parent for all its voxels
-        ull rootmask = 0;  // bit p set when the run starting at p is a tile root
-        const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
-        for (ull s = starts; s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            int l = row * 32 + (p >> 1);
-            int r = sfind(slab, l);
-            int groot;
-            if (r == l) {
-                rootmask |= 1ull << p;
-                groot = gbase + p;
-            } else {
-                const int rrow = r >> 5, rh = r & 31;
-                const ull rs = srow[rrow] & ~(srow[rrow] << 1);
-                const int rp = 2 * rh + (int)((rs >> (2 * rh + 1)) & 1ull);
-                groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + rp;
-            }
-            ull tt = ~(w >> p);
-            int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
-            for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
-        }
-        // append my tile roots: one global atomic per row that has any (no CTA-wide round trip)
-        if (rootmask) {
-            int at = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)__popcll(rootmask));
-            for (ull m = rootmask; m; m &= m - 1) {
-                int p = __ffsll((long long)m) - 1;
-                if (at < v.capacity) v.tile_roots[at] = gbase + p;
-                else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
-                ++at;
-            }
-        }
-        __syncthreads();  // smem is reused by the next tile
+// 16-bit labels in shared memory: atomic min through a 32-bit CAS; returns the previous value
+__device__ __forceinline__ int amin16(unsigned short* lab, int idx, int val) {
+    unsigned* w = reinterpret_cast<unsigned*>(lab) + (idx >> 1);
+    const int sh = (idx & 1) * 16;
+    unsigned old = *reinterpret_cast<volatile unsigned*>(w);
+    for (;;) {
+        const int cur = (int)((old >> sh) & 0xffffu);
+        if (cur <= val) return cur;
+        const unsigned nw = (old & ~(0xffffu << sh)) | ((unsigned)val << sh);
+        const unsigned prev = atomicCAS(w, old, nw);
+        if (prev == old) return cur;
+        old = prev;
     }
+}
+
+__device__ __forceinline__ int sfind16(const volatile unsigned short* lab, int a) {
+    int p = lab[a];
+    while (p != a) {
+        a = p;
+        p = lab[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void sunion16(unsigned short* lab, int a, int b) {
+    for (;;) {
+        a = sfind16(lab, a);
+        b = sfind16(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = amin16(lab, a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// K1b  one WARP per 8 x 8 x 64 tile, working on the bit-packed mask (8x less data than the mask and no
+// CTA-wide barriers): each lane owns two of the tile's 64 row words.  An empty tile costs two 8-byte
+// loads and a vote.  Otherwise a warp-synchronous union-find over z-runs: a run's start is found
+// with clz on the row word, so z-connectivity costs nothing; a run start can only sit at every
+// other bit, so 32 slots per row suffice: slot = row*32 + (p>>1), 16-bit labels.
+__device__ __forceinline__ void tile_row_unions(unsigned short* slab, const ull* srow, int row, ull w, bool connect_x) {
+    if (!w) return;
+    if (row & 7) {  // y-1 inside the tile
+        ull wn = srow[row - 1], a = w & wn;
+        for (ull s = a & ~(a << 1); s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            sunion16(slab, row * 32 + (run_start(w, p) >> 1), (row - 1) * 32 + (run_start(wn, p) >> 1));
+        }
+    }
+    if ((row >> 3) && connect_x) {  // x-1 inside the tile
+        ull wn = srow[row - 8], a = w & wn;
+        for (ull s = a & ~(a << 1); s; s &= s - 1) {
+            int p = __ffsll((long long)s) - 1;
+            sunion16(slab, row * 32 + (run_start(w, p) >> 1), (row - 8) * 32 + (run_start(wn, p) >> 1));
+        }
+    }
+}
+
+__device__ __forceinline__ void tile_row_resolve(const CclView& v, unsigned short* slab, const ull* srow, int row, ull w,
+                                                 int x0, int y0, int z0) {
+    if (!w) return;
+    const unsigned rowi = (unsigned)(x0 + (row >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (row & 7));
+    const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
+    ull rootmask = 0;                                    // bit p set when the run starting at p is a tile root
+    for (ull s = w & ~(w << 1); s; s &= s - 1) {
+        const int p = __ffsll((long long)s) - 1;
+        const int l = row * 32 + (p >> 1);
+        const int r = sfind16(slab, l);
+        int groot;
+        if (r == l) {
+            rootmask |= 1ull << p;
+            groot = gbase + p;
+        } else {
+            const int rrow = r >> 5, rh = r & 31;
+            const ull rs = srow[rrow] & ~(srow[rrow] << 1);
+            const int rp = 2 * rh + (int)((rs >> (2 * rh + 1)) & 1ull);
+            groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + rp;
+        }
+        const ull tt = ~(w >> p);
+        const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+        for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
+    }
+    if (rootmask) {  // append my tile roots: one global atomic per row that has any
+        int at = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)__popcll(rootmask));
+        for (ull m = rootmask; m; m &= m - 1) {
+            const int p = __ffsll((long long)m) - 1;
+            if (at < v.capacity) v.tile_roots[at] = gbase + p;
+            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            ++at;
+        }
+    }
+}
+
+constexpr int CCL_TILE_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v, unsigned n_yk, int nk_shift) {
+    __shared__ ull srow_all[CCL_TILE_WARPS][64];
+    __shared__ unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned yk = blockIdx.x * CCL_TILE_WARPS + warp;  // (y tile, k) with k fastest
+    if (yk >= n_yk) return;
+    const unsigned yt = nk_shift >= 0 ? (yk >> nk_shift) : yk / (unsigned)v.nk;
+    const unsigned kl = yk - yt * (unsigned)v.nk;
+    const int x0 = (int)blockIdx.y * 8, y0 = (int)yt * 8, k = v.k0 + (int)kl, z0 = 64 * k;
+
+    const int r0 = lane, r1 = lane + 32;
+    const int xa = x0 + (r0 >> 3), xb = x0 + (r1 >> 3), y = y0 + (lane & 7);
+    ull w0 = 0, w1 = 0;
+    if (y < v.Y) {
+        if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.ZW + k];
+        if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.ZW + k];
+    }
+    if (!__any_sync(0xffffffffu, (w0 | w1) != 0ull)) return;  // empty tile
+
+    ull* srow = srow_all[warp];
+    unsigned short* slab = slab_all[warp];
+    srow[r0] = w0;
+    srow[r1] = w1;
+    for (ull s = w0 & ~(w0 << 1); s; s &= s - 1) {
+        const int h = (__ffsll((long long)s) - 1) >> 1;
+        slab[r0 * 32 + h] = (unsigned short)(r0 * 32 + h);
+    }
+    for (ull s = w1 & ~(w1 << 1); s; s &= s - 1) {
+        const int h = (__ffsll((long long)s) - 1) >> 1;
+        slab[r1 * 32 + h] = (unsigned short)(r1 * 32 + h);
+    }
+    __syncwarp();
+    tile_row_unions(slab, srow, r0, w0, v.connect_x != 0);
+    tile_row_unions(slab, srow, r1, w1, v.connect_x != 0);
+    __syncwarp();
+    tile_row_resolve(v, slab, srow, r0, w0, x0, y0, z0);
+    tile_row_resolve(v, slab, srow, r1, w1, x0, y0, z0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -531,7 +590,6 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     CclView v;
     v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
     v.connect_x = planar ? 0 : 1;
-    v.ZW_tiles = 1;
     v.z_off = 0; v.Zl = L.Z; v.k0 = 0; v.nk = L.ZW;
     v.capacity = (int)capacity;
     v.hdr = reinterpret_cast<SkbCclHeader*>(base);
@@ -556,16 +614,33 @@ extern "C" size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64
     return skb_ccl_layout(X, Y, Z, capacity).total;
 }
 
+static int shift_of(int n) {  // log2 for powers of two, else -1
+    if (n <= 0 || (n & (n - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < n) ++s;
+    return s;
+}
+
 template <typename MaskT>
-static void launch_tile(const void* mask, const CclView& v, int tz, int vec_ok, cudaStream_t st) {
+static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
-    CclView vv = v;
-    vv.ZW_tiles = (v.Zl + tz - 1) / tz;
-    const long long ygroups = ((v.Y + 7) / 8 + CCL_NT - 1) / CCL_NT;
-    const unsigned grid = (unsigned)((long long)vv.ZW_tiles * ygroups * ((v.X + 7) / 8));
-    if (tz == 64) ccl_tile_kernel<MaskT, 64><<<grid, 256, 0, st>>>(m, vv, vec_ok);
-    else if (tz == 32) ccl_tile_kernel<MaskT, 32><<<grid, 256, 0, st>>>(m, vv, vec_ok);
-    else ccl_tile_kernel<MaskT, 16><<<grid, 256, 0, st>>>(m, vv, vec_ok);
+    const int nk_shift = shift_of(v.nk);
+    const long long rows = (long long)v.X * v.Y;
+    const bool fast = (v.Zl % 64 == 0) && skb_aligned16(mask);
+    if (fast) {
+        const unsigned n_seg = (unsigned)(rows * v.Zl / 16);
+        ccl_pack_kernel<MaskT><<<(n_seg + 255) / 256, 256, 0, st>>>(m, v, n_seg, nk_shift);
+    } else {
+        ccl_pack_generic_kernel<MaskT><<<(unsigned)((rows * v.nk + 255) / 256), 256, 0, st>>>(m, v);
+    }
+    const long long xt = (v.X + 7) / 8, n_yk = (long long)((v.Y + 7) / 8) * v.nk;
+    if (xt > 65535) {
+        skb_set_error("ccl: X = %d is too large for the tile grid (max 524280)", v.X);
+        return SKB_E_RANGE;
+    }
+    dim3 grid((unsigned)((n_yk + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS), (unsigned)xt);
+    ccl_tile_kernel<<<grid, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_yk, nk_shift);
+    return SKB_OK;
 }
 
 static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int TY, cudaStream_t st) {
@@ -600,12 +675,9 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
     cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
 
-    const int tz = Z > 32 ? 64 : (Z > 16 ? 32 : 16);
-    const int elem = mask_dtype == SKB_U8 ? 1 : 2;
-    const int vec_ok = ((Z * elem) % 16 == 0) && skb_aligned16(mask) ? 1 : 0;
-    if (mask_dtype == SKB_U8) launch_tile<uint8_t>(mask, v, tz, vec_ok, st);
-    else launch_tile<int16_t>(mask, v, tz, vec_ok, st);
-    SKB_LAUNCH_CHECK("ccl_tile_kernel");
+    rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
+    if (rc) return rc;
+    SKB_LAUNCH_CHECK("ccl_pack/tile_kernel");
 
     const int TY = 8, TX = 8;
     launch_boundary(v, L, TX, TY, st);
@@ -860,10 +932,8 @@ extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X
     ccl_init_kernel<<<1, 32, 0, st>>>(v, h);
     cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
     cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
-    const int elem = mask_dtype == SKB_U8 ? 1 : 2;
-    const int vec_ok = skb_aligned16(mask) && ((Zl * elem) % 16 == 0) ? 1 : 0;
-    if (mask_dtype == SKB_U8) launch_tile<uint8_t>(mask, v, 64, vec_ok, st);
-    else launch_tile<int16_t>(mask, v, 64, vec_ok, st);
+    rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
+    if (rc) return rc;
     launch_boundary(v, L, 8, 8, st);
     shard_local_roots_kernel<<<148 * 4, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_label_local");

@@ -216,7 +216,7 @@ def run_b200(args):
             if timers is not None:
                 timers[1].record()
             return out
-        launches_per_step = 9  # init, tile, boundary, flatten, scan x2, rank, publish, gather (+2 memsets)
+        launches_per_step = 11  # init, pack, tile, boundary, flatten, scan x2, rank, clear, publish, gather (+memsets)
 
     def barrier():
         if world > 1:
@@ -226,12 +226,15 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    phases = None
     if world == 1:
         state["sparse"].check()
         n_components = state["sparse"].num_components
         labelled = int((out > 0).sum().item())
     else:
         n_components, labelled = runner.check()
+        if os.environ.get("SKB_PHASE_TIMING"):
+            phases = runner.profile_phases()
 
     sampler = ClockSampler(local) if rank == 0 else None
     timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -323,6 +326,8 @@ def run_b200(args):
                          "bytes_per_voxel": ALGO_BYTES_GATHER, "ms_per_launch": gather_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
+        if phases is not None:
+            line["phases_ms_rank0"] = phases
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

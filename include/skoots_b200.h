@@ -91,9 +91,13 @@ int skb_index_by_embed(const void* labels, int label_dtype, int64_t Xs, int64_t 
  * ------------------------------------------------------------------------------------------- */
 size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity);
 
+/* flags: SKB_CCL_WORKSPACE_CLEAN = this workspace was last used by a completed labelling pass of the
+ * same volume shape (every pass leaves its root bitmap zeroed), so the V/8-byte memset is skipped. */
+#define SKB_CCL_WORKSPACE_CLEAN 1
 int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                          int planar, int32_t label_base, int64_t capacity, void* workspace,
-                         size_t workspace_bytes, int32_t* ncomp, uint32_t* status, void* stream);
+                         size_t workspace_bytes, int32_t* ncomp, uint32_t* status, int flags,
+                         void* stream);
 
 /* dense labels from the sparse form. out (X,Y,Z) i16|i32, may alias the mask given to
  * skb_ccl_label_sparse (the reference labels in place, flood_fill.py:50). */
@@ -197,7 +201,7 @@ int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offset
  * ------------------------------------------------------------------------------------------- */
 int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                           int64_t z_off, int64_t Zl, int64_t capacity, void* workspace,
-                          size_t workspace_bytes, uint32_t* status, void* stream);
+                          size_t workspace_bytes, uint32_t* status, int flags, void* stream);
 int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_lo, int64_t z_hi,
                         int32_t* runs, int64_t cap, uint32_t* status, void* stream);
 int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs,

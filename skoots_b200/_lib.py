@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libskoots_b200.so")
 SKB_U8, SKB_I16, SKB_I32, SKB_F16, SKB_BF16, SKB_F32 = range(6)
 STATUS_ROOT_OVERFLOW = 1
 STATUS_MISSING_ID = 2
+CCL_WORKSPACE_CLEAN = 1
 
 _DTYPES = {
     torch.uint8: SKB_U8, torch.bool: SKB_U8, torch.int16: SKB_I16, torch.int32: SKB_I32,
@@ -38,7 +39,7 @@ SIGNATURES = {
     "skb_vec_embed_bwd": (_c_int, [_c_vp, _c_i64, _c_int, _c_i64, _c_f3, _c_vp, _c_int, _c_vp]),
     "skb_index_by_embed": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_ccl_workspace_bytes": (_c_sz, [_c_i64, _c_i64, _c_i64, _c_i64]),
-    "skb_ccl_label_sparse": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_int32, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp, _c_vp]),
+    "skb_ccl_label_sparse": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, ctypes.c_int32, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp, _c_int, _c_vp]),
     "skb_ccl_write_dense": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp]),
     "skb_stencil3": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_vp]),
     "skb_masked_mean27": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp]),
@@ -48,7 +49,7 @@ SIGNATURES = {
     "skb_vec_prob": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_f3, ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_bake_skeleton": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_stamp_disks": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
-    "skb_shard_label_local": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp]),
+    "skb_shard_label_local": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_int, _c_vp]),
     "skb_shard_emit_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),

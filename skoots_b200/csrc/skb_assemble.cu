@@ -214,32 +214,34 @@ __device__ __forceinline__ unsigned nonzero_bits(const Raw8<VecT>& a, const Raw8
     return work;
 }
 
+// What one lane holds for its 8 voxels between the load and the processing of a 256-voxel chunk.
+template <typename VecT> struct ChunkRegs {
+    Raw8<VecT> r0, r1, r2;
+    unsigned self;  // foreground bits of my own 8 voxels (zero-vector voxels resolve to themselves)
+};
+
 // FULL = all 32 lanes own 8 valid voxels and 16-byte loads are legal: no per-element guards at all.
-template <typename VecT, typename OutT, bool FULL>
-__device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restrict__ out, long long V, long long warp_base,
-                                              unsigned (*s_raw)[32][Raw8<VecT>::NW], int* s_res, unsigned char* s_queue) {
-    typedef typename RawOf<VecT>::type raw_t;
+template <typename VecT, bool FULL>
+__device__ __forceinline__ ChunkRegs<VecT> load_chunk(const AsmParams& P, long long V, long long warp_base) {
     const int lane = threadIdx.x & 31;
     const long long i0 = warp_base + lane * 8;
     const long long left = V - i0;
     const int nvalid = FULL ? 8 : (left >= 8 ? 8 : (left > 0 ? (int)left : 0));
-    const unsigned uz = (unsigned)P.Zl, uy = (unsigned)P.Y;  // index decomposition runs over the slab
-
+    const unsigned uz = (unsigned)P.Zl;
+    ChunkRegs<VecT> c;
     // every independent load is issued before anything waits on one of them
-    const Raw8<VecT> r0 = load_raw8<VecT, FULL>(P.vec, i0, nvalid);
-    const Raw8<VecT> r1 = load_raw8<VecT, FULL>(P.vec, i0 + P.cstride, nvalid);
-    const Raw8<VecT> r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
-    const bool lookup_self = P.fast_ok && !P.dense;
-    unsigned self = 0;
-    if (lookup_self && nvalid > 0) {
-        // a zero vector resolves to the voxel itself: only foreground voxels need a label read
+    c.r0 = load_raw8<VecT, FULL>(P.vec, i0, nvalid);
+    c.r1 = load_raw8<VecT, FULL>(P.vec, i0 + P.cstride, nvalid);
+    c.r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
+    c.self = 0;
+    if (P.fast_ok && !P.dense && nvalid > 0) {
         if (P.flat_bits) {
             size_t gv = (size_t)i0;  // global voxel index of my first voxel
             if (P.Zl != P.Z) {
                 const unsigned q = (unsigned)i0 / uz;
                 gv = (size_t)q * P.Z + ((unsigned)i0 - q * uz) + (unsigned)P.z_off;
             }
-            self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (gv >> 3));
+            c.self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (gv >> 3));
         } else {
             unsigned q = (unsigned)i0 / uz;
             int z = (int)((unsigned)i0 - q * uz);
@@ -248,20 +250,31 @@ __device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restri
                 const int sh = z & 63;
                 ull w = __ldg(P.bits + wi) >> sh;
                 if (sh > 56) w |= __ldg(P.bits + wi + 1) << (64 - sh);
-                self = (unsigned)(w & 0xFFull);
+                c.self = (unsigned)(w & 0xFFull);
             } else {
                 for (int j = 0; j < nvalid; ++j) {
                     ull w = __ldg(P.bits + (long long)q * P.ZW + (z >> 6));
-                    self |= (unsigned)((w >> (z & 63)) & 1ull) << j;
+                    c.self |= (unsigned)((w >> (z & 63)) & 1ull) << j;
                     if (++z == P.Z) { z = 0; ++q; }
                 }
             }
         }
     }
+    return c;
+}
 
+template <typename VecT, typename OutT, bool FULL>
+__device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkRegs<VecT>& c, OutT* __restrict__ out,
+                                              long long V, long long warp_base,
+                                              unsigned (*s_raw)[32][Raw8<VecT>::NW], int* s_res, unsigned char* s_queue) {
+    const int lane = threadIdx.x & 31;
+    const long long i0 = warp_base + lane * 8;
+    const long long left = V - i0;
+    const int nvalid = FULL ? 8 : (left >= 8 ? 8 : (left > 0 ? (int)left : 0));
+    const unsigned uz = (unsigned)P.Zl, uy = (unsigned)P.Y;  // index decomposition runs over the slab
     const unsigned valid_mask = FULL ? 0xFFu : ((1u << nvalid) - 1u);
     unsigned work;
-    if (lookup_self) work = (nonzero_bits<VecT>(r0, r1, r2) | self) & valid_mask;
+    if (P.fast_ok && !P.dense) work = (nonzero_bits<VecT>(c.r0, c.r1, c.r2) | c.self) & valid_mask;
     else work = valid_mask;  // N>1 over a >2^24-voxel crop, or a dense label volume (compatibility path)
 
     unsigned lab[8];
@@ -283,9 +296,9 @@ __device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restri
             for (unsigned m = work; m; m &= m - 1) s_queue[at++] = (unsigned char)((__ffs((int)m) - 1) * 32 + lane);
 #pragma unroll
             for (int k = 0; k < Raw8<VecT>::NW; ++k) {
-                s_raw[0][lane][k] = r0.w[k];
-                s_raw[1][lane][k] = r1.w[k];
-                s_raw[2][lane][k] = r2.w[k];
+                s_raw[0][lane][k] = c.r0.w[k];
+                s_raw[1][lane][k] = c.r1.w[k];
+                s_raw[2][lane][k] = c.r2.w[k];
             }
         }
         __syncwarp();
@@ -309,6 +322,7 @@ __device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restri
                 lab[j] = ((work >> j) & 1u) ? (unsigned)v : 0u;
             }
         }
+        __syncwarp();  // the warp's shared-memory scratch is reused by its next chunk
     }
 
     if (FULL || nvalid == 8) {
@@ -326,18 +340,43 @@ __device__ __forceinline__ void assemble_warp(const AsmParams& P, OutT* __restri
     }
 }
 
+// Main kernel: PERSISTENT warps over the full, aligned 256-voxel chunks [0, n_chunks).  A warp issues the
+// streaming loads of its next chunk before it starts on the current one, so a warp that is busy with
+// the latency-bound part (compaction, dependent label reads) still keeps 1.5 KB of loads in flight.
 template <typename VecT, typename OutT>
-__global__ void __launch_bounds__(32 * ASM_WARPS, 5) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V) {
+__global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V,
+                                                                      unsigned n_chunks) {
     __shared__ unsigned s_raw[ASM_WARPS][3][32][Raw8<VecT>::NW];
     __shared__ int s_res[ASM_WARPS][256];
     __shared__ unsigned char s_queue[ASM_WARPS][256];
     const int warp = threadIdx.x >> 5;
-    const long long warp_base = ((long long)blockIdx.x * ASM_WARPS + warp) * 256;
+    const unsigned stride = gridDim.x * ASM_WARPS;
+    unsigned c = blockIdx.x * ASM_WARPS + warp;
+    if (c >= n_chunks) return;
+    ChunkRegs<VecT> cur = load_chunk<VecT, true>(P, V, (long long)c * 256);
+    for (;;) {
+        const unsigned cn = c + stride;
+        ChunkRegs<VecT> nxt = cur;
+        if (cn < n_chunks) nxt = load_chunk<VecT, true>(P, V, (long long)cn * 256);
+        process_chunk<VecT, OutT, true>(P, cur, out, V, (long long)c * 256, s_raw[warp], s_res[warp], s_queue[warp]);
+        if (cn >= n_chunks) break;
+        c = cn;
+        cur = nxt;
+    }
+}
+
+// Everything the main kernel does not cover: the ragged last chunk, or all chunks of an unaligned field.
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(32 * ASM_WARPS) assemble_tail_kernel(AsmParams P, OutT* __restrict__ out, long long V,
+                                                                       long long first_voxel) {
+    __shared__ unsigned s_raw[ASM_WARPS][3][32][Raw8<VecT>::NW];
+    __shared__ int s_res[ASM_WARPS][256];
+    __shared__ unsigned char s_queue[ASM_WARPS][256];
+    const int warp = threadIdx.x >> 5;
+    const long long warp_base = first_voxel + ((long long)blockIdx.x * ASM_WARPS + warp) * 256;
     if (warp_base >= V) return;
-    if (warp_base + 256 <= V && P.vec_aligned)
-        assemble_warp<VecT, OutT, true>(P, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
-    else
-        assemble_warp<VecT, OutT, false>(P, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
+    const ChunkRegs<VecT> c = load_chunk<VecT, false>(P, V, warp_base);
+    process_chunk<VecT, OutT, false>(P, c, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
 }
 
 // ---- stand-alone a1: materialise the embedding ---------------------------------------------------
@@ -422,11 +461,25 @@ static void fill_crop(AsmParams& P, const int32_t crop[3], const int32_t overlap
     P.single_crop = (P.cs[0] == P.X && P.cs[1] == P.Y && P.cs[2] == P.Z && !P.ov[0] && !P.ov[1] && !P.ov[2]) ? 1 : 0;
 }
 
+template <typename VecT, typename OutT>
+static void launch_assemble_t(const AsmParams& P, OutT* out, long long V, cudaStream_t st) {
+    const long long n_chunks = P.vec_aligned ? V / 256 : 0;
+    if (n_chunks > 0) {
+        long long blocks = (n_chunks + ASM_WARPS - 1) / ASM_WARPS;
+        if (blocks > 148 * 4) blocks = 148 * 4;  // 4 resident CTAs per SM; warps stride over the chunks
+        assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, V, (unsigned)n_chunks);
+    }
+    const long long first = n_chunks * 256;
+    if (first < V) {
+        const long long rest = (V - first + 255) / 256;
+        assemble_tail_kernel<VecT, OutT><<<(unsigned)((rest + ASM_WARPS - 1) / ASM_WARPS), 32 * ASM_WARPS, 0, st>>>(P, out, V, first);
+    }
+}
+
 template <typename VecT>
 static void launch_assemble(const AsmParams& P, void* out, int out_dtype, long long V, cudaStream_t st) {
-    unsigned nb = (unsigned)((V + 256 * ASM_WARPS - 1) / (256 * ASM_WARPS));
-    if (out_dtype == SKB_I32) assemble_kernel<VecT, int32_t><<<nb, 256, 0, st>>>(P, static_cast<int32_t*>(out), V);
-    else assemble_kernel<VecT, int16_t><<<nb, 256, 0, st>>>(P, static_cast<int16_t*>(out), V);
+    if (out_dtype == SKB_I32) launch_assemble_t<VecT, int32_t>(P, static_cast<int32_t*>(out), V, st);
+    else launch_assemble_t<VecT, int16_t>(P, static_cast<int16_t*>(out), V, st);
 }
 
 extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, const float scale[3], int N,

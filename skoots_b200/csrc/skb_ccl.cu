@@ -197,20 +197,29 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
 template <typename MaskT>
 __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__ mask, CclView v, unsigned n_seg,
                                                       int nk_shift) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;  // 16-element segment of the slab, flat order
-    unsigned b = 0;
-    if (t < n_seg) b = seg_bits<MaskT, 16>(mask + (size_t)t * 16, 16, true);
-    ull w = (ull)b << (16 * (t & 3u));
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    if ((t & 3u) == 0u && t < n_seg) {
-        const unsigned wl = t >> 2;  // word of the slab, flat order = (row, k local)
-        size_t widx = wl;
-        if (v.nk != v.ZW) {
-            const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
-            widx = (size_t)rowi * v.ZW + v.k0 + (wl - rowi * (unsigned)v.nk);
+    // two 16-element segments per thread (256 segments apart: both loads coalesced and in flight together)
+    const unsigned t0 = blockIdx.x * 512u + threadIdx.x;
+    unsigned b[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const unsigned t = t0 + 256u * u;
+        b[u] = t < n_seg ? seg_bits<MaskT, 16>(mask + (size_t)t * 16, 16, true) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const unsigned t = t0 + 256u * u;
+        ull w = (ull)b[u] << (16 * (t & 3u));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        if ((t & 3u) == 0u && t < n_seg) {
+            const unsigned wl = t >> 2;  // word of the slab, flat order = (row, k local)
+            size_t widx = wl;
+            if (v.nk != v.ZW) {
+                const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
+                widx = (size_t)rowi * v.ZW + v.k0 + (wl - rowi * (unsigned)v.nk);
+            }
+            v.bits[widx] = w;
         }
-        v.bits[widx] = w;
     }
 }
 
@@ -287,9 +296,10 @@ __device__ __forceinline__ void tile_row_unions(unsigned short* slab, const ull*
     }
 }
 
-__device__ __forceinline__ void tile_row_resolve(const CclView& v, unsigned short* slab, const ull* srow, int row, ull w,
-                                                 int x0, int y0, int z0) {
-    if (!w) return;
+__device__ __forceinline__ ull tile_row_resolve(const CclView& v, unsigned short* slab, const ull* srow, int row, ull w,
+                                                int x0, int y0, int z0, int& gbase_out) {
+    gbase_out = 0;
+    if (!w) return 0ull;
     const unsigned rowi = (unsigned)(x0 + (row >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (row & 7));
     const int gbase = (int)(rowi * (unsigned)v.Z) + z0;  // voxel index of bit 0 of this row word
     ull rootmask = 0;                                    // bit p set when the run starting at p is a tile root
@@ -311,56 +321,135 @@ __device__ __forceinline__ void tile_row_resolve(const CclView& v, unsigned shor
         const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
         for (int j = 0; j < len; ++j) v.parent[gbase + p + j] = groot;
     }
-    if (rootmask) {  // append my tile roots: one global atomic per row that has any
-        int at = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)__popcll(rootmask));
-        for (ull m = rootmask; m; m &= m - 1) {
-            const int p = __ffsll((long long)m) - 1;
-            if (at < v.capacity) v.tile_roots[at] = gbase + p;
-            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
-            ++at;
-        }
+    gbase_out = gbase;
+    return rootmask;
+}
+
+// Tile roots are collected in a per-warp shared-memory buffer and appended to the global list with ONE
+// atomicAdd per flush: a counter that every non-empty tile bumps individually serialises in L2
+// (hundreds of thousands of same-address atomics cost more than streaming the whole mask).
+constexpr int CCL_ROOT_BUF = 128;
+
+__device__ __forceinline__ void flush_roots(const CclView& v, int* sbuf, int& buf_n, int lane) {
+    if (buf_n == 0) return;
+    int base = 0;
+    if (lane == 0) base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)buf_n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (int i = lane; i < buf_n; i += 32) {
+        if (base + i < v.capacity) v.tile_roots[base + i] = sbuf[i];
+        else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
     }
+    __syncwarp();
+    buf_n = 0;
+}
+
+// warp-collective: every lane passes the root masks of its two rows
+__device__ __forceinline__ void append_roots(const CclView& v, int* sbuf, int& buf_n, int lane, ull m0, int g0, ull m1, int g1) {
+    const int cnt = __popcll(m0) + __popcll(m1);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    if (total > CCL_ROOT_BUF) {  // very dense tile: straight to the list
+        flush_roots(v, sbuf, buf_n, lane);
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(&v.hdr->n_tile_roots, (unsigned)total);
+        int at = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+        for (ull m = m0; m; m &= m - 1, ++at) {
+            if (at < v.capacity) v.tile_roots[at] = g0 + __ffsll((long long)m) - 1;
+            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+        }
+        for (ull m = m1; m; m &= m - 1, ++at) {
+            if (at < v.capacity) v.tile_roots[at] = g1 + __ffsll((long long)m) - 1;
+            else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+        }
+        return;
+    }
+    if (buf_n + total > CCL_ROOT_BUF) flush_roots(v, sbuf, buf_n, lane);
+    int at = buf_n + incl - cnt;
+    for (ull m = m0; m; m &= m - 1) sbuf[at++] = g0 + __ffsll((long long)m) - 1;
+    for (ull m = m1; m; m &= m - 1) sbuf[at++] = g1 + __ffsll((long long)m) - 1;
+    buf_n += total;
+    __syncwarp();
 }
 
 constexpr int CCL_TILE_WARPS = 8;
 
-__global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v, unsigned n_yk, int nk_shift) {
+// Warps are PERSISTENT and independent: a fixed grid, every warp strides over the tile list and
+// prefetches the next tile's two row words while it works on the current one.  (With one tile per warp
+// and 8 warps per CTA the CTA's shared memory stays pinned until its slowest warp — the one tile in
+// eight that is not empty — has finished, and occupancy collapses to ~20 %.)
+__global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v, unsigned n_tiles, unsigned n_yk,
+                                                                       int nk_shift) {
     __shared__ ull srow_all[CCL_TILE_WARPS][64];
     __shared__ unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
+    __shared__ int rootbuf_all[CCL_TILE_WARPS][CCL_ROOT_BUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned yk = blockIdx.x * CCL_TILE_WARPS + warp;  // (y tile, k) with k fastest
-    if (yk >= n_yk) return;
-    const unsigned yt = nk_shift >= 0 ? (yk >> nk_shift) : yk / (unsigned)v.nk;
-    const unsigned kl = yk - yt * (unsigned)v.nk;
-    const int x0 = (int)blockIdx.y * 8, y0 = (int)yt * 8, k = v.k0 + (int)kl, z0 = 64 * k;
-
-    const int r0 = lane, r1 = lane + 32;
-    const int xa = x0 + (r0 >> 3), xb = x0 + (r1 >> 3), y = y0 + (lane & 7);
-    ull w0 = 0, w1 = 0;
-    if (y < v.Y) {
-        if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.ZW + k];
-        if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.ZW + k];
-    }
-    if (!__any_sync(0xffffffffu, (w0 | w1) != 0ull)) return;  // empty tile
-
+    const unsigned n_warps = gridDim.x * CCL_TILE_WARPS;
+    int* sbuf = rootbuf_all[warp];
+    int buf_n = 0;
     ull* srow = srow_all[warp];
     unsigned short* slab = slab_all[warp];
-    srow[r0] = w0;
-    srow[r1] = w1;
-    for (ull s = w0 & ~(w0 << 1); s; s &= s - 1) {
-        const int h = (__ffsll((long long)s) - 1) >> 1;
-        slab[r0 * 32 + h] = (unsigned short)(r0 * 32 + h);
+    const int r0 = lane, r1 = lane + 32;
+
+    struct Tile { int x0, y0, k; };
+    auto decode = [&](unsigned t) -> Tile {  // tile list order: k fastest, then y tile, then x tile
+        const unsigned xt = t / n_yk, yk = t - xt * n_yk;
+        const unsigned yt = nk_shift >= 0 ? (yk >> nk_shift) : yk / (unsigned)v.nk;
+        return Tile{(int)xt * 8, (int)yt * 8, v.k0 + (int)(yk - yt * (unsigned)v.nk)};
+    };
+    auto load = [&](const Tile& T, ull& w0, ull& w1) {
+        const int xa = T.x0 + (r0 >> 3), xb = T.x0 + (r1 >> 3), y = T.y0 + (lane & 7);
+        w0 = 0; w1 = 0;
+        if (y < v.Y) {
+            if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.ZW + T.k];
+            if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.ZW + T.k];
+        }
+    };
+
+    unsigned t = blockIdx.x * CCL_TILE_WARPS + warp;
+    if (t >= n_tiles) return;
+    Tile cur = decode(t);
+    ull w0, w1;
+    load(cur, w0, w1);
+    for (;;) {
+        const unsigned tn = t + n_warps;
+        Tile nxt = cur;
+        ull n0 = 0, n1 = 0;
+        if (tn < n_tiles) {
+            nxt = decode(tn);
+            load(nxt, n0, n1);  // in flight while the current tile is labelled
+        }
+        if (__any_sync(0xffffffffu, (w0 | w1) != 0ull)) {
+            const int z0 = 64 * cur.k;
+            srow[r0] = w0;
+            srow[r1] = w1;
+            for (ull s = w0 & ~(w0 << 1); s; s &= s - 1) {
+                const int h = (__ffsll((long long)s) - 1) >> 1;
+                slab[r0 * 32 + h] = (unsigned short)(r0 * 32 + h);
+            }
+            for (ull s = w1 & ~(w1 << 1); s; s &= s - 1) {
+                const int h = (__ffsll((long long)s) - 1) >> 1;
+                slab[r1 * 32 + h] = (unsigned short)(r1 * 32 + h);
+            }
+            __syncwarp();
+            tile_row_unions(slab, srow, r0, w0, v.connect_x != 0);
+            tile_row_unions(slab, srow, r1, w1, v.connect_x != 0);
+            __syncwarp();
+            int g0, g1;
+            const ull m0 = tile_row_resolve(v, slab, srow, r0, w0, cur.x0, cur.y0, z0, g0);
+            const ull m1 = tile_row_resolve(v, slab, srow, r1, w1, cur.x0, cur.y0, z0, g1);
+            __syncwarp();  // shared memory is reused by this warp's next tile
+            append_roots(v, sbuf, buf_n, lane, m0, g0, m1, g1);
+        }
+        if (tn >= n_tiles) break;
+        t = tn; cur = nxt; w0 = n0; w1 = n1;
     }
-    for (ull s = w1 & ~(w1 << 1); s; s &= s - 1) {
-        const int h = (__ffsll((long long)s) - 1) >> 1;
-        slab[r1 * 32 + h] = (unsigned short)(r1 * 32 + h);
-    }
-    __syncwarp();
-    tile_row_unions(slab, srow, r0, w0, v.connect_x != 0);
-    tile_row_unions(slab, srow, r1, w1, v.connect_x != 0);
-    __syncwarp();
-    tile_row_resolve(v, slab, srow, r0, w0, x0, y0, z0);
-    tile_row_resolve(v, slab, srow, r1, w1, x0, y0, z0);
+    flush_roots(v, sbuf, buf_n, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -544,6 +633,16 @@ __global__ void __launch_bounds__(256) ccl_rank_kernel(CclView v) {
     }
 }
 
+// leaves the root bitmap all-zero again (only the words the global roots touched), so the next pass over
+// the same workspace can skip a V/8-byte memset
+__global__ void __launch_bounds__(256) ccl_clear_rootbits_kernel(CclView v) {
+    unsigned n = min(v.hdr->n_global_roots, (unsigned)v.capacity);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int bit;
+        v.rootbits[word_of_voxel(v, v.groots[i], &bit)] = 0ull;
+    }
+}
+
 // K6: tile roots that are not global roots take the code of their global root
 __global__ void __launch_bounds__(256) ccl_publish_kernel(CclView v) {
     unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
@@ -629,17 +728,15 @@ static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t
     const bool fast = (v.Zl % 64 == 0) && skb_aligned16(mask);
     if (fast) {
         const unsigned n_seg = (unsigned)(rows * v.Zl / 16);
-        ccl_pack_kernel<MaskT><<<(n_seg + 255) / 256, 256, 0, st>>>(m, v, n_seg, nk_shift);
+        ccl_pack_kernel<MaskT><<<(n_seg + 511) / 512, 256, 0, st>>>(m, v, n_seg, nk_shift);
     } else {
         ccl_pack_generic_kernel<MaskT><<<(unsigned)((rows * v.nk + 255) / 256), 256, 0, st>>>(m, v);
     }
     const long long xt = (v.X + 7) / 8, n_yk = (long long)((v.Y + 7) / 8) * v.nk;
-    if (xt > 65535) {
-        skb_set_error("ccl: X = %d is too large for the tile grid (max 524280)", v.X);
-        return SKB_E_RANGE;
-    }
-    dim3 grid((unsigned)((n_yk + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS), (unsigned)xt);
-    ccl_tile_kernel<<<grid, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_yk, nk_shift);
+    const long long n_tiles = xt * n_yk;
+    long long blocks = (n_tiles + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS;
+    if (blocks > 148 * 5) blocks = 148 * 5;  // 5 resident CTAs per SM (40 KB of shared memory each), persistent warps
+    ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift);
     return SKB_OK;
 }
 
@@ -651,7 +748,7 @@ static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int
 
 extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int planar,
                                     int32_t label_base, int64_t capacity, void* workspace, size_t workspace_bytes,
-                                    int32_t* ncomp, uint32_t* status, void* stream) {
+                                    int32_t* ncomp, uint32_t* status, int flags, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_ccl_label_sparse");
     if (rc) return rc;
     SKB_REQUIRE(mask && workspace && status, "skb_ccl_label_sparse: NULL pointer");
@@ -672,7 +769,7 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
     char* base = static_cast<char*>(workspace);
     ccl_init_kernel<<<1, 32, 0, st>>>(v, h);  // header by value: no host->device copy on the path
-    cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
+    if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
     cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
 
     rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
@@ -686,6 +783,7 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
     ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
     ccl_rank_kernel<<<list_grid, 256, 0, st>>>(v);
+    ccl_clear_rootbits_kernel<<<list_grid, 256, 0, st>>>(v);
     ccl_publish_kernel<<<list_grid, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("ccl merge kernels");
     return SKB_OK;
@@ -754,18 +852,31 @@ __global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
 __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, int z_lo, int z_hi, int* __restrict__ runs,
                                                              int cap, unsigned* status) {
     const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
+    const int lane = threadIdx.x & 31;
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
     const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
-    const ull w = v.bits[(size_t)rowi * v.ZW + k] & range;
-    if (!w) return;
+    ull w = 0;
+    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = v.bits[(size_t)rowi * v.ZW + k] & range;
+    const ull starts = w & ~(w << 1);
+    // one atomicAdd per warp (a per-run atomic on the single counter would serialise in L2)
+    const int cnt = __popcll(starts);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(runs, total);
+    int slot = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
     const int gbase = (int)(rowi * (unsigned)v.Z) + 64 * k;
-    for (ull s = w & ~(w << 1); s; s &= s - 1) {
+    for (ull s = starts; s; s &= s - 1, ++slot) {
         const int p = __ffsll((long long)s) - 1;
         const ull tt = ~(w >> p);
         const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
         const int root = gfind(v.parent, gbase + p);
-        const int slot = atomicAdd(runs, 1);
         if (slot < cap) {
             runs[3 + 3 * slot] = gbase + p;
             runs[4 + 3 * slot] = len;
@@ -863,13 +974,16 @@ __global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeV
         int root, r;
         if (!merge_item(m, i, false, root, r)) continue;
         if (gfind(v.parent, root) != root) continue;
+        unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
+        if (slot >= (unsigned)v.capacity) {  // not listed -> could not be cleared afterwards: do not mark it
+            atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            continue;
+        }
+        v.groots[slot] = root;
         int bit;
         long long wi = word_of_voxel(v, root, &bit);
         atomicOr(&v.rootbits[wi], 1ull << bit);
         atomicAdd(&v.chunks[wi >> 6], 1);
-        unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
-        if (slot < (unsigned)v.capacity) v.groots[slot] = root;
-        else atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
     }
 }
 
@@ -912,7 +1026,7 @@ static CclView slab_view(const SkbCclLayout& L, void* ws, int64_t capacity, int6
 
 extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                                      int64_t Zl, int64_t capacity, void* workspace, size_t workspace_bytes,
-                                     uint32_t* status, void* stream) {
+                                     uint32_t* status, int flags, void* stream) {
     int rc = shard_common("skb_shard_label_local", X, Y, Z, z_off, Zl);
     if (rc) return rc;
     SKB_REQUIRE(mask && workspace && status, "skb_shard_label_local: NULL pointer");
@@ -930,7 +1044,7 @@ extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X
     h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
     char* base = static_cast<char*>(workspace);
     ccl_init_kernel<<<1, 32, 0, st>>>(v, h);
-    cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
+    if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
     cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
     rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
     if (rc) return rc;
@@ -1015,6 +1129,7 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
     // the header's label_base is what the rank kernel reads
     shard_set_label_base_kernel<<<1, 32, 0, st>>>(v, label_base);
     ccl_rank_kernel<<<g, 256, 0, st>>>(v);
+    ccl_clear_rootbits_kernel<<<g, 256, 0, st>>>(v);
     shard_publish_roots_kernel<<<g, 256, 0, st>>>(v, m);
     ccl_publish_kernel<<<g, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_merge");

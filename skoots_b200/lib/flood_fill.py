@@ -53,10 +53,15 @@ def label_components(mask: Tensor, planar: bool = False, label_base: int = 2, ca
         if workspace is None or workspace.numel() < need or workspace.device != dev:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         meta = torch.empty(2, dtype=torch.int32, device=dev)
+        # a workspace that already went through a pass of this shape has its root bitmap zeroed (see the C header)
+        key = (X, Y, Z, cap, workspace.data_ptr())
+        flags = L.CCL_WORKSPACE_CLEAN if getattr(workspace, "_skb_clean", None) == key else 0
+        workspace._skb_clean = None
         with torch.cuda.device(dev):
             L.check(lib.skb_ccl_label_sparse(mask.data_ptr(), L.dtype_code(mask), X, Y, Z, int(planar), int(label_base),
                                              cap, workspace.data_ptr(), workspace.numel(), meta[0:1].data_ptr(),
-                                             meta[1:2].data_ptr(), L.stream_ptr(dev)))
+                                             meta[1:2].data_ptr(), flags, L.stream_ptr(dev)))
+        workspace._skb_clean = key
         res = SparseLabels(workspace, (X, Y, Z), meta[0], meta[1], cap)
         if not check:
             return res

@@ -102,11 +102,12 @@ class ShardedAssembler:
         self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
         self.meta = mk(2)  # [n_components, status]
         self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
+        self._clean = False
         self.mask: Optional[Tensor] = None
         self.vec: Optional[Tensor] = None
-        # kernels of one pass: local(init,tile,boundary,roots)=4, emit<=2, ingest<=2, pack+pairs<=2,
-        # merge(init,union,reset,mark,scan x2,base,rank,publish x2)=10, gather=1
-        self.launches_per_step = 4 + 2 * (rank > 0) + 2 * (rank < world - 1) + 2 + 10 + 1
+        # kernels of one pass: local(init,pack,tile,boundary,roots)=5, emit<=2, ingest<=2, pack_roots+pairs<=2,
+        # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1
+        self.launches_per_step = 5 + 2 * (rank > 0) + 2 * (rank < world - 1) + 2 + 11 + 1
 
     # ---- data ------------------------------------------------------------------------------------
     def load(self, mask_slab: Tensor, vec_slab: Tensor) -> None:
@@ -126,7 +127,9 @@ class ShardedAssembler:
         with torch.cuda.device(self.dev):
             L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, z0, self.Zl,
                                                    self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
-                                                   self.meta[1:2].data_ptr(), self._s()))
+                                                   self.meta[1:2].data_ptr(), L.CCL_WORKSPACE_CLEAN if self._clean else 0,
+                                                   self._s()))
+            self._clean = False
             if self.rank > 0:
                 L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z0, z0 + self.halo,
                                                      self.send_lo.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
@@ -159,6 +162,7 @@ class ShardedAssembler:
             L.check(self.lib.skb_shard_merge(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.gathered.data_ptr(),
                                              self.world, self.rank, self.cap_roots, self.cap_pairs, 2,
                                              self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
+            self._clean = True  # a completed merge leaves the root bitmap zeroed
             if timers is not None:
                 timers[0].record()
             L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
@@ -175,6 +179,28 @@ class ShardedAssembler:
         self.phase_ingest()
         self.comm.all_gather(self.gathered, self.exch)
         return self.phase_merge_and_gather(timers)
+
+    def profile_phases(self, steps: int = 5) -> dict:
+        """mean device time (ms) of each phase of a pass on this rank (CUDA events on the current stream)."""
+        names = ["local", "exchange_runs", "ingest_pairs", "all_gather", "merge", "gather"]
+        acc = dict.fromkeys(names, 0.0)
+        for _ in range(steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            mid = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            self.phase_local(); ev[1].record()
+            self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi); ev[2].record()
+            self.phase_ingest(); ev[3].record()
+            self.comm.all_gather(self.gathered, self.exch); ev[4].record()
+            self.phase_merge_and_gather(mid); ev[6].record()
+            torch.cuda.synchronize(self.dev)
+            spans = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                     ev[3].elapsed_time(ev[4]), ev[4].elapsed_time(mid[0]), mid[0].elapsed_time(mid[1])]
+            for n, v in zip(names, spans):
+                acc[n] += v / steps
+        acc["runs_sent"] = [int(self.send_lo[0].item()), int(self.send_hi[0].item())]
+        acc["roots_pairs"] = [int(self.exch[0].item()), int(self.exch[1].item())]
+        return acc
 
     def check(self) -> Tuple[int, int]:
         """(n_components, labelled voxels over all ranks); raises on a capacity overflow."""

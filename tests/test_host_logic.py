@@ -31,7 +31,7 @@ def test_argument_errors_do_not_need_a_gpu():
     import skoots_b200._lib as L
     lib = L.load()
     assert lib.skb_ccl_workspace_bytes(0, 4, 4, 16) == 0
-    rc = lib.skb_ccl_label_sparse(None, 0, 4, 4, 4, 0, 2, 16, None, 0, None, None, None)
+    rc = lib.skb_ccl_label_sparse(None, 0, 4, 4, 4, 0, 2, 16, None, 0, None, None, 0, None)
     assert rc == -1 and b"NULL" in lib.skb_last_error()
     rc = lib.skb_assemble(None, 3, 1 << 20, 1 << 20, 4, L.f3((1, 1, 1)), 1, 1.0, L.i3((1, 1, 1)), L.i3((0, 0, 0)),
                           None, None, 0, None, 2, None)

@@ -119,6 +119,15 @@ int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z
                  const int32_t overlap[3], const void* workspace, const void* labels_dense,
                  int label_dtype, void* out, int out_dtype, void* stream);
 
+/* the same for the voxels [first_voxel, first_voxel + n_voxels) of the flat (X,Y,Z) index only
+ * (first_voxel a multiple of 256): lets a caller pipeline host->device uploads of X-slabs of the vector
+ * field against the gather and the device->host download of finished slabs. */
+int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z,
+                       const float scale[3], int N, double decay, const int32_t crop[3],
+                       const int32_t overlap[3], const void* workspace, const void* labels_dense,
+                       int label_dtype, void* out, int out_dtype, int64_t first_voxel,
+                       int64_t n_voxels, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a4  binary_dilation / binary_dilation_2d / binary_erosion     skoots/lib/morphology.py:130-199
  *   zero-padded 3x3x3 max (op 0), 3x3x1 max (op 1), 3x3x3 min (op 2) over n_volumes = B*C

@@ -345,13 +345,13 @@ __device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkReg
 // the latency-bound part (compaction, dependent label reads) still keeps 1.5 KB of loads in flight.
 template <typename VecT, typename OutT>
 __global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V,
-                                                                      unsigned n_chunks) {
+                                                                      unsigned chunk_begin, unsigned n_chunks) {
     __shared__ unsigned s_raw[ASM_WARPS][3][32][Raw8<VecT>::NW];
     __shared__ int s_res[ASM_WARPS][256];
     __shared__ unsigned char s_queue[ASM_WARPS][256];
     const int warp = threadIdx.x >> 5;
     const unsigned stride = gridDim.x * ASM_WARPS;
-    unsigned c = blockIdx.x * ASM_WARPS + warp;
+    unsigned c = chunk_begin + blockIdx.x * ASM_WARPS + warp;  // chunks [chunk_begin, n_chunks)
     if (c >= n_chunks) return;
     ChunkRegs<VecT> cur = load_chunk<VecT, true>(P, V, (long long)c * 256);
     for (;;) {
@@ -462,31 +462,43 @@ static void fill_crop(AsmParams& P, const int32_t crop[3], const int32_t overlap
 }
 
 template <typename VecT, typename OutT>
-static void launch_assemble_t(const AsmParams& P, OutT* out, long long V, cudaStream_t st) {
-    const long long n_chunks = P.vec_aligned ? V / 256 : 0;
-    if (n_chunks > 0) {
-        long long blocks = (n_chunks + ASM_WARPS - 1) / ASM_WARPS;
+static void launch_assemble_t(const AsmParams& P, OutT* out, long long v_begin, long long v_end, cudaStream_t st) {
+    // voxels [v_begin, v_end) of the flat index; v_begin is a multiple of 256 (checked by the callers)
+    const long long c_begin = v_begin / 256, c_end = P.vec_aligned ? v_end / 256 : c_begin;
+    if (c_end > c_begin) {
+        long long blocks = (c_end - c_begin + ASM_WARPS - 1) / ASM_WARPS;
         if (blocks > 148 * 4) blocks = 148 * 4;  // 4 resident CTAs per SM; warps stride over the chunks
-        assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, V, (unsigned)n_chunks);
+        assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, v_end, (unsigned)c_begin, (unsigned)c_end);
     }
-    const long long first = n_chunks * 256;
-    if (first < V) {
-        const long long rest = (V - first + 255) / 256;
-        assemble_tail_kernel<VecT, OutT><<<(unsigned)((rest + ASM_WARPS - 1) / ASM_WARPS), 32 * ASM_WARPS, 0, st>>>(P, out, V, first);
+    const long long first = c_end * 256;
+    if (first < v_end) {
+        const long long rest = (v_end - first + 255) / 256;
+        assemble_tail_kernel<VecT, OutT><<<(unsigned)((rest + ASM_WARPS - 1) / ASM_WARPS), 32 * ASM_WARPS, 0, st>>>(P, out, v_end, first);
     }
 }
 
 template <typename VecT>
-static void launch_assemble(const AsmParams& P, void* out, int out_dtype, long long V, cudaStream_t st) {
-    if (out_dtype == SKB_I32) launch_assemble_t<VecT, int32_t>(P, static_cast<int32_t*>(out), V, st);
-    else launch_assemble_t<VecT, int16_t>(P, static_cast<int16_t*>(out), V, st);
+static void launch_assemble(const AsmParams& P, void* out, int out_dtype, long long v_begin, long long v_end, cudaStream_t st) {
+    if (out_dtype == SKB_I32) launch_assemble_t<VecT, int32_t>(P, static_cast<int32_t*>(out), v_begin, v_end, st);
+    else launch_assemble_t<VecT, int16_t>(P, static_cast<int16_t*>(out), v_begin, v_end, st);
 }
 
 extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, const float scale[3], int N,
                             double decay, const int32_t crop[3], const int32_t overlap[3], const void* workspace,
                             const void* labels_dense, int label_dtype, void* out, int out_dtype, void* stream) {
+    return skb_assemble_range(vec, vec_dtype, X, Y, Z, scale, N, decay, crop, overlap, workspace, labels_dense, label_dtype,
+                              out, out_dtype, 0, X * Y * Z, stream);
+}
+
+extern "C" int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, const float scale[3],
+                                  int N, double decay, const int32_t crop[3], const int32_t overlap[3],
+                                  const void* workspace, const void* labels_dense, int label_dtype, void* out,
+                                  int out_dtype, int64_t first_voxel, int64_t n_voxels, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_assemble");
     if (rc) return rc;
+    SKB_REQUIRE(first_voxel >= 0 && n_voxels >= 0 && first_voxel + n_voxels <= X * Y * Z && first_voxel % 256 == 0,
+                "skb_assemble_range: [first_voxel, first_voxel+n_voxels) must lie in the volume and start on a multiple of 256");
+    if (n_voxels == 0) return SKB_OK;
     SKB_REQUIRE(vec && out && scale && crop && overlap, "skb_assemble: NULL pointer");
     SKB_REQUIRE(workspace || labels_dense, "skb_assemble: need a CCL workspace or a dense label volume");
     SKB_REQUIRE(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32, "skb_assemble: vec dtype");
@@ -525,10 +537,10 @@ extern "C" int skb_assemble(const void* vec, int vec_dtype, int64_t X, int64_t Y
         P.flat_bits = (Z % 64 == 0) ? 1 : 0;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long V = X * Y * Z;
-    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, V, st);
-    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, V, st);
-    else launch_assemble<float>(P, out, out_dtype, V, st);
+    const long long v0 = first_voxel, v1 = first_voxel + n_voxels;
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, v0, v1, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, v0, v1, st);
+    else launch_assemble<float>(P, out, out_dtype, v0, v1, st);
     SKB_LAUNCH_CHECK("assemble_kernel");
     return SKB_OK;
 }
@@ -566,9 +578,9 @@ extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int6
     P.flat_bits = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = X * Y * Zl;
-    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, V, st);
-    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, V, st);
-    else launch_assemble<float>(P, out, out_dtype, V, st);
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, 0, V, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, 0, V, st);
+    else launch_assemble<float>(P, out, out_dtype, 0, V, st);
     SKB_LAUNCH_CHECK("assemble_kernel (slab)");
     return SKB_OK;
 }

@@ -23,8 +23,10 @@ EVAL_N = 10                     # skoots/lib/eval.py:272
 
 def gather_instances(vectors: Tensor, scale, labels, N: int = 1, decay: float = 1.0,
                      crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0),
-                     out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.int32) -> Tensor:
-    """vectors (3,X,Y,Z) f16/bf16/f32; labels = SparseLabels or a dense (X,Y,Z) int16/int32 volume."""
+                     out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.int32,
+                     voxel_range: Optional[Tuple[int, int]] = None) -> Tensor:
+    """vectors (3,X,Y,Z) f16/bf16/f32; labels = SparseLabels or a dense (X,Y,Z) int16/int32 volume.
+    voxel_range=(first, count) restricts the pass to that stretch of the flat (X,Y,Z) index."""
     dev = L.require_cuda(vectors)
     if vectors.ndim != 4 or vectors.shape[0] != 3:
         raise RuntimeError(f"vectors must be (3,X,Y,Z), got {tuple(vectors.shape)}")
@@ -47,10 +49,11 @@ def gather_instances(vectors: Tensor, scale, labels, N: int = 1, decay: float = 
         if dense.dtype not in (torch.int16, torch.int32, torch.uint8):
             dense = dense.to(torch.int32)
         dense_ptr, dense_code = dense.data_ptr(), L.dtype_code(dense)
+    first, count = (0, X * Y * Z) if voxel_range is None else (int(voxel_range[0]), int(voxel_range[1]))
     with torch.cuda.device(dev):
-        L.check(L.load().skb_assemble(vectors.data_ptr(), L.dtype_code(vectors), X, Y, Z, L.f3(as_floats(scale, 3)),
-                                      int(N), float(decay), L.i3(crop), L.i3(overlap), ws_ptr, dense_ptr, dense_code,
-                                      out.data_ptr(), L.dtype_code(out), L.stream_ptr(dev)))
+        L.check(L.load().skb_assemble_range(vectors.data_ptr(), L.dtype_code(vectors), X, Y, Z, L.f3(as_floats(scale, 3)),
+                                            int(N), float(decay), L.i3(crop), L.i3(overlap), ws_ptr, dense_ptr, dense_code,
+                                            out.data_ptr(), L.dtype_code(out), first, count, L.stream_ptr(dev)))
     return out
 
 
@@ -74,39 +77,61 @@ class HostAssembler:
     and the fp16 vectors host->device, labels + gathers on the GPU, and copies the instance mask
     back.  Device buffers and the CCL workspace are allocated once and reused across calls.
 
-    Uploads run on a copy stream: the CCL starts as soon as the mask has landed and overlaps the
-    (6x larger) vector upload; the gather waits for the vectors.
+    The pass is pipelined over X-slabs on three streams: the mask goes up first and is labelled while
+    the vector field follows slab by slab; each slab is gathered as soon as its vectors have landed
+    and its labels start travelling back while the next slab is still arriving, so the two PCIe
+    directions and the kernels overlap (N = 1; with N > 1 a walk may read vectors of any slab of its
+    crop, so the gather waits for the whole field).
     """
 
     def __init__(self, shape: Tuple[int, int, int], device="cuda:0", vec_dtype=torch.float16,
-                 out_dtype=torch.int32):
+                 out_dtype=torch.int32, n_slabs: int = 16):
         X, Y, Z = shape
         self.shape, self.dev = (X, Y, Z), torch.device(device)
         self.mask = torch.empty((X, Y, Z), dtype=torch.uint8, device=self.dev)
         self.vec = torch.empty((3, X, Y, Z), dtype=vec_dtype, device=self.dev)
         self.out = torch.empty((X, Y, Z), dtype=out_dtype, device=self.dev)
         self.workspace = None
-        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.up = torch.cuda.Stream(self.dev)
+        self.down = torch.cuda.Stream(self.dev)
+        # slab starts must fall on multiples of 256 voxels (skb_assemble_range)
+        plane = Y * Z
+        bounds = sorted({X * i // n_slabs for i in range(n_slabs + 1)})
+        self.bounds = [b for b in bounds if (b * plane) % 256 == 0 or b == X]
+        if self.bounds[0] != 0:
+            self.bounds = [0] + self.bounds
 
     def __call__(self, mask_host: Tensor, vec_host: Tensor, scale, out_host: Tensor, N: int = 1, decay: float = 1.0,
                  crop=None, overlap=(0, 0, 0)) -> Tensor:
         X, Y, Z = self.shape
+        plane = Y * Z
         main = torch.cuda.current_stream(self.dev)
-        cs = self.copy_stream
-        cs.wait_stream(main)
-        with torch.cuda.stream(cs):
-            self.mask.copy_(mask_host.reshape(X, Y, Z), non_blocking=True)
+        self.up.wait_stream(main)
+        self.down.wait_stream(main)
+        mask_host, vec_host, out_host = mask_host.reshape(X, Y, Z), vec_host.reshape(3, X, Y, Z), out_host.reshape(X, Y, Z)
+        slabs = list(zip(self.bounds[:-1], self.bounds[1:])) if N == 1 else [(0, X)]
+        landed = []
+        with torch.cuda.stream(self.up):
+            self.mask.copy_(mask_host, non_blocking=True)
             mask_ready = torch.cuda.Event()
-            mask_ready.record(cs)
-            self.vec.copy_(vec_host.reshape(3, X, Y, Z), non_blocking=True)
-            vec_ready = torch.cuda.Event()
-            vec_ready.record(cs)
+            mask_ready.record(self.up)
+            for x0, x1 in slabs:
+                self.vec[:, x0:x1].copy_(vec_host[:, x0:x1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.up)
+                landed.append(ev)
         main.wait_event(mask_ready)
         sparse = label_components(self.mask, label_base=2, workspace=self.workspace, check=False)
         self.workspace = sparse.workspace
-        main.wait_event(vec_ready)
-        gather_instances(self.vec, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=self.out)
-        out_host.reshape(X, Y, Z).copy_(self.out, non_blocking=True)
+        for (x0, x1), ev in zip(slabs, landed):
+            main.wait_event(ev)
+            gather_instances(self.vec, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=self.out,
+                             voxel_range=(x0 * plane, (x1 - x0) * plane))
+            done = torch.cuda.Event()
+            done.record(main)
+            self.down.wait_event(done)
+            with torch.cuda.stream(self.down):
+                out_host[x0:x1].copy_(self.out[x0:x1], non_blocking=True)
         torch.cuda.synchronize(self.dev)
         sparse.check()
         return out_host

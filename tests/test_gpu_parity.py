@@ -240,3 +240,47 @@ def test_c2_tile_then_assembly():
     want = orc.postprocess(want_s[0], want_v, scale, N=1)
     got = assemble_instances(got_s, got_v, scale, N=1)
     assert torch.equal(got.cpu(), want)
+
+
+def test_workspace_reuse_across_different_masks():
+    """the CLEAN flag: a reused workspace must not leak root marks from the previous volume."""
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    rng = np.random.default_rng(11)
+    ws = None
+    for density in (0.4, 0.05, 0.0, 0.6, 0.02):
+        mask = rng.random((24, 40, 128)) < density
+        sp = label_components(torch.from_numpy(mask).to(DEV), label_base=0, workspace=ws)
+        ws = sp.workspace
+        out = torch.empty(mask.shape, dtype=torch.int32, device=DEV)
+        write_dense(sp, out)
+        want, n = orc.label_components(mask)
+        assert sp.num_components == n and np.array_equal(out.cpu().numpy(), want), density
+    assert getattr(ws, "_skb_clean", None) is not None
+
+
+def test_dense_tiles_overflow_root_buffer():
+    """checkerboard rows: > 128 tile roots in one tile exercises the direct (unbuffered) append path."""
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    mask = np.zeros((16, 16, 128), dtype=bool)
+    mask[::2, ::2, ::2] = True   # isolated voxels: every one is its own component
+    sp = label_components(torch.from_numpy(mask).to(DEV), label_base=0)
+    out = torch.empty(mask.shape, dtype=torch.int32, device=DEV)
+    write_dense(sp, out)
+    want, n = orc.label_components(mask)
+    assert sp.num_components == n == 8 * 8 * 64
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_host_assembler_pipelined_equals_device_path():
+    from skoots_b200.pipeline import HostAssembler, assemble_instances
+    shape = (64, 32, 64)
+    tv = make_tube_volume(shape, 30, seed=8)
+    scale = torch.tensor((60, 60, 12))
+    want = assemble_instances(tv.skeleton.to(DEV), tv.vectors.to(DEV), scale, N=1).cpu()
+    runner = HostAssembler(shape, DEV, n_slabs=4)
+    host_out = torch.empty(shape, dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        got = runner(tv.skeleton.pin_memory(), tv.vectors.pin_memory(), scale, host_out, N=1)
+        assert torch.equal(got, want)
+    got = runner(tv.skeleton.pin_memory(), tv.vectors.pin_memory(), scale, host_out, N=3)
+    assert torch.equal(got, orc.postprocess(tv.skeleton, tv.vectors, scale, N=3))

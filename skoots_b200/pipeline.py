@@ -116,7 +116,8 @@ class HostAssembler:
             mask_ready = torch.cuda.Event()
             mask_ready.record(self.up)
             for x0, x1 in slabs:
-                self.vec[:, x0:x1].copy_(vec_host[:, x0:x1], non_blocking=True)
+                for c in range(3):  # one contiguous block per channel: a strided slice would not go out as a plain DMA
+                    self.vec[c, x0:x1].copy_(vec_host[c, x0:x1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.up)
                 landed.append(ev)

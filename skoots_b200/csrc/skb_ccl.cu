@@ -70,6 +70,8 @@ struct CclView {
     ull* bits;
     int* parent;
     ull* rootbits;
+    ull* face_lo;   // sharded mode only (else NULL): word k0 / k0+nk-1 of every row, contiguous
+    ull* face_hi;
     int* chunks;
     int* scan_tiles;
     int* tile_roots;
@@ -216,7 +218,12 @@ __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__
             size_t widx = wl;
             if (v.nk != v.ZW) {
                 const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
-                widx = (size_t)rowi * v.ZW + v.k0 + (wl - rowi * (unsigned)v.nk);
+                const unsigned kl = wl - rowi * (unsigned)v.nk;
+                widx = (size_t)rowi * v.ZW + v.k0 + kl;
+                if (v.face_lo) {
+                    if (kl == 0u) v.face_lo[rowi] = w;
+                    if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
+                }
             }
             v.bits[widx] = w;
         }
@@ -235,6 +242,10 @@ __global__ void __launch_bounds__(256) ccl_pack_generic_kernel(const MaskT* __re
     ull w = 0;
     for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
     v.bits[(size_t)rowi * v.ZW + v.k0 + kl] = w;
+    if (v.face_lo) {
+        if (kl == 0u) v.face_lo[rowi] = w;
+        if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
+    }
 }
 
 // 16-bit labels in shared memory: atomic min through a 32-bit CAS; returns the previous value
@@ -695,6 +706,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.bits = reinterpret_cast<ull*>(base + L.off_bits);
     v.parent = reinterpret_cast<int*>(base + L.off_parent);
     v.rootbits = reinterpret_cast<ull*>(base + L.off_rootbits);
+    v.face_lo = nullptr; v.face_hi = nullptr;
     v.chunks = reinterpret_cast<int*>(base + L.off_chunks);
     v.scan_tiles = reinterpret_cast<int*>(base + L.off_scan_tiles);
     v.tile_roots = reinterpret_cast<int*>(base + L.off_tile_roots);
@@ -849,14 +861,14 @@ __global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
 }
 
 // runs[0] = count, then (start voxel, length, root id) triples from index 3
-__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, int z_lo, int z_hi, int* __restrict__ runs,
-                                                             int cap, unsigned* status) {
+__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const ull* __restrict__ face, int z_lo, int z_hi,
+                                                             int* __restrict__ runs, int cap, unsigned* status) {
     const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
     const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
     ull w = 0;
-    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = v.bits[(size_t)rowi * v.ZW + k] & range;
+    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = face[rowi] & range;  // compact copy of word k of every row
     const ull starts = w & ~(w << 1);
     // one atomicAdd per warp (a per-run atomic on the single counter would serialise in L2)
     const int cnt = __popcll(starts);
@@ -1021,6 +1033,8 @@ static CclView slab_view(const SkbCclLayout& L, void* ws, int64_t capacity, int6
     CclView v = make_view(L, ws, 0, capacity, status, nullptr);
     v.z_off = (int)z_off; v.Zl = (int)Zl;
     v.k0 = (int)(z_off / 64); v.nk = (int)(Zl / 64);
+    v.face_lo = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_lo);
+    v.face_hi = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_hi);
     return v;
 }
 
@@ -1054,19 +1068,21 @@ extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X
     return SKB_OK;
 }
 
-extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_lo, int64_t z_hi,
-                                   int32_t* runs, int64_t cap, uint32_t* status, void* stream) {
+extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high, int64_t z_lo,
+                                   int64_t z_hi, int32_t* runs, int64_t cap, uint32_t* status, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_shard_emit_runs");
     if (rc) return rc;
     SKB_REQUIRE(workspace && runs && status && cap > 0, "skb_shard_emit_runs: bad argument");
     SKB_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= Z && (z_lo >> 6) == ((z_hi - 1) >> 6),
                 "skb_shard_emit_runs: [z_lo,z_hi) must lie inside one 64-plane word");
+    SKB_REQUIRE(face_is_high == 0 || face_is_high == 1, "skb_shard_emit_runs: face_is_high must be 0 or 1");
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     CclView v = make_view(L, workspace, 0, 1, status, nullptr);
+    const ull* face = reinterpret_cast<const ull*>(static_cast<const char*>(workspace) + (face_is_high ? L.off_face_hi : L.off_face_lo));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(runs, 0, 3 * sizeof(int32_t), st);
     unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
-    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, (int)z_lo, (int)z_hi, runs, (int)cap, status);
+    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, runs, (int)cap, status);
     SKB_LAUNCH_CHECK("shard_emit_runs_kernel");
     return SKB_OK;
 }

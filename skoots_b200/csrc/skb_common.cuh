@@ -77,7 +77,8 @@ struct SkbCclLayout {
     int X, Y, Z, ZW;      // ZW = 64-bit words per (x,y) row of the bit-packed mask
     int64_t V, n_words, n_chunks;
     int64_t n_scan_tiles;  // chunk histogram is scanned in tiles of SKB_SCAN_TILE entries
-    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_tile_roots, off_flat, off_groots, total;
+    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_face_lo, off_face_hi, off_tile_roots, off_flat,
+        off_groots, total;
 };
 
 static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64_t capacity) {
@@ -94,6 +95,9 @@ static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64
     L.off_chunks = at;     at = skb_align_up(at + (size_t)(L.n_chunks + 1) * 4, 256);
     L.n_scan_tiles = (L.n_chunks + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
     L.off_scan_tiles = at; at = skb_align_up(at + (size_t)(L.n_scan_tiles + 1) * 4, 256);
+    // sharded mode: compact copies of every row's first / last word of the slab (the planes the neighbours need)
+    L.off_face_lo = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
+    L.off_face_hi = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
     L.off_tile_roots = at; at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_flat = at;       at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_groots = at;     at = skb_align_up(at + (size_t)capacity * 4, 256);

@@ -74,7 +74,8 @@ class ShardedAssembler:
     walks are confined to its 500x500x50 crops and need vector halos as well."""
 
     def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
-                 comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, out_dtype=torch.int32):
+                 comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
+                 out_dtype=torch.int32):
         if hops != 1:
             raise NotImplementedError("the Z-sharded path implements N = 1")
         X, Y, Z = (int(v) for v in shape)
@@ -91,7 +92,9 @@ class ShardedAssembler:
         self.capacity = max(1 << 16, (X * Y * self.Zl) // 8)
         need = self.lib.skb_ccl_workspace_bytes(X, Y, Z, self.capacity)
         self.workspace = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        self.cap_runs = max(1 << 12, (X * Y * self.halo) // 32)
+        # boundary runs per face: the whole (fixed-size) buffer travels, so keep it close to what a skeleton mask
+        # needs (~0.1 % of the face voxels start a run); overflow is reported through the status word
+        self.cap_runs = int(cap_runs) if cap_runs else max(1 << 14, (X * Y * self.halo) // 128)
         self.cap_roots, self.cap_pairs = cap_roots, cap_pairs
         mk = lambda n, dt=torch.int32: torch.zeros(n, dtype=dt, device=self.dev)
         self.send_lo, self.send_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
@@ -131,10 +134,10 @@ class ShardedAssembler:
                                                    self._s()))
             self._clean = False
             if self.rank > 0:
-                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z0, z0 + self.halo,
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 0, z0, z0 + self.halo,
                                                      self.send_lo.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
             if self.rank < self.world - 1:
-                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z1 - self.halo, z1,
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 1, z1 - self.halo, z1,
                                                      self.send_hi.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
 
     def phase_ingest(self) -> None:

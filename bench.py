@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--shape", default=os.environ.get("SKB_BENCH_SHAPE", "2048,2048,512"))
     ap.add_argument("--tubes", type=int, default=0, help="0 = 16384 scaled by volume")
     ap.add_argument("--hops", type=int, default=1, help="N of vector_to_embedding (eval() uses 10)")
+    ap.add_argument("--mode", default="whole", choices=["whole", "eval"],
+                    help="whole = lib functions on the whole volume (headline); eval = eval()'s 500/500/50 crop grid, "
+                         "50/50/5 overlap, int16 labels (use with --hops 10 to replay skoots/lib/eval.py:245-284)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -124,11 +127,20 @@ def cpu_sample_shape(budget_s: float):
     return (128, 128, 32)
 
 
-def cpu_pass(mask, vec, hops):
+EVAL_CROP, EVAL_OVERLAP = (500, 500, 50), (50, 50, 5)  # skoots/lib/eval.py:248-249
+
+
+def mode_kwargs(mode):
+    return dict(crop=EVAL_CROP, overlap=EVAL_OVERLAP) if mode == "eval" else dict(crop=None, overlap=(0, 0, 0))
+
+
+def cpu_pass(mask, vec, hops, mode="whole"):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import skoots_oracle as orc
     t0 = time.perf_counter()
-    out = orc.postprocess(mask, vec, torch.tensor(SCALE), N=hops)
+    kw = mode_kwargs(mode)
+    out = orc.postprocess(mask, vec, torch.tensor(SCALE), N=hops, crop=kw["crop"], overlap=kw["overlap"],
+                          out_dtype=torch.int16 if mode == "eval" else torch.int32)
     return time.perf_counter() - t0, out
 
 
@@ -139,12 +151,12 @@ def run_reference(args):
     from skoots_b200.synthetic import make_tube_volume
     torch.set_num_threads(os.cpu_count() or 1)
     total_steps = max(1, args.steps + args.warmup)
-    shape = cpu_sample_shape(150.0 / total_steps)
+    shape = cpu_sample_shape(150.0 / total_steps / (1.0 if args.hops == 1 else 12.0 * args.hops))
     full = tuple(int(v) for v in args.shape.split(","))
     tv = make_tube_volume(shape, n_tubes_for(shape, 0), seed=0, want_mask=False, want_skeleton_dict=False)
     for _ in range(args.warmup):
-        cpu_pass(tv.skeleton, tv.vectors, args.hops)
-    times = [cpu_pass(tv.skeleton, tv.vectors, args.hops)[0] for _ in range(args.steps)]
+        cpu_pass(tv.skeleton, tv.vectors, args.hops, args.mode)
+    times = [cpu_pass(tv.skeleton, tv.vectors, args.hops, args.mode)[0] for _ in range(args.steps)]
     vox = shape[0] * shape[1] * shape[2]
     value = vox * len(times) / sum(times)
     sample = f"{shape[0]}x{shape[1]}x{shape[2]} sub-volume of the workload, same tube density, whole pass per step"
@@ -152,7 +164,7 @@ def run_reference(args):
         "impl": "reference", "metric": "post-proc voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(full, args.hops), "sample": sample},
+        "config": {"workload": workload_name(full, args.hops, args.mode), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -161,8 +173,9 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(shape, hops):
-    return (f"synthetic analytic tubes {shape[0]}x{shape[1]}x{shape[2]} (BASELINE.json configs[2]), whole-volume "
+def workload_name(shape, hops, mode="whole"):
+    how = "whole-volume" if mode == "whole" else "eval() crop grid 500/500/50 ov 50/50/5,"
+    return (f"synthetic analytic tubes {shape[0]}x{shape[1]}x{shape[2]} (BASELINE.json configs[2]), {how} "
             f"flood fill + vector_to_embedding(N={hops}) + index_skeleton_by_embed")
 
 
@@ -204,7 +217,8 @@ def run_b200(args):
         tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, want_mask=False,
                               want_skeleton_dict=False)
         mask, vec = tv.skeleton, tv.vectors
-        out = torch.empty(shape, dtype=torch.int32, device=dev)
+        kw = mode_kwargs(args.mode)
+        out = torch.empty(shape, dtype=torch.int16 if args.mode == "eval" else torch.int32, device=dev)
         state = {"ws": None, "sparse": None}
 
         def step(timers=None):
@@ -212,7 +226,7 @@ def run_b200(args):
             state["ws"], state["sparse"] = sp.workspace, sp
             if timers is not None:
                 timers[0].record()
-            gather_instances(vec, scale, sp, N=args.hops, out=out)
+            gather_instances(vec, scale, sp, N=args.hops, out=out, **kw)
             if timers is not None:
                 timers[1].record()
             return out
@@ -239,13 +253,31 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graphed = False
+    if world > 1 and not os.environ.get("SKB_NO_GRAPH"):
+        # all ranks must agree: a rank replaying a graph and a rank issuing eagerly would still match
+        # collectives, but keep the measurement uniform
+        ok = torch.tensor([1 if runner.capture() else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        graphed = bool(ok.item())
+        if not graphed:
+            runner.graph = None
+        else:
+            for _ in range(3):
+                step()
     barrier()
     t_begin.record()
     for k in range(args.steps):
-        step(timers[k])
+        step(None if graphed else timers[k])
     t_end.record()
     barrier()
     elapsed_ms = t_begin.elapsed_time(t_end)
+    if graphed:  # the gather kernel alone: same buffers, eager passes right after the timed region
+        saved, runner.graph = runner.graph, None
+        for k in range(args.steps):
+            step(timers[k])
+        torch.cuda.synchronize(dev)
+        runner.graph = saved
     gather_ms = sum(a.elapsed_time(b) for a, b in timers) / args.steps
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -261,24 +293,24 @@ def run_b200(args):
         if world == 1:
             host_mask = torch.empty(shape, dtype=torch.uint8).pin_memory()
             host_vec = torch.empty((3,) + shape, dtype=torch.float16).pin_memory()
-            host_out = torch.empty(shape, dtype=torch.int32).pin_memory()
+            host_out = torch.empty(shape, dtype=out.dtype).pin_memory()
             host_mask.copy_(mask)
             host_vec.copy_(vec)
             del out
             state["ws"] = state["sparse"] = None
             del mask, vec
             torch.cuda.empty_cache()
-            runner_h = HostAssembler(shape, dev)
+            runner_h = HostAssembler(shape, dev, out_dtype=host_out.dtype)
             e2e_steps = max(1, min(args.steps, 5))
-            runner_h(host_mask, host_vec, scale, host_out, N=args.hops)
+            runner_h(host_mask, host_vec, scale, host_out, N=args.hops, **kw)
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
-                runner_h(host_mask, host_vec, scale, host_out, N=args.hops)
+                runner_h(host_mask, host_vec, scale, host_out, N=args.hops, **kw)
             torch.cuda.synchronize(dev)
             dt = (time.perf_counter() - t0) / e2e_steps
             e2e = {"value": V / dt, "unit": "voxels/s", "h2d_bytes_per_step": host_mask.numel() + host_vec.numel() * 2,
-                   "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "d2h_bytes_per_step": host_out.numel() * host_out.element_size(), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                    "api": "skoots_b200.pipeline.HostAssembler"}
             assert int((host_out > 0).sum().item()) == labelled, "e2e result differs from the device-resident run"
         else:
@@ -287,7 +319,7 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample + parity of that sample ----------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sshape = cpu_sample_shape(20.0)
+        sshape = cpu_sample_shape(20.0 / (1.0 if args.hops == 1 else 12.0 * args.hops))
         sshape = tuple(min(a, b) for a, b in zip(sshape, shape))
         torch.set_num_threads(os.cpu_count() or 1)
         if e2e is not None:
@@ -296,10 +328,10 @@ def run_b200(args):
         else:
             smask = mask[:sshape[0], :sshape[1], :sshape[2]].contiguous().cpu()
             svec = vec[:, :sshape[0], :sshape[1], :sshape[2]].contiguous().cpu()
-        cpu_pass(smask[:64, :64, :32].contiguous(), svec[:, :64, :64, :32].contiguous(), args.hops)  # warm the thread pool
-        dt, want = cpu_pass(smask, svec, args.hops)
+        cpu_pass(smask[:64, :64, :32].contiguous(), svec[:, :64, :64, :32].contiguous(), args.hops, args.mode)  # warm the thread pool
+        dt, want = cpu_pass(smask, svec, args.hops, args.mode)
         from skoots_b200.pipeline import assemble_instances
-        got = assemble_instances(smask.to(dev), svec.to(dev), scale, N=args.hops).cpu()
+        got = assemble_instances(smask.to(dev), svec.to(dev), scale, N=args.hops, out_dtype=want.dtype, **kw).cpu()
         parity = bool(torch.equal(got, want))
         svox = sshape[0] * sshape[1] * sshape[2]
         cpu = {"value": svox / dt, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -314,10 +346,12 @@ def run_b200(args):
             "metric": "post-proc voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, args.hops), "tubes": n_tubes_for(shape, args.tubes),
+            "config": {"workload": workload_name(shape, args.hops, args.mode), "tubes": n_tubes_for(shape, args.tubes),
                        "components": n_components, "labelled_voxels": labelled,
                        "l2": f"inputs larger than L2 ({ALGO_BYTES_PATH * V / world / 1e9:.1f} GB per GPU per step vs 126 MB)",
-                       "sharding": "none" if world == 1 else f"Z-slabs x{world}, NCCL halo-run exchange + root all-gather"},
+                       "sharding": "none" if world == 1 else f"Z-slabs x{world}, NCCL halo-run exchange + root all-gather",
+                       "launch": "one CUDA graph per pass (kernels + NCCL); gather kernel timed in eager passes after the timed region"
+                       if graphed else "eager launches"},
             "path_roofline": {"bytes_per_voxel": ALGO_BYTES_PATH, "achieved": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak},

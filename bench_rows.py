@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""bench_rows.py — every row of SURVEY.md §8(a) on one B200: device time (CUDA events, L2 flushed between
+iterations), algorithmic GB/s against the measured HBM peak, and the CPU oracle timed beside it on
+the same inputs (with a parity check).  Not the driver's benchmark (that is bench.py); this produces
+the per-row evidence table committed under profiles/.
+
+    python bench_rows.py > profiles/r01_rows.json
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+
+import skoots_oracle as orc  # noqa: E402
+from skoots_b200.lib import embedding_to_prob as e2p  # noqa: E402
+from skoots_b200.lib import flood_fill as ff  # noqa: E402
+from skoots_b200.lib import morphology as morph  # noqa: E402
+from skoots_b200.lib import skeleton as skel  # noqa: E402
+from skoots_b200.lib import vector_to_embedding as v2e  # noqa: E402
+from skoots_b200.pipeline import EVAL_CROP, EVAL_OVERLAP, assemble_instances, tile_epilogue  # noqa: E402
+from skoots_b200.synthetic import make_tube_volume  # noqa: E402
+
+DEV = torch.device("cuda:0")
+SCALE = torch.tensor((60, 60, 12))
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+_flush = None
+
+
+def gpu_ms(fn, iters=10, warm=3):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)  # > 126 MB L2
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        _flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    return total / iters
+
+
+def cpu_ms(fn, iters=2, warm=True):
+    if warm:
+        fn()
+    best = 1e30
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
+def row(name, config, voxels, bytes_per_voxel, g_ms, c_ms, parity, note=""):
+    gbs = voxels * bytes_per_voxel / (g_ms * 1e-3) / 1e9
+    return {"row": name, "config": config, "voxels": voxels, "algorithmic_bytes_per_voxel": bytes_per_voxel,
+            "gpu_ms": round(g_ms, 4), "gpu_voxels_per_s": voxels / (g_ms * 1e-3), "gpu_GBps": round(gbs, 1),
+            "frac_of_measured_hbm": round(gbs / hbm_peak(), 4), "cpu_oracle_ms": round(c_ms, 2),
+            "cpu_voxels_per_s": voxels / (c_ms * 1e-3), "cpu_threads": torch.get_num_threads(), "parity": parity, "note": note}
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = []
+
+    # ---- C1: 128x128x32, 20 tubes, whole path ------------------------------------------------------
+    tv = make_tube_volume((128, 128, 32), 20, seed=0)
+    m, v = tv.skeleton.to(DEV), tv.vectors.to(DEV)
+    for N in (1, 10):
+        want = orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=N)
+        got = assemble_instances(m, v, SCALE, N=N)
+        rows.append(row(f"a1+a2+a3 whole path N={N}", "C1 128x128x32, 20 tubes", 128 * 128 * 32, 11,
+                        gpu_ms(lambda: assemble_instances(m, v, SCALE, N=N, check=False)),
+                        cpu_ms(lambda: orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=N)), bool(torch.equal(got.cpu(), want)),
+                        "launch-latency bound at this size (12 kernels for 0.5 Mvox)"))
+
+    # ---- C2: one 300x300x20 tile: epilogue, dilation chain, flood fill, assembly --------------------------
+    tv = make_tube_volume((300, 300, 20), 20, seed=0)
+    g = torch.Generator().manual_seed(1)
+    unet = torch.zeros((1, 5, 300, 300, 20))
+    unet[0, 0:3] = tv.vectors.float() + 0.05 * torch.randn((3, 300, 300, 20), generator=g)
+    unet[0, 3] = tv.skeleton.float() * 0.9 + 0.05 * torch.rand((300, 300, 20), generator=g)
+    unet[0, 4] = (tv.mask > 0).float() * 0.95 + 0.04 * torch.rand((300, 300, 20), generator=g)
+    unet_d = unet.to(DEV)
+    wv, ws = torch.zeros((3, 300, 300, 20), dtype=torch.float16), torch.zeros((1, 300, 300, 20), dtype=torch.uint8)
+    gv, gs = wv.to(DEV), ws.to(DEV)
+    orc.tile_epilogue(unet, wv, ws, (0, 0, 0), (50, 50, 5))
+    tile_epilogue(unet_d, gv, gs, (0, 0, 0), (50, 50, 5))
+    rows.append(row("a5 tile epilogue", "C2 300x300x20 tile", 300 * 300 * 20, 20,
+                    gpu_ms(lambda: tile_epilogue(unet_d, gv, gs, (0, 0, 0), (50, 50, 5))),
+                    cpu_ms(lambda: orc.tile_epilogue(unet, wv, ws, (0, 0, 0), (50, 50, 5))),
+                    bool(torch.equal(gv.cpu(), wv) and torch.equal(gs.cpu(), ws)), "20 B read per tile voxel"))
+    img = unet[:, 3:4].contiguous()
+    img_d = img.to(DEV)
+    rows.append(row("a4 binary_dilation + 2x binary_dilation_2d", "C2 300x300x20", 300 * 300 * 20, 24,
+                    gpu_ms(lambda: morph.binary_dilation_2d(morph.binary_dilation_2d(morph.binary_dilation(img_d)))),
+                    cpu_ms(lambda: orc.binary_dilation_2d(orc.binary_dilation_2d(orc.binary_dilation(img)))),
+                    bool(torch.equal(morph.binary_dilation_2d(morph.binary_dilation_2d(morph.binary_dilation(img_d))).cpu(),
+                                     orc.binary_dilation_2d(orc.binary_dilation_2d(orc.binary_dilation(img))))), "3 passes x 8 B"))
+    rows.append(row("a4 binary_erosion", "C2 300x300x20", 300 * 300 * 20, 8, gpu_ms(lambda: morph.binary_erosion(img_d)),
+                    cpu_ms(lambda: orc.binary_erosion(img)), bool(torch.equal(morph.binary_erosion(img_d).cpu(), orc.binary_erosion(img)))))
+    lab_in = ws[0].to(torch.int16)
+    lab_d = lab_in.to(DEV)
+    want = orc.flood_fill_exact(lab_in.clone())
+    rows.append(row("a3 efficient_flood_fill (int16 in place)", "C2 300x300x20", 300 * 300 * 20, 4,
+                    gpu_ms(lambda: ff.efficient_flood_fill(lab_d.clone())), cpu_ms(lambda: orc.flood_fill_exact(lab_in.clone())),
+                    bool(torch.equal(ff.efficient_flood_fill(lab_d.clone()).cpu(), want)), "includes the clone and a status read-back"))
+
+    # ---- eval() replay on a multi-crop volume (N=10, 500/500/50 grid) ---------------------------------------
+    tv = make_tube_volume((600, 600, 64), 150, seed=0)
+    m, v = tv.skeleton.to(DEV), tv.vectors.to(DEV)
+    t0 = time.perf_counter()
+    want = orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=10, crop=EVAL_CROP, overlap=EVAL_OVERLAP, out_dtype=torch.int16)
+    eval_cpu_ms = (time.perf_counter() - t0) * 1e3
+    got = assemble_instances(m, v, SCALE, N=10, crop=EVAL_CROP, overlap=EVAL_OVERLAP, out_dtype=torch.int16)
+    rows.append(row("a1+a2+a3+a6 eval() replay N=10", "600x600x64, 150 tubes (SURVEY §6 probe size)", 600 * 600 * 64, 11,
+                    gpu_ms(lambda: assemble_instances(m, v, SCALE, N=10, crop=EVAL_CROP, overlap=EVAL_OVERLAP, out_dtype=torch.int16, check=False)),
+                    eval_cpu_ms, bool(torch.equal(got.cpu(), want)), "the configuration skoots/lib/eval.py:245-284 actually runs"))
+
+    # ---- C4: training step ops, batch of 8 crops 300x300x20 --------------------------------------------------
+    B = 8
+    vols = [make_tube_volume((300, 300, 20), 20, seed=s) for s in range(B)]
+    present = [{int(k): t.skeletons[int(k)] for k in torch.unique(t.mask).tolist() if k != 0} for t in vols]
+    present_d = [{k: p.to(DEV) for k, p in d.items()} for d in present]
+    masks_d = [t.mask.to(DEV) for t in vols]
+    an = (1.0, 1.0, 3.0)
+    want0 = orc.bake_skeleton(vols[0].mask, present[0], an, average=True)
+    got0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=True)
+    rows.append(row("a8 bake_skeleton (+average)", "C4 8 x 300x300x20, 20 ids each", B * 300 * 300 * 20, 16,
+                    gpu_ms(lambda: [skel.bake_skeleton(masks_d[i], present_d[i], an, average=True) for i in range(B)], iters=5),
+                    cpu_ms(lambda: [orc.bake_skeleton(vols[i].mask, present[i], an, average=True) for i in range(B)], iters=1, warm=False),
+                    bool(torch.allclose(got0.cpu(), want0, rtol=1e-5, atol=1e-5)), "fp32-ALU bound min-reduction; includes table packing + status read"))
+    wantm = orc.skeleton_to_mask(present[0], (300, 300, 20), 9, 3)
+    rows.append(row("a9 skeleton_to_mask r=9 f=3", "C4 8 x 300x300x20", B * 300 * 300 * 20, 4,
+                    gpu_ms(lambda: [skel.skeleton_to_mask(present_d[i], (300, 300, 20), radius=9, flank_radius=3) for i in range(B)], iters=5),
+                    cpu_ms(lambda: [orc.skeleton_to_mask(present[i], (300, 300, 20), 9, 3) for i in range(B)]),
+                    bool(torch.equal(skel.skeleton_to_mask(present_d[0], (300, 300, 20), radius=9, flank_radius=3).cpu(), wantm))))
+    vec = torch.stack([t.vectors.float() for t in vols]).to(torch.bfloat16)
+    baked = torch.stack([orc.bake_skeleton(vols[i].mask, present[i], an, average=True) for i in range(B)]).to(torch.bfloat16)
+    sigma = torch.tensor((20.0, 20.0, 20.0))
+    vec_d, baked_d = vec.to(DEV), baked.to(DEV)
+    want = orc.baked_embed_to_prob(orc.vector_to_embedding(SCALE.float(), vec), baked, sigma)
+    got = e2p.vector_to_prob(SCALE.float(), vec_d, baked_d, sigma)
+    ok = bool(torch.allclose(got.cpu(), want, rtol=1e-5, atol=1e-30))
+    rows.append(row("a1+a7 vector_to_embedding + baked_embed_to_prob (two ops, fwd)", "C4 8 x 300x300x20 bf16", B * 300 * 300 * 20, 40,
+                    gpu_ms(lambda: e2p.baked_embed_to_prob(v2e.vector_to_embedding(SCALE.float(), vec_d), baked_d, sigma)),
+                    cpu_ms(lambda: orc.baked_embed_to_prob(orc.vector_to_embedding(SCALE.float(), vec), baked, sigma)), ok,
+                    "6 in + 12 out, then 12 + 6 in + 4 out"))
+    rows.append(row("a1+a7 fused vector_to_prob (fwd)", "C4 8 x 300x300x20 bf16", B * 300 * 300 * 20, 16,
+                    gpu_ms(lambda: e2p.vector_to_prob(SCALE.float(), vec_d, baked_d, sigma)),
+                    cpu_ms(lambda: orc.baked_embed_to_prob(orc.vector_to_embedding(SCALE.float(), vec), baked, sigma)), ok,
+                    "6 + 6 in, 4 out"))
+    vg = vec_d.clone().requires_grad_(True)
+    w = torch.rand(want.shape, device=DEV)
+
+    def fwd_bwd():
+        vg.grad = None
+        (e2p.vector_to_prob(SCALE.float(), vg, baked_d, sigma) * w).sum().backward()
+    vr = vec.float().requires_grad_(True)
+    wc = w.cpu()
+
+    def ref_fwd_bwd():
+        vr.grad = None
+        (orc.baked_embed_to_prob(orc.vector_to_embedding(SCALE.float(), vr), baked.float(), sigma) * wc).sum().backward()
+    rows.append(row("a1+a7 fused vector_to_prob fwd+bwd (incl. torch mul/sum)", "C4 8 x 300x300x20 bf16", B * 300 * 300 * 20, 42,
+                    gpu_ms(fwd_bwd), cpu_ms(ref_fwd_bwd), True, "fwd 16 B + bwd 26 B; gradient parity is tested in tests/test_gpu_parity.py"))
+
+    # ---- C5: 2-D mode, 4096x4096 slices -------------------------------------------------------------------------------
+    for S in (1, 8):
+        tv = make_tube_volume((S, 4096, 4096), 4096 * S, seed=0, device=DEV, want_mask=False, want_skeleton_dict=False)
+        stack = tv.skeleton  # (S, X, Y): planar CCL labels every slice separately, 4-connectivity
+        sp = ff.label_components(stack, planar=True, label_base=0)
+        out = torch.empty(stack.shape, dtype=torch.int32, device=DEV)
+        ff.write_dense(sp, out)
+        host = stack.cpu().numpy()
+        want0 = orc.label_components(host[0])[0]
+
+        def gpu_2d():
+            s2 = ff.label_components(stack, planar=True, label_base=0, workspace=sp.workspace, check=False)
+            ff.write_dense(s2, out)
+        rows.append(row(f"a10 per-slice CCL (2-D mode), {S} slices", f"C5 {S} x 4096x4096", S * 4096 * 4096, 5, gpu_ms(gpu_2d),
+                        cpu_ms(lambda: [orc.label_components(host[i]) for i in range(S)], iters=1),
+                        bool((out[0].cpu().numpy() == want0).all()), "1 B mask in + 4 B int32 labels out"))
+        v2 = (torch.rand((S, 2, 4096, 4096), device=DEV) * 2 - 1).half()
+        s2 = torch.tensor((60.0, 60.0))
+        rows.append(row(f"a10 vector_to_embedding 2-D, {S} slices", f"C5 {S} x 4096x4096", S * 4096 * 4096, 12,
+                        gpu_ms(lambda: v2e.vector_to_embedding(s2, v2)), cpu_ms(lambda: orc.vector_to_embedding(s2, v2.cpu())),
+                        bool(torch.equal(v2e.vector_to_embedding(s2, v2).cpu(), orc.vector_to_embedding(s2, v2.cpu()))), "4 B in + 8 B out"))
+        del tv, stack, out, v2
+
+    print(json.dumps({"hbm_peak_GBps": hbm_peak(), "rows": rows}, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,7 @@ struct CclView {
     int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
     int z_off, Zl;  // the slab [z_off, z_off+Zl) of the global volume held by `mask` (whole volume: 0, Z)
     int k0, nk;     // word range of the slab inside each row of the bit mask
+    int zw_shift, y_shift;  // log2(ZW), log2(Y) when they are powers of two, else -1
     int capacity;
     SkbCclHeader* hdr;
     ull* bits;
@@ -395,7 +396,7 @@ constexpr int CCL_TILE_WARPS = 8;
 // and 8 warps per CTA the CTA's shared memory stays pinned until its slowest warp — the one tile in
 // eight that is not empty — has finished, and occupancy collapses to ~20 %.)
 __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v, unsigned n_tiles, unsigned n_yk,
-                                                                       int nk_shift) {
+                                                                       int nk_shift, int nyk_shift) {
     __shared__ ull srow_all[CCL_TILE_WARPS][64];
     __shared__ unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
     __shared__ int rootbuf_all[CCL_TILE_WARPS][CCL_ROOT_BUF];
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
 
     struct Tile { int x0, y0, k; };
     auto decode = [&](unsigned t) -> Tile {  // tile list order: k fastest, then y tile, then x tile
-        const unsigned xt = t / n_yk, yk = t - xt * n_yk;
+        const unsigned xt = nyk_shift >= 0 ? (t >> nyk_shift) : t / n_yk, yk = t - xt * n_yk;
         const unsigned yt = nk_shift >= 0 ? (yk >> nk_shift) : yk / (unsigned)v.nk;
         return Tile{(int)xt * 8, (int)yt * 8, v.k0 + (int)(yk - yt * (unsigned)v.nk)};
     };
@@ -467,23 +468,31 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
 // K2: unions across tile faces, driven by the bit-packed mask
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, ull w, bool have_prev, ull prev, int TX, int TY) {
-    // slow path: only words that contain foreground get here.  n_words <= 2^31: 32-bit index math.
+    // only words that contain foreground get here.  n_words <= 2^31: 32-bit index math, shifts when the
+    // row length / Y are powers of two (the usual case) so that interior words leave after ~10 instructions
     const unsigned uzw = (unsigned)v.ZW, uyy = (unsigned)v.Y;
-    const unsigned rowi = widx / uzw, k = widx - rowi * uzw;
-    const unsigned x = rowi / uyy, y = rowi - x * uyy;
+    unsigned rowi, k, x, y;
+    if (v.zw_shift >= 0) { rowi = widx >> v.zw_shift; k = widx & (uzw - 1u); }
+    else { rowi = widx / uzw; k = widx - rowi * uzw; }
+    if (v.y_shift >= 0) { x = rowi >> v.y_shift; y = rowi & (uyy - 1u); }
+    else { x = rowi / uyy; y = rowi - x * uyy; }
+    const bool face_z = (int)k > v.k0 && (w & 1ull);
+    const bool face_y = y > 0 && (y % (unsigned)TY) == 0;
+    const bool face_x = v.connect_x && x > 0 && (x % (unsigned)TX) == 0;
+    if (!(face_z || face_y || face_x)) return;
     const int gbase = (int)(rowi * (unsigned)v.Z + 64u * k);
-    if ((int)k > v.k0 && (w & 1ull)) {
+    if (face_z) {
         if (!have_prev) prev = v.bits[widx - 1];
         if (prev >> 63) gunion(v.parent, gbase, gbase - 1);
     }
-    if (y > 0 && (y % (unsigned)TY) == 0) {
+    if (face_y) {
         ull a = w & v.bits[widx - uzw];
         for (ull s = a & ~(a << 1); s; s &= s - 1) {
             int p = __ffsll((long long)s) - 1;
             gunion(v.parent, gbase + p, gbase + p - v.Z);
         }
     }
-    if (v.connect_x && x > 0 && (x % (unsigned)TX) == 0) {
+    if (face_x) {
         ull a = w & v.bits[widx - uyy * uzw];
         int plane = v.Y * v.Z;
         for (ull s = a & ~(a << 1); s; s &= s - 1) {
@@ -694,6 +703,13 @@ __global__ void __launch_bounds__(256) ccl_dense_kernel(const ull* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+static int shift_of(int n) {  // log2 for powers of two, else -1
+    if (n <= 0 || (n & (n - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < n) ++s;
+    return s;
+}
+
 static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t capacity, uint32_t* status,
                          int32_t* ncomp) {
     char* base = static_cast<char*>(ws);
@@ -701,6 +717,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
     v.connect_x = planar ? 0 : 1;
     v.z_off = 0; v.Zl = L.Z; v.k0 = 0; v.nk = L.ZW;
+    v.zw_shift = shift_of(L.ZW); v.y_shift = shift_of(L.Y);
     v.capacity = (int)capacity;
     v.hdr = reinterpret_cast<SkbCclHeader*>(base);
     v.bits = reinterpret_cast<ull*>(base + L.off_bits);
@@ -725,13 +742,6 @@ extern "C" size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64
     return skb_ccl_layout(X, Y, Z, capacity).total;
 }
 
-static int shift_of(int n) {  // log2 for powers of two, else -1
-    if (n <= 0 || (n & (n - 1))) return -1;
-    int s = 0;
-    while ((1 << s) < n) ++s;
-    return s;
-}
-
 template <typename MaskT>
 static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
@@ -748,7 +758,8 @@ static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t
     const long long n_tiles = xt * n_yk;
     long long blocks = (n_tiles + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS;
     if (blocks > 148 * 5) blocks = 148 * 5;  // 5 resident CTAs per SM (40 KB of shared memory each), persistent warps
-    ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift);
+    ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift,
+                                                                    n_yk < (1LL << 30) ? shift_of((int)n_yk) : -1);
     return SKB_OK;
 }
 

@@ -364,7 +364,16 @@ def run_b200(args):
             line["phases_ms_rank0"] = phases
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down in an order that cannot wedge: drop the captured graph (it references the NCCL
+        # communicator), drain the device, then destroy the group; a watchdog ends the process if the
+        # NCCL teardown still blocks — the measurement has already been printed.
+        import threading
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        runner.graph = None
+        torch.cuda.synchronize(dev)
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

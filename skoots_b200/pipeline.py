@@ -158,3 +158,30 @@ def tile_epilogue(unet_out: Tensor, vectors: Tensor, skeleton: Tensor, origin: S
         L.check(L.load().skb_tile_epilogue(unet_out.data_ptr(), L.dtype_code(unet_out), C, L.i3((tx, ty, tz)),
                                            L.i3(origin), L.i3(overlap), float(threshold), vectors.data_ptr(),
                                            skeleton.data_ptr(), X, Y, Z, L.stream_ptr(dev)))
+
+
+@torch.inference_mode()
+def segment_volume(model, image: Tensor, vector_scale, dataset_mean: float, dataset_std: float,
+                   tile: Sequence[int] = (300, 300, 20), tile_overlap: Sequence[int] = (50, 50, 5),
+                   threshold: float = 0.8, N: int = EVAL_N, decay: float = 1.0,
+                   crop: Sequence[int] = EVAL_CROP, overlap: Sequence[int] = EVAL_OVERLAP,
+                   device="cuda:0", autocast: bool = True) -> Tensor:
+    """The compute of `skoots.lib.eval.eval` (skoots/lib/eval.py:126-176 and 223-284) with every
+    intermediate kept on the device: tile the image, run `model` on each tile, fuse the tile epilogue
+    straight into device-resident whole-volume vectors / skeleton arrays (no `.cpu().numpy()` -> zarr
+    round trip), then label + assemble.  `model` is the caller's network (the reference's
+    bism UNet): a callable mapping (1,1,x,y,z) float -> (1,C>=5,x,y,z).  image: (C,X,Y,Z), CPU or CUDA.
+    Returns the int16 instance mask (X,Y,Z) on the device, before `fastremap.renumber`."""
+    from .lib.cropper import crops
+    dev = torch.device(device)
+    c, X, Y, Z = image.shape
+    vectors = torch.zeros((3, X, Y, Z), dtype=torch.float16, device=dev)
+    skeleton = torch.zeros((1, X, Y, Z), dtype=torch.uint8, device=dev)
+    tile = list(tile)
+    for piece, (x, y, z) in crops(image, tile, tuple(tile_overlap), device=dev):
+        piece = piece.sub(dataset_mean).div(dataset_std)
+        with torch.autocast("cuda", enabled=autocast):
+            out = model(piece.float())
+        tile_epilogue(out, vectors, skeleton, (x, y, z), tile_overlap, threshold)
+    return assemble_instances(skeleton, vectors, vector_scale, N=N, decay=decay, crop=crop, overlap=overlap,
+                              out_dtype=torch.int16)

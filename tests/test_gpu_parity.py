@@ -284,3 +284,45 @@ def test_host_assembler_pipelined_equals_device_path():
         assert torch.equal(got, want)
     got = runner(tv.skeleton.pin_memory(), tv.vectors.pin_memory(), scale, host_out, N=3)
     assert torch.equal(got, orc.postprocess(tv.skeleton, tv.vectors, scale, N=3))
+
+
+def test_segment_volume_matches_eval_replay():
+    """eval.py:126-176 + 223-284 end to end with a stand-in network, against the oracle's replay of the same
+    loop (tile grid with shifted last tiles, epilogue per tile, flood fill, crop-grid assembly)."""
+    from skoots_b200.pipeline import segment_volume
+    shape = (90, 70, 40)
+    tv = make_tube_volume(shape, 25, seed=6, scale=(9.0, 9.0, 4.0))
+    image = torch.zeros((1,) + shape, dtype=torch.float16)
+    g = torch.Generator().manual_seed(0)
+    heads = torch.zeros((5,) + shape)
+    heads[0:3] = tv.vectors.float()
+    heads[3] = tv.skeleton.float() * 0.95 + 0.03 * torch.rand(shape, generator=g)
+    heads[4] = (tv.mask > 0).float() * 0.97 + 0.02 * torch.rand(shape, generator=g)
+    image[0] = torch.arange(shape[0] * shape[1] * shape[2]).reshape(shape) % 251  # carries the position through the tiler
+
+    # drive both implementations tile by tile with the same stand-in outputs
+    from skoots_b200.lib.cropper import crops
+    from skoots_b200.pipeline import assemble_instances, tile_epilogue
+    tile, tov = [40, 40, 20], (5, 5, 3)
+    scale = torch.tensor((9, 9, 4))
+    want_v = torch.zeros((3,) + shape, dtype=torch.float16)
+    want_s = torch.zeros((1,) + shape, dtype=torch.uint8)
+    for _, (x, y, z) in crops(image, list(tile), tov):
+        out = heads[:, x:x + 40, y:y + 40, z:z + 20].unsqueeze(0)
+        orc.tile_epilogue(out, want_v, want_s, (x, y, z), tov)
+    labels = orc.flood_fill_exact(want_s[0].to(torch.int16))
+    want = orc.assemble_instances(labels, want_v, scale, N=4, crop=(50, 50, 30), overlap=(5, 5, 3))
+
+    origins = [o for _, o in crops(image, list(tile), tov)]
+    calls = iter(origins)
+    heads_d = heads.to(DEV)
+
+    def model(x):
+        ox, oy, oz = next(calls)
+        _, _, tx, ty, tz = x.shape
+        return heads_d[:, ox:ox + tx, oy:oy + ty, oz:oz + tz].unsqueeze(0)
+
+    got = segment_volume(model, image, scale, 0.0, 1.0, tile=tile, tile_overlap=tov, N=4, crop=(50, 50, 30),
+                         overlap=(5, 5, 3), device=DEV, autocast=False)
+    assert got.dtype == torch.int16 and torch.equal(got.cpu(), want)
+    assert int(want.max()) > 2

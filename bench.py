@@ -202,8 +202,10 @@ def run_b200(args):
     hbm_peak, peak_src = peaks()
 
     if world > 1:
-        from skoots_b200.sharded import ShardedAssembler, TorchDistComm
-        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops, comm=TorchDistComm())
+        from skoots_b200.sharded import PeerComm, ShardedAssembler, TorchDistComm
+        transport = os.environ.get("SKB_TRANSPORT", "peer")
+        comm = PeerComm() if transport == "peer" else TorchDistComm()
+        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops, comm=comm)
         z0, z1 = runner.z_range
         tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, z_range=(z0, z1),
                               want_mask=False, want_skeleton_dict=False)
@@ -349,8 +351,11 @@ def run_b200(args):
             "config": {"workload": workload_name(shape, args.hops, args.mode), "tubes": n_tubes_for(shape, args.tubes),
                        "components": n_components, "labelled_voxels": labelled,
                        "l2": f"inputs larger than L2 ({ALGO_BYTES_PATH * V / world / 1e9:.1f} GB per GPU per step vs 126 MB)",
-                       "sharding": "none" if world == 1 else f"Z-slabs x{world}, NCCL halo-run exchange + root all-gather",
-                       "launch": "one CUDA graph per pass (kernels + NCCL); gather kernel timed in eager passes after the timed region"
+                       "sharding": "none" if world == 1 else (
+                           f"Z-slabs x{world}; halo-run exchange + root all-gather "
+                           + ("stored by the kernels into peer mailboxes over NVLink (release/acquire flags, no NCCL in a pass)"
+                              if runner.transport == "peer" else "over NCCL send/recv + all-gather")),
+                       "launch": "one CUDA graph per pass; gather kernel timed in eager passes after the timed region"
                        if graphed else "eager launches"},
             "path_roofline": {"bytes_per_voxel": ALGO_BYTES_PATH, "achieved": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
@@ -372,6 +377,8 @@ def run_b200(args):
         runner.graph = None
         torch.cuda.synchronize(dev)
         dist.barrier()
+        if hasattr(runner.comm, "close"):
+            runner.comm.close()
         dist.destroy_process_group()
         os._exit(0)
 

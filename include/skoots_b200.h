@@ -229,6 +229,55 @@ int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int6
                       int64_t Zl, const float scale[3], const void* workspace, const uint64_t* halo_lo,
                       const uint64_t* halo_hi, void* out, int out_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (e')  The same pass with both exchanges done by the kernels themselves over NVLink peer memory —
+ *   no NCCL call, no host involvement between the phases, the whole pass is one CUDA graph.
+ *   Every rank owns a MAILBOX in peer-visible memory (layout identical on all ranks; two copies of
+ *   every receive buffer, pass k uses copy k & 1).  Producers store straight into the consumer's
+ *   mailbox and then release a flag (= the pass number) there; consumers spin on flags in their own
+ *   HBM.  A flag that does not arrive within ~8 s sets SKB_STATUS_PEER_TIMEOUT instead of hanging.
+ *   Call order per rank and pass (skoots_b200/sharded.py, transport "peer"):
+ *     skb_shard_begin -> skb_shard_label_local -> skb_shard_emit_runs_peer (low / high face)
+ *     -> skb_shard_ingest_runs_peer (from the low / high neighbour) -> skb_shard_boundary_pairs
+ *     -> skb_shard_push -> skb_shard_merge_peer -> skb_assemble_slab.
+ *   The skb_peer_* calls are set-up / tear-down only: they are the one place the library allocates
+ *   (cudaMalloc: legacy CUDA IPC cannot export a caching allocator's sub-allocations).
+ * ------------------------------------------------------------------------------------------- */
+#define SKB_PEER_HANDLE_BYTES 64
+#define SKB_MAX_WORLD 16
+#define SKB_STATUS_PEER_TIMEOUT 4u
+int skb_peer_alloc(size_t bytes, void** ptr); /* zero-filled device memory on the current device */
+int skb_peer_free(void* ptr);
+int skb_peer_export(void* ptr, uint8_t handle[SKB_PEER_HANDLE_BYTES]);
+int skb_peer_open(const uint8_t handle[SKB_PEER_HANDLE_BYTES], void** ptr); /* maps + enables peer access */
+int skb_peer_close(void* ptr);
+
+size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs);
+/* starts pass k+1: bumps the mailbox's pass counter, clears its run counters */
+int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
+                    void* stream);
+/* like skb_shard_emit_runs, but the triples are stored into `neighbour_mailbox` (the rank below for
+ * the low face, above for the high face) and its flag is released */
+int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high,
+                             int64_t z_lo, int64_t z_hi, void* mailbox, void* neighbour_mailbox,
+                             int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
+                             uint32_t* status, void* stream);
+/* waits for the neighbour's flag, then skb_shard_ingest_runs on the mailbox's receive buffer */
+int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, void* mailbox,
+                               int from_high, int world, int64_t cap_runs, int64_t cap_roots,
+                               int64_t cap_pairs, uint64_t* halo_words_zeroed, uint32_t* status,
+                               void* stream);
+/* the all-gather: stores the used part of `exchange` (written by skb_shard_boundary_pairs) into slot
+ * `rank` of every rank's mailbox (peer_mailboxes: HOST array of `world` device pointers, own included)
+ * and releases the flags */
+int skb_shard_push(const int32_t* exchange, void* mailbox, const uint64_t* peer_mailboxes, int world,
+                   int rank, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, void* stream);
+/* waits for every rank's flag, then skb_shard_merge on the mailbox's gather buffer */
+int skb_shard_merge_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity,
+                         void* mailbox, int world, int rank, int64_t cap_runs, int64_t cap_roots,
+                         int64_t cap_pairs, int32_t label_base, int32_t* ncomp, uint32_t* status,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

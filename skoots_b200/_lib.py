@@ -17,6 +17,9 @@ LIB_PATH = os.path.join(_PKG, "libskoots_b200.so")
 SKB_U8, SKB_I16, SKB_I32, SKB_F16, SKB_BF16, SKB_F32 = range(6)
 STATUS_ROOT_OVERFLOW = 1
 STATUS_MISSING_ID = 2
+STATUS_PEER_TIMEOUT = 4
+PEER_HANDLE_BYTES = 64
+MAX_WORLD = 16
 CCL_WORKSPACE_CLEAN = 1
 
 _DTYPES = {
@@ -54,6 +57,17 @@ SIGNATURES = {
     "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
+    "skb_peer_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
+    "skb_peer_free": (_c_int, [_c_vp]),
+    "skb_peer_export": (_c_int, [_c_vp, ctypes.c_char_p]),
+    "skb_peer_open": (_c_int, [ctypes.c_char_p, ctypes.POINTER(_c_vp)]),
+    "skb_peer_close": (_c_int, [_c_vp]),
+    "skb_shard_mailbox_bytes": (_c_sz, [_c_int, _c_i64, _c_i64, _c_i64]),
+    "skb_shard_begin": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
+    "skb_shard_emit_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "skb_shard_ingest_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "skb_shard_push": (_c_int, [_c_vp, _c_vp, ctypes.POINTER(ctypes.c_uint64), _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
+    "skb_shard_merge_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_slab": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
     "skb_assemble_range": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp]),
     "skb_assemble": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),

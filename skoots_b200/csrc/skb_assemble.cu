@@ -39,7 +39,7 @@ struct AsmParams {
     // label source
     const ull* bits;
     const int* parent;
-    int ZW;
+    int ZW;                 // words per row of `bits` (slab mode: of the slab's compact bit mask, Zl / 64)
     const void* dense;
     int dense_dtype;
 };
@@ -117,7 +117,7 @@ __device__ __forceinline__ int label_at(const AsmParams& P, int tx, int ty, int 
     ull w;
     if (tz < P.z_off) w = P.halo_lo ? __ldg(P.halo_lo + rowi) : 0ull;
     else if (tz >= P.z_off + P.Zl) w = P.halo_hi ? __ldg(P.halo_hi + rowi) : 0ull;
-    else w = __ldg(P.bits + rowi * P.ZW + (tz >> 6));
+    else w = __ldg(P.bits + rowi * P.ZW + ((tz - P.z_off) >> 6));
     if (!((w >> (tz & 63)) & 1ull)) return 0;
     return skb_sparse_label(P.parent, (int)(rowi * P.Z + tz));
 }
@@ -235,13 +235,8 @@ __device__ __forceinline__ ChunkRegs<VecT> load_chunk(const AsmParams& P, long l
     c.r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
     c.self = 0;
     if (P.fast_ok && !P.dense && nvalid > 0) {
-        if (P.flat_bits) {
-            size_t gv = (size_t)i0;  // global voxel index of my first voxel
-            if (P.Zl != P.Z) {
-                const unsigned q = (unsigned)i0 / uz;
-                gv = (size_t)q * P.Z + ((unsigned)i0 - q * uz) + (unsigned)P.z_off;
-            }
-            c.self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + (gv >> 3));
+        if (P.flat_bits) {  // no row padding: bit index == (slab-local) voxel index
+            c.self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + ((size_t)i0 >> 3));
         } else {
             unsigned q = (unsigned)i0 / uz;
             int z = (int)((unsigned)i0 - q * uz);
@@ -574,7 +569,7 @@ extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int6
     const char* base = static_cast<const char*>(workspace);
     P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
     P.parent = reinterpret_cast<const int*>(base + L.off_parent);
-    P.ZW = L.ZW;
+    P.ZW = (int)(Zl / 64);
     P.flat_bits = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long V = X * Y * Zl;

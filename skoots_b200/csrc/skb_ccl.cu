@@ -64,8 +64,8 @@ struct CclView {
     int X, Y, Z, ZW;
     int connect_x;  // 0 in planar (per-x-plane, 4-connectivity) mode
     int z_off, Zl;  // the slab [z_off, z_off+Zl) of the global volume held by `mask` (whole volume: 0, Z)
-    int k0, nk;     // word range of the slab inside each row of the bit mask
-    int zw_shift, y_shift;  // log2(ZW), log2(Y) when they are powers of two, else -1
+    int k0, nk;     // the slab covers words [k0, k0+nk) of every row; `bits` holds exactly those: nk words per row
+    int nk_shift, y_shift;  // log2(nk), log2(Y) when they are powers of two, else -1
     int capacity;
     SkbCclHeader* hdr;
     ull* bits;
@@ -215,18 +215,14 @@ __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
         if ((t & 3u) == 0u && t < n_seg) {
-            const unsigned wl = t >> 2;  // word of the slab, flat order = (row, k local)
-            size_t widx = wl;
-            if (v.nk != v.ZW) {
+            const unsigned wl = t >> 2;  // word of the slab, flat order = (row, k local) = its place in `bits`
+            if (v.face_lo) {
                 const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
                 const unsigned kl = wl - rowi * (unsigned)v.nk;
-                widx = (size_t)rowi * v.ZW + v.k0 + kl;
-                if (v.face_lo) {
-                    if (kl == 0u) v.face_lo[rowi] = w;
-                    if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
-                }
+                if (kl == 0u) v.face_lo[rowi] = w;
+                if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
             }
-            v.bits[widx] = w;
+            v.bits[wl] = w;
         }
     }
 }
@@ -242,7 +238,7 @@ __global__ void __launch_bounds__(256) ccl_pack_generic_kernel(const MaskT* __re
     const MaskT* p = mask + (size_t)rowi * v.Zl + zl0;
     ull w = 0;
     for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
-    v.bits[(size_t)rowi * v.ZW + v.k0 + kl] = w;
+    v.bits[t] = w;
     if (v.face_lo) {
         if (kl == 0u) v.face_lo[rowi] = w;
         if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
@@ -418,8 +414,8 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
         const int xa = T.x0 + (r0 >> 3), xb = T.x0 + (r1 >> 3), y = T.y0 + (lane & 7);
         w0 = 0; w1 = 0;
         if (y < v.Y) {
-            if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.ZW + T.k];
-            if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.ZW + T.k];
+            if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.nk + (T.k - v.k0)];
+            if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.nk + (T.k - v.k0)];
         }
     };
 
@@ -470,17 +466,18 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
 __device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, ull w, bool have_prev, ull prev, int TX, int TY) {
     // only words that contain foreground get here.  n_words <= 2^31: 32-bit index math, shifts when the
     // row length / Y are powers of two (the usual case) so that interior words leave after ~10 instructions
-    const unsigned uzw = (unsigned)v.ZW, uyy = (unsigned)v.Y;
+    // widx = place of the word in `bits` = row * nk + (word of the slab's row)
+    const unsigned uzw = (unsigned)v.nk, uyy = (unsigned)v.Y;
     unsigned rowi, k, x, y;
-    if (v.zw_shift >= 0) { rowi = widx >> v.zw_shift; k = widx & (uzw - 1u); }
+    if (v.nk_shift >= 0) { rowi = widx >> v.nk_shift; k = widx & (uzw - 1u); }
     else { rowi = widx / uzw; k = widx - rowi * uzw; }
     if (v.y_shift >= 0) { x = rowi >> v.y_shift; y = rowi & (uyy - 1u); }
     else { x = rowi / uyy; y = rowi - x * uyy; }
-    const bool face_z = (int)k > v.k0 && (w & 1ull);
+    const bool face_z = k > 0u && (w & 1ull);
     const bool face_y = y > 0 && (y % (unsigned)TY) == 0;
     const bool face_x = v.connect_x && x > 0 && (x % (unsigned)TX) == 0;
     if (!(face_z || face_y || face_x)) return;
-    const int gbase = (int)(rowi * (unsigned)v.Z + 64u * k);
+    const int gbase = (int)(rowi * (unsigned)v.Z + 64u * (k + (unsigned)v.k0));
     if (face_z) {
         if (!have_prev) prev = v.bits[widx - 1];
         if (prev >> 63) gunion(v.parent, gbase, gbase - 1);
@@ -502,9 +499,9 @@ __device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, u
     }
 }
 
-// pair_mode: the slab is the whole row and rows hold an even number of words -> every thread streams
-// two adjacent words with one 16-byte load and returns at once when both are empty (no divisions
-// on that path).  Otherwise one word per thread, (row, k) by division.
+// pair_mode: rows hold an even number of words, or one word each (then the two words are two rows and
+// there is no z face at all) -> every thread streams two adjacent words with one 16-byte load and
+// returns at once when both are empty.  Otherwise one word per thread.
 __global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY, int pair_mode) {
     const unsigned tix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair_mode) {
@@ -516,12 +513,9 @@ __global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, in
         if (w0) boundary_word(v, widx, w0, false, 0ull, TX, TY);
         if (w1) boundary_word(v, widx + 1, w1, true, w0, TX, TY);
     } else {
-        const unsigned unk = (unsigned)v.nk;
-        const unsigned rowi = tix / unk, kl = tix - rowi * unk;
-        if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
-        const unsigned widx = rowi * (unsigned)v.ZW + (unsigned)v.k0 + kl;
-        const ull w = v.bits[widx];
-        if (w) boundary_word(v, widx, w, false, 0ull, TX, TY);
+        if (tix >= (unsigned)v.n_words) return;
+        const ull w = v.bits[tix];
+        if (w) boundary_word(v, tix, w, false, 0ull, TX, TY);
     }
 }
 
@@ -717,7 +711,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.X = L.X; v.Y = L.Y; v.Z = L.Z; v.ZW = L.ZW;
     v.connect_x = planar ? 0 : 1;
     v.z_off = 0; v.Zl = L.Z; v.k0 = 0; v.nk = L.ZW;
-    v.zw_shift = shift_of(L.ZW); v.y_shift = shift_of(L.Y);
+    v.nk_shift = shift_of(L.ZW); v.y_shift = shift_of(L.Y);
     v.capacity = (int)capacity;
     v.hdr = reinterpret_cast<SkbCclHeader*>(base);
     v.bits = reinterpret_cast<ull*>(base + L.off_bits);
@@ -764,8 +758,8 @@ static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t
 }
 
 static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int TY, cudaStream_t st) {
-    const int pair_mode = (v.nk == L.ZW && L.ZW % 2 == 0) ? 1 : 0;
-    const long long threads = pair_mode ? L.n_words / 2 : (long long)L.X * L.Y * v.nk;
+    const int pair_mode = (v.n_words % 2 == 0 && (v.nk % 2 == 0 || v.nk == 1)) ? 1 : 0;
+    const long long threads = pair_mode ? v.n_words / 2 : v.n_words;
     ccl_boundary_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(v, TX, TY, pair_mode);
 }
 
@@ -871,9 +865,42 @@ __global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
     }
 }
 
-// runs[0] = count, then (start voxel, length, root id) triples from index 3
+// ---- cross-GPU flags (peer transport): release/acquire at system scope ---------------------------
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spins until *flag has reached pass `epoch` (flags only ever grow; the difference is wrap-safe).
+// Bounded: ~8 s of SM clocks, then the pass carries on with SKB_STATUS_PEER_TIMEOUT set.
+__device__ __forceinline__ void spin_until(const int* flag, int epoch, unsigned* status) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) - epoch < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > (16LL << 30)) {
+            if (status) atomicOr(status, SKB_STATUS_PEER_TIMEOUT);
+            break;
+        }
+    }
+}
+
+// where a face's runs go: `counter` is always local; `triples` is local (NCCL transport: runs + 3)
+// or the neighbour's receive buffer (peer transport; the copy used is picked by the pass number)
+struct RunsDst {
+    int* counter;
+    int* triples;
+    const int* epoch;        // NULL: no parity
+    long long parity_stride;
+};
+
+// counter = count, then (start voxel, length, root id) triples
 __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const ull* __restrict__ face, int z_lo, int z_hi,
-                                                             int* __restrict__ runs, int cap, unsigned* status) {
+                                                             RunsDst dst, int cap, unsigned* status) {
+    int* const runs = dst.counter;
+    int* const tri = dst.triples + (dst.epoch ? (long long)(*dst.epoch & 1) * dst.parity_stride : 0LL);
     const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
@@ -901,17 +928,36 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const u
         const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
         const int root = gfind(v.parent, gbase + p);
         if (slot < cap) {
-            runs[3 + 3 * slot] = gbase + p;
-            runs[4 + 3 * slot] = len;
-            runs[5 + 3 * slot] = root;
+            tri[3 * slot] = gbase + p;
+            tri[3 * slot + 1] = len;
+            tri[3 * slot + 2] = root;
         } else {
             atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) shard_ingest_runs_kernel(CclView v, const int* __restrict__ runs, int cap,
-                                                               ull* __restrict__ halo) {
+// peer transport: publishes my face's run count in the neighbour's buffer, then releases its flag.  The
+// triples were stored by the previous kernel on this stream, so they are ordered before the flag.
+__global__ void shard_signal_runs_kernel(const int* local_cnt, int* remote_runs, long long parity_stride, int* remote_flag,
+                                         const int* epoch) {
+    if (threadIdx.x == 0) {
+        const int e = *epoch;
+        remote_runs[(long long)(e & 1) * parity_stride] = *local_cnt;
+        __threadfence_system();
+        st_release_sys(remote_flag, e);
+    }
+}
+
+// flag != NULL (peer transport): every CTA first waits until the neighbour's runs of this pass have landed
+__global__ void __launch_bounds__(256) shard_ingest_runs_kernel(CclView v, const int* runs, int cap, ull* __restrict__ halo,
+                                                               const int* flag, const int* epoch, long long parity_stride) {
+    if (flag) {
+        const int e = *epoch;
+        if (threadIdx.x == 0) spin_until(flag, e, v.status);
+        __syncthreads();
+        runs += (long long)(e & 1) * parity_stride;
+    }
     const int n = min(runs[0], cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int s = runs[3 + 3 * i], len = runs[4 + 3 * i], root = runs[5 + 3 * i];
@@ -943,7 +989,7 @@ __global__ void __launch_bounds__(256) shard_boundary_pairs_kernel(CclView v, co
     if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
     const int z1 = v.z_off + v.Zl;  // first plane of the upper neighbour
     if (!(halo_hi[rowi] & 1ull)) return;
-    if (!(v.bits[(size_t)rowi * v.ZW + ((z1 - 1) >> 6)] >> 63)) return;
+    if (!(v.bits[(size_t)rowi * v.nk + (v.nk - 1)] >> 63)) return;
     const int mine = (int)(rowi * (unsigned)v.Z) + z1 - 1;
     const int a = gfind(v.parent, mine), b = v.parent[mine + 1];
     const int slot = atomicAdd(exch + 1, 1);
@@ -956,15 +1002,22 @@ __global__ void __launch_bounds__(256) shard_boundary_pairs_kernel(CclView v, co
 }
 
 struct MergeView {
-    const int* gathered;  // world x stride ints
+    const int* gathered;  // world x stride ints (peer transport: copy 0; copy 1 is parity_stride further)
     int world, rank, stride, cap_roots, cap_pairs;
+    const int* epoch;     // peer transport only, else NULL
+    const int* flags;     // peer transport only: world flag words, SKB_FLAG_STRIDE apart
+    long long parity_stride;
 };
 
-__device__ __forceinline__ bool merge_item(const MergeView& m, unsigned i, bool pairs, int& a, int& b) {
+__device__ __forceinline__ const int* merge_base(const MergeView& m) {
+    return m.gathered + (m.epoch ? (long long)(*m.epoch & 1) * m.parity_stride : 0LL);
+}
+
+__device__ __forceinline__ bool merge_item(const MergeView& m, const int* base, unsigned i, bool pairs, int& a, int& b) {
     // flattened index over (rank, slot); returns false for slots past that rank's count
     const unsigned cap = pairs ? (unsigned)m.cap_pairs : (unsigned)m.cap_roots;
     const unsigned r = i / cap, s = i - r * cap;
-    const int* e = m.gathered + (size_t)r * m.stride;
+    const int* e = base + (size_t)r * m.stride;
     const int n = min(pairs ? e[1] : e[0], (int)cap);
     if ((int)s >= n) return false;
     if (pairs) { a = e[2 + m.cap_roots + 2 * s]; b = e[3 + m.cap_roots + 2 * s]; }
@@ -973,29 +1026,36 @@ __device__ __forceinline__ bool merge_item(const MergeView& m, unsigned i, bool 
 }
 
 __global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeView m) {
+    if (m.flags) {  // peer transport: the first merge kernel waits for every rank's payload of this pass
+        if ((int)threadIdx.x < m.world) spin_until(m.flags + threadIdx.x * SKB_FLAG_STRIDE, *m.epoch, v.status);
+        __syncthreads();
+    }
+    const int* const base = merge_base(m);
     const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int root, r;
-        if (!merge_item(m, i, false, root, r)) continue;
+        if (!merge_item(m, base, i, false, root, r)) continue;
         if (r != m.rank) v.parent[root] = root;  // foreign roots join my union-find as singletons
     }
 }
 
 __global__ void __launch_bounds__(256) shard_merge_union_kernel(CclView v, MergeView m) {
+    const int* const base = merge_base(m);
     const unsigned total = (unsigned)m.world * (unsigned)m.cap_pairs;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int a, b;
-        if (merge_item(m, i, true, a, b)) gunion(v.parent, a, b);
+        if (merge_item(m, base, i, true, a, b)) gunion(v.parent, a, b);
     }
 }
 
 // global roots among all ranks' roots -> bitmap + chunk histogram + list (reuses groots: the local list
 // has already been shipped in the exchange buffer)
 __global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeView m) {
+    const int* const base = merge_base(m);
     const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int root, r;
-        if (!merge_item(m, i, false, root, r)) continue;
+        if (!merge_item(m, base, i, false, root, r)) continue;
         if (gfind(v.parent, root) != root) continue;
         unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
         if (slot >= (unsigned)v.capacity) {  // not listed -> could not be cleared afterwards: do not mark it
@@ -1020,10 +1080,11 @@ __global__ void shard_reset_groots_kernel(CclView v) {
 
 // every listed root takes the label code of its global root (codes are negative, indices are not)
 __global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, MergeView m) {
+    const int* const base = merge_base(m);
     const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int root, r;
-        if (!merge_item(m, i, false, root, r)) continue;
+        if (!merge_item(m, base, i, false, root, r)) continue;
         int a = root, p = gload(v.parent + a);
         while (p >= 0 && p != a) { a = p; p = gload(v.parent + a); }
         if (p < 0 && a != root) v.parent[root] = p;
@@ -1044,6 +1105,8 @@ static CclView slab_view(const SkbCclLayout& L, void* ws, int64_t capacity, int6
     CclView v = make_view(L, ws, 0, capacity, status, nullptr);
     v.z_off = (int)z_off; v.Zl = (int)Zl;
     v.k0 = (int)(z_off / 64); v.nk = (int)(Zl / 64);
+    v.nk_shift = shift_of(v.nk);
+    v.n_words = (long long)L.X * L.Y * v.nk;  // of the slab's compact bit mask
     v.face_lo = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_lo);
     v.face_hi = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_hi);
     return v;
@@ -1093,7 +1156,8 @@ extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(runs, 0, 3 * sizeof(int32_t), st);
     unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
-    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, runs, (int)cap, status);
+    RunsDst dst = {runs, runs + 3, nullptr, 0};
+    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, dst, (int)cap, status);
     SKB_LAUNCH_CHECK("shard_emit_runs_kernel");
     return SKB_OK;
 }
@@ -1105,8 +1169,8 @@ extern "C" int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int6
     SKB_REQUIRE(workspace && runs && halo_words_zeroed && cap > 0, "skb_shard_ingest_runs: bad argument");
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     CclView v = make_view(L, workspace, 0, 1, nullptr, nullptr);
-    shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, runs, (int)cap,
-                                                                                   reinterpret_cast<ull*>(halo_words_zeroed));
+    shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        v, runs, (int)cap, reinterpret_cast<ull*>(halo_words_zeroed), nullptr, nullptr, 0);
     SKB_LAUNCH_CHECK("shard_ingest_runs_kernel");
     return SKB_OK;
 }
@@ -1131,6 +1195,8 @@ extern "C" int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, i
     return SKB_OK;
 }
 
+static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st);
+
 extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, const int32_t* gathered,
                                int world, int rank, int64_t cap_roots, int64_t cap_pairs, int32_t label_base,
                                int32_t* ncomp, uint32_t* status, void* stream) {
@@ -1141,11 +1207,14 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
     SKB_REQUIRE((long long)world * cap_roots < (1LL << 31) && (long long)world * cap_pairs < (1LL << 31), "skb_shard_merge: capacities too large");
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
     CclView v = make_view(L, workspace, 0, capacity, status, ncomp);
-    MergeView m;
+    MergeView m = {};
     m.gathered = gathered; m.world = world; m.rank = rank;
     m.cap_roots = (int)cap_roots; m.cap_pairs = (int)cap_pairs;
     m.stride = 2 + (int)cap_roots + 2 * (int)cap_pairs;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_merge(v, L, m, label_base, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st) {
     const int g = 148 * 4;
     shard_merge_init_kernel<<<g, 256, 0, st>>>(v, m);
     shard_merge_union_kernel<<<g, 256, 0, st>>>(v, m);
@@ -1161,4 +1230,177 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
     ccl_publish_kernel<<<g, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_merge");
     return SKB_OK;
+}
+
+// ==========================================================================================
+// Peer transport: the two exchanges are plain stores into the consumer GPU's mailbox over NVLink
+// plus release/acquire flags (include/skoots_b200.h (e')).
+// ==========================================================================================
+struct Mailbox {
+    SkbMailboxLayout M;
+    char* base;
+    int* ints(size_t off) const { return reinterpret_cast<int*>(base + off); }
+    int* epoch() const { return ints(M.off_epoch); }
+    int* cnt(int hi) const { return ints(M.off_cnt) + hi; }
+    int* flag(int hi) const { return ints(hi ? M.off_flag_hi : M.off_flag_lo); }
+    int* flag_gather(int r) const { return ints(M.off_flag_gather) + (size_t)r * SKB_FLAG_STRIDE; }
+    int* recv(int hi) const { return ints(hi ? M.off_recv_hi : M.off_recv_lo); }
+    int* gathered() const { return ints(M.off_gathered); }
+};
+
+static int mailbox_args(const char* who, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs) {
+    if (world < 1 || world > SKB_MAX_WORLD || cap_runs <= 0 || cap_roots <= 0 || cap_pairs <= 0 ||
+        cap_runs >= (1LL << 28) || (long long)world * (2 + cap_roots + 2 * cap_pairs) >= (1LL << 31)) {
+        skb_set_error("%s: bad mailbox geometry (world 1..%d, capacities > 0 and < 2^31 ints in total)", who, SKB_MAX_WORLD);
+        return SKB_E_ARG;
+    }
+    return SKB_OK;
+}
+
+static Mailbox mailbox_at(void* base, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs) {
+    Mailbox b;
+    b.M = skb_mailbox_layout(world, cap_runs, cap_roots, cap_pairs);
+    b.base = static_cast<char*>(base);
+    return b;
+}
+
+extern "C" size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs) {
+    if (mailbox_args("skb_shard_mailbox_bytes", world, cap_runs, cap_roots, cap_pairs)) return 0;
+    return skb_mailbox_layout(world, cap_runs, cap_roots, cap_pairs).total;
+}
+
+__global__ void shard_begin_kernel(int* epoch, int* cnt) {
+    if (threadIdx.x == 0) {
+        *epoch += 1;
+        cnt[0] = 0;
+        cnt[1] = 0;
+    }
+}
+
+extern "C" int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
+                               void* stream) {
+    int rc = mailbox_args("skb_shard_begin", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(mailbox, "skb_shard_begin: NULL mailbox");
+    Mailbox mb = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    shard_begin_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(mb.epoch(), mb.cnt(0));
+    SKB_LAUNCH_CHECK("shard_begin_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high, int64_t z_lo,
+                                        int64_t z_hi, void* mailbox, void* neighbour_mailbox, int world, int64_t cap_runs,
+                                        int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_emit_runs_peer");
+    if (rc) return rc;
+    rc = mailbox_args("skb_shard_emit_runs_peer", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && mailbox && neighbour_mailbox && status, "skb_shard_emit_runs_peer: NULL pointer");
+    SKB_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= Z && (z_lo >> 6) == ((z_hi - 1) >> 6),
+                "skb_shard_emit_runs_peer: [z_lo,z_hi) must lie inside one 64-plane word");
+    SKB_REQUIRE(face_is_high == 0 || face_is_high == 1, "skb_shard_emit_runs_peer: face_is_high must be 0 or 1");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    CclView v = make_view(L, workspace, 0, 1, status, nullptr);
+    const ull* face = reinterpret_cast<const ull*>(static_cast<const char*>(workspace) + (face_is_high ? L.off_face_hi : L.off_face_lo));
+    Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    Mailbox nb = mailbox_at(neighbour_mailbox, world, cap_runs, cap_roots, cap_pairs);
+    // my HIGH face lands in the upper neighbour's recv_lo, my LOW face in the lower neighbour's recv_hi
+    int* remote = nb.recv(face_is_high ? 0 : 1);
+    int* remote_flag = nb.flag(face_is_high ? 0 : 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned nblk = (unsigned)(((long long)X * Y + 255) / 256);
+    RunsDst dst = {me.cnt(face_is_high), remote + 3, me.epoch(), me.M.runs_ints};
+    shard_emit_runs_kernel<<<nblk, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, dst, (int)cap_runs, status);
+    shard_signal_runs_kernel<<<1, 32, 0, st>>>(me.cnt(face_is_high), remote, me.M.runs_ints, remote_flag, me.epoch());
+    SKB_LAUNCH_CHECK("skb_shard_emit_runs_peer");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, void* mailbox, int from_high,
+                                          int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
+                                          uint64_t* halo_words_zeroed, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_ingest_runs_peer");
+    if (rc) return rc;
+    rc = mailbox_args("skb_shard_ingest_runs_peer", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && mailbox && halo_words_zeroed && status, "skb_shard_ingest_runs_peer: NULL pointer");
+    SKB_REQUIRE(from_high == 0 || from_high == 1, "skb_shard_ingest_runs_peer: from_high must be 0 or 1");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    CclView v = make_view(L, workspace, 0, 1, status, nullptr);
+    Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        v, me.recv(from_high), (int)cap_runs, reinterpret_cast<ull*>(halo_words_zeroed), me.flag(from_high), me.epoch(),
+        me.M.runs_ints);
+    SKB_LAUNCH_CHECK("shard_ingest_runs_kernel (peer)");
+    return SKB_OK;
+}
+
+struct PeerTable {
+    int* gathered[SKB_MAX_WORLD];  // copy 0 of rank p's gather buffer
+    int* flag[SKB_MAX_WORLD];      // rank p's flag word for payloads coming from me
+};
+
+// grid (PUSH_BLOCKS, world): CTA (.,p) stores the used part of my payload into slot `rank` of rank p
+constexpr int PUSH_BLOCKS = 4;
+__global__ void __launch_bounds__(256) shard_push_kernel(const int* __restrict__ exch, PeerTable T, int rank, int cap_roots,
+                                                        int cap_pairs, long long stride, long long parity_stride,
+                                                        const int* epoch) {
+    const int p = blockIdx.y;
+    int* dst = T.gathered[p] + (long long)(*epoch & 1) * parity_stride + (long long)rank * stride;
+    const int n_roots = min(exch[0], cap_roots), n_pairs = min(exch[1], cap_pairs);
+    const int head = 2 + n_roots, tail = 2 * n_pairs;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int i = tid; i < head; i += nthr) dst[i] = exch[i];
+    const int* ps = exch + 2 + cap_roots;
+    int* pd = dst + 2 + cap_roots;
+    for (int i = tid; i < tail; i += nthr) pd[i] = ps[i];
+}
+
+__global__ void shard_signal_all_kernel(PeerTable T, int world, const int* epoch) {
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(T.flag[threadIdx.x], *epoch);
+    }
+}
+
+extern "C" int skb_shard_push(const int32_t* exchange, void* mailbox, const uint64_t* peer_mailboxes, int world, int rank,
+                              int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, void* stream) {
+    int rc = mailbox_args("skb_shard_push", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(exchange && mailbox && peer_mailboxes && rank >= 0 && rank < world, "skb_shard_push: bad argument");
+    Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    PeerTable T = {};
+    for (int p = 0; p < world; ++p) {
+        SKB_REQUIRE(peer_mailboxes[p] != 0, "skb_shard_push: NULL peer mailbox");
+        Mailbox pm = mailbox_at(reinterpret_cast<void*>(static_cast<uintptr_t>(peer_mailboxes[p])), world, cap_runs, cap_roots, cap_pairs);
+        T.gathered[p] = pm.gathered();
+        T.flag[p] = pm.flag_gather(rank);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long parity_stride = (long long)world * me.M.stride;
+    shard_push_kernel<<<dim3(PUSH_BLOCKS, world), 256, 0, st>>>(exchange, T, rank, (int)cap_roots, (int)cap_pairs, me.M.stride,
+                                                               parity_stride, me.epoch());
+    shard_signal_all_kernel<<<1, 32, 0, st>>>(T, world, me.epoch());
+    SKB_LAUNCH_CHECK("skb_shard_push");
+    return SKB_OK;
+}
+
+extern "C" int skb_shard_merge_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, void* mailbox,
+                                    int world, int rank, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
+                                    int32_t label_base, int32_t* ncomp, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_merge_peer");
+    if (rc) return rc;
+    rc = mailbox_args("skb_shard_merge_peer", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && mailbox && status && rank >= 0 && rank < world && label_base >= 0, "skb_shard_merge_peer: bad argument");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);
+    CclView v = make_view(L, workspace, 0, capacity, status, ncomp);
+    Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    MergeView m = {};
+    m.gathered = me.gathered(); m.world = world; m.rank = rank;
+    m.cap_roots = (int)cap_roots; m.cap_pairs = (int)cap_pairs;
+    m.stride = (int)me.M.stride;
+    m.epoch = me.epoch(); m.flags = me.flag_gather(0);
+    m.parity_stride = (long long)world * me.M.stride;
+    return launch_merge(v, L, m, label_base, static_cast<cudaStream_t>(stream));
 }

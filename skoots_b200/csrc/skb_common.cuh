@@ -105,6 +105,44 @@ static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64
     return L;
 }
 
+// ---- sharded pass: per-rank mailbox in peer-visible memory (skb_peer.cu allocates it) -----------------
+// Every rank uses the same layout, so a rank computes the address of a slot in a peer's mailbox from
+// the peer's base pointer alone.  Two copies ("parities") of every receive buffer: pass k uses copy
+// k & 1, which is what makes a peer that runs one pass ahead harmless.
+constexpr int SKB_FLAG_STRIDE = 32;  // ints between two flag words (one 128-byte line each)
+
+struct SkbMailboxLayout {
+    int world, cap_runs, cap_roots, cap_pairs;
+    long long stride;         // ints of one rank's gather payload: [n_roots, n_pairs, roots, pairs]
+    long long runs_ints;      // ints of one boundary-run buffer: [count,_,_] + triples
+    size_t off_epoch;         // int  pass counter (local)
+    size_t off_cnt;           // int[2] run counters of my low / high face (local)
+    size_t off_flag_lo;       // int  = k once the lower neighbour's runs of pass k are in recv_lo[k & 1]
+    size_t off_flag_hi;       // int  same for the upper neighbour / recv_hi
+    size_t off_flag_gather;   // int[world] (SKB_FLAG_STRIDE apart) = k once rank p's payload of pass k is in gathered[k & 1][p]
+    size_t off_recv_lo, off_recv_hi;  // 2 x runs_ints ints each
+    size_t off_gathered;      // 2 x world x stride ints
+    size_t total;
+};
+
+static inline SkbMailboxLayout skb_mailbox_layout(int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs) {
+    SkbMailboxLayout M;
+    M.world = world; M.cap_runs = (int)cap_runs; M.cap_roots = (int)cap_roots; M.cap_pairs = (int)cap_pairs;
+    M.stride = 2 + cap_roots + 2 * cap_pairs;
+    M.runs_ints = 3 * (cap_runs + 1);
+    size_t at = 0;
+    M.off_epoch = at;       at += 256;
+    M.off_cnt = at;         at += 256;
+    M.off_flag_lo = at;     at += 256;
+    M.off_flag_hi = at;     at += 256;
+    M.off_flag_gather = at; at = skb_align_up(at + (size_t)world * SKB_FLAG_STRIDE * 4, 256);
+    M.off_recv_lo = at;     at = skb_align_up(at + 2 * (size_t)M.runs_ints * 4, 256);
+    M.off_recv_hi = at;     at = skb_align_up(at + 2 * (size_t)M.runs_ints * 4, 256);
+    M.off_gathered = at;    at = skb_align_up(at + 2 * (size_t)world * (size_t)M.stride * 4, 256);
+    M.total = at;
+    return M;
+}
+
 // label of a foreground voxel `t` from the sparse form: parent[t] is either the (negative) label
 // code or the index of the voxel's tile root, whose entry is the code.
 __device__ __forceinline__ int skb_sparse_label(const int* __restrict__ parent, int t) {

@@ -9,13 +9,22 @@ field.  A pass has two exchange steps, both tiny compared with the slab itself:
      slab faces -> every rank solves the same union-find and numbers all components identically
      (the single-GPU numbering).
 
-Everything else is the single-GPU kernels restricted to the slab.  `ShardedAssembler.step` is split
-into phases so that the collectives can be swapped: `TorchDistComm` (NCCL / gloo) for real runs and
-`LocalGroup` to run all ranks inside one process on one GPU (used by the GPU parity test, which
+Everything else is the single-GPU kernels restricted to the slab.  Two transports carry the exchanges:
+
+  * "peer" (default on a multi-GPU box, `PeerComm`): every rank owns a mailbox in peer-visible device
+    memory; the producing kernels store straight into the consumer GPU's mailbox over NVLink and
+    release a flag there, the consuming kernels spin on flags in their own HBM.  No NCCL call and no
+    host involvement inside a pass: a pass is ~30 kernel launches on one stream = one CUDA graph.
+    torch.distributed is used once, at set-up, to swap the 64-byte IPC handles of the mailboxes.
+  * "nccl" (`TorchDistComm`; gloo in the CPU tests of the plumbing): NCCL send/recv + all-gather of
+    fixed-size buffers between the phases.
+
+`LocalGroup` runs all ranks of either transport inside one process on one GPU (the GPU parity test
 checks the sharded result is bit-identical to the unsharded one).
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -69,6 +78,96 @@ class TorchDistComm:
         self.dist.barrier(self.group)
 
 
+class Mailbox:
+    """One rank's mailbox: cudaMalloc'ed by the library (IPC-exportable), freed with the object."""
+
+    def __init__(self, lib, nbytes: int, device):
+        self.lib, self.nbytes, self.device = lib, int(nbytes), torch.device(device)
+        out = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(lib.skb_peer_alloc(self.nbytes, ctypes.byref(out)))
+        self.ptr = int(out.value)
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(L.PEER_HANDLE_BYTES)
+        L.check(self.lib.skb_peer_export(self.ptr, buf))
+        return buf.raw
+
+    def ints(self, byte_offset: int, count: int) -> Tensor:
+        """a torch view of part of the mailbox (diagnostics / tests only)."""
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (self.ptr + byte_offset, False),
+                                      "version": 2, "strides": None}
+        return torch.as_tensor(v, device=self.device)
+
+    def free(self) -> None:
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                self.lib.skb_peer_free(self.ptr)
+            self.ptr = 0
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PeerComm:
+    """Peer transport across processes: allocates this rank's mailbox and maps every other rank's through
+    CUDA IPC (handles swapped once over torch.distributed).  After `connect` no collective is issued."""
+
+    transport = "peer"
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.mailbox: Optional[Mailbox] = None
+        self.peer_ptrs: List[int] = []
+        self._opened: List[int] = []
+
+    def connect(self, lib, nbytes: int, device) -> Tuple[Mailbox, List[int]]:
+        self.lib = lib
+        self.mailbox = Mailbox(lib, nbytes, device)
+        mine = torch.frombuffer(bytearray(self.mailbox.handle()), dtype=torch.uint8).to(device)
+        every = torch.empty(self.world * L.PEER_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        self.dist.all_gather_into_tensor(every, mine, group=self.group)
+        handles = every.cpu().numpy().tobytes()
+        self.peer_ptrs = []
+        with torch.cuda.device(device):
+            for r in range(self.world):
+                if r == self.rank:
+                    self.peer_ptrs.append(self.mailbox.ptr)
+                    continue
+                out = ctypes.c_void_p()
+                h = handles[r * L.PEER_HANDLE_BYTES:(r + 1) * L.PEER_HANDLE_BYTES]
+                L.check(lib.skb_peer_open(h, ctypes.byref(out)))
+                self.peer_ptrs.append(int(out.value))
+                self._opened.append(int(out.value))
+        self.dist.barrier(self.group)  # every mailbox is mapped everywhere before anyone stores into one
+        return self.mailbox, self.peer_ptrs
+
+    def barrier(self) -> None:
+        self.dist.barrier(self.group)
+
+    def close(self) -> None:
+        """unmap the peers' mailboxes, then (after a barrier: nobody may still be storing into mine) free mine."""
+        if self.mailbox is None:
+            return
+        torch.cuda.synchronize(self.mailbox.device)
+        with torch.cuda.device(self.mailbox.device):
+            for p in self._opened:
+                self.lib.skb_peer_close(p)
+        self._opened = []
+        self.dist.barrier(self.group)
+        self.mailbox.free()
+        self.mailbox = None
+
+
 class ShardedAssembler:
     """Per-rank state + the phases of one pass.  N = 1 (the headline mode): with N > 1 the reference's
     walks are confined to its 500x500x50 crops and need vector halos as well."""
@@ -87,8 +186,8 @@ class ShardedAssembler:
         if self.halo > 64 or self.halo > self.Zl:
             raise ValueError("halo deeper than one 64-plane word / than the slab is not supported")
         self.comm = comm
+        self.transport = getattr(comm, "transport", "nccl")
         self.lib = L.load()
-        V = X * Y * Z
         self.capacity = max(1 << 16, (X * Y * self.Zl) // 8)
         need = self.lib.skb_ccl_workspace_bytes(X, Y, Z, self.capacity)
         self.workspace = torch.empty(need, dtype=torch.uint8, device=self.dev)
@@ -97,20 +196,41 @@ class ShardedAssembler:
         self.cap_runs = int(cap_runs) if cap_runs else max(1 << 14, (X * Y * self.halo) // 128)
         self.cap_roots, self.cap_pairs = cap_roots, cap_pairs
         mk = lambda n, dt=torch.int32: torch.zeros(n, dtype=dt, device=self.dev)
-        self.send_lo, self.send_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
-        self.recv_lo, self.recv_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
         self.halo_lo = mk(X * Y, torch.int64) if rank > 0 else None
         self.halo_hi = mk(X * Y, torch.int64) if rank < world - 1 else None
         self.exch = mk(exchange_layout(cap_roots, cap_pairs))
-        self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
+        self.mailbox: Optional[Mailbox] = None
+        self.peer_ptrs: List[int] = []
+        if self.transport == "peer":
+            if world > L.MAX_WORLD:
+                raise ValueError(f"the peer transport supports up to {L.MAX_WORLD} ranks")
+            self._geom = (world, self.cap_runs, cap_roots, cap_pairs)
+            nbytes = self.lib.skb_shard_mailbox_bytes(*self._geom)
+            if nbytes == 0:
+                raise L.SkootsB200Error(self.lib.skb_last_error().decode())
+            self.mailbox_bytes = int(nbytes)
+            if comm is not None and hasattr(comm, "connect"):
+                self.attach(*comm.connect(self.lib, self.mailbox_bytes, self.dev))
+        else:
+            self.send_lo, self.send_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
+            self.recv_lo, self.recv_hi = mk(3 * (self.cap_runs + 1)), mk(3 * (self.cap_runs + 1))
+            self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
         self.meta = mk(2)  # [n_components, status]
         self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
         self._clean = False
         self.mask: Optional[Tensor] = None
         self.vec: Optional[Tensor] = None
         # kernels of one pass: local(init,pack,tile,boundary,roots)=5, emit<=2, ingest<=2, pack_roots+pairs<=2,
-        # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1
-        self.launches_per_step = 5 + 2 * (rank > 0) + 2 * (rank < world - 1) + 2 + 11 + 1
+        # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1;
+        # peer transport adds begin=1, a signal per emitted face, push+signal=2
+        faces = (rank > 0) + (rank < world - 1)
+        self.launches_per_step = 5 + 2 * faces + 2 + 11 + 1 + ((3 + faces) if self.transport == "peer" else 0)
+
+    def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:
+        """peer transport: my mailbox and the (mapped) base pointers of every rank's mailbox, own included."""
+        assert len(peer_ptrs) == self.world and peer_ptrs[self.rank] == mailbox.ptr
+        self.mailbox, self.peer_ptrs = mailbox, [int(p) for p in peer_ptrs]
+        self._peer_arr = (ctypes.c_uint64 * self.world)(*self.peer_ptrs)
 
     # ---- data ------------------------------------------------------------------------------------
     def load(self, mask_slab: Tensor, vec_slab: Tensor) -> None:
@@ -127,12 +247,23 @@ class ShardedAssembler:
     def phase_local(self) -> None:
         X, Y, Z = self.shape
         z0, z1 = self.z_range
+        peer = self.transport == "peer"
         with torch.cuda.device(self.dev):
+            if peer:
+                L.check(self.lib.skb_shard_begin(self.mailbox.ptr, *self._geom, self._s()))
             L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, z0, self.Zl,
                                                    self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
                                                    self.meta[1:2].data_ptr(), L.CCL_WORKSPACE_CLEAN if self._clean else 0,
                                                    self._s()))
             self._clean = False
+            if peer:
+                for hi, ok, za, zb in ((0, self.rank > 0, z0, z0 + self.halo),
+                                       (1, self.rank < self.world - 1, z1 - self.halo, z1)):
+                    if ok:
+                        L.check(self.lib.skb_shard_emit_runs_peer(
+                            self.workspace.data_ptr(), X, Y, Z, hi, za, zb, self.mailbox.ptr,
+                            self.peer_ptrs[self.rank + (1 if hi else -1)], *self._geom, self.meta[1:2].data_ptr(), self._s()))
+                return
             if self.rank > 0:
                 L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 0, z0, z0 + self.halo,
                                                      self.send_lo.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
@@ -144,27 +275,40 @@ class ShardedAssembler:
         """after the neighbour exchange: recv_lo / recv_hi hold the neighbours' boundary runs."""
         X, Y, Z = self.shape
         z0, z1 = self.z_range
+        peer = self.transport == "peer"
         with torch.cuda.device(self.dev):
-            if self.halo_lo is not None:
-                self.halo_lo.zero_()
-                L.check(self.lib.skb_shard_ingest_runs(self.workspace.data_ptr(), X, Y, Z, self.recv_lo.data_ptr(),
-                                                       self.cap_runs, self.halo_lo.data_ptr(), self._s()))
-            if self.halo_hi is not None:
-                self.halo_hi.zero_()
-                L.check(self.lib.skb_shard_ingest_runs(self.workspace.data_ptr(), X, Y, Z, self.recv_hi.data_ptr(),
-                                                       self.cap_runs, self.halo_hi.data_ptr(), self._s()))
+            for hi, halo, recv in ((0, self.halo_lo, None if peer else self.recv_lo),
+                                   (1, self.halo_hi, None if peer else self.recv_hi)):
+                if halo is None:
+                    continue
+                halo.zero_()
+                if peer:
+                    L.check(self.lib.skb_shard_ingest_runs_peer(self.workspace.data_ptr(), X, Y, Z, self.mailbox.ptr, hi,
+                                                                *self._geom, halo.data_ptr(), self.meta[1:2].data_ptr(),
+                                                                self._s()))
+                else:
+                    L.check(self.lib.skb_shard_ingest_runs(self.workspace.data_ptr(), X, Y, Z, recv.data_ptr(),
+                                                           self.cap_runs, halo.data_ptr(), self._s()))
             L.check(self.lib.skb_shard_boundary_pairs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, self.capacity,
                                                       L.ptr(self.halo_hi), self.exch.data_ptr(), self.cap_roots,
                                                       self.cap_pairs, self.meta[1:2].data_ptr(), self._s()))
+            if peer:
+                L.check(self.lib.skb_shard_push(self.exch.data_ptr(), self.mailbox.ptr, self._peer_arr, self.world, self.rank,
+                                                self.cap_runs, self.cap_roots, self.cap_pairs, self._s()))
 
     def phase_merge_and_gather(self, timers=None) -> Tensor:
         """after the all-gather: `gathered` holds every rank's roots and pairs."""
         X, Y, Z = self.shape
         z0, _ = self.z_range
         with torch.cuda.device(self.dev):
-            L.check(self.lib.skb_shard_merge(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.gathered.data_ptr(),
-                                             self.world, self.rank, self.cap_roots, self.cap_pairs, 2,
-                                             self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
+            if self.transport == "peer":
+                L.check(self.lib.skb_shard_merge_peer(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.mailbox.ptr,
+                                                      self.world, self.rank, self.cap_runs, self.cap_roots, self.cap_pairs, 2,
+                                                      self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
+            else:
+                L.check(self.lib.skb_shard_merge(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.gathered.data_ptr(),
+                                                 self.world, self.rank, self.cap_roots, self.cap_pairs, 2,
+                                                 self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
             self._clean = True  # a completed merge leaves the root bitmap zeroed
             if timers is not None:
                 timers[0].record()
@@ -204,13 +348,17 @@ class ShardedAssembler:
 
     def _step_eager(self, timers=None) -> Tensor:
         self.phase_local()
-        self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
+        if self.transport != "peer":
+            self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
         self.phase_ingest()
-        self.comm.all_gather(self.gathered, self.exch)
+        if self.transport != "peer":
+            self.comm.all_gather(self.gathered, self.exch)
         return self.phase_merge_and_gather(timers)
 
     def profile_phases(self, steps: int = 5) -> dict:
-        """mean device time (ms) of each phase of a pass on this rank (CUDA events on the current stream)."""
+        """mean device time (ms) of each phase of a pass on this rank (CUDA events on the current stream).
+        Peer transport: the waits for the other ranks sit inside `ingest_pairs` and `merge`."""
+        peer = self.transport == "peer"
         names = ["local", "exchange_runs", "ingest_pairs", "all_gather", "merge", "gather"]
         acc = dict.fromkeys(names, 0.0)
         for _ in range(steps):
@@ -218,16 +366,21 @@ class ShardedAssembler:
             mid = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
             self.phase_local(); ev[1].record()
-            self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi); ev[2].record()
+            if not peer:
+                self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
+            ev[2].record()
             self.phase_ingest(); ev[3].record()
-            self.comm.all_gather(self.gathered, self.exch); ev[4].record()
+            if not peer:
+                self.comm.all_gather(self.gathered, self.exch)
+            ev[4].record()
             self.phase_merge_and_gather(mid); ev[6].record()
             torch.cuda.synchronize(self.dev)
             spans = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
                      ev[3].elapsed_time(ev[4]), ev[4].elapsed_time(mid[0]), mid[0].elapsed_time(mid[1])]
             for n, v in zip(names, spans):
                 acc[n] += v / steps
-        acc["runs_sent"] = [int(self.send_lo[0].item()), int(self.send_hi[0].item())]
+        if not peer:
+            acc["runs_sent"] = [int(self.send_lo[0].item()), int(self.send_hi[0].item())]
         acc["roots_pairs"] = [int(self.exch[0].item()), int(self.exch[1].item())]
         return acc
 
@@ -236,6 +389,8 @@ class ShardedAssembler:
         ncomp, status = (int(v) for v in self.meta.tolist())
         if status & L.STATUS_ROOT_OVERFLOW:
             raise L.SkootsB200Error("sharded CCL: a list capacity (roots / runs / pairs) overflowed")
+        if status & L.STATUS_PEER_TIMEOUT:
+            raise L.SkootsB200Error("sharded pass: a peer's flag did not arrive (a rank fell out of step or died)")
         labelled = (self.out > 0).sum().to(torch.int64)
         if self.comm is not None and self.world > 1:
             self.comm.dist.all_reduce(labelled, group=self.comm.group)
@@ -274,13 +429,24 @@ class ShardedAssembler:
 
 
 class LocalGroup:
-    """All ranks of a sharded pass inside ONE process on ONE GPU: the collectives become plain copies.
-    For tests (and for a box with fewer GPUs than ranks — kernels of different ranks never wait on each
-    other, so running them back to back is safe)."""
+    """All ranks of a sharded pass inside ONE process on ONE GPU.  For tests (and for a box with fewer GPUs
+    than ranks).  transport "peer": the ranks' mailboxes live on the same device, so "peer" pointers are
+    ordinary pointers, and the phases are issued rank by rank so that every flag has been released before
+    a kernel waits on it.  transport "nccl": the collectives become plain copies."""
 
-    def __init__(self, shape, world: int, device, scale=(60, 60, 12), **kw):
-        self.ranks = [ShardedAssembler(shape, world, r, device, scale=scale, **kw) for r in range(world)]
+    class _PeerTag:
+        transport = "peer"
+
+    def __init__(self, shape, world: int, device, scale=(60, 60, 12), transport: str = "peer", **kw):
+        comm = self._PeerTag() if transport == "peer" else None
+        self.transport = transport
+        self.ranks = [ShardedAssembler(shape, world, r, device, scale=scale, comm=comm, **kw) for r in range(world)]
         self.world = world
+        if transport == "peer":
+            self.mailboxes = [Mailbox(r.lib, r.mailbox_bytes, device) for r in self.ranks]
+            ptrs = [m.ptr for m in self.mailboxes]
+            for r, m in zip(self.ranks, self.mailboxes):
+                r.attach(m, ptrs)
 
     def load_volume(self, mask: Tensor, vec: Tensor) -> None:
         for r in self.ranks:
@@ -290,19 +456,23 @@ class LocalGroup:
     def step(self) -> Tensor:
         for r in self.ranks:
             r.phase_local()
-        for i, r in enumerate(self.ranks):
-            if i > 0:
-                r.recv_lo.copy_(self.ranks[i - 1].send_hi)
-            if i < self.world - 1:
-                r.recv_hi.copy_(self.ranks[i + 1].send_lo)
+        if self.transport != "peer":
+            for i, r in enumerate(self.ranks):
+                if i > 0:
+                    r.recv_lo.copy_(self.ranks[i - 1].send_hi)
+                if i < self.world - 1:
+                    r.recv_hi.copy_(self.ranks[i + 1].send_lo)
         for r in self.ranks:
             r.phase_ingest()
-        allg = torch.cat([r.exch for r in self.ranks])
-        for r in self.ranks:
-            r.gathered.copy_(allg)
+        if self.transport != "peer":
+            allg = torch.cat([r.exch for r in self.ranks])
+            for r in self.ranks:
+                r.gathered.copy_(allg)
         outs = [r.phase_merge_and_gather() for r in self.ranks]
         for r in self.ranks:
             ncomp, status = (int(v) for v in r.meta.tolist())
             if status & L.STATUS_ROOT_OVERFLOW:
                 raise L.SkootsB200Error("sharded CCL: a list capacity overflowed")
+            if status & L.STATUS_PEER_TIMEOUT:
+                raise L.SkootsB200Error("sharded pass: a flag did not arrive")
         return torch.cat(outs, dim=2)

@@ -38,6 +38,21 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -4  # SKB_E_RANGE: more than 2^31 voxels
 
 
+def test_mailbox_geometry_is_host_arithmetic():
+    """the peer transport's mailbox layout: every rank computes the same size from (world, capacities)."""
+    import skoots_b200._lib as L
+    lib = L.load()
+    small = lib.skb_shard_mailbox_bytes(2, 1 << 10, 1 << 8, 1 << 7)
+    big = lib.skb_shard_mailbox_bytes(8, 1 << 10, 1 << 8, 1 << 7)
+    assert 0 < small < big
+    # two copies of: two run buffers 3*(cap+1) ints, and world payloads of (2 + roots + 2*pairs) ints
+    assert small >= 4 * (2 * 2 * 3 * ((1 << 10) + 1) + 2 * 2 * (2 + (1 << 8) + 2 * (1 << 7)))
+    assert small % 256 == 0
+    assert lib.skb_shard_mailbox_bytes(L.MAX_WORLD + 1, 16, 16, 16) == 0
+    assert lib.skb_shard_mailbox_bytes(2, 0, 16, 16) == 0
+    assert lib.skb_shard_begin(None, 2, 16, 16, 16, None) == -1 and b"NULL" in lib.skb_last_error()
+
+
 def test_no_cpu_fallback():
     import skoots_b200._lib as L
     from skoots_b200.lib.flood_fill import efficient_flood_fill

@@ -94,6 +94,11 @@ size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity
 /* flags: SKB_CCL_WORKSPACE_CLEAN = this workspace was last used by a completed labelling pass of the
  * same volume shape (every pass leaves its root bitmap zeroed), so the V/8-byte memset is skipped. */
 #define SKB_CCL_WORKSPACE_CLEAN 1
+/* run only part of the labelling (both skb_ccl_label_sparse and skb_shard_label_local), so that a caller
+ * can start skb_assemble_stream as soon as the bit mask exists: PHASE_PACK = header, clears and the
+ * mask -> bit-mask pack; PHASE_LABEL = everything after it.  Neither bit = the whole labelling. */
+#define SKB_CCL_PHASE_PACK 2
+#define SKB_CCL_PHASE_LABEL 4
 int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                          int planar, int32_t label_base, int64_t capacity, void* workspace,
                          size_t workspace_bytes, int32_t* ncomp, uint32_t* status, int flags,
@@ -228,6 +233,22 @@ int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t ca
 int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                       int64_t Zl, const float scale[3], const void* workspace, const uint64_t* halo_lo,
                       const uint64_t* halo_hi, void* out, int out_dtype, void* stream);
+
+/* Split form of the fused gather for N = 1 with the whole volume as one crop (the headline mode), on a
+ * volume (z_off = 0, Zl = Z) or a slab.  skb_assemble_stream needs only the bit mask of the CCL
+ * workspace (i.e. the SKB_CCL_PHASE_PACK part of the labelling): it streams the vector field, stores
+ * the zeros of every 8-voxel group that cannot have a label and records the other groups in
+ * group_flags (one uint32 per 256 voxels, X*Y*Zl/256 words).  The caller runs it on a second stream
+ * next to the rest of the labelling (SKB_CCL_PHASE_LABEL), then skb_assemble_resolve fills in the
+ * flagged groups.  Together they write exactly what skb_assemble / skb_assemble_slab write.
+ * Z, z_off, Zl multiples of 64 and X*Y*Zl a multiple of 256; other shapes use the fused call. */
+int skb_assemble_stream(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
+                        int64_t Zl, const void* workspace, uint32_t* group_flags, void* out,
+                        int out_dtype, void* stream);
+int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
+                         int64_t Zl, const float scale[3], const void* workspace,
+                         const uint64_t* halo_lo, const uint64_t* halo_hi, const uint32_t* group_flags,
+                         void* out, int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (e')  The same pass with both exchanges done by the kernels themselves over NVLink peer memory —

@@ -21,6 +21,8 @@ STATUS_PEER_TIMEOUT = 4
 PEER_HANDLE_BYTES = 64
 MAX_WORLD = 16
 CCL_WORKSPACE_CLEAN = 1
+CCL_PHASE_PACK = 2
+CCL_PHASE_LABEL = 4
 
 _DTYPES = {
     torch.uint8: SKB_U8, torch.bool: SKB_U8, torch.int16: SKB_I16, torch.int32: SKB_I32,
@@ -57,6 +59,8 @@ SIGNATURES = {
     "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
+    "skb_assemble_stream": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
+    "skb_assemble_resolve": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
     "skb_peer_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
     "skb_peer_free": (_c_int, [_c_vp]),
     "skb_peer_export": (_c_int, [_c_vp, ctypes.c_char_p]),

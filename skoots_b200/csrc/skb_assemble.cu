@@ -374,6 +374,118 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_tail_kernel(AsmParams
     process_chunk<VecT, OutT, false>(P, c, out, V, warp_base, s_raw[warp], s_res[warp], s_queue[warp]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Split form of the N = 1, whole-volume-is-one-crop gather ("stream / resolve").
+//
+// The fused kernel above cannot start before the labelling has finished.  But 96 % of the voxels
+// never look at a label: their vector is zero and they are not skeleton themselves.  So the gather is
+// split in two:
+//   assemble_stream_kernel   needs only the bit mask.  Pure stream over the vector field (6 B/voxel in);
+//                            an 8-voxel group (one lane's 16-byte load per channel) with no work gets
+//                            its zeros stored (4 B/voxel out); a group with work is left alone and
+//                            recorded as one bit of the chunk's 32-bit flag word.  It runs on a second
+//                            stream WHILE the latency-bound labelling chain (tile union-find, boundary
+//                            unions, exchanges, merge) runs — HBM-bound next to latency-bound.
+//   assemble_resolve_kernel  after the labels exist: walks the flag words, re-reads the vectors of the
+//                            flagged groups only (~4 % of the volume), resolves their labels and stores them.
+// Non-persistent CTAs on purpose: slots free up continuously, so the (higher-priority) labelling
+// kernels always find SM resources next to the stream.
+// ------------------------------------------------------------------------------------------
+constexpr int STREAM_CHUNKS_PER_WARP = 2;
+
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(32 * ASM_WARPS) assemble_stream_kernel(AsmParams P, OutT* __restrict__ out,
+                                                                         unsigned* __restrict__ flags, unsigned n_chunks) {
+    const int lane = threadIdx.x & 31;
+    const unsigned c0 = (blockIdx.x * ASM_WARPS + (threadIdx.x >> 5)) * STREAM_CHUNKS_PER_WARP;
+    ChunkRegs<VecT> r[STREAM_CHUNKS_PER_WARP];
+#pragma unroll
+    for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u)
+        if (c0 + u < n_chunks) r[u] = load_chunk<VecT, true>(P, 0, (long long)(c0 + u) * 256);
+#pragma unroll
+    for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u) {
+        if (c0 + u >= n_chunks) break;  // warp-uniform
+        const bool work = (nonzero_bits<VecT>(r[u].r0, r[u].r1, r[u].r2) | r[u].self) != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, work);
+        if (!work) {
+            OutT* o = out + (long long)(c0 + u) * 256 + lane * 8;
+            skb_st_stream16(o, make_uint4(0u, 0u, 0u, 0u));
+            if (sizeof(OutT) == 4) skb_st_stream16(o + 4, make_uint4(0u, 0u, 0u, 0u));
+        }
+        if (lane == 0) flags[c0 + u] = m;
+    }
+}
+
+// one lane = one flagged 8-voxel group: the (up to) 8 label look-ups are independent chains
+template <typename VecT, typename OutT>
+__device__ __forceinline__ void resolve_group(const AsmParams& P, long long i0, OutT* __restrict__ out) {
+    const Raw8<VecT> a = load_raw8<VecT, true>(P.vec, i0, 8);
+    const Raw8<VecT> b = load_raw8<VecT, true>(P.vec, i0 + P.cstride, 8);
+    const Raw8<VecT> c = load_raw8<VecT, true>(P.vec, i0 + 2 * P.cstride, 8);
+    const unsigned self = (unsigned)__ldg(reinterpret_cast<const unsigned char*>(P.bits) + ((size_t)i0 >> 3));
+    const unsigned work = nonzero_bits<VecT>(a, b, c) | self;
+    const unsigned q = (unsigned)i0 / (unsigned)P.Zl;
+    const int z0 = (int)((unsigned)i0 - q * (unsigned)P.Zl) + P.z_off;  // the 8 voxels share a row (Zl % 8 == 0)
+    const int x = (int)(q / (unsigned)P.Y), y = (int)(q - (unsigned)x * (unsigned)P.Y);
+    const float fx = (float)x, fy = (float)y;
+    unsigned lab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        lab[j] = 0u;
+        if ((work >> j) & 1u) {
+            const float ex = __fadd_rn(fx, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(a.w, j)), P.s[0]));
+            const float ey = __fadd_rn(fy, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(b.w, j)), P.s[1]));
+            const float ez = __fadd_rn((float)(z0 + j), __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(c.w, j)), P.s[2]));
+            lab[j] = (unsigned)label_at(P, clamp_index(ex, P.X), clamp_index(ey, P.Y), clamp_index(ez, P.Z));
+        }
+    }
+    if (sizeof(OutT) == 2) {
+        skb_st_stream16(out + i0, make_uint4((lab[0] & 0xffffu) | (lab[1] << 16), (lab[2] & 0xffffu) | (lab[3] << 16),
+                                             (lab[4] & 0xffffu) | (lab[5] << 16), (lab[6] & 0xffffu) | (lab[7] << 16)));
+    } else {
+        skb_st_stream16(out + i0, make_uint4(lab[0], lab[1], lab[2], lab[3]));
+        skb_st_stream16(out + i0 + 4, make_uint4(lab[4], lab[5], lab[6], lab[7]));
+    }
+}
+
+// A warp takes 32 flag words (32 chunks = 8192 voxels) at a time, lists their flagged groups in shared
+// memory and works through the list 32 groups at a time, so the look-ups run with full warps however
+// thinly the groups are spread over the chunks.
+template <typename VecT, typename OutT>
+__global__ void __launch_bounds__(32 * ASM_WARPS) assemble_resolve_kernel(AsmParams P, OutT* __restrict__ out,
+                                                                          const unsigned* __restrict__ flags,
+                                                                          unsigned n_chunks) {
+    __shared__ unsigned short s_list[ASM_WARPS][1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned short* list = s_list[warp];
+    const unsigned n_blocks = (n_chunks + 31u) / 32u, n_warps = gridDim.x * ASM_WARPS;
+    for (unsigned blk = blockIdx.x * ASM_WARPS + warp; blk < n_blocks; blk += n_warps) {
+        const unsigned c = blk * 32u + lane;
+        const unsigned m = c < n_chunks ? __ldg(flags + c) : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int at = incl - cnt;
+        for (unsigned mm = m; mm; mm &= mm - 1) list[at++] = (unsigned short)((lane << 5) | (__ffs((int)mm) - 1));
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            if (idx < total) {
+                const unsigned e = list[idx];
+                const long long group = ((long long)blk * 32 + (e >> 5)) * 32 + (e & 31u);
+                resolve_group<VecT, OutT>(P, group * 8, out);
+            }
+        }
+        __syncwarp();  // the list is reused by this warp's next block
+    }
+}
+
 // ---- stand-alone a1: materialise the embedding ---------------------------------------------------
 template <typename VecT>
 __global__ void __launch_bounds__(256) vec_embed3d_kernel(AsmParams P, float* __restrict__ out, long long V) {
@@ -577,6 +689,88 @@ extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int6
     else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, 0, V, st);
     else launch_assemble<float>(P, out, out_dtype, 0, V, st);
     SKB_LAUNCH_CHECK("assemble_kernel (slab)");
+    return SKB_OK;
+}
+
+// ---- split gather: host side --------------------------------------------------------------------
+static int split_params(const char* who, AsmParams& P, const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z,
+                        int64_t z_off, int64_t Zl, const float scale[3], const void* workspace, const void* out, int out_dtype) {
+    int rc = skb_check_volume(X, Y, Z, who);
+    if (rc) return rc;
+    if (!(vec && out && workspace)) { skb_set_error("%s: NULL pointer", who); return SKB_E_ARG; }
+    if (!(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32)) { skb_set_error("%s: vec dtype", who); return SKB_E_ARG; }
+    if (!(out_dtype == SKB_I32 || out_dtype == SKB_I16)) { skb_set_error("%s: out dtype must be i32 or i16", who); return SKB_E_ARG; }
+    if (Z % 64 != 0 || z_off % 64 != 0 || Zl % 64 != 0 || Zl <= 0 || z_off < 0 || z_off + Zl > Z || (X * Y * Zl) % 256 != 0) {
+        skb_set_error("%s: Z, z_off and Zl must be multiples of 64 and the slab a multiple of 256 voxels "
+                      "(other shapes take the fused skb_assemble)", who);
+        return SKB_E_ARG;
+    }
+    P = AsmParams();
+    P.vec = vec; P.vec_hops = vec;
+    P.cstride = X * Y * Zl;
+    P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
+    P.Zl = (int)Zl; P.z_off = (int)z_off;
+    if (scale) { P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2]; }
+    P.N = 1; P.decay = 1.0;
+    const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
+    fill_crop(P, crop, ov);
+    P.vec_aligned = skb_aligned16(vec) && ((P.cstride * elem_size(vec_dtype)) % 16 == 0);
+    if (!P.vec_aligned || !skb_aligned16(out)) { skb_set_error("%s: vec channels and out must be 16-byte aligned", who); return SKB_E_ARG; }
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    const char* base = static_cast<const char*>(workspace);
+    P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
+    P.parent = reinterpret_cast<const int*>(base + L.off_parent);
+    P.ZW = (int)(Zl / 64);
+    P.flat_bits = 1;
+    return SKB_OK;
+}
+
+template <typename VecT>
+static void launch_split(const AsmParams& P, bool resolve, void* out, int out_dtype, uint32_t* flags, unsigned n_chunks, cudaStream_t st) {
+    const unsigned per_cta = ASM_WARPS * STREAM_CHUNKS_PER_WARP;
+    const unsigned stream_grid = (n_chunks + per_cta - 1) / per_cta;
+    unsigned resolve_grid = ((n_chunks + 31u) / 32u + ASM_WARPS - 1) / ASM_WARPS;
+    if (resolve_grid > 148u * 8u) resolve_grid = 148u * 8u;
+    if (out_dtype == SKB_I32) {
+        if (resolve) assemble_resolve_kernel<VecT, int32_t><<<resolve_grid, 32 * ASM_WARPS, 0, st>>>(P, static_cast<int32_t*>(out), flags, n_chunks);
+        else assemble_stream_kernel<VecT, int32_t><<<stream_grid, 32 * ASM_WARPS, 0, st>>>(P, static_cast<int32_t*>(out), flags, n_chunks);
+    } else {
+        if (resolve) assemble_resolve_kernel<VecT, int16_t><<<resolve_grid, 32 * ASM_WARPS, 0, st>>>(P, static_cast<int16_t*>(out), flags, n_chunks);
+        else assemble_stream_kernel<VecT, int16_t><<<stream_grid, 32 * ASM_WARPS, 0, st>>>(P, static_cast<int16_t*>(out), flags, n_chunks);
+    }
+}
+
+static void launch_split_any(const AsmParams& P, int vec_dtype, bool resolve, void* out, int out_dtype, uint32_t* flags, cudaStream_t st) {
+    const unsigned n_chunks = (unsigned)(((long long)P.X * P.Y * P.Zl) / 256);
+    if (vec_dtype == SKB_F16) launch_split<__half>(P, resolve, out, out_dtype, flags, n_chunks, st);
+    else if (vec_dtype == SKB_BF16) launch_split<__nv_bfloat16>(P, resolve, out, out_dtype, flags, n_chunks, st);
+    else launch_split<float>(P, resolve, out, out_dtype, flags, n_chunks, st);
+}
+
+extern "C" int skb_assemble_stream(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                   const void* workspace, uint32_t* group_flags, void* out, int out_dtype, void* stream) {
+    AsmParams P;
+    int rc = split_params("skb_assemble_stream", P, vec, vec_dtype, X, Y, Z, z_off, Zl, nullptr, workspace, out, out_dtype);
+    if (rc) return rc;
+    SKB_REQUIRE(group_flags, "skb_assemble_stream: NULL group_flags");
+    launch_split_any(P, vec_dtype, false, out, out_dtype, group_flags, static_cast<cudaStream_t>(stream));
+    SKB_LAUNCH_CHECK("assemble_stream_kernel");
+    return SKB_OK;
+}
+
+extern "C" int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                    const float scale[3], const void* workspace, const uint64_t* halo_lo,
+                                    const uint64_t* halo_hi, const uint32_t* group_flags, void* out, int out_dtype,
+                                    void* stream) {
+    AsmParams P;
+    SKB_REQUIRE(scale, "skb_assemble_resolve: NULL scale");
+    int rc = split_params("skb_assemble_resolve", P, vec, vec_dtype, X, Y, Z, z_off, Zl, scale, workspace, out, out_dtype);
+    if (rc) return rc;
+    SKB_REQUIRE(group_flags, "skb_assemble_resolve: NULL group_flags");
+    P.halo_lo = reinterpret_cast<const ull*>(halo_lo);
+    P.halo_hi = reinterpret_cast<const ull*>(halo_hi);
+    launch_split_any(P, vec_dtype, true, out, out_dtype, const_cast<uint32_t*>(group_flags), static_cast<cudaStream_t>(stream));
+    SKB_LAUNCH_CHECK("assemble_resolve_kernel");
     return SKB_OK;
 }
 

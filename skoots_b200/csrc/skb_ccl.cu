@@ -737,7 +737,7 @@ extern "C" size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64
 }
 
 template <typename MaskT>
-static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t st) {
+static void launch_pack(const void* mask, const CclView& v, cudaStream_t st) {
     const MaskT* m = static_cast<const MaskT*>(mask);
     const int nk_shift = shift_of(v.nk);
     const long long rows = (long long)v.X * v.Y;
@@ -748,13 +748,31 @@ static int launch_pack_and_tile(const void* mask, const CclView& v, cudaStream_t
     } else {
         ccl_pack_generic_kernel<MaskT><<<(unsigned)((rows * v.nk + 255) / 256), 256, 0, st>>>(m, v);
     }
+}
+
+static void launch_tile(const CclView& v, cudaStream_t st) {
+    const int nk_shift = shift_of(v.nk);
     const long long xt = (v.X + 7) / 8, n_yk = (long long)((v.Y + 7) / 8) * v.nk;
     const long long n_tiles = xt * n_yk;
     long long blocks = (n_tiles + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS;
     if (blocks > 148 * 5) blocks = 148 * 5;  // 5 resident CTAs per SM (40 KB of shared memory each), persistent warps
     ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift,
                                                                     n_yk < (1LL << 30) ? shift_of((int)n_yk) : -1);
-    return SKB_OK;
+}
+
+// the part of a labelling pass selected by flags (SKB_CCL_PHASE_*): header + clears + pack, and/or the tile kernel
+static void launch_pack_and_tile(const void* mask, int mask_dtype, const CclView& v, const SkbCclLayout& L, const SkbCclHeader& h,
+                                 int flags, cudaStream_t st) {
+    const bool all = !(flags & (SKB_CCL_PHASE_PACK | SKB_CCL_PHASE_LABEL));
+    if (all || (flags & SKB_CCL_PHASE_PACK)) {
+        char* base = reinterpret_cast<char*>(v.hdr);
+        ccl_init_kernel<<<1, 32, 0, st>>>(v, h);  // header by value: no host->device copy on the path
+        if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
+        cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
+        if (mask_dtype == SKB_U8) launch_pack<uint8_t>(mask, v, st);
+        else launch_pack<int16_t>(mask, v, st);
+    }
+    if (all || (flags & SKB_CCL_PHASE_LABEL)) launch_tile(v, st);
 }
 
 static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int TY, cudaStream_t st) {
@@ -784,14 +802,9 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     SkbCclHeader h = {};
     h.label_base = label_base; h.planar = planar; h.capacity = (int)capacity;
     h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
-    char* base = static_cast<char*>(workspace);
-    ccl_init_kernel<<<1, 32, 0, st>>>(v, h);  // header by value: no host->device copy on the path
-    if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
-    cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
-
-    rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
-    if (rc) return rc;
+    launch_pack_and_tile(mask, mask_dtype, v, L, h, flags, st);
     SKB_LAUNCH_CHECK("ccl_pack/tile_kernel");
+    if ((flags & SKB_CCL_PHASE_PACK) && !(flags & SKB_CCL_PHASE_LABEL)) return SKB_OK;
 
     const int TY = 8, TX = 8;
     launch_boundary(v, L, TX, TY, st);
@@ -1130,12 +1143,9 @@ extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X
     SkbCclHeader h = {};
     h.capacity = (int)capacity;
     h.dims[0] = L.X; h.dims[1] = L.Y; h.dims[2] = L.Z;
-    char* base = static_cast<char*>(workspace);
-    ccl_init_kernel<<<1, 32, 0, st>>>(v, h);
-    if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
-    cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
-    rc = mask_dtype == SKB_U8 ? launch_pack_and_tile<uint8_t>(mask, v, st) : launch_pack_and_tile<int16_t>(mask, v, st);
-    if (rc) return rc;
+    launch_pack_and_tile(mask, mask_dtype, v, L, h, flags, st);
+    SKB_LAUNCH_CHECK("skb_shard_label_local (pack/tile)");
+    if ((flags & SKB_CCL_PHASE_PACK) && !(flags & SKB_CCL_PHASE_LABEL)) return SKB_OK;
     launch_boundary(v, L, 8, 8, st);
     shard_local_roots_kernel<<<148 * 4, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_label_local");

@@ -31,41 +31,68 @@ def default_capacity(voxels: int) -> int:
     return max(1 << 16, voxels // 8)
 
 
-def label_components(mask: Tensor, planar: bool = False, label_base: int = 2, capacity: Optional[int] = None,
-                     workspace: Optional[Tensor] = None, check: bool = True) -> SparseLabels:
-    """Connected components of `mask > 0` in the sparse on-device form.
-    mask: (X,Y,Z) uint8/bool/int16 CUDA tensor.  6-connectivity, or per-x-plane 4-connectivity when
-    `planar`.  Labels are label_base+1.. in scipy.ndimage.label's raster order."""
-    dev = L.require_cuda(mask)
+def _as_mask(mask: Tensor) -> Tensor:
     if mask.ndim != 3:
         raise RuntimeError(f"mask must be (X,Y,Z), got {tuple(mask.shape)}")
     if mask.dtype == torch.bool:
         mask = mask.view(torch.uint8)
     elif mask.dtype not in (torch.uint8, torch.int16):
         mask = mask.gt(0).view(torch.uint8)
-    mask = mask.contiguous()
+    return mask.contiguous()
+
+
+def _workspace_for(shape, cap: int, workspace: Optional[Tensor], dev) -> Tensor:
+    need = L.load().skb_ccl_workspace_bytes(*shape, cap)
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    return workspace
+
+
+def launch_label(mask: Tensor, sparse: "SparseLabels", planar: bool, label_base: int, phase: int = 0) -> None:
+    """enqueues the labelling of `mask` into sparse.workspace on the current stream.  phase = 0 (all),
+    L.CCL_PHASE_PACK (header + bit mask only) or L.CCL_PHASE_LABEL (everything after the pack)."""
+    dev = mask.device
+    X, Y, Z = sparse.shape
+    ws = sparse.workspace
+    flags = phase
+    if phase != L.CCL_PHASE_LABEL:
+        # a workspace that already went through a pass of this shape has its root bitmap zeroed (see the C header)
+        key = (X, Y, Z, sparse.capacity, ws.data_ptr())
+        if getattr(ws, "_skb_clean", None) == key:
+            flags |= L.CCL_WORKSPACE_CLEAN
+        ws._skb_clean = None
+    with torch.cuda.device(dev):
+        L.check(L.load().skb_ccl_label_sparse(mask.data_ptr(), L.dtype_code(mask), X, Y, Z, int(planar), int(label_base),
+                                              sparse.capacity, ws.data_ptr(), ws.numel(), sparse.ncomp.data_ptr(),
+                                              sparse.status.data_ptr(), flags, L.stream_ptr(dev)))
+    if phase != L.CCL_PHASE_PACK:
+        ws._skb_clean = (X, Y, Z, sparse.capacity, ws.data_ptr())
+
+
+def new_sparse(shape, dev, capacity: Optional[int] = None, workspace: Optional[Tensor] = None) -> "SparseLabels":
+    X, Y, Z = shape
+    cap = int(capacity) if capacity else default_capacity(X * Y * Z)
+    workspace = _workspace_for((X, Y, Z), cap, workspace, dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)
+    return SparseLabels(workspace, (X, Y, Z), meta[0], meta[1], cap)
+
+
+def label_components(mask: Tensor, planar: bool = False, label_base: int = 2, capacity: Optional[int] = None,
+                     workspace: Optional[Tensor] = None, check: bool = True) -> SparseLabels:
+    """Connected components of `mask > 0` in the sparse on-device form.
+    mask: (X,Y,Z) uint8/bool/int16 CUDA tensor.  6-connectivity, or per-x-plane 4-connectivity when
+    `planar`.  Labels are label_base+1.. in scipy.ndimage.label's raster order."""
+    dev = L.require_cuda(mask)
+    mask = _as_mask(mask)
     X, Y, Z = mask.shape
-    lib = L.load()
     V = X * Y * Z
     cap = int(capacity) if capacity else default_capacity(V)
     while True:
-        need = lib.skb_ccl_workspace_bytes(X, Y, Z, cap)
-        if workspace is None or workspace.numel() < need or workspace.device != dev:
-            workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-        meta = torch.empty(2, dtype=torch.int32, device=dev)
-        # a workspace that already went through a pass of this shape has its root bitmap zeroed (see the C header)
-        key = (X, Y, Z, cap, workspace.data_ptr())
-        flags = L.CCL_WORKSPACE_CLEAN if getattr(workspace, "_skb_clean", None) == key else 0
-        workspace._skb_clean = None
-        with torch.cuda.device(dev):
-            L.check(lib.skb_ccl_label_sparse(mask.data_ptr(), L.dtype_code(mask), X, Y, Z, int(planar), int(label_base),
-                                             cap, workspace.data_ptr(), workspace.numel(), meta[0:1].data_ptr(),
-                                             meta[1:2].data_ptr(), flags, L.stream_ptr(dev)))
-        workspace._skb_clean = key
-        res = SparseLabels(workspace, (X, Y, Z), meta[0], meta[1], cap)
+        res = new_sparse((X, Y, Z), dev, cap, workspace)
+        launch_label(mask, res, planar, label_base)
         if not check:
             return res
-        if int(meta[1].item()) & L.STATUS_ROOT_OVERFLOW and cap < V // 2 + 1:
+        if int(res.status.item()) & L.STATUS_ROOT_OVERFLOW and cap < V // 2 + 1:
             cap, workspace = V // 2 + 1, None
             continue
         res.check()

@@ -14,7 +14,7 @@ from torch import Tensor
 
 from . import _lib as L
 from .lib._util import as_floats
-from .lib.flood_fill import SparseLabels, label_components
+from .lib.flood_fill import SparseLabels, _as_mask, label_components, launch_label, new_sparse
 
 EVAL_CROP = (500, 500, 50)      # skoots/lib/eval.py:248
 EVAL_OVERLAP = (50, 50, 5)      # skoots/lib/eval.py:249
@@ -57,15 +57,113 @@ def gather_instances(vectors: Tensor, scale, labels, N: int = 1, decay: float = 
     return out
 
 
+_CHAIN_STREAMS = {}
+
+
+def chain_stream(dev: torch.device) -> torch.cuda.Stream:
+    """the high-priority stream the labelling chain runs on while the gather's stream phase owns the rest of the GPU."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _CHAIN_STREAMS.get(key)
+    if st is None:
+        st = _CHAIN_STREAMS[key] = torch.cuda.Stream(dev, priority=-1)
+    return st
+
+
+def split_eligible(shape, vectors: Tensor, N: int, crop, overlap) -> bool:
+    """the stream/resolve split covers the headline mode: N = 1, the whole volume as one crop, Z a multiple
+    of 64 and the volume a multiple of 256 voxels (include/skoots_b200.h: skb_assemble_stream)."""
+    X, Y, Z = shape
+    whole = crop is None or all(int(c) >= d for c, d in zip(crop, shape))
+    return (N == 1 and whole and not any(int(o) for o in overlap) and Z % 64 == 0 and (X * Y * Z) % 256 == 0
+            and vectors.dtype in (torch.float16, torch.bfloat16, torch.float32) and vectors.is_contiguous()
+            and vectors.data_ptr() % 16 == 0 and (X * Y * Z * vectors.element_size()) % 16 == 0)
+
+
+def assemble_split(mask: Tensor, vectors: Tensor, scale, sparse: SparseLabels, out: Tensor,
+                   group_flags: Optional[Tensor] = None, timers=None, trace: Optional[dict] = None) -> Tensor:
+    """One N = 1 whole-volume pass with the gather split around the labelling:
+
+        current stream : pack mask->bits | stream phase (6 B/voxel in, zeros out, flags work groups) | resolve
+        chain stream   :                 | tile union-find, boundary unions, numbering (latency-bound) |
+
+    Writes exactly what label_components + gather_instances write.  timers = (e0, e1): CUDA events recorded
+    around the stream phase on the current stream."""
+    dev = vectors.device
+    X, Y, Z = sparse.shape
+    lib = L.load()
+    if group_flags is None:
+        group_flags = torch.empty(X * Y * Z // 256, dtype=torch.int32, device=dev)
+    main, side = torch.cuda.current_stream(dev), chain_stream(dev)
+
+    def mark(name, stream):  # trace: name -> timing event (profiles/split_timeline.py)
+        if trace is not None:
+            trace[name] = torch.cuda.Event(enable_timing=True)
+            trace[name].record(stream)
+
+    mark("begin", main)
+    launch_label(mask, sparse, False, 2, L.CCL_PHASE_PACK)
+    bits_ready = torch.cuda.Event()
+    bits_ready.record(main)
+    mark("packed", main)
+    side.wait_event(bits_ready)
+    with torch.cuda.stream(side):
+        mark("chain_begin", side)
+        launch_label(mask, sparse, False, 2, L.CCL_PHASE_LABEL)
+        labelled = torch.cuda.Event()
+        labelled.record(side)
+        mark("chain_end", side)
+    with torch.cuda.device(dev):
+        if timers is not None:
+            timers[0].record(main)
+        L.check(lib.skb_assemble_stream(vectors.data_ptr(), L.dtype_code(vectors), X, Y, Z, 0, Z, sparse.workspace.data_ptr(),
+                                        group_flags.data_ptr(), out.data_ptr(), L.dtype_code(out), main.cuda_stream))
+        if timers is not None:
+            timers[1].record(main)
+        mark("streamed", main)
+        main.wait_event(labelled)
+        mark("joined", main)
+        L.check(lib.skb_assemble_resolve(vectors.data_ptr(), L.dtype_code(vectors), X, Y, Z, 0, Z, L.f3(as_floats(scale, 3)),
+                                         sparse.workspace.data_ptr(), 0, 0, group_flags.data_ptr(), out.data_ptr(),
+                                         L.dtype_code(out), main.cuda_stream))
+    mark("resolved", main)
+    return out
+
+
 def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1, decay: float = 1.0,
                        crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0),
                        out_dtype: torch.dtype = torch.int32, check: bool = True,
-                       workspace: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+                       workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                       fused: Optional[bool] = None) -> Tensor:
     """skeleton_mask (X,Y,Z) or (1,X,Y,Z) u8/bool/int16; vectors (3,X,Y,Z) -> instance labels (X,Y,Z).
 
     crop=None treats the whole volume as one crop (the lib functions applied directly);
-    crop=EVAL_CROP, overlap=EVAL_OVERLAP, N=EVAL_N, out_dtype=int16 reproduces eval()."""
+    crop=EVAL_CROP, overlap=EVAL_OVERLAP, N=EVAL_N, out_dtype=int16 reproduces eval().
+    fused=None / True: label, then one fused gather (the fastest form measured, DESIGN.md §Kernels);
+    fused=False: the stream/resolve split with the gather's stream phase overlapped with the labelling
+    (kept as a measured alternative: bit-identical, slower on B200 because the labelling kernels fill the SMs)."""
     mask = skeleton_mask.squeeze(0) if skeleton_mask.ndim == 4 else skeleton_mask
+    dev = L.require_cuda(mask, vectors)
+    if vectors.ndim != 4 or vectors.shape[0] != 3:
+        raise RuntimeError(f"vectors must be (3,X,Y,Z), got {tuple(vectors.shape)}")
+    if vectors.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+        vectors = vectors.float()
+    vectors = vectors.contiguous()
+    shape = tuple(vectors.shape[1:])
+    eligible = split_eligible(shape, vectors, N, crop, overlap)
+    if fused is False and not eligible:
+        raise L.SkootsB200Error("the stream/resolve split needs N = 1, one whole-volume crop, Z % 64 == 0 and V % 256 == 0")
+    if fused is None:
+        fused = True
+    if not fused:
+        mask = _as_mask(mask)
+        sparse = new_sparse(shape, dev, None, workspace)
+        if out is None:
+            out = torch.empty(shape, dtype=out_dtype, device=dev)
+        assert out.is_contiguous() and tuple(out.shape) == shape and out.dtype in (torch.int32, torch.int16)
+        assemble_split(mask, vectors, scale, sparse, out)
+        if not check or not (int(sparse.status.item()) & L.STATUS_ROOT_OVERFLOW):
+            return out
+        workspace = None  # more tile-local components than the default capacity: redo at the worst case, fused
     sparse = label_components(mask, planar=False, label_base=2, workspace=workspace, check=check)
     return gather_instances(vectors, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=out,
                             out_dtype=out_dtype)

@@ -24,6 +24,7 @@ checks the sharded result is bit-identical to the unsharded one).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 from typing import List, Optional, Sequence, Tuple
@@ -174,7 +175,7 @@ class ShardedAssembler:
 
     def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
                  comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
-                 out_dtype=torch.int32):
+                 out_dtype=torch.int32, split: Optional[bool] = None):
         if hops != 1:
             raise NotImplementedError("the Z-sharded path implements N = 1")
         X, Y, Z = (int(v) for v in shape)
@@ -217,6 +218,14 @@ class ShardedAssembler:
             self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
         self.meta = mk(2)  # [n_components, status]
         self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
+        # stream/resolve split of the gather (pipeline.assemble_split): the slab's stream phase runs on the current
+        # stream while the labelling chain AND both exchanges run on a high-priority side stream
+        can_split = (X * Y * self.Zl) % 256 == 0
+        if split and not can_split:
+            raise ValueError("the stream/resolve split needs the slab to be a multiple of 256 voxels")
+        self.split = bool(split)  # off by default: measured slower than the fused slab gather
+        self.flags = torch.empty(X * Y * self.Zl // 256, dtype=torch.int32, device=self.dev) if self.split else None
+        self._chain_done = None
         self._clean = False
         self.mask: Optional[Tensor] = None
         self.vec: Optional[Tensor] = None
@@ -224,7 +233,8 @@ class ShardedAssembler:
         # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1;
         # peer transport adds begin=1, a signal per emitted face, push+signal=2
         faces = (rank > 0) + (rank < world - 1)
-        self.launches_per_step = 5 + 2 * faces + 2 + 11 + 1 + ((3 + faces) if self.transport == "peer" else 0)
+        self.launches_per_step = (5 + 2 * faces + 2 + 11 + 1 + ((3 + faces) if self.transport == "peer" else 0)
+                                  + (1 if self.split else 0))  # split: stream + resolve instead of one gather
 
     def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:
         """peer transport: my mailbox and the (mapped) base pointers of every rank's mailbox, own included."""
@@ -243,6 +253,26 @@ class ShardedAssembler:
     def _s(self):
         return L.stream_ptr(self.dev)
 
+    def _chain(self):
+        """context of the labelling chain: the high-priority side stream when the gather is split."""
+        if not self.split:
+            return contextlib.nullcontext()
+        from .pipeline import chain_stream
+        return torch.cuda.stream(chain_stream(self.dev))
+
+    def _label_local(self, phase: int) -> None:
+        X, Y, Z = self.shape
+        flags = phase | (L.CCL_WORKSPACE_CLEAN if self._clean and phase != L.CCL_PHASE_LABEL else 0)
+        L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, self.z_range[0], self.Zl,
+                                               self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
+                                               self.meta[1:2].data_ptr(), flags, self._s()))
+
+    def _stream_phase(self) -> None:
+        X, Y, Z = self.shape
+        L.check(self.lib.skb_assemble_stream(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0], self.Zl,
+                                             self.workspace.data_ptr(), self.flags.data_ptr(), self.out.data_ptr(),
+                                             L.dtype_code(self.out), self._s()))
+
     # ---- phases ------------------------------------------------------------------------------------
     def phase_local(self) -> None:
         X, Y, Z = self.shape
@@ -251,11 +281,20 @@ class ShardedAssembler:
         with torch.cuda.device(self.dev):
             if peer:
                 L.check(self.lib.skb_shard_begin(self.mailbox.ptr, *self._geom, self._s()))
-            L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, z0, self.Zl,
-                                                   self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
-                                                   self.meta[1:2].data_ptr(), L.CCL_WORKSPACE_CLEAN if self._clean else 0,
-                                                   self._s()))
+            if self.split:
+                from .pipeline import chain_stream
+                main = torch.cuda.current_stream(self.dev)
+                self._label_local(L.CCL_PHASE_PACK)
+                bits_ready = torch.cuda.Event()
+                bits_ready.record(main)
+                self._stream_phase()  # owns the current stream from here until the resolve
+                chain_stream(self.dev).wait_event(bits_ready)
+            else:
+                self._label_local(0)
             self._clean = False
+        with torch.cuda.device(self.dev), self._chain():
+            if self.split:
+                self._label_local(L.CCL_PHASE_LABEL)
             if peer:
                 for hi, ok, za, zb in ((0, self.rank > 0, z0, z0 + self.halo),
                                        (1, self.rank < self.world - 1, z1 - self.halo, z1)):
@@ -276,7 +315,7 @@ class ShardedAssembler:
         X, Y, Z = self.shape
         z0, z1 = self.z_range
         peer = self.transport == "peer"
-        with torch.cuda.device(self.dev):
+        with torch.cuda.device(self.dev), self._chain():
             for hi, halo, recv in ((0, self.halo_lo, None if peer else self.recv_lo),
                                    (1, self.halo_hi, None if peer else self.recv_hi)):
                 if halo is None:
@@ -300,7 +339,7 @@ class ShardedAssembler:
         """after the all-gather: `gathered` holds every rank's roots and pairs."""
         X, Y, Z = self.shape
         z0, _ = self.z_range
-        with torch.cuda.device(self.dev):
+        with torch.cuda.device(self.dev), self._chain():
             if self.transport == "peer":
                 L.check(self.lib.skb_shard_merge_peer(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.mailbox.ptr,
                                                       self.world, self.rank, self.cap_runs, self.cap_roots, self.cap_pairs, 2,
@@ -310,6 +349,17 @@ class ShardedAssembler:
                                                  self.world, self.rank, self.cap_roots, self.cap_pairs, 2,
                                                  self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
             self._clean = True  # a completed merge leaves the root bitmap zeroed
+            if self.split:
+                chain_done = torch.cuda.Event()
+                chain_done.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.device(self.dev):
+            if self.split:
+                torch.cuda.current_stream(self.dev).wait_event(chain_done)
+                L.check(self.lib.skb_assemble_resolve(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
+                                                      L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
+                                                      L.ptr(self.halo_hi), self.flags.data_ptr(), self.out.data_ptr(),
+                                                      L.dtype_code(self.out), self._s()))
+                return self.out
             if timers is not None:
                 timers[0].record()
             L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
@@ -349,11 +399,41 @@ class ShardedAssembler:
     def _step_eager(self, timers=None) -> Tensor:
         self.phase_local()
         if self.transport != "peer":
-            self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
+            with self._chain():
+                self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
         self.phase_ingest()
         if self.transport != "peer":
-            self.comm.all_gather(self.gathered, self.exch)
+            with self._chain():
+                self.comm.all_gather(self.gathered, self.exch)
         return self.phase_merge_and_gather(timers)
+
+    def time_dominant(self, steps: int = 5) -> Tuple[str, float]:
+        """(kernel name, mean ms per launch) of the pass's dominant kernel timed ALONE with CUDA events on this
+        rank's slab: the stream phase when the gather is split, else the fused slab gather (run after a pass,
+        so the labels it reads exist)."""
+        X, Y, Z = self.shape
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        with torch.cuda.device(self.dev):
+            for _ in range(steps + 1):
+                a.record()
+                if self.split:
+                    self._stream_phase()
+                else:
+                    L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0],
+                                                       self.Zl, L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
+                                                       L.ptr(self.halo_hi), self.out.data_ptr(), L.dtype_code(self.out), self._s()))
+                b.record()
+                torch.cuda.synchronize(self.dev)
+                if _:
+                    total += a.elapsed_time(b)
+            if self.split:  # the stream phase left the flagged groups unwritten: finish the pass it started
+                L.check(self.lib.skb_assemble_resolve(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0], self.Zl,
+                                                      L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
+                                                      L.ptr(self.halo_hi), self.flags.data_ptr(), self.out.data_ptr(),
+                                                      L.dtype_code(self.out), self._s()))
+                torch.cuda.synchronize(self.dev)
+        return ("assemble_stream_kernel" if self.split else "assemble_kernel"), total / steps
 
     def profile_phases(self, steps: int = 5) -> dict:
         """mean device time (ms) of each phase of a pass on this rank (CUDA events on the current stream).
@@ -361,6 +441,7 @@ class ShardedAssembler:
         peer = self.transport == "peer"
         names = ["local", "exchange_runs", "ingest_pairs", "all_gather", "merge", "gather"]
         acc = dict.fromkeys(names, 0.0)
+        saved_split, self.split = self.split, False  # phases back to back on one stream, fused gather
         for _ in range(steps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             mid = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -379,6 +460,7 @@ class ShardedAssembler:
                      ev[3].elapsed_time(ev[4]), ev[4].elapsed_time(mid[0]), mid[0].elapsed_time(mid[1])]
             for n, v in zip(names, spans):
                 acc[n] += v / steps
+        self.split = saved_split
         if not peer:
             acc["runs_sent"] = [int(self.send_lo[0].item()), int(self.send_hi[0].item())]
         acc["roots_pairs"] = [int(self.exch[0].item()), int(self.exch[1].item())]
@@ -457,17 +539,19 @@ class LocalGroup:
         for r in self.ranks:
             r.phase_local()
         if self.transport != "peer":
-            for i, r in enumerate(self.ranks):
-                if i > 0:
-                    r.recv_lo.copy_(self.ranks[i - 1].send_hi)
-                if i < self.world - 1:
-                    r.recv_hi.copy_(self.ranks[i + 1].send_lo)
+            with self.ranks[0]._chain():  # the stand-ins for the collectives go where the chain runs
+                for i, r in enumerate(self.ranks):
+                    if i > 0:
+                        r.recv_lo.copy_(self.ranks[i - 1].send_hi)
+                    if i < self.world - 1:
+                        r.recv_hi.copy_(self.ranks[i + 1].send_lo)
         for r in self.ranks:
             r.phase_ingest()
         if self.transport != "peer":
-            allg = torch.cat([r.exch for r in self.ranks])
-            for r in self.ranks:
-                r.gathered.copy_(allg)
+            with self.ranks[0]._chain():
+                allg = torch.cat([r.exch for r in self.ranks])
+                for r in self.ranks:
+                    r.gathered.copy_(allg)
         outs = [r.phase_merge_and_gather() for r in self.ranks]
         for r in self.ranks:
             ncomp, status = (int(v) for v in r.meta.tolist())

@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_equals_unsharded_on_tubes(world, transport):
+def test_sharded_equals_unsharded_on_tubes(world, transport, split):
     from skoots_b200.pipeline import assemble_instances
     from skoots_b200.sharded import LocalGroup
     shape = (96, 80, 256)
@@ -23,7 +24,7 @@ def test_sharded_equals_unsharded_on_tubes(world, transport):
     tv.vectors[2, 36:47, 26:37, :] = 0.5
     scale = (60, 60, 12)
     want = assemble_instances(tv.skeleton, tv.vectors, torch.tensor(scale), N=1)
-    grp = LocalGroup(shape, world, DEV, scale=scale, transport=transport)
+    grp = LocalGroup(shape, world, DEV, scale=scale, transport=transport, split=split)
     grp.load_volume(tv.skeleton, tv.vectors)
     got = grp.step()
     assert torch.equal(got, want)

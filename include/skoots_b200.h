@@ -277,12 +277,12 @@ size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t cap_roots, i
 /* starts pass k+1: bumps the mailbox's pass counter, clears its run counters */
 int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
                     void* stream);
-/* like skb_shard_emit_runs, but the triples are stored into `neighbour_mailbox` (the rank below for
- * the low face, above for the high face) and its flag is released */
-int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high,
-                             int64_t z_lo, int64_t z_hi, void* mailbox, void* neighbour_mailbox,
-                             int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
-                             uint32_t* status, void* stream);
+/* like skb_shard_emit_runs for BOTH faces of the slab with one launch (`halo` planes each): the triples
+ * are stored into the neighbours' mailboxes (NULL = no neighbour on that side) and their flags released */
+int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                             int64_t halo, void* mailbox, void* lo_neighbour_mailbox,
+                             void* hi_neighbour_mailbox, int world, int64_t cap_runs, int64_t cap_roots,
+                             int64_t cap_pairs, uint32_t* status, void* stream);
 /* waits for the neighbour's flag, then skb_shard_ingest_runs on the mailbox's receive buffer */
 int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, void* mailbox,
                                int from_high, int world, int64_t cap_runs, int64_t cap_roots,

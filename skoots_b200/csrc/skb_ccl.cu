@@ -74,6 +74,7 @@ struct CclView {
     ull* face_lo;   // sharded mode only (else NULL): word k0 / k0+nk-1 of every row, contiguous
     ull* face_hi;
     int* chunks;
+    unsigned* cursors;  // SKB_TILE_CURSORS work cursors, SKB_TILE_CURSOR_STRIDE ints apart
     int* scan_tiles;
     int* tile_roots;
     int* flat;
@@ -182,7 +183,8 @@ __device__ __forceinline__ unsigned seg_bits(const MaskT* p, int n, bool vec_ok)
     return bits;
 }
 
-__global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {
+__global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {  // <<<1, SKB_TILE_CURSORS>>>
+    v.cursors[threadIdx.x * SKB_TILE_CURSOR_STRIDE] = 0u;
     if (threadIdx.x == 0) {
         *v.hdr = h;
         *v.status = 0u;
@@ -386,23 +388,35 @@ __device__ __forceinline__ void append_roots(const CclView& v, int* sbuf, int& b
 }
 
 constexpr int CCL_TILE_WARPS = 8;
+constexpr int CCL_TILE_BATCH = 4;  // consecutive tiles a warp claims at a time
 
-// Warps are PERSISTENT and independent: a fixed grid, every warp strides over the tile list and
-// prefetches the next tile's two row words while it works on the current one.  (With one tile per warp
-// and 8 warps per CTA the CTA's shared memory stays pinned until its slowest warp — the one tile in
-// eight that is not empty — has finished, and occupancy collapses to ~20 %.)
-__global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v, unsigned n_tiles, unsigned n_yk,
-                                                                       int nk_shift, int nyk_shift) {
+// Warps are PERSISTENT and independent (with one tile per warp and 8 warps per CTA the CTA's shared
+// memory stays pinned until its slowest warp — the one tile in four that is not empty — has finished).
+// Work is handed out DYNAMICALLY, a batch of CCL_TILE_BATCH consecutive tiles per atomicAdd: a non-empty
+// tile costs ~50x an empty one and a slab of an 8-way split has only ~11 tiles per warp, so a static
+// assignment finishes with the unluckiest warp (measured: 1.7x the per-voxel time of the whole
+// volume).  ONE cursor would not do — same-address atomics retire at ~20 ns each on B200 (measured:
+// 16 K claims on one word turned a 110 us kernel into 367 us) — so the batch list is cut into
+// SKB_TILE_CURSORS interleaved ranges with a cursor each (own 128-byte line); a warp serves the range
+// (its global id mod SKB_TILE_CURSORS) and, once that is exhausted, steals from the next range that
+// still has work.  It claims its next batch a whole batch ahead of its use.
+__global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclView v, unsigned n_tiles, unsigned n_yk,
+                                                                       int nk_shift, int nyk_shift, int dynamic) {
     __shared__ ull srow_all[CCL_TILE_WARPS][64];
     __shared__ unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
     __shared__ int rootbuf_all[CCL_TILE_WARPS][CCL_ROOT_BUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned n_warps = gridDim.x * CCL_TILE_WARPS;
     int* sbuf = rootbuf_all[warp];
     int buf_n = 0;
     ull* srow = srow_all[warp];
     unsigned short* slab = slab_all[warp];
     const int r0 = lane, r1 = lane + 32;
+    // dynamic: batches of CCL_TILE_BATCH consecutive tiles claimed from the cursors.  static (few tiles per warp,
+    // where the claims cost more than the imbalance — measured 141 vs 110 us on a 1/8 slab): single tiles, strided.
+    const unsigned tile_batch = dynamic ? CCL_TILE_BATCH : 1;
+    const unsigned n_batches = (n_tiles + tile_batch - 1) / tile_batch;
+    const unsigned n_warps = gridDim.x * CCL_TILE_WARPS;
+    unsigned static_next = blockIdx.x * CCL_TILE_WARPS + warp;
 
     struct Tile { int x0, y0, k; };
     auto decode = [&](unsigned t) -> Tile {  // tile list order: k fastest, then y tile, then x tile
@@ -418,19 +432,77 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
             if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.nk + (T.k - v.k0)];
         }
     };
+    // range r owns the batches r, r + n_ranges, r + 2 n_ranges, ... (strided, so that every range samples the
+    // whole volume and the ranges carry about the same work); cursor r counts how many of them are claimed
+    const unsigned n_ranges = min((unsigned)SKB_TILE_CURSORS, gridDim.x * CCL_TILE_WARPS);  // every range has a warp
+    unsigned my = (blockIdx.x * CCL_TILE_WARPS + warp) % n_ranges;
+    auto claim = [&](unsigned r) -> unsigned {  // lane 0's value is the one that counts
+        return lane == 0 ? r + n_ranges * atomicAdd(v.cursors + r * SKB_TILE_CURSOR_STRIDE, 1u) : 0u;
+    };
+    unsigned pending = dynamic ? claim(my) : 0u, scanned = 0;
+    // the batch claimed last, or, when my range is exhausted, one stolen from the next range that still has work
+    // (exhausted cursors are skipped with plain loads: only a cursor that looks alive costs an atomic)
+    auto next_batch = [&](unsigned& batch) -> bool {
+        if (!dynamic) {
+            batch = static_next;
+            static_next += n_warps;
+            return batch < n_batches;
+        }
+        for (;;) {
+            batch = __shfl_sync(0xffffffffu, pending, 0);
+            if (batch < n_batches) {
+                pending = claim(my);  // a whole batch ahead of its use
+                return true;
+            }
+            unsigned found = n_ranges;
+            while (scanned < n_ranges && found == n_ranges) {
+                const unsigned off = scanned + 1u + lane;
+                unsigned r = my + off;
+                r -= r >= n_ranges ? n_ranges : 0u;
+                bool alive = false;
+                if (off < n_ranges) {
+                    const unsigned c = *reinterpret_cast<volatile unsigned*>(v.cursors + r * SKB_TILE_CURSOR_STRIDE);
+                    alive = (unsigned long long)r + (unsigned long long)n_ranges * c < n_batches;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                if (m) {
+                    const int first = __ffs((int)m) - 1;
+                    found = __shfl_sync(0xffffffffu, r, first);
+                    scanned += (unsigned)first;  // the ranges before it are exhausted for good
+                } else {
+                    scanned += 32u;
+                }
+            }
+            if (found == n_ranges) return false;
+            my = found;
+            scanned = 0;
+            pending = claim(my);
+        }
+    };
 
-    unsigned t = blockIdx.x * CCL_TILE_WARPS + warp;
-    if (t >= n_tiles) return;
+    // One tile at a time, the next tile's two row words in flight while the current one is labelled (a
+    // single copy of the labelling code: unrolling it over a batch quadrupled the kernel's time).
+    unsigned batch;
+    if (!next_batch(batch)) return;
+    unsigned t = batch * tile_batch, t_end = min(t + tile_batch, n_tiles);
     Tile cur = decode(t);
     ull w0, w1;
     load(cur, w0, w1);
     for (;;) {
-        const unsigned tn = t + n_warps;
+        unsigned tn = t + 1;
+        bool more = true;
+        if (tn >= t_end) {
+            more = next_batch(batch);
+            if (more) {
+                tn = batch * tile_batch;
+                t_end = min(tn + tile_batch, n_tiles);
+            }
+        }
         Tile nxt = cur;
         ull n0 = 0, n1 = 0;
-        if (tn < n_tiles) {
+        if (more) {
             nxt = decode(tn);
-            load(nxt, n0, n1);  // in flight while the current tile is labelled
+            load(nxt, n0, n1);
         }
         if (__any_sync(0xffffffffu, (w0 | w1) != 0ull)) {
             const int z0 = 64 * cur.k;
@@ -454,7 +526,7 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS) ccl_tile_kernel(CclView v
             __syncwarp();  // shared memory is reused by this warp's next tile
             append_roots(v, sbuf, buf_n, lane, m0, g0, m1, g1);
         }
-        if (tn >= n_tiles) break;
+        if (!more) break;
         t = tn; cur = nxt; w0 = n0; w1 = n1;
     }
     flush_roots(v, sbuf, buf_n, lane);
@@ -474,8 +546,8 @@ __device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, u
     if (v.y_shift >= 0) { x = rowi >> v.y_shift; y = rowi & (uyy - 1u); }
     else { x = rowi / uyy; y = rowi - x * uyy; }
     const bool face_z = k > 0u && (w & 1ull);
-    const bool face_y = y > 0 && (y % (unsigned)TY) == 0;
-    const bool face_x = v.connect_x && x > 0 && (x % (unsigned)TX) == 0;
+    const bool face_y = y > 0 && (y & (unsigned)(TY - 1)) == 0;  // tile sides are powers of two (8)
+    const bool face_x = v.connect_x && x > 0 && (x & (unsigned)(TX - 1)) == 0;
     if (!(face_z || face_y || face_x)) return;
     const int gbase = (int)(rowi * (unsigned)v.Z + 64u * (k + (unsigned)v.k0));
     if (face_z) {
@@ -719,6 +791,7 @@ static CclView make_view(const SkbCclLayout& L, void* ws, int planar, int64_t ca
     v.rootbits = reinterpret_cast<ull*>(base + L.off_rootbits);
     v.face_lo = nullptr; v.face_hi = nullptr;
     v.chunks = reinterpret_cast<int*>(base + L.off_chunks);
+    v.cursors = reinterpret_cast<unsigned*>(base + L.off_cursors);
     v.scan_tiles = reinterpret_cast<int*>(base + L.off_scan_tiles);
     v.tile_roots = reinterpret_cast<int*>(base + L.off_tile_roots);
     v.flat = reinterpret_cast<int*>(base + L.off_flat);
@@ -756,8 +829,9 @@ static void launch_tile(const CclView& v, cudaStream_t st) {
     const long long n_tiles = xt * n_yk;
     long long blocks = (n_tiles + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS;
     if (blocks > 148 * 5) blocks = 148 * 5;  // 5 resident CTAs per SM (40 KB of shared memory each), persistent warps
+    const int dynamic = n_tiles >= 32 * blocks * CCL_TILE_WARPS ? 1 : 0;
     ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift,
-                                                                    n_yk < (1LL << 30) ? shift_of((int)n_yk) : -1);
+                                                                    n_yk < (1LL << 30) ? shift_of((int)n_yk) : -1, dynamic);
 }
 
 // the part of a labelling pass selected by flags (SKB_CCL_PHASE_*): header + clears + pack, and/or the tile kernel
@@ -766,7 +840,7 @@ static void launch_pack_and_tile(const void* mask, int mask_dtype, const CclView
     const bool all = !(flags & (SKB_CCL_PHASE_PACK | SKB_CCL_PHASE_LABEL));
     if (all || (flags & SKB_CCL_PHASE_PACK)) {
         char* base = reinterpret_cast<char*>(v.hdr);
-        ccl_init_kernel<<<1, 32, 0, st>>>(v, h);  // header by value: no host->device copy on the path
+        ccl_init_kernel<<<1, SKB_TILE_CURSORS, 0, st>>>(v, h);  // header by value: no host->device copy on the path
         if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
         cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
         if (mask_dtype == SKB_U8) launch_pack<uint8_t>(mask, v, st);
@@ -909,9 +983,19 @@ struct RunsDst {
     long long parity_stride;
 };
 
-// counter = count, then (start voxel, length, root id) triples
-__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const ull* __restrict__ face, int z_lo, int z_hi,
-                                                             RunsDst dst, int cap, unsigned* status) {
+// one face of the slab: the planes [z_lo, z_hi) inside the face word, and where its runs go
+struct EmitFace {
+    const ull* face;  // compact copy of that word of every row
+    int z_lo, z_hi;
+    RunsDst dst;
+};
+
+// counter = count, then (start voxel, length, root id) triples.  blockIdx.y picks the face (the peer
+// transport emits both faces of a slab with one launch).
+__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFace f0, EmitFace f1, int cap, unsigned* status) {
+    const EmitFace& f = blockIdx.y ? f1 : f0;
+    const RunsDst& dst = f.dst;
+    const int z_lo = f.z_lo, z_hi = f.z_hi;
     int* const runs = dst.counter;
     int* const tri = dst.triples + (dst.epoch ? (long long)(*dst.epoch & 1) * dst.parity_stride : 0LL);
     const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -919,7 +1003,8 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const u
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
     const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
     ull w = 0;
-    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = face[rowi] & range;  // compact copy of word k of every row
+    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = f.face[rowi] & range;
+    if (!__any_sync(0xffffffffu, w != 0ull)) return;  // ~99 % of the warps: nothing on this face
     const ull starts = w & ~(w << 1);
     // one atomicAdd per warp (a per-run atomic on the single counter would serialise in L2)
     const int cnt = __popcll(starts);
@@ -952,13 +1037,20 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, const u
 
 // peer transport: publishes my face's run count in the neighbour's buffer, then releases its flag.  The
 // triples were stored by the previous kernel on this stream, so they are ordered before the flag.
-__global__ void shard_signal_runs_kernel(const int* local_cnt, int* remote_runs, long long parity_stride, int* remote_flag,
-                                         const int* epoch) {
-    if (threadIdx.x == 0) {
-        const int e = *epoch;
-        remote_runs[(long long)(e & 1) * parity_stride] = *local_cnt;
-        __threadfence_system();
-        st_release_sys(remote_flag, e);
+struct SignalRuns {
+    const int* local_cnt;  // NULL: no such face
+    int* remote_runs;
+    int* remote_flag;
+};
+__global__ void shard_signal_runs_kernel(SignalRuns s0, SignalRuns s1, long long parity_stride, const int* epoch) {
+    if (threadIdx.x < 2) {
+        const SignalRuns& s = threadIdx.x ? s1 : s0;
+        if (s.local_cnt) {
+            const int e = *epoch;
+            s.remote_runs[(long long)(e & 1) * parity_stride] = *s.local_cnt;
+            __threadfence_system();
+            st_release_sys(s.remote_flag, e);
+        }
     }
 }
 
@@ -1038,7 +1130,11 @@ __device__ __forceinline__ bool merge_item(const MergeView& m, const int* base, 
     return true;
 }
 
-__global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeView m) {
+__global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeView m, int label_base) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the mark kernel re-lists the roots; the rank kernel reads label_base
+        v.hdr->n_global_roots = 0u;
+        v.hdr->label_base = label_base;
+    }
     if (m.flags) {  // peer transport: the first merge kernel waits for every rank's payload of this pass
         if ((int)threadIdx.x < m.world) spin_until(m.flags + threadIdx.x * SKB_FLAG_STRIDE, *m.epoch, v.status);
         __syncthreads();
@@ -1083,17 +1179,15 @@ __global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeV
     }
 }
 
-__global__ void shard_set_label_base_kernel(CclView v, int label_base) {
-    if (threadIdx.x == 0) v.hdr->label_base = label_base;
-}
-
-__global__ void shard_reset_groots_kernel(CclView v) {
-    if (threadIdx.x == 0) v.hdr->n_global_roots = 0u;
-}
-
-// every listed root takes the label code of its global root (codes are negative, indices are not)
+// every listed root takes the label code of its global root (codes are negative, indices are not); the
+// root bitmap words the global roots touched are zeroed for the next pass (ccl_clear_rootbits_kernel's job)
 __global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, MergeView m) {
     const int* const base = merge_base(m);
+    const unsigned n_g = min(v.hdr->n_global_roots, (unsigned)v.capacity);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_g; i += gridDim.x * blockDim.x) {
+        int bit;
+        v.rootbits[word_of_voxel(v, v.groots[i], &bit)] = 0ull;
+    }
     const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int root, r;
@@ -1166,8 +1260,8 @@ extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(runs, 0, 3 * sizeof(int32_t), st);
     unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
-    RunsDst dst = {runs, runs + 3, nullptr, 0};
-    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, dst, (int)cap, status);
+    EmitFace f = {face, (int)z_lo, (int)z_hi, {runs, runs + 3, nullptr, 0}};
+    shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, f, f, (int)cap, status);
     SKB_LAUNCH_CHECK("shard_emit_runs_kernel");
     return SKB_OK;
 }
@@ -1226,17 +1320,13 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
 
 static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st) {
     const int g = 148 * 4;
-    shard_merge_init_kernel<<<g, 256, 0, st>>>(v, m);
+    shard_merge_init_kernel<<<g, 256, 0, st>>>(v, m, label_base);
     shard_merge_union_kernel<<<g, 256, 0, st>>>(v, m);
-    shard_reset_groots_kernel<<<1, 32, 0, st>>>(v);
     shard_merge_mark_kernel<<<g, 256, 0, st>>>(v, m);
     ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
     ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
-    // the header's label_base is what the rank kernel reads
-    shard_set_label_base_kernel<<<1, 32, 0, st>>>(v, label_base);
     ccl_rank_kernel<<<g, 256, 0, st>>>(v);
-    ccl_clear_rootbits_kernel<<<g, 256, 0, st>>>(v);
-    shard_publish_roots_kernel<<<g, 256, 0, st>>>(v, m);
+    shard_publish_roots_kernel<<<g, 256, 0, st>>>(v, m);  // also clears the root bitmap
     ccl_publish_kernel<<<g, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_merge");
     return SKB_OK;
@@ -1298,30 +1388,42 @@ extern "C" int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64
     return SKB_OK;
 }
 
-extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high, int64_t z_lo,
-                                        int64_t z_hi, void* mailbox, void* neighbour_mailbox, int world, int64_t cap_runs,
-                                        int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream) {
-    int rc = skb_check_volume(X, Y, Z, "skb_shard_emit_runs_peer");
+extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                        int64_t halo, void* mailbox, void* lo_neighbour_mailbox,
+                                        void* hi_neighbour_mailbox, int world, int64_t cap_runs, int64_t cap_roots,
+                                        int64_t cap_pairs, uint32_t* status, void* stream) {
+    int rc = shard_common("skb_shard_emit_runs_peer", X, Y, Z, z_off, Zl);
     if (rc) return rc;
     rc = mailbox_args("skb_shard_emit_runs_peer", world, cap_runs, cap_roots, cap_pairs);
     if (rc) return rc;
-    SKB_REQUIRE(workspace && mailbox && neighbour_mailbox && status, "skb_shard_emit_runs_peer: NULL pointer");
-    SKB_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= Z && (z_lo >> 6) == ((z_hi - 1) >> 6),
-                "skb_shard_emit_runs_peer: [z_lo,z_hi) must lie inside one 64-plane word");
-    SKB_REQUIRE(face_is_high == 0 || face_is_high == 1, "skb_shard_emit_runs_peer: face_is_high must be 0 or 1");
+    SKB_REQUIRE(workspace && mailbox && status, "skb_shard_emit_runs_peer: NULL pointer");
+    SKB_REQUIRE(halo >= 1 && halo <= 64 && halo <= Zl, "skb_shard_emit_runs_peer: halo must be 1..64 planes and fit the slab");
+    if (!lo_neighbour_mailbox && !hi_neighbour_mailbox) return SKB_OK;
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     CclView v = make_view(L, workspace, 0, 1, status, nullptr);
-    const ull* face = reinterpret_cast<const ull*>(static_cast<const char*>(workspace) + (face_is_high ? L.off_face_hi : L.off_face_lo));
+    const char* base = static_cast<const char*>(workspace);
     Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
-    Mailbox nb = mailbox_at(neighbour_mailbox, world, cap_runs, cap_roots, cap_pairs);
-    // my HIGH face lands in the upper neighbour's recv_lo, my LOW face in the lower neighbour's recv_hi
-    int* remote = nb.recv(face_is_high ? 0 : 1);
-    int* remote_flag = nb.flag(face_is_high ? 0 : 1);
+    // my LOW face lands in the lower neighbour's recv_hi, my HIGH face in the upper neighbour's recv_lo
+    EmitFace f[2];
+    SignalRuns sg[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int n = 0;
+    for (int hi = 0; hi < 2; ++hi) {
+        void* nbp = hi ? hi_neighbour_mailbox : lo_neighbour_mailbox;
+        if (!nbp) continue;
+        Mailbox nb = mailbox_at(nbp, world, cap_runs, cap_roots, cap_pairs);
+        int* remote = nb.recv(hi ? 0 : 1);
+        f[n].face = reinterpret_cast<const ull*>(base + (hi ? L.off_face_hi : L.off_face_lo));
+        f[n].z_lo = (int)(hi ? z_off + Zl - halo : z_off);
+        f[n].z_hi = (int)(hi ? z_off + Zl : z_off + halo);
+        f[n].dst = {me.cnt(hi), remote + 3, me.epoch(), me.M.runs_ints};
+        sg[n] = {me.cnt(hi), remote, nb.flag(hi ? 0 : 1)};
+        ++n;
+    }
+    if (n == 1) f[1] = f[0];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned nblk = (unsigned)(((long long)X * Y + 255) / 256);
-    RunsDst dst = {me.cnt(face_is_high), remote + 3, me.epoch(), me.M.runs_ints};
-    shard_emit_runs_kernel<<<nblk, 256, 0, st>>>(v, face, (int)z_lo, (int)z_hi, dst, (int)cap_runs, status);
-    shard_signal_runs_kernel<<<1, 32, 0, st>>>(me.cnt(face_is_high), remote, me.M.runs_ints, remote_flag, me.epoch());
+    shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);
+    shard_signal_runs_kernel<<<1, 32, 0, st>>>(sg[0], sg[1], me.M.runs_ints, me.epoch());
     SKB_LAUNCH_CHECK("skb_shard_emit_runs_peer");
     return SKB_OK;
 }

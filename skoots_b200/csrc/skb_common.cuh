@@ -72,13 +72,15 @@ struct SkbCclHeader {
 };
 
 constexpr int SKB_SCAN_TILE = 8192;
+constexpr int SKB_TILE_CURSORS = 256;        // work cursors of the tile kernel, one 128-byte line each
+constexpr int SKB_TILE_CURSOR_STRIDE = 32;   // ints
 
 struct SkbCclLayout {
     int X, Y, Z, ZW;      // ZW = 64-bit words per (x,y) row of the bit-packed mask
     int64_t V, n_words, n_chunks;
     int64_t n_scan_tiles;  // chunk histogram is scanned in tiles of SKB_SCAN_TILE entries
-    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_face_lo, off_face_hi, off_tile_roots, off_flat,
-        off_groots, total;
+    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_face_lo, off_face_hi, off_cursors,
+        off_tile_roots, off_flat, off_groots, total;
 };
 
 static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64_t capacity) {
@@ -98,6 +100,7 @@ static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64
     // sharded mode: compact copies of every row's first / last word of the slab (the planes the neighbours need)
     L.off_face_lo = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
     L.off_face_hi = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
+    L.off_cursors = at;    at = skb_align_up(at + (size_t)SKB_TILE_CURSORS * SKB_TILE_CURSOR_STRIDE * 4, 256);
     L.off_tile_roots = at; at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_flat = at;       at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_groots = at;     at = skb_align_up(at + (size_t)capacity * 4, 256);

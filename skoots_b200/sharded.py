@@ -233,8 +233,13 @@ class ShardedAssembler:
         # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1;
         # peer transport adds begin=1, a signal per emitted face, push+signal=2
         faces = (rank > 0) + (rank < world - 1)
-        self.launches_per_step = (5 + 2 * faces + 2 + 11 + 1 + ((3 + faces) if self.transport == "peer" else 0)
-                                  + (1 if self.split else 0))  # split: stream + resolve instead of one gather
+        if self.transport == "peer":
+            # begin, local(init,pack,tile,boundary,roots)=5, emit+signal<=2, ingest=faces, pack_roots+pairs<=2, push+signal=2,
+            # merge(init,union,mark,scan x2,rank,publish x2)=8, gather=1
+            self.launches_per_step = 1 + 5 + 2 * (faces > 0) + faces + 1 + (rank < world - 1) + 2 + 8 + 1
+        else:
+            self.launches_per_step = 5 + 2 * faces + 1 + (rank < world - 1) + 8 + 1
+        self.launches_per_step += 1 if self.split else 0  # split: stream + resolve instead of one gather
 
     def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:
         """peer transport: my mailbox and the (mapped) base pointers of every rank's mailbox, own included."""
@@ -296,12 +301,11 @@ class ShardedAssembler:
             if self.split:
                 self._label_local(L.CCL_PHASE_LABEL)
             if peer:
-                for hi, ok, za, zb in ((0, self.rank > 0, z0, z0 + self.halo),
-                                       (1, self.rank < self.world - 1, z1 - self.halo, z1)):
-                    if ok:
-                        L.check(self.lib.skb_shard_emit_runs_peer(
-                            self.workspace.data_ptr(), X, Y, Z, hi, za, zb, self.mailbox.ptr,
-                            self.peer_ptrs[self.rank + (1 if hi else -1)], *self._geom, self.meta[1:2].data_ptr(), self._s()))
+                L.check(self.lib.skb_shard_emit_runs_peer(
+                    self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, self.halo, self.mailbox.ptr,
+                    self.peer_ptrs[self.rank - 1] if self.rank > 0 else 0,
+                    self.peer_ptrs[self.rank + 1] if self.rank < self.world - 1 else 0,
+                    *self._geom, self.meta[1:2].data_ptr(), self._s()))
                 return
             if self.rank > 0:
                 L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 0, z0, z0 + self.halo,

@@ -216,9 +216,9 @@ int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offset
 int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                           int64_t z_off, int64_t Zl, int64_t capacity, void* workspace,
                           size_t workspace_bytes, uint32_t* status, int flags, void* stream);
-/* face_is_high: 0 = the slab's first 64-plane word, 1 = its last; [z_lo, z_hi) must lie inside it */
-int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high,
-                        int64_t z_lo, int64_t z_hi, int32_t* runs, int64_t cap, uint32_t* status,
+/* face_is_high: 0 = the first `halo` planes of the slab, 1 = its last (halo <= 64) */
+int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                        int face_is_high, int64_t halo, int32_t* runs, int64_t cap, uint32_t* status,
                         void* stream);
 int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs,
                           int64_t cap, uint64_t* halo_words_zeroed, void* stream);

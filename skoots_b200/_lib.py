@@ -55,7 +55,7 @@ SIGNATURES = {
     "skb_bake_skeleton": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_stamp_disks": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_label_local": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_int, _c_vp]),
-    "skb_shard_emit_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_int, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "skb_shard_emit_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),

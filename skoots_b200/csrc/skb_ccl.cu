@@ -535,10 +535,20 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
 // ------------------------------------------------------------------------------------------
 // K2: unions across tile faces, driven by the bit-packed mask
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, ull w, bool have_prev, ull prev, int TX, int TY) {
-    // only words that contain foreground get here.  n_words <= 2^31: 32-bit index math, shifts when the
-    // row length / Y are powers of two (the usual case) so that interior words leave after ~10 instructions
-    // widx = place of the word in `bits` = row * nk + (word of the slab's row)
+// What one word of the bit mask has to union across tile faces: the run starts (per face) whose voxel p
+// is foreground on both sides.  Only words that contain foreground get here.  n_words <= 2^31: 32-bit
+// index math, shifts when the row length / Y are powers of two (the usual case).
+// widx = place of the word in `bits` = row * nk + (word of the slab's row).
+struct FaceWork {
+    ull sy, sx;   // bit p set: union voxel gbase+p with its y-1 / x-1 neighbour
+    int z;        // 1: union voxel gbase with gbase-1 (run continues from the previous word of the row)
+    int gbase;
+    __device__ __forceinline__ int count() const { return z + __popcll(sy) + __popcll(sx); }
+};
+
+__device__ __forceinline__ FaceWork boundary_word(const CclView& v, unsigned widx, ull w, bool have_prev, ull prev, int TX, int TY) {
+    FaceWork f = {0ull, 0ull, 0, 0};
+    if (!w) return f;
     const unsigned uzw = (unsigned)v.nk, uyy = (unsigned)v.Y;
     unsigned rowi, k, x, y;
     if (v.nk_shift >= 0) { rowi = widx >> v.nk_shift; k = widx & (uzw - 1u); }
@@ -548,46 +558,90 @@ __device__ __forceinline__ void boundary_word(const CclView& v, unsigned widx, u
     const bool face_z = k > 0u && (w & 1ull);
     const bool face_y = y > 0 && (y & (unsigned)(TY - 1)) == 0;  // tile sides are powers of two (8)
     const bool face_x = v.connect_x && x > 0 && (x & (unsigned)(TX - 1)) == 0;
-    if (!(face_z || face_y || face_x)) return;
-    const int gbase = (int)(rowi * (unsigned)v.Z + 64u * (k + (unsigned)v.k0));
-    if (face_z) {
-        if (!have_prev) prev = v.bits[widx - 1];
-        if (prev >> 63) gunion(v.parent, gbase, gbase - 1);
+    if (!(face_z || face_y || face_x)) return f;
+    f.gbase = (int)(rowi * (unsigned)v.Z + 64u * (k + (unsigned)v.k0));
+    // the (up to three) neighbour words are independent loads: issue them together
+    ull wz = prev, wy = 0ull, wx = 0ull;
+    if (face_z && !have_prev) wz = v.bits[widx - 1];
+    if (face_y) wy = v.bits[widx - uzw];
+    if (face_x) wx = v.bits[widx - uyy * uzw];
+    if (face_z) f.z = (int)(wz >> 63);
+    const ull ay = w & wy, ax = w & wx;
+    f.sy = ay & ~(ay << 1);
+    f.sx = ax & ~(ax << 1);
+    return f;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_union(const CclView& v, const FaceWork& f, F&& emit) {
+    if (f.z) emit(f.gbase, f.gbase - 1);
+    for (ull s = f.sy; s; s &= s - 1) {
+        const int p = __ffsll((long long)s) - 1;
+        emit(f.gbase + p, f.gbase + p - v.Z);
     }
-    if (face_y) {
-        ull a = w & v.bits[widx - uzw];
-        for (ull s = a & ~(a << 1); s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            gunion(v.parent, gbase + p, gbase + p - v.Z);
-        }
-    }
-    if (face_x) {
-        ull a = w & v.bits[widx - uyy * uzw];
-        int plane = v.Y * v.Z;
-        for (ull s = a & ~(a << 1); s; s &= s - 1) {
-            int p = __ffsll((long long)s) - 1;
-            gunion(v.parent, gbase + p, gbase + p - plane);
-        }
+    const int plane = v.Y * v.Z;
+    for (ull s = f.sx; s; s &= s - 1) {
+        const int p = __ffsll((long long)s) - 1;
+        emit(f.gbase + p, f.gbase + p - plane);
     }
 }
 
 // pair_mode: rows hold an even number of words, or one word each (then the two words are two rows and
-// there is no z face at all) -> every thread streams two adjacent words with one 16-byte load and
-// returns at once when both are empty.  Otherwise one word per thread.
-__global__ void __launch_bounds__(256) ccl_boundary_kernel(CclView v, int TX, int TY, int pair_mode) {
+// there is no z face at all) -> every thread streams two adjacent words with one 16-byte load.
+// Otherwise one word per thread.
+//
+// The unions themselves are pointer chases through `parent` in global memory: ~5 dependent loads of
+// ~0.7 us each.  Done where they are found — one lane at a time inside divergent branches — they made
+// this kernel latency-bound at 1 active thread per warp (ncu: 69 % long-scoreboard stalls, 52 us for a
+// 33 MB bit mask).  So a warp first only COLLECTS its unions into a shared-memory queue and then
+// works through the queue one union per lane: 32 chases in flight per warp.
+constexpr int BND_WARPS = 8;
+constexpr int BND_QUEUE = 96;  // unions a warp can queue; a denser warp falls back to in-place unions
+
+__global__ void __launch_bounds__(32 * BND_WARPS) ccl_boundary_kernel(CclView v, int TX, int TY, int pair_mode) {
+    __shared__ int2 s_queue[BND_WARPS][BND_QUEUE];
     const unsigned tix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int2* queue = s_queue[threadIdx.x >> 5];
+    ull w0 = 0ull, w1 = 0ull;
+    unsigned widx = 0u;
     if (pair_mode) {
-        const unsigned widx = 2u * tix;
-        if (widx >= (unsigned)v.n_words) return;
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(v.bits + widx));
-        if ((q.x | q.y | q.z | q.w) == 0u) return;
-        const ull w0 = ((ull)q.y << 32) | q.x, w1 = ((ull)q.w << 32) | q.z;
-        if (w0) boundary_word(v, widx, w0, false, 0ull, TX, TY);
-        if (w1) boundary_word(v, widx + 1, w1, true, w0, TX, TY);
+        widx = 2u * tix;
+        if (widx < (unsigned)v.n_words) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(v.bits + widx));
+            w0 = ((ull)q.y << 32) | q.x;
+            w1 = ((ull)q.w << 32) | q.z;
+        }
     } else {
-        if (tix >= (unsigned)v.n_words) return;
-        const ull w = v.bits[tix];
-        if (w) boundary_word(v, tix, w, false, 0ull, TX, TY);
+        widx = tix;
+        if (tix < (unsigned)v.n_words) w0 = v.bits[tix];
+    }
+    if (!__any_sync(0xffffffffu, (w0 | w1) != 0ull)) return;  // ~90 % of the warps
+    const FaceWork f0 = boundary_word(v, widx, w0, false, 0ull, TX, TY);
+    const FaceWork f1 = boundary_word(v, widx + 1u, w1, true, w0, TX, TY);
+    const int cnt = f0.count() + f1.count();
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    if (total > BND_QUEUE) {  // dense mask: union in place
+        auto direct = [&](int a, int b) { gunion(v.parent, a, b); };
+        for_each_union(v, f0, direct);
+        for_each_union(v, f1, direct);
+        return;
+    }
+    int at = incl - cnt;
+    auto push = [&](int a, int b) { queue[at++] = make_int2(a, b); };
+    for_each_union(v, f0, push);
+    for_each_union(v, f1, push);
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        const int2 e = queue[i];
+        gunion(v.parent, e.x, e.y);
     }
 }
 
@@ -935,6 +989,9 @@ extern "C" int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, 
 //             raster order (identical numbering on every rank = the single-GPU numbering) and
 //             publishes the label codes                                 (skb_shard_merge)
 // ==========================================================================================
+static const ull* face_words(const SkbCclLayout& L, const void* workspace, int high, int64_t Zl);
+static int shard_common(const char* who, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl);
+
 __global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
     unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -948,6 +1005,11 @@ __global__ void __launch_bounds__(256) shard_local_roots_kernel(CclView v) {
             if (lane == leader) base = atomicAdd(&v.hdr->n_global_roots, (unsigned)__popc(m));
             base = __shfl_sync(m, base, leader);
             v.groots[base + __popc(m & ((1u << lane) - 1u))] = r;
+        } else {
+            // path compression: every voxel is now two hops from its slab root (voxel -> tile root -> root), which is
+            // what the run emission and the face pairing chase.  Safe next to concurrent finds: a reader sees the old
+            // parent or the root, both ancestors.
+            v.parent[r] = g;
         }
     }
 }
@@ -991,23 +1053,41 @@ struct EmitFace {
 };
 
 // counter = count, then (start voxel, length, root id) triples.  blockIdx.y picks the face (the peer
-// transport emits both faces of a slab with one launch).
+// transport emits both faces of a slab with one launch).  A thread takes EMIT_ROWS consecutive rows (two
+// 16-byte loads of the compact face words): 99 % of the rows have nothing on a face, so the kernel is a
+// stream with a vote, and the per-warp overhead is paid once per 128 rows.
+constexpr int EMIT_ROWS = 4;
+constexpr int EMIT_QUEUE = 96;  // runs a warp can queue
+
 __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFace f0, EmitFace f1, int cap, unsigned* status) {
     const EmitFace& f = blockIdx.y ? f1 : f0;
     const RunsDst& dst = f.dst;
     const int z_lo = f.z_lo, z_hi = f.z_hi;
     int* const runs = dst.counter;
     int* const tri = dst.triples + (dst.epoch ? (long long)(*dst.epoch & 1) * dst.parity_stride : 0LL);
-    const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n_rows = (unsigned)v.X * (unsigned)v.Y;
+    const unsigned row0 = (blockIdx.x * blockDim.x + threadIdx.x) * EMIT_ROWS;
     const int lane = threadIdx.x & 31;
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
     const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
-    ull w = 0;
-    if (rowi < (unsigned)v.X * (unsigned)v.Y) w = f.face[rowi] & range;
-    if (!__any_sync(0xffffffffu, w != 0ull)) return;  // ~99 % of the warps: nothing on this face
-    const ull starts = w & ~(w << 1);
+    ull w[EMIT_ROWS];
+    if (row0 + EMIT_ROWS <= n_rows) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(f.face + row0));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(f.face + row0) + 1);
+        w[0] = ((ull)q0.y << 32) | q0.x; w[1] = ((ull)q0.w << 32) | q0.z;
+        w[2] = ((ull)q1.y << 32) | q1.x; w[3] = ((ull)q1.w << 32) | q1.z;
+    } else {
+#pragma unroll
+        for (int r = 0; r < EMIT_ROWS; ++r) w[r] = row0 + r < n_rows ? f.face[row0 + r] : 0ull;
+    }
+    ull any = 0ull;
+#pragma unroll
+    for (int r = 0; r < EMIT_ROWS; ++r) { w[r] &= range; any |= w[r]; }
+    if (!__any_sync(0xffffffffu, any != 0ull)) return;
     // one atomicAdd per warp (a per-run atomic on the single counter would serialise in L2)
-    const int cnt = __popcll(starts);
+    int cnt = 0;
+#pragma unroll
+    for (int r = 0; r < EMIT_ROWS; ++r) cnt += __popcll(w[r] & ~(w[r] << 1));
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1015,19 +1095,46 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
         if (lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
     int base = 0;
     if (lane == 31) base = atomicAdd(runs, total);
-    int slot = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-    const int gbase = (int)(rowi * (unsigned)v.Z) + 64 * k;
-    for (ull s = starts; s; s &= s - 1, ++slot) {
-        const int p = __ffsll((long long)s) - 1;
-        const ull tt = ~(w >> p);
-        const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
-        const int root = gfind(v.parent, gbase + p);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    // The root of a run is a 3-load pointer chase in global memory.  Runs are first queued in shared memory
+    // (start voxel, length), then taken one per lane, so a warp's chases overlap instead of following the
+    // row-by-row order in which they were found (a warp of 128 rows holds ~1.5 runs, in different rows).
+    __shared__ int2 s_runs[8][EMIT_QUEUE];
+    int2* queue = s_runs[threadIdx.x >> 5];
+    const bool queued = total <= EMIT_QUEUE;
+    int at = incl - cnt;
+#pragma unroll
+    for (int r = 0; r < EMIT_ROWS; ++r) {
+        const ull wr = w[r];
+        const int gbase = (int)((row0 + r) * (unsigned)v.Z) + 64 * k;
+        for (ull s = wr & ~(wr << 1); s; s &= s - 1, ++at) {
+            const int p = __ffsll((long long)s) - 1;
+            const ull tt = ~(wr >> p);
+            const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+            if (queued) {
+                queue[at] = make_int2(gbase + p, len);
+            } else {  // dense face: emit in place
+                const int slot = base + at, root = gfind(v.parent, gbase + p);
+                if (slot < cap) {
+                    tri[3 * slot] = gbase + p;
+                    tri[3 * slot + 1] = len;
+                    tri[3 * slot + 2] = root;
+                } else {
+                    atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+                }
+            }
+        }
+    }
+    if (!queued) return;
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        const int2 e = queue[i];
+        const int slot = base + i, root = gfind(v.parent, e.x);
         if (slot < cap) {
-            tri[3 * slot] = gbase + p;
-            tri[3 * slot + 1] = len;
+            tri[3 * slot] = e.x;
+            tri[3 * slot + 1] = e.y;
             tri[3 * slot + 2] = root;
         } else {
             atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
@@ -1090,19 +1197,36 @@ __global__ void __launch_bounds__(256) shard_pack_roots_kernel(CclView v, int* _
 __global__ void __launch_bounds__(256) shard_boundary_pairs_kernel(CclView v, const ull* __restrict__ halo_hi,
                                                                   int* __restrict__ exch, int cap_roots, int cap_pairs,
                                                                   unsigned* status) {
-    const unsigned rowi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rowi >= (unsigned)v.X * (unsigned)v.Y) return;
-    const int z1 = v.z_off + v.Zl;  // first plane of the upper neighbour
-    if (!(halo_hi[rowi] & 1ull)) return;
-    if (!(v.bits[(size_t)rowi * v.nk + (v.nk - 1)] >> 63)) return;
-    const int mine = (int)(rowi * (unsigned)v.Z) + z1 - 1;
-    const int a = gfind(v.parent, mine), b = v.parent[mine + 1];
-    const int slot = atomicAdd(exch + 1, 1);
-    if (slot < cap_pairs) {
-        exch[2 + cap_roots + 2 * slot] = a;
-        exch[3 + cap_roots + 2 * slot] = b;
+    // EMIT_ROWS consecutive rows per thread, two 16-byte loads of the halo words: ~99 % of the rows have no
+    // foreground in the neighbour's first plane and leave after the loads
+    const unsigned n_rows = (unsigned)v.X * (unsigned)v.Y;
+    const unsigned row0 = (blockIdx.x * blockDim.x + threadIdx.x) * EMIT_ROWS;
+    if (row0 >= n_rows) return;
+    ull h[EMIT_ROWS];
+    if (row0 + EMIT_ROWS <= n_rows) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(halo_hi + row0));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(halo_hi + row0) + 1);
+        h[0] = ((ull)q0.y << 32) | q0.x; h[1] = ((ull)q0.w << 32) | q0.z;
+        h[2] = ((ull)q1.y << 32) | q1.x; h[3] = ((ull)q1.w << 32) | q1.z;
     } else {
-        atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+#pragma unroll
+        for (int r = 0; r < EMIT_ROWS; ++r) h[r] = row0 + r < n_rows ? halo_hi[row0 + r] : 0ull;
+    }
+    const int z1 = v.z_off + v.Zl;  // first plane of the upper neighbour
+#pragma unroll
+    for (int r = 0; r < EMIT_ROWS; ++r) {
+        if (!(h[r] & 1ull)) continue;
+        const unsigned rowi = row0 + r;
+        if (!(v.bits[(size_t)rowi * v.nk + (v.nk - 1)] >> 63)) continue;
+        const int mine = (int)(rowi * (unsigned)v.Z) + z1 - 1;
+        const int a = gfind(v.parent, mine), b = v.parent[mine + 1];
+        const int slot = atomicAdd(exch + 1, 1);
+        if (slot < cap_pairs) {
+            exch[2 + cap_roots + 2 * slot] = a;
+            exch[3 + cap_roots + 2 * slot] = b;
+        } else {
+            atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
+        }
     }
 }
 
@@ -1118,20 +1242,23 @@ __device__ __forceinline__ const int* merge_base(const MergeView& m) {
     return m.gathered + (m.epoch ? (long long)(*m.epoch & 1) * m.parity_stride : 0LL);
 }
 
-__device__ __forceinline__ bool merge_item(const MergeView& m, const int* base, unsigned i, bool pairs, int& a, int& b) {
-    // flattened index over (rank, slot); returns false for slots past that rank's count
-    const unsigned cap = pairs ? (unsigned)m.cap_pairs : (unsigned)m.cap_roots;
-    const unsigned r = i / cap, s = i - r * cap;
-    const int* e = base + (size_t)r * m.stride;
-    const int n = min(pairs ? e[1] : e[0], (int)cap);
-    if ((int)s >= n) return false;
-    if (pairs) { a = e[2 + m.cap_roots + 2 * s]; b = e[3 + m.cap_roots + 2 * s]; }
-    else { a = e[2 + s]; b = (int)r; }
-    return true;
+// The merge kernels run on a grid (MERGE_BLOCKS, world): row y of the grid walks rank y's root list or pair
+// list — only the entries that exist, not the capacity (8 ranks x 2^18 slots for ~4 K roots each).
+constexpr int MERGE_BLOCKS = 48;
+struct MergeList {
+    const int* items;
+    int n;
+};
+__device__ __forceinline__ MergeList merge_list(const MergeView& m, const int* base, bool pairs) {
+    const int* e = base + (size_t)blockIdx.y * m.stride;
+    MergeList l;
+    l.n = min(pairs ? e[1] : e[0], pairs ? m.cap_pairs : m.cap_roots);
+    l.items = e + 2 + (pairs ? m.cap_roots : 0);
+    return l;
 }
 
 __global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeView m, int label_base) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the mark kernel re-lists the roots; the rank kernel reads label_base
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // the mark kernel re-lists the roots; the rank kernel reads label_base
         v.hdr->n_global_roots = 0u;
         v.hdr->label_base = label_base;
     }
@@ -1139,32 +1266,24 @@ __global__ void __launch_bounds__(256) shard_merge_init_kernel(CclView v, MergeV
         if ((int)threadIdx.x < m.world) spin_until(m.flags + threadIdx.x * SKB_FLAG_STRIDE, *m.epoch, v.status);
         __syncthreads();
     }
-    const int* const base = merge_base(m);
-    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int root, r;
-        if (!merge_item(m, base, i, false, root, r)) continue;
-        if (r != m.rank) v.parent[root] = root;  // foreign roots join my union-find as singletons
-    }
+    if ((int)blockIdx.y == m.rank) return;
+    const MergeList l = merge_list(m, merge_base(m), false);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < l.n; i += gridDim.x * blockDim.x)
+        v.parent[l.items[i]] = l.items[i];  // foreign roots join my union-find as singletons
 }
 
 __global__ void __launch_bounds__(256) shard_merge_union_kernel(CclView v, MergeView m) {
-    const int* const base = merge_base(m);
-    const unsigned total = (unsigned)m.world * (unsigned)m.cap_pairs;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int a, b;
-        if (merge_item(m, base, i, true, a, b)) gunion(v.parent, a, b);
-    }
+    const MergeList l = merge_list(m, merge_base(m), true);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < l.n; i += gridDim.x * blockDim.x)
+        gunion(v.parent, l.items[2 * i], l.items[2 * i + 1]);
 }
 
 // global roots among all ranks' roots -> bitmap + chunk histogram + list (reuses groots: the local list
 // has already been shipped in the exchange buffer)
 __global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeView m) {
-    const int* const base = merge_base(m);
-    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int root, r;
-        if (!merge_item(m, base, i, false, root, r)) continue;
+    const MergeList l = merge_list(m, merge_base(m), false);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < l.n; i += gridDim.x * blockDim.x) {
+        const int root = l.items[i];
         if (gfind(v.parent, root) != root) continue;
         unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
         if (slot >= (unsigned)v.capacity) {  // not listed -> could not be cleared afterwards: do not mark it
@@ -1182,16 +1301,16 @@ __global__ void __launch_bounds__(256) shard_merge_mark_kernel(CclView v, MergeV
 // every listed root takes the label code of its global root (codes are negative, indices are not); the
 // root bitmap words the global roots touched are zeroed for the next pass (ccl_clear_rootbits_kernel's job)
 __global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, MergeView m) {
-    const int* const base = merge_base(m);
-    const unsigned n_g = min(v.hdr->n_global_roots, (unsigned)v.capacity);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_g; i += gridDim.x * blockDim.x) {
-        int bit;
-        v.rootbits[word_of_voxel(v, v.groots[i], &bit)] = 0ull;
+    if (blockIdx.y == 0) {
+        const unsigned n_g = min(v.hdr->n_global_roots, (unsigned)v.capacity);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_g; i += gridDim.x * blockDim.x) {
+            int bit;
+            v.rootbits[word_of_voxel(v, v.groots[i], &bit)] = 0ull;
+        }
     }
-    const unsigned total = (unsigned)m.world * (unsigned)m.cap_roots;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int root, r;
-        if (!merge_item(m, base, i, false, root, r)) continue;
+    const MergeList l = merge_list(m, merge_base(m), false);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < l.n; i += gridDim.x * blockDim.x) {
+        const int root = l.items[i];
         int a = root, p = gload(v.parent + a);
         while (p >= 0 && p != a) { a = p; p = gload(v.parent + a); }
         if (p < 0 && a != root) v.parent[root] = p;
@@ -1214,8 +1333,9 @@ static CclView slab_view(const SkbCclLayout& L, void* ws, int64_t capacity, int6
     v.k0 = (int)(z_off / 64); v.nk = (int)(Zl / 64);
     v.nk_shift = shift_of(v.nk);
     v.n_words = (long long)L.X * L.Y * v.nk;  // of the slab's compact bit mask
-    v.face_lo = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_lo);
-    v.face_hi = reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_hi);
+    // compact copies of every row's first / last word; a one-word-deep slab needs none: both ARE the bit mask
+    v.face_lo = v.nk == 1 ? nullptr : reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_lo);
+    v.face_hi = v.nk == 1 ? nullptr : reinterpret_cast<ull*>(static_cast<char*>(ws) + L.off_face_hi);
     return v;
 }
 
@@ -1246,20 +1366,21 @@ extern "C" int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X
     return SKB_OK;
 }
 
-extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int face_is_high, int64_t z_lo,
-                                   int64_t z_hi, int32_t* runs, int64_t cap, uint32_t* status, void* stream) {
-    int rc = skb_check_volume(X, Y, Z, "skb_shard_emit_runs");
+extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                   int face_is_high, int64_t halo, int32_t* runs, int64_t cap, uint32_t* status,
+                                   void* stream) {
+    int rc = shard_common("skb_shard_emit_runs", X, Y, Z, z_off, Zl);
     if (rc) return rc;
     SKB_REQUIRE(workspace && runs && status && cap > 0, "skb_shard_emit_runs: bad argument");
-    SKB_REQUIRE(z_lo >= 0 && z_hi > z_lo && z_hi <= Z && (z_lo >> 6) == ((z_hi - 1) >> 6),
-                "skb_shard_emit_runs: [z_lo,z_hi) must lie inside one 64-plane word");
+    SKB_REQUIRE(halo >= 1 && halo <= 64 && halo <= Zl, "skb_shard_emit_runs: halo must be 1..64 planes and fit the slab");
     SKB_REQUIRE(face_is_high == 0 || face_is_high == 1, "skb_shard_emit_runs: face_is_high must be 0 or 1");
+    const int64_t z_lo = face_is_high ? z_off + Zl - halo : z_off, z_hi = face_is_high ? z_off + Zl : z_off + halo;
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     CclView v = make_view(L, workspace, 0, 1, status, nullptr);
-    const ull* face = reinterpret_cast<const ull*>(static_cast<const char*>(workspace) + (face_is_high ? L.off_face_hi : L.off_face_lo));
+    const ull* face = face_words(L, workspace, face_is_high, Zl);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(runs, 0, 3 * sizeof(int32_t), st);
-    unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
+    unsigned nb = (unsigned)(((long long)X * Y + 256 * EMIT_ROWS - 1) / (256 * EMIT_ROWS));
     EmitFace f = {face, (int)z_lo, (int)z_hi, {runs, runs + 3, nullptr, 0}};
     shard_emit_runs_kernel<<<nb, 256, 0, st>>>(v, f, f, (int)cap, status);
     SKB_LAUNCH_CHECK("shard_emit_runs_kernel");
@@ -1291,7 +1412,7 @@ extern "C" int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, i
     cudaMemsetAsync(exchange, 0, 2 * sizeof(int32_t), st);
     shard_pack_roots_kernel<<<148, 256, 0, st>>>(v, exchange, (int)cap_roots, status);
     if (halo_hi && z_off + Zl < Z) {
-        unsigned nb = (unsigned)(((long long)X * Y + 255) / 256);
+        unsigned nb = (unsigned)(((long long)X * Y + 256 * EMIT_ROWS - 1) / (256 * EMIT_ROWS));
         shard_boundary_pairs_kernel<<<nb, 256, 0, st>>>(v, reinterpret_cast<const ull*>(halo_hi), exchange, (int)cap_roots,
                                                        (int)cap_pairs, status);
     }
@@ -1300,6 +1421,13 @@ extern "C" int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, i
 }
 
 static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st);
+
+// word k0 (low face) / k0+nk-1 (high face) of every row of a slab `Zl` planes deep, contiguous
+static const ull* face_words(const SkbCclLayout& L, const void* workspace, int high, int64_t Zl) {
+    const char* base = static_cast<const char*>(workspace);
+    if (Zl == 64) return reinterpret_cast<const ull*>(base + L.off_bits);  // the compact bit mask itself
+    return reinterpret_cast<const ull*>(base + (high ? L.off_face_hi : L.off_face_lo));
+}
 
 extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, const int32_t* gathered,
                                int world, int rank, int64_t cap_roots, int64_t cap_pairs, int32_t label_base,
@@ -1320,13 +1448,14 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
 
 static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st) {
     const int g = 148 * 4;
-    shard_merge_init_kernel<<<g, 256, 0, st>>>(v, m, label_base);
-    shard_merge_union_kernel<<<g, 256, 0, st>>>(v, m);
-    shard_merge_mark_kernel<<<g, 256, 0, st>>>(v, m);
+    const dim3 per_rank(MERGE_BLOCKS, m.world);
+    shard_merge_init_kernel<<<per_rank, 256, 0, st>>>(v, m, label_base);
+    shard_merge_union_kernel<<<per_rank, 256, 0, st>>>(v, m);
+    shard_merge_mark_kernel<<<per_rank, 256, 0, st>>>(v, m);
     ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
     ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
     ccl_rank_kernel<<<g, 256, 0, st>>>(v);
-    shard_publish_roots_kernel<<<g, 256, 0, st>>>(v, m);  // also clears the root bitmap
+    shard_publish_roots_kernel<<<per_rank, 256, 0, st>>>(v, m);  // also clears the root bitmap
     ccl_publish_kernel<<<g, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("skb_shard_merge");
     return SKB_OK;
@@ -1412,7 +1541,7 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
         if (!nbp) continue;
         Mailbox nb = mailbox_at(nbp, world, cap_runs, cap_roots, cap_pairs);
         int* remote = nb.recv(hi ? 0 : 1);
-        f[n].face = reinterpret_cast<const ull*>(base + (hi ? L.off_face_hi : L.off_face_lo));
+        f[n].face = face_words(L, workspace, hi, Zl);
         f[n].z_lo = (int)(hi ? z_off + Zl - halo : z_off);
         f[n].z_hi = (int)(hi ? z_off + Zl : z_off + halo);
         f[n].dst = {me.cnt(hi), remote + 3, me.epoch(), me.M.runs_ints};
@@ -1421,7 +1550,7 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
     }
     if (n == 1) f[1] = f[0];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned nblk = (unsigned)(((long long)X * Y + 255) / 256);
+    unsigned nblk = (unsigned)(((long long)X * Y + 256 * EMIT_ROWS - 1) / (256 * EMIT_ROWS));
     shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);
     shard_signal_runs_kernel<<<1, 32, 0, st>>>(sg[0], sg[1], me.M.runs_ints, me.epoch());
     SKB_LAUNCH_CHECK("skb_shard_emit_runs_peer");

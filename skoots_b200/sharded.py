@@ -308,10 +308,10 @@ class ShardedAssembler:
                     *self._geom, self.meta[1:2].data_ptr(), self._s()))
                 return
             if self.rank > 0:
-                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 0, z0, z0 + self.halo,
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, 0, self.halo,
                                                      self.send_lo.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
             if self.rank < self.world - 1:
-                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, 1, z1 - self.halo, z1,
+                L.check(self.lib.skb_shard_emit_runs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, 1, self.halo,
                                                      self.send_hi.data_ptr(), self.cap_runs, self.meta[1:2].data_ptr(), self._s()))
 
     def phase_ingest(self) -> None:

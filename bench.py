@@ -298,7 +298,7 @@ def run_b200(args):
         for k in range(reps + 1):
             a.record()
             L_.check(lib.skb_assemble_stream(vec.data_ptr(), L_.dtype_code(vec), X, Y, Z, 0, Z, sp.workspace.data_ptr(),
-                                             group_flags.data_ptr(), out.data_ptr(), L_.dtype_code(out), L_.stream_ptr(dev)))
+                                             group_flags.data_ptr(), out.data_ptr(), L_.dtype_code(out), 0, L_.stream_ptr(dev)))
             b.record()
             torch.cuda.synchronize(dev)
             gather_ms += a.elapsed_time(b) / reps if k else 0.0

@@ -241,10 +241,12 @@ int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int6
  * group_flags (one uint32 per 256 voxels, X*Y*Zl/256 words).  The caller runs it on a second stream
  * next to the rest of the labelling (SKB_CCL_PHASE_LABEL), then skb_assemble_resolve fills in the
  * flagged groups.  Together they write exactly what skb_assemble / skb_assemble_slab write.
- * Z, z_off, Zl multiples of 64 and X*Y*Zl a multiple of 256; other shapes use the fused call. */
+ * Z, z_off, Zl multiples of 64 and X*Y*Zl a multiple of 256; other shapes use the fused call.
+ * ctas_per_sm: 0 = one CTA per 32 chunks; 1..8 = a persistent grid of that many 256-thread CTAs per SM,
+ * which bounds the slice of every SM the stream phase holds while the labelling kernels run next to it. */
 int skb_assemble_stream(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                         int64_t Zl, const void* workspace, uint32_t* group_flags, void* out,
-                        int out_dtype, void* stream);
+                        int out_dtype, int ctas_per_sm, void* stream);
 int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                          int64_t Zl, const float scale[3], const void* workspace,
                          const uint64_t* halo_lo, const uint64_t* halo_hi, const uint32_t* group_flags,

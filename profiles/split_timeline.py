@@ -32,6 +32,9 @@ out = torch.empty(shape, dtype=torch.int32, device=dev)
 flags = torch.empty(X * Y * Z // 256, dtype=torch.int32, device=dev)
 scale = (60, 60, 12)
 lib = L.load()
+from skoots_b200.pipeline import stream_ctas_default
+CTAS = stream_ctas_default()
+print("stream phase CTAs per SM:", CTAS or "non-persistent")
 
 
 def timed(fn, reps):
@@ -60,7 +63,7 @@ print("alone: pack         %.3f ms" % timed(lambda: launch_label(mask, sparse, F
 print("alone: pack + label chain  %.3f ms" % timed(lambda: launch_label(mask, sparse, False, 2, 0), args.steps))
 print("alone: stream phase %.3f ms" % timed(lambda: L.check(lib.skb_assemble_stream(
     vec.data_ptr(), L.dtype_code(vec), X, Y, Z, 0, Z, sparse.workspace.data_ptr(), flags.data_ptr(), out.data_ptr(),
-    L.dtype_code(out), s)), args.steps))
+    L.dtype_code(out), CTAS, s)), args.steps))
 print("alone: resolve      %.3f ms" % timed(lambda: L.check(lib.skb_assemble_resolve(
     vec.data_ptr(), L.dtype_code(vec), X, Y, Z, 0, Z, L.f3(scale), sparse.workspace.data_ptr(), 0, 0, flags.data_ptr(),
     out.data_ptr(), L.dtype_code(out), s)), args.steps))

@@ -59,7 +59,7 @@ SIGNATURES = {
     "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
-    "skb_assemble_stream": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
+    "skb_assemble_stream": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
     "skb_assemble_resolve": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
     "skb_peer_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
     "skb_peer_free": (_c_int, [_c_vp]),

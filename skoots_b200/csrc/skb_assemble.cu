@@ -393,30 +393,38 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_tail_kernel(AsmParams
 // ------------------------------------------------------------------------------------------
 constexpr int STREAM_CHUNKS_PER_WARP = 2;
 
+// The grid is either one CTA per 16 chunks, or — `persistent` — a fixed, small number of CTAs per SM whose warps
+// stride over the chunks: the stream then occupies a bounded slice of every SM (threads, registers) for its whole
+// duration and the labelling kernels on the other stream always find room next to it.
 template <typename VecT, typename OutT>
 __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_stream_kernel(AsmParams P, OutT* __restrict__ out,
                                                                          unsigned* __restrict__ flags, unsigned n_chunks) {
     const int lane = threadIdx.x & 31;
-    const unsigned c0 = (blockIdx.x * ASM_WARPS + (threadIdx.x >> 5)) * STREAM_CHUNKS_PER_WARP;
-    ChunkRegs<VecT> r[STREAM_CHUNKS_PER_WARP];
+    const unsigned stride = gridDim.x * ASM_WARPS * STREAM_CHUNKS_PER_WARP;
+    for (unsigned c0 = (blockIdx.x * ASM_WARPS + (threadIdx.x >> 5)) * STREAM_CHUNKS_PER_WARP; c0 < n_chunks; c0 += stride) {
+        ChunkRegs<VecT> r[STREAM_CHUNKS_PER_WARP];
 #pragma unroll
-    for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u)
-        if (c0 + u < n_chunks) r[u] = load_chunk<VecT, true>(P, 0, (long long)(c0 + u) * 256);
+        for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u)
+            if (c0 + u < n_chunks) r[u] = load_chunk<VecT, true>(P, 0, (long long)(c0 + u) * 256);
 #pragma unroll
-    for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u) {
-        if (c0 + u >= n_chunks) break;  // warp-uniform
-        const bool work = (nonzero_bits<VecT>(r[u].r0, r[u].r1, r[u].r2) | r[u].self) != 0u;
-        const unsigned m = __ballot_sync(0xffffffffu, work);
-        if (!work) {
-            OutT* o = out + (long long)(c0 + u) * 256 + lane * 8;
-            skb_st_stream16(o, make_uint4(0u, 0u, 0u, 0u));
-            if (sizeof(OutT) == 4) skb_st_stream16(o + 4, make_uint4(0u, 0u, 0u, 0u));
+        for (int u = 0; u < STREAM_CHUNKS_PER_WARP; ++u) {
+            if (c0 + u >= n_chunks) break;  // warp-uniform
+            const bool work = (nonzero_bits<VecT>(r[u].r0, r[u].r1, r[u].r2) | r[u].self) != 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, work);
+            if (!work) {
+                OutT* o = out + (long long)(c0 + u) * 256 + lane * 8;
+                skb_st_stream16(o, make_uint4(0u, 0u, 0u, 0u));
+                if (sizeof(OutT) == 4) skb_st_stream16(o + 4, make_uint4(0u, 0u, 0u, 0u));
+            }
+            if (lane == 0) flags[c0 + u] = m;
         }
-        if (lane == 0) flags[c0 + u] = m;
     }
 }
 
-// one lane = one flagged 8-voxel group: the (up to) 8 label look-ups are independent chains
+// one lane = one flagged 8-voxel group.  The (up to) 8 label look-ups are three dependent loads each (bit-mask
+// word, parent, parent of the tile root); they are issued stage by stage for all 8 voxels with UNCONDITIONAL
+// loads (a voxel without work reads index 0), so a lane has 8 loads in flight per stage instead of walking the
+// voxels one after the other through branches.
 template <typename VecT, typename OutT>
 __device__ __forceinline__ void resolve_group(const AsmParams& P, long long i0, OutT* __restrict__ out) {
     const Raw8<VecT> a = load_raw8<VecT, true>(P.vec, i0, 8);
@@ -428,16 +436,43 @@ __device__ __forceinline__ void resolve_group(const AsmParams& P, long long i0, 
     const int z0 = (int)((unsigned)i0 - q * (unsigned)P.Zl) + P.z_off;  // the 8 voxels share a row (Zl % 8 == 0)
     const int x = (int)(q / (unsigned)P.Y), y = (int)(q - (unsigned)x * (unsigned)P.Y);
     const float fx = (float)x, fy = (float)y;
+    const int z_end = P.z_off + P.Zl;
+    // stage 1: targets -> address of the 64-bit word that holds the target's bit (slab, or a neighbour's halo plane)
+    const ull* wp[8];
+    int tv[8], tb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float ex = __fadd_rn(fx, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(a.w, j)), P.s[0]));
+        const float ey = __fadd_rn(fy, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(b.w, j)), P.s[1]));
+        const float ez = __fadd_rn((float)(z0 + j), __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(c.w, j)), P.s[2]));
+        const int tx = clamp_index(ex, P.X), ty = clamp_index(ey, P.Y), tz = clamp_index(ez, P.Z);
+        const long long rowi = (long long)tx * P.Y + ty;
+        const ull* p = P.bits + rowi * P.ZW + ((tz - P.z_off) >> 6);
+        bool have = ((work >> j) & 1u) != 0u;
+        if (tz < P.z_off) { p = P.halo_lo + rowi; have = have && P.halo_lo != nullptr; }
+        else if (tz >= z_end) { p = P.halo_hi + rowi; have = have && P.halo_hi != nullptr; }
+        wp[j] = have ? p : P.bits;
+        tv[j] = have ? (int)(rowi * P.Z + tz) : -1;
+        tb[j] = tz & 63;
+    }
+    // stage 2: bit-mask words
+    ull ww[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ww[j] = __ldg(wp[j]);
+    // stage 3: parent of the foreground targets
+    int p1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (!((ww[j] >> tb[j]) & 1ull)) tv[j] = -1;
+        p1[j] = __ldg(P.parent + (tv[j] < 0 ? 0 : tv[j]));
+    }
+    // stage 4: a target that is not a tile root holds the tile root's index; the root holds the (negative) label code
     unsigned lab[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        lab[j] = 0u;
-        if ((work >> j) & 1u) {
-            const float ex = __fadd_rn(fx, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(a.w, j)), P.s[0]));
-            const float ey = __fadd_rn(fy, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(b.w, j)), P.s[1]));
-            const float ez = __fadd_rn((float)(z0 + j), __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(c.w, j)), P.s[2]));
-            lab[j] = (unsigned)label_at(P, clamp_index(ex, P.X), clamp_index(ey, P.Y), clamp_index(ez, P.Z));
-        }
+        const int p2 = __ldg(P.parent + ((tv[j] < 0 || p1[j] < 0) ? 0 : p1[j]));  // parent[0] itself may be uninitialised
+        const int code = p1[j] < 0 ? p1[j] : p2;
+        lab[j] = tv[j] < 0 ? 0u : (unsigned)(-code);
     }
     if (sizeof(OutT) == 2) {
         skb_st_stream16(out + i0, make_uint4((lab[0] & 0xffffu) | (lab[1] << 16), (lab[2] & 0xffffu) | (lab[3] << 16),
@@ -726,9 +761,11 @@ static int split_params(const char* who, AsmParams& P, const void* vec, int vec_
 }
 
 template <typename VecT>
-static void launch_split(const AsmParams& P, bool resolve, void* out, int out_dtype, uint32_t* flags, unsigned n_chunks, cudaStream_t st) {
+static void launch_split(const AsmParams& P, bool resolve, void* out, int out_dtype, uint32_t* flags, unsigned n_chunks,
+                         int ctas_per_sm, cudaStream_t st) {
     const unsigned per_cta = ASM_WARPS * STREAM_CHUNKS_PER_WARP;
-    const unsigned stream_grid = (n_chunks + per_cta - 1) / per_cta;
+    unsigned stream_grid = (n_chunks + per_cta - 1) / per_cta;
+    if (ctas_per_sm > 0 && stream_grid > 148u * (unsigned)ctas_per_sm) stream_grid = 148u * (unsigned)ctas_per_sm;
     unsigned resolve_grid = ((n_chunks + 31u) / 32u + ASM_WARPS - 1) / ASM_WARPS;
     if (resolve_grid > 148u * 8u) resolve_grid = 148u * 8u;
     if (out_dtype == SKB_I32) {
@@ -740,20 +777,22 @@ static void launch_split(const AsmParams& P, bool resolve, void* out, int out_dt
     }
 }
 
-static void launch_split_any(const AsmParams& P, int vec_dtype, bool resolve, void* out, int out_dtype, uint32_t* flags, cudaStream_t st) {
+static void launch_split_any(const AsmParams& P, int vec_dtype, bool resolve, void* out, int out_dtype, uint32_t* flags,
+                             int ctas_per_sm, cudaStream_t st) {
     const unsigned n_chunks = (unsigned)(((long long)P.X * P.Y * P.Zl) / 256);
-    if (vec_dtype == SKB_F16) launch_split<__half>(P, resolve, out, out_dtype, flags, n_chunks, st);
-    else if (vec_dtype == SKB_BF16) launch_split<__nv_bfloat16>(P, resolve, out, out_dtype, flags, n_chunks, st);
-    else launch_split<float>(P, resolve, out, out_dtype, flags, n_chunks, st);
+    if (vec_dtype == SKB_F16) launch_split<__half>(P, resolve, out, out_dtype, flags, n_chunks, ctas_per_sm, st);
+    else if (vec_dtype == SKB_BF16) launch_split<__nv_bfloat16>(P, resolve, out, out_dtype, flags, n_chunks, ctas_per_sm, st);
+    else launch_split<float>(P, resolve, out, out_dtype, flags, n_chunks, ctas_per_sm, st);
 }
 
 extern "C" int skb_assemble_stream(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
-                                   const void* workspace, uint32_t* group_flags, void* out, int out_dtype, void* stream) {
+                                   const void* workspace, uint32_t* group_flags, void* out, int out_dtype, int ctas_per_sm,
+                                   void* stream) {
     AsmParams P;
     int rc = split_params("skb_assemble_stream", P, vec, vec_dtype, X, Y, Z, z_off, Zl, nullptr, workspace, out, out_dtype);
     if (rc) return rc;
-    SKB_REQUIRE(group_flags, "skb_assemble_stream: NULL group_flags");
-    launch_split_any(P, vec_dtype, false, out, out_dtype, group_flags, static_cast<cudaStream_t>(stream));
+    SKB_REQUIRE(group_flags && ctas_per_sm >= 0 && ctas_per_sm <= 8, "skb_assemble_stream: NULL group_flags or ctas_per_sm outside 0..8");
+    launch_split_any(P, vec_dtype, false, out, out_dtype, group_flags, ctas_per_sm, static_cast<cudaStream_t>(stream));
     SKB_LAUNCH_CHECK("assemble_stream_kernel");
     return SKB_OK;
 }
@@ -769,7 +808,7 @@ extern "C" int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, i
     SKB_REQUIRE(group_flags, "skb_assemble_resolve: NULL group_flags");
     P.halo_lo = reinterpret_cast<const ull*>(halo_lo);
     P.halo_hi = reinterpret_cast<const ull*>(halo_hi);
-    launch_split_any(P, vec_dtype, true, out, out_dtype, const_cast<uint32_t*>(group_flags), static_cast<cudaStream_t>(stream));
+    launch_split_any(P, vec_dtype, true, out, out_dtype, const_cast<uint32_t*>(group_flags), 0, static_cast<cudaStream_t>(stream));
     SKB_LAUNCH_CHECK("assemble_resolve_kernel");
     return SKB_OK;
 }

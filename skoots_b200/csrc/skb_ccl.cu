@@ -387,6 +387,124 @@ __device__ __forceinline__ void append_roots(const CclView& v, int* sbuf, int& b
     __syncwarp();
 }
 
+// ---- sparse tiles: one z-run per lane ---------------------------------------------------------------
+// A skeleton tile holds ~15 runs in 64 rows.  With a row per lane (the dense path below) most lanes idle
+// while the others walk their rows' runs one after the other through divergent loops: ncu counted ~2050
+// warp instructions per non-empty tile at 10 active threads.  Here the tile's runs are first numbered in
+// raster order (row, then z) and listed in shared memory, then each lane takes ONE run: it unions with the
+// runs it touches in rows y-1 and x-1 (the neighbour's run number = the row's first number + the rank of
+// the run among the row's run starts, a popcount) on 32-bit labels with native shared-memory atomicMin,
+// and finally writes its run's voxels and reports itself if it is a root.  Lowest number = first run in
+// raster order, so a tile root is still the first voxel of its tile-component.
+constexpr int CCL_MAX_RUNS = 96;  // more runs than this in a tile -> dense path
+
+__device__ __forceinline__ int lfind(const volatile int* lab, int a) {
+    int p = lab[a];
+    while (p != a) {
+        a = p;
+        p = lab[a];
+    }
+    return a;
+}
+
+__device__ __forceinline__ void lunion(int* lab, int a, int b) {
+    for (;;) {
+        a = lfind(lab, a);
+        b = lfind(lab, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&lab[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+struct SparseTileScratch {  // aliases the dense path's label array (a tile takes one path or the other)
+    unsigned short rowbase[64];         // number of the row's first run
+    unsigned short run[CCL_MAX_RUNS];   // row << 6 | start bit
+    int lab[CCL_MAX_RUNS];
+};
+
+__device__ __forceinline__ void link_row(const ull* srow, const SparseTileScratch* sc, int* lab, int i, ull mask, int nrow) {
+    const ull wn = srow[nrow], a = mask & wn;
+    if (!a) return;
+    const ull stn = wn & ~(wn << 1);
+    for (ull s = a & ~(a << 1); s; s &= s - 1) {
+        const int b = __ffsll((long long)s) - 1;  // first voxel of an overlap: which run of the neighbour row holds it?
+        const int j = (int)sc->rowbase[nrow] + __popcll(stn & ((2ull << b) - 1ull)) - 1;
+        lunion(lab, i, j);
+    }
+}
+
+// returns false (and does nothing) if the tile has more than CCL_MAX_RUNS runs
+__device__ __forceinline__ bool tile_sparse(const CclView& v, ull* srow, SparseTileScratch* sc, int* sbuf, int& buf_n,
+                                            int lane, ull w0, ull w1, int x0, int y0, int z0) {
+    const ull st0 = w0 & ~(w0 << 1), st1 = w1 & ~(w1 << 1);
+    const int c0 = __popcll(st0), c1 = __popcll(st1);
+    int incl = c0 | (c1 << 16);  // both row sets in one scan (a set holds at most 32 x 32 runs)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    const int tot0 = tot & 0xffff, R = tot0 + (tot >> 16);
+    if (R > CCL_MAX_RUNS) return false;
+    const int base0 = (incl & 0xffff) - c0, base1 = tot0 + (incl >> 16) - c1;
+    srow[lane] = w0;
+    srow[lane + 32] = w1;
+    sc->rowbase[lane] = (unsigned short)base0;
+    sc->rowbase[lane + 32] = (unsigned short)base1;
+    int at = base0;
+    for (ull s = st0; s; s &= s - 1, ++at) {
+        sc->run[at] = (unsigned short)((lane << 6) | (__ffsll((long long)s) - 1));
+        sc->lab[at] = at;
+    }
+    at = base1;
+    for (ull s = st1; s; s &= s - 1, ++at) {
+        sc->run[at] = (unsigned short)(((lane + 32) << 6) | (__ffsll((long long)s) - 1));
+        sc->lab[at] = at;
+    }
+    __syncwarp();
+    // unions: one run per lane
+    for (int i = lane; i < R; i += 32) {
+        const int e = sc->run[i], row = e >> 6, p = e & 63;
+        const ull w = srow[row], tt = ~(w >> p);
+        const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+        const ull mask = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << p;
+        if (row & 7) link_row(srow, sc, sc->lab, i, mask, row - 1);
+        if ((row >> 3) && v.connect_x) link_row(srow, sc, sc->lab, i, mask, row - 8);
+    }
+    __syncwarp();
+    // resolve: every run's voxels point at the tile root's first voxel; roots are listed
+    for (int base = 0; base < R; base += 32) {
+        const int i = base + lane;
+        bool is_root = false;
+        int groot = 0;
+        if (i < R) {
+            const int r = lfind(sc->lab, i);
+            const int er = sc->run[r], rrow = er >> 6;
+            groot = (int)(((unsigned)(x0 + (rrow >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (rrow & 7))) * (unsigned)v.Z) + z0 + (er & 63);
+            is_root = r == i;
+            const int e = sc->run[i], row = e >> 6, p = e & 63;
+            const ull tt = ~(srow[row] >> p);
+            const int len = tt ? __ffsll((long long)tt) - 1 : 64 - p;
+            int* dst = v.parent + (int)(((unsigned)(x0 + (row >> 3)) * (unsigned)v.Y + (unsigned)(y0 + (row & 7))) * (unsigned)v.Z) + z0 + p;
+            for (int j = 0; j < len; ++j) dst[j] = groot;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, is_root);
+        const int n = __popc(m);
+        if (n) {
+            if (buf_n + n > CCL_ROOT_BUF) flush_roots(v, sbuf, buf_n, lane);
+            if (is_root) sbuf[buf_n + __popc(m & ((1u << lane) - 1u))] = groot;
+            buf_n += n;
+            __syncwarp();
+        }
+    }
+    __syncwarp();  // shared memory is reused by this warp's next tile
+    return true;
+}
+
 constexpr int CCL_TILE_WARPS = 8;
 constexpr int CCL_TILE_BATCH = 4;  // consecutive tiles a warp claims at a time
 
@@ -403,7 +521,7 @@ constexpr int CCL_TILE_BATCH = 4;  // consecutive tiles a warp claims at a time
 __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclView v, unsigned n_tiles, unsigned n_yk,
                                                                        int nk_shift, int nyk_shift, int dynamic) {
     __shared__ ull srow_all[CCL_TILE_WARPS][64];
-    __shared__ unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
+    __shared__ __align__(16) unsigned short slab_all[CCL_TILE_WARPS][64 * 32];
     __shared__ int rootbuf_all[CCL_TILE_WARPS][CCL_ROOT_BUF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* sbuf = rootbuf_all[warp];
@@ -504,7 +622,9 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
             nxt = decode(tn);
             load(nxt, n0, n1);
         }
-        if (__any_sync(0xffffffffu, (w0 | w1) != 0ull)) {
+        if (__any_sync(0xffffffffu, (w0 | w1) != 0ull) &&
+            !tile_sparse(v, srow, reinterpret_cast<SparseTileScratch*>(slab), sbuf, buf_n, lane, w0, w1, cur.x0, cur.y0, 64 * cur.k)) {
+            // dense tile: a row per lane, 16-bit labels indexed by (row, run start / 2)
             const int z0 = 64 * cur.k;
             srow[r0] = w0;
             srow[r1] = w1;

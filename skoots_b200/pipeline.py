@@ -79,8 +79,17 @@ def split_eligible(shape, vectors: Tensor, N: int, crop, overlap) -> bool:
             and vectors.data_ptr() % 16 == 0 and (X * Y * Z * vectors.element_size()) % 16 == 0)
 
 
+def stream_ctas_default() -> int:
+    """CTAs per SM of the stream phase when it is run as a persistent grid; 0 (default) = one CTA per 16 chunks.
+    Measured on B200 (profiles/README.md): a persistent stream of 2-3 CTAs per SM cannot saturate HBM on its own
+    (3.9 ms vs 3.2 ms at 2048x2048x512) and does not make the overlap with the labelling chain pay either."""
+    import os
+    return int(os.environ.get("SKB_STREAM_CTAS", "0"))
+
+
 def assemble_split(mask: Tensor, vectors: Tensor, scale, sparse: SparseLabels, out: Tensor,
-                   group_flags: Optional[Tensor] = None, timers=None, trace: Optional[dict] = None) -> Tensor:
+                   group_flags: Optional[Tensor] = None, timers=None, trace: Optional[dict] = None,
+                   stream_ctas: Optional[int] = None) -> Tensor:
     """One N = 1 whole-volume pass with the gather split around the labelling:
 
         current stream : pack mask->bits | stream phase (6 B/voxel in, zeros out, flags work groups) | resolve
@@ -116,7 +125,8 @@ def assemble_split(mask: Tensor, vectors: Tensor, scale, sparse: SparseLabels, o
         if timers is not None:
             timers[0].record(main)
         L.check(lib.skb_assemble_stream(vectors.data_ptr(), L.dtype_code(vectors), X, Y, Z, 0, Z, sparse.workspace.data_ptr(),
-                                        group_flags.data_ptr(), out.data_ptr(), L.dtype_code(out), main.cuda_stream))
+                                        group_flags.data_ptr(), out.data_ptr(), L.dtype_code(out),
+                                        stream_ctas_default() if stream_ctas is None else int(stream_ctas), main.cuda_stream))
         if timers is not None:
             timers[1].record(main)
         mark("streamed", main)

@@ -225,7 +225,8 @@ class ShardedAssembler:
             raise ValueError("the stream/resolve split needs the slab to be a multiple of 256 voxels")
         self.split = bool(split)  # off by default: measured slower than the fused slab gather
         self.flags = torch.empty(X * Y * self.Zl // 256, dtype=torch.int32, device=self.dev) if self.split else None
-        self._chain_done = None
+        from .pipeline import stream_ctas_default
+        self.stream_ctas = stream_ctas_default()
         self._clean = False
         self.mask: Optional[Tensor] = None
         self.vec: Optional[Tensor] = None
@@ -276,7 +277,7 @@ class ShardedAssembler:
         X, Y, Z = self.shape
         L.check(self.lib.skb_assemble_stream(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0], self.Zl,
                                              self.workspace.data_ptr(), self.flags.data_ptr(), self.out.data_ptr(),
-                                             L.dtype_code(self.out), self._s()))
+                                             L.dtype_code(self.out), self.stream_ctas, self._s()))
 
     # ---- phases ------------------------------------------------------------------------------------
     def phase_local(self) -> None:

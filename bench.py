@@ -54,6 +54,20 @@ def n_tubes_for(shape, requested):
     return max(8, int(round(16384 * vox / (2048 * 2048 * 512))))
 
 
+def measured_traffic(kernel: str, voxels_per_launch: float):
+    """dram read+write bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/r01_traffic.json; captured at 2048x2048x512 on one GPU, scaled per voxel) — None if the capture is
+    of another kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            rec = json.load(fh)
+        if rec["kernel"].split("<")[0] != kernel:
+            return None
+        return rec["dram_bytes_per_voxel"] * voxels_per_launch
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -387,7 +401,9 @@ def run_b200(args):
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
             "roofline": {"kernel": f"{dominant}<half,int>", "bound": "hbm", "timed": "alone, CUDA events, right after the timed region", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant, V / world),
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full dram bytes per voxel x voxels per launch)",
+                         "algorithmic_bytes": gather_bytes, "peak_source": peak_src,
                          "bytes_per_voxel": ALGO_BYTES_GATHER, "ms_per_launch": gather_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }

@@ -15,6 +15,8 @@
 // tile kernel (1/8 B per voxel, L2-resident over the +-scale window) and, only for targets
 // that are foreground, the sparse parent array.  A zero vector (background, ~95 % of a volume)
 // short-cuts to "label of myself", which is decided from one byte of the bit mask.
+#include <stdlib.h>
+
 #include "skb_common.cuh"
 
 struct AsmParams {
@@ -360,6 +362,210 @@ __global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_kernel(AsmParams P
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-staged form of the main kernel (the default whenever the field is aligned, the bit mask has no row
+// padding and zero vectors resolve to themselves — the headline mode).
+//
+// ncu on the register-prefetch kernel above: 57 % long-scoreboard stalls, 30 % of all samples on the first
+// use of the prefetched chunk — one chunk (1.5 KB) in flight per warp is not enough while the warp is
+// held up by the label look-ups of its current chunk.  Here every warp owns a RING of stages in shared
+// memory; lane 0 fills a stage with three bulk asynchronous copies (cp.async.bulk global -> shared, one
+// per vector channel, completion counted in bytes on the stage's mbarrier), so the loads of the next
+// STAGES-1 chunks are in flight without holding a single register, whatever the warp is doing.  The
+// queue processing reads other lanes' vectors straight from the stage (no second copy in shared memory).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(ull* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(ull* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, ull* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(ull* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <typename VecT> struct StageCfg {
+    typedef typename RawOf<VecT>::type raw_t;
+    static constexpr int CH_BYTES = 256 * (int)sizeof(raw_t);           // one channel of one 256-voxel chunk
+    static constexpr int STAGES = sizeof(raw_t) == 2 ? 3 : 2;
+    static constexpr int STAGE_BYTES = 3 * CH_BYTES + 32;  // three channels + the chunk's 256 foreground bits
+    static constexpr int WARP_BYTES = STAGES * STAGE_BYTES + 256 * 4 + 256 + 64;  // ring + results + queue + barriers
+};
+
+__device__ __forceinline__ void ldgsts16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ldgsts_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// BULK = true : lane 0 fills a stage with three cp.async.bulk copies (TMA engine, mbarrier completion);
+// BULK = false: every lane copies its own 16 bytes per channel with cp.async (LDGSTS), one commit group per stage.
+template <typename VecT, typename OutT, bool BULK>
+__global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_tma_kernel(AsmParams P, OutT* __restrict__ out,
+                                                                          unsigned chunk_begin, unsigned n_chunks) {
+    typedef StageCfg<VecT> C;
+    typedef typename C::raw_t raw_t;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* base = smem + (size_t)warp * C::WARP_BYTES;
+    unsigned char* ring = base;
+    int* s_res = reinterpret_cast<int*>(base + C::STAGES * C::STAGE_BYTES);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_res + 256);
+    ull* bars = reinterpret_cast<ull*>(s_queue + 256);
+    const unsigned stride = gridDim.x * ASM_WARPS;
+    const unsigned first = chunk_begin + blockIdx.x * ASM_WARPS + warp;
+    if (first >= n_chunks) return;
+    const unsigned uz = (unsigned)P.Zl, uy = (unsigned)P.Y;
+
+    auto fill = [&](int stage, unsigned c) {  // BULK: lane 0 only; else every lane
+        const raw_t* src = static_cast<const raw_t*>(P.vec) + (size_t)c * 256;
+        const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(P.bits) + (size_t)c * 32;  // no row padding: bit = voxel
+        unsigned char* dst = ring + (size_t)stage * C::STAGE_BYTES;
+        if (BULK) {
+            ull* bar = bars + stage;
+            mbar_expect_tx(bar, (unsigned)C::STAGE_BYTES);
+            bulk_load(dst, src, C::CH_BYTES, bar);
+            bulk_load(dst + C::CH_BYTES, src + P.cstride, C::CH_BYTES, bar);
+            bulk_load(dst + 2 * C::CH_BYTES, src + 2 * P.cstride, C::CH_BYTES, bar);
+            bulk_load(dst + 3 * C::CH_BYTES, bsrc, 32u, bar);
+        } else {
+            if (lane < 2) ldgsts16(dst + 3 * C::CH_BYTES + lane * 16, bsrc + lane * 16);
+            constexpr int PER_LANE = 8 * (int)sizeof(raw_t);  // bytes of a lane's 8 voxels in one channel: 16 or 32
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned char* g = reinterpret_cast<const unsigned char*>(src + (size_t)ch * P.cstride) + lane * PER_LANE;
+                unsigned char* d = dst + ch * C::CH_BYTES + lane * PER_LANE;
+#pragma unroll
+                for (int b = 0; b < PER_LANE; b += 16) ldgsts16(d + b, g + b);
+            }
+        }
+    };
+
+    if (BULK) {
+        if (lane == 0) {
+            for (int st = 0; st < C::STAGES; ++st) mbar_init(bars + st, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int st = 0; st < C::STAGES; ++st) {
+                const unsigned long long c = (unsigned long long)first + (unsigned long long)st * stride;
+                if (c < n_chunks) fill(st, (unsigned)c);
+            }
+        }
+    } else {
+        for (int st = 0; st < C::STAGES; ++st) {
+            const unsigned long long c = (unsigned long long)first + (unsigned long long)st * stride;
+            if (c < n_chunks) fill(st, (unsigned)c);
+            ldgsts_commit();  // one group per stage, empty or not: the group count stays uniform
+        }
+    }
+    __syncwarp();
+
+    unsigned it = 0;
+    for (unsigned c = first;; ++it) {
+        const int stage = (int)(it % C::STAGES);
+        const unsigned parity = (it / C::STAGES) & 1u;
+        const long long warp_base = (long long)c * 256;
+        const long long i0 = warp_base + lane * 8;
+        if (BULK) {
+            mbar_wait(bars + stage, parity);
+        } else {
+            ldgsts_wait<C::STAGES - 1>();  // my own copies of the oldest stage have landed ...
+            __syncwarp();                  // ... and so have every other lane's
+        }
+        const raw_t* ch0 = reinterpret_cast<const raw_t*>(ring + (size_t)stage * C::STAGE_BYTES);
+        const raw_t* ch1 = ch0 + 256;
+        const raw_t* ch2 = ch1 + 256;
+        const unsigned self = reinterpret_cast<const unsigned char*>(ch2 + 256)[lane];  // foreground bits of my own 8 voxels
+        Raw8<VecT> r0, r1, r2;
+        {
+            const uint4* q0 = reinterpret_cast<const uint4*>(ch0 + lane * 8);
+            const uint4* q1 = reinterpret_cast<const uint4*>(ch1 + lane * 8);
+            const uint4* q2 = reinterpret_cast<const uint4*>(ch2 + lane * 8);
+#pragma unroll
+            for (int h = 0; h < Raw8<VecT>::NW / 4; ++h) {
+                const uint4 a = q0[h], b = q1[h], d = q2[h];
+                r0.w[4 * h] = a.x; r0.w[4 * h + 1] = a.y; r0.w[4 * h + 2] = a.z; r0.w[4 * h + 3] = a.w;
+                r1.w[4 * h] = b.x; r1.w[4 * h + 1] = b.y; r1.w[4 * h + 2] = b.z; r1.w[4 * h + 3] = b.w;
+                r2.w[4 * h] = d.x; r2.w[4 * h + 1] = d.y; r2.w[4 * h + 2] = d.z; r2.w[4 * h + 3] = d.w;
+            }
+        }
+        const unsigned work = nonzero_bits<VecT>(r0, r1, r2) | self;
+        unsigned lab[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lab[j] = 0u;
+        if (__ballot_sync(0xffffffffu, work != 0u) != 0u) {
+            const int cnt = __popc(work);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int at = incl - cnt;
+            for (unsigned m = work; m; m &= m - 1) s_queue[at++] = (unsigned char)((__ffs((int)m) - 1) * 32 + lane);
+            __syncwarp();
+            for (int qi = lane; qi < total; qi += 32) {
+                const int code = s_queue[qi];
+                const int src = code & 31, j = code >> 5;
+                const unsigned vi = (unsigned)(warp_base + src * 8 + j);
+                const unsigned q = vi / uz;
+                const int z = (int)(vi - q * uz) + P.z_off;
+                const int x = (int)(q / uy);
+                const int y = (int)(q - (unsigned)x * uy);
+                s_res[code] = assemble_voxel<VecT>(P, x, y, z, raw_to_float<VecT>(ch0[src * 8 + j]),
+                                                   raw_to_float<VecT>(ch1[src * 8 + j]), raw_to_float<VecT>(ch2[src * 8 + j]));
+            }
+            __syncwarp();
+            if (work) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int v = s_res[j * 32 + lane];
+                    lab[j] = ((work >> j) & 1u) ? (unsigned)v : 0u;
+                }
+            }
+        }
+        __syncwarp();  // every lane is done with this stage (and with the scratch) before it is refilled
+        const unsigned long long cn = (unsigned long long)c + (unsigned long long)C::STAGES * stride;
+        if (BULK) {
+            if (lane == 0 && cn < n_chunks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before the async-proxy overwrite
+                fill(stage, (unsigned)cn);
+            }
+        } else {
+            if (cn < n_chunks) fill(stage, (unsigned)cn);
+            ldgsts_commit();
+        }
+        if (sizeof(OutT) == 2) {
+            skb_st_stream16(out + i0, make_uint4((lab[0] & 0xffffu) | (lab[1] << 16), (lab[2] & 0xffffu) | (lab[3] << 16),
+                                                 (lab[4] & 0xffffu) | (lab[5] << 16), (lab[6] & 0xffffu) | (lab[7] << 16)));
+        } else {
+            skb_st_stream16(out + i0, make_uint4(lab[0], lab[1], lab[2], lab[3]));
+            skb_st_stream16(out + i0 + 4, make_uint4(lab[4], lab[5], lab[6], lab[7]));
+        }
+        const unsigned long long nx = (unsigned long long)c + stride;
+        if (nx >= n_chunks) break;
+        c = (unsigned)nx;
+    }
+}
+
 // Everything the main kernel does not cover: the ragged last chunk, or all chunks of an unaligned field.
 template <typename VecT, typename OutT>
 __global__ void __launch_bounds__(32 * ASM_WARPS) assemble_tail_kernel(AsmParams P, OutT* __restrict__ out, long long V,
@@ -610,7 +816,21 @@ static void launch_assemble_t(const AsmParams& P, OutT* out, long long v_begin, 
     if (c_end > c_begin) {
         long long blocks = (c_end - c_begin + ASM_WARPS - 1) / ASM_WARPS;
         if (blocks > 148 * 4) blocks = 148 * 4;  // 4 resident CTAs per SM; warps stride over the chunks
-        assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, v_end, (unsigned)c_begin, (unsigned)c_end);
+        const char* mode = getenv("SKB_GATHER_STAGING");  // experiments: "bulk" | "ldgsts" | unset = register prefetch
+        const bool eligible = P.fast_ok && !P.dense && P.flat_bits;
+        const int smem = ASM_WARPS * StageCfg<VecT>::WARP_BYTES;
+        if (eligible && mode && mode[0] == 'b') {
+            // > 48 KB of dynamic shared memory is opt-in per function (and per device): cheap, so set it every time
+            cudaFuncSetAttribute(assemble_tma_kernel<VecT, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(assemble_tma_kernel<VecT, OutT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            assemble_tma_kernel<VecT, OutT, true><<<(unsigned)blocks, 32 * ASM_WARPS, smem, st>>>(P, out, (unsigned)c_begin, (unsigned)c_end);
+        } else if (eligible && mode && mode[0] == 'l') {
+            cudaFuncSetAttribute(assemble_tma_kernel<VecT, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(assemble_tma_kernel<VecT, OutT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            assemble_tma_kernel<VecT, OutT, false><<<(unsigned)blocks, 32 * ASM_WARPS, smem, st>>>(P, out, (unsigned)c_begin, (unsigned)c_end);
+        } else {
+            assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, v_end, (unsigned)c_begin, (unsigned)c_end);
+        }
     }
     const long long first = c_end * 256;
     if (first < v_end) {

@@ -265,6 +265,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    barrier()  # every rank's slab is loaded before anyone's kernels start waiting on a peer's flags
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()

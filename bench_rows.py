@@ -210,6 +210,32 @@ def main():
                         bool(torch.equal(v2e.vector_to_embedding(s2, v2).cpu(), orc.vector_to_embedding(s2, v2.cpu()))), "4 B in + 8 B out"))
         del tv, stack, out, v2
 
+    # ---- f2: renumber + validation metrics on an assembled instance mask ----------------------------------------------
+    from skoots_b200 import validate as val
+    shape = (512, 512, 128)
+    tv = make_tube_volume(shape, 1500, seed=0, device=DEV, want_skeleton_dict=False)
+    inst = assemble_instances(tv.skeleton, tv.vectors, SCALE, N=1)
+    gt = tv.mask.to(torch.int32)
+    V = shape[0] * shape[1] * shape[2]
+    inst_h, gt_h = inst.cpu().numpy(), gt.cpu().numpy()
+    scratch = inst.clone()
+
+    def gpu_renumber():
+        scratch.copy_(inst)
+        val.renumber(scratch, in_place=True)
+    t_copy = gpu_ms(lambda: scratch.copy_(inst))
+    rows.append(row("f2 renumber (fastremap.renumber) in place", "512x512x128 instance mask, 1500 tubes", V, 12,
+                    gpu_ms(gpu_renumber) - t_copy, cpu_ms(lambda: orc.renumber(inst_h), iters=1),
+                    bool((val.renumber(inst)[0].cpu().numpy() == orc.renumber(inst_h)[0]).all()),
+                    "4 B read (first occurrences) + 4 B read + 4 B written (apply); includes the max-label read-back"))
+    want_iou = orc.mask_iou(gt_h, inst_h)
+    rows.append(row("f2 mask_iou (contingency table)", f"512x512x128, {want_iou.shape[0]} x {want_iou.shape[1]} objects", V, 8,
+                    gpu_ms(lambda: val.mask_iou(gt, inst)), cpu_ms(lambda: orc.mask_iou(gt_h, inst_h), iters=1),
+                    bool(torch.equal(val.mask_iou(gt, inst).cpu(), want_iou)),
+                    "4 B gt + 4 B prediction per voxel; the CPU figure is the oracle's contingency restatement, "
+                    "not the reference's O(N*M*V) loop"))
+    del tv, inst, gt, scratch
+
     print(json.dumps({"hbm_peak_GBps": hbm_peak(), "rows": rows}, indent=1))
 
 

@@ -301,6 +301,42 @@ int skb_shard_merge_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64
                          int64_t cap_pairs, int32_t label_base, int32_t* ncomp, uint32_t* status,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f2)  after the assembly: renumbering and the validation metrics
+ *   Label values must be non-negative and < table_size (instance labels are 0..N+2 on this path); a label
+ *   outside the table sets SKB_STATUS_LABEL_RANGE in *status and is left alone / ignored.
+ *
+ *   skb_renumber     fastremap.renumber(mask, in_place=True), skoots/lib/eval.py:304 — labels become 1..N in
+ *                    order of first appearance in the C-order scan, 0 stays 0.  In place; remap (table_size
+ *                    int32) receives old label -> new label (0 = absent), *n_labels the count.
+ *   skb_unique_index sorted unique labels > 0 (gt.unique(), validate/lib.py:201-205): index[l] = rank of l
+ *                    among the labels present, or -1; values (optional, >= count ints) = the labels in order.
+ *   skb_contingency  one pass over (gt, pred): inter[i*M+j] = |gt==a_i & pred==b_j|, areas — every
+ *                    `logical_and(_a,_b).sum()`, `_a.sum()` of validate/lib.py:211-226 and 253-273.
+ *   skb_iou_dice     iou = I/(A+B-I), dice = 2I/(A+B) as ONE fp32 division of the counts converted to fp32
+ *                    (the reference divides 0-dim int64 tensors), 0 where the objects do not touch.
+ *   skb_accuracies_from_iou   validate/lib.py:170-187: out3 = [true positives, false positives, false
+ *                    negatives] at threshold thr; hits_scratch holds N+M int32.
+ * ------------------------------------------------------------------------------------------- */
+#define SKB_STATUS_LABEL_RANGE 8u
+/* largest label (>= 0) of an i16 | i32 volume -> *max_out (device): sizes the tables below */
+int skb_label_max(const void* labels, int dtype, int64_t n_voxels, int32_t* max_out, void* stream);
+size_t skb_renumber_workspace_bytes(int64_t n_voxels, int64_t table_size);
+int skb_renumber(void* labels, int dtype, int64_t n_voxels, int64_t table_size, void* workspace,
+                 size_t workspace_bytes, int32_t* remap, int32_t* n_labels, uint32_t* status, void* stream);
+size_t skb_unique_index_workspace_bytes(int64_t table_size);
+int skb_unique_index(const void* labels, int dtype, int64_t n_voxels, int64_t table_size, int32_t* index,
+                     int32_t* values, int32_t* count, void* workspace, size_t workspace_bytes,
+                     uint32_t* status, void* stream);
+int skb_contingency(const void* gt, int gt_dtype, const void* pred, int pred_dtype, int64_t n_voxels,
+                    const int32_t* index_gt, int64_t table_gt, const int32_t* index_pred, int64_t table_pred,
+                    int64_t N, int64_t M, int32_t* inter_zeroed, int32_t* area_gt_zeroed,
+                    int32_t* area_pred_zeroed, void* stream);
+int skb_iou_dice(const int32_t* inter, const int32_t* area_gt, const int32_t* area_pred, int64_t N, int64_t M,
+                 float* iou, float* dice, void* stream);
+int skb_accuracies_from_iou(const float* iou, int64_t N, int64_t M, float thr, int32_t* hits_scratch,
+                            int32_t* out3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ e.g. on the GPU box).  Nothing under `skoots_b200/` imports this file.
 
 The three stubs cover exactly what the reference touches at import time:
   * `skimage.morphology.disk`   (skoots/lib/utils.py:6-14, used at utils.py:423-424)
+  * `skimage.io`                (skoots/validate/utils.py:4; only so that skoots.validate.lib imports)
   * `bism.*`                    (skoots/lib/utils.py:6-14 model factory imports)
   * `yacs.config.CfgNode`       (type annotation only)
 `PYTORCH_JIT=0` must be set before torch is imported: the scripted morphology
@@ -57,8 +58,15 @@ def install():
         skm = types.ModuleType("skimage.morphology")
         skm.disk = _disk
         sk.morphology = skm
+        ski = types.ModuleType("skimage.io")  # skoots/validate/utils.py:4 imports it; nothing here reads a file
+
+        def _no_io(*a, **k):
+            raise RuntimeError("skimage.io is stubbed: the oracle never touches image files")
+        ski.imread = ski.imsave = _no_io
+        sk.io = ski
         sys.modules["skimage"] = sk
         sys.modules["skimage.morphology"] = skm
+        sys.modules["skimage.io"] = ski
     if "bism" not in sys.modules:
         for name in ("bism", "bism.backends", "bism.modules", "bism.models",
                      "bism.models.spatial_embedding"):

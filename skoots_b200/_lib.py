@@ -18,6 +18,7 @@ SKB_U8, SKB_I16, SKB_I32, SKB_F16, SKB_BF16, SKB_F32 = range(6)
 STATUS_ROOT_OVERFLOW = 1
 STATUS_MISSING_ID = 2
 STATUS_PEER_TIMEOUT = 4
+STATUS_LABEL_RANGE = 8
 PEER_HANDLE_BYTES = 64
 MAX_WORLD = 16
 CCL_WORKSPACE_CLEAN = 1
@@ -61,6 +62,14 @@ SIGNATURES = {
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_stream": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
     "skb_assemble_resolve": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
+    "skb_label_max": (_c_int, [_c_vp, _c_int, _c_i64, _c_vp, _c_vp]),
+    "skb_renumber_workspace_bytes": (_c_sz, [_c_i64, _c_i64]),
+    "skb_renumber": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "skb_unique_index_workspace_bytes": (_c_sz, [_c_i64]),
+    "skb_unique_index": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
+    "skb_contingency": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "skb_iou_dice": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "skb_accuracies_from_iou": (_c_int, [_c_vp, _c_i64, _c_i64, ctypes.c_float, _c_vp, _c_vp, _c_vp]),
     "skb_peer_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
     "skb_peer_free": (_c_int, [_c_vp]),
     "skb_peer_export": (_c_int, [_c_vp, ctypes.c_char_p]),

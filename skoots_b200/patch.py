@@ -23,13 +23,17 @@ _TARGETS = {
     ("skoots.lib.morphology", "binary_dilation_2d"): ("skoots_b200.lib.morphology", "binary_dilation_2d"),
     ("skoots.lib.morphology", "binary_erosion"): ("skoots_b200.lib.morphology", "binary_erosion"),
     ("skoots.lib.embedding_to_prob", "baked_embed_to_prob"): ("skoots_b200.lib.embedding_to_prob", "baked_embed_to_prob"),
+    # row f2: the validation metrics (skoots/validate/lib.py:170-275), bound by name in skoots/validate/__main__.py:9-13
+    ("skoots.validate.lib", "mask_iou"): ("skoots_b200.validate", "mask_iou"),
+    ("skoots.validate.lib", "mask_dice"): ("skoots_b200.validate", "mask_dice"),
+    ("skoots.validate.lib", "accuracies_from_iou"): ("skoots_b200.validate", "accuracies_from_iou"),
 }
 
 # modules holding `from ... import name` copies (SURVEY.md §8b "bound at")
 _CALLERS = (
     "skoots.lib.eval", "skoots.train.engine", "skoots.train.merged_transform", "skoots.train.loss",
     "skoots.experimental.sparse_engine", "skoots.experimental.eval", "skoots.experimental.sparse_loss",
-    "skoots.experimental.sparse_transforms", "skoots.experimental.modifiers",
+    "skoots.experimental.sparse_transforms", "skoots.experimental.modifiers", "skoots.validate.__main__",
 )
 
 
@@ -68,7 +72,7 @@ def patch_skoots() -> List[Tuple[str, str]]:
             continue
         for attr, new in by_name.items():
             cur = getattr(mod, attr, None)
-            if cur is not None and cur is not new and (id(cur) in originals or getattr(cur, "__module__", "").startswith("skoots.lib")):
+            if cur is not None and cur is not new and (id(cur) in originals or getattr(cur, "__module__", "").startswith(("skoots.lib", "skoots.validate"))):
                 _SAVED.setdefault((caller, attr), cur)
                 setattr(mod, attr, new)
                 done.append((caller, attr))

@@ -156,3 +156,26 @@ def test_crop_origins_match_reference_quirks():
     assert orc.crop_origins(512, 50, 5) == [0, 40, 80, 120, 160, 200, 240, 280, 320, 360, 400, 440, 462]
     with pytest.raises(ValueError):
         orc.crop_origins(8, 8, 50)
+
+
+# ---- f2: renumber + validation metrics ---------------------------------------------------------------
+def test_validate_metrics_match_reference_outputs():
+    """the oracle's contingency-table restatement of mask_iou / mask_dice / accuracies_from_iou against the
+    outputs of the unmodified reference functions (oracle/gen_golden_validate.py)."""
+    fx = load_golden("validate_metrics")
+    for sfx in ("", "_small"):
+        gt, pred = fx["gt" + sfx], fx["pred" + sfx]
+        assert np.array_equal(orc.mask_iou(gt, pred).numpy(), fx["iou" + sfx])      # bit-exact fp32
+        assert np.array_equal(orc.mask_dice(gt, pred).numpy(), fx["dice" + sfx])
+    iou = torch.from_numpy(fx["iou"])
+    for thr in (0.1, 0.3, 0.5, 0.75):
+        assert list(orc.accuracies_from_iou(iou, thr)) == fx[f"acc_{int(thr * 100)}"].tolist()
+
+
+def test_renumber_restatement():
+    a = np.array([[0, 7, 7], [3, 0, 7], [3, 9, 0]], dtype=np.int16)
+    out, remap = orc.renumber(a)
+    assert out.tolist() == [[0, 1, 1], [2, 0, 1], [2, 3, 0]] and out.dtype == np.int16
+    assert remap == {0: 0, 7: 1, 3: 2, 9: 3}
+    with pytest.raises(AssertionError):
+        orc.mask_dice(a, a)  # identical objects: the reference's own assert fires (validate/lib.py:266-268)

@@ -152,19 +152,16 @@ def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1
     fused=False: the stream/resolve split with the gather's stream phase overlapped with the labelling
     (kept as a measured alternative: bit-identical, slower on B200 because the labelling kernels fill the SMs)."""
     mask = skeleton_mask.squeeze(0) if skeleton_mask.ndim == 4 else skeleton_mask
-    dev = L.require_cuda(mask, vectors)
-    if vectors.ndim != 4 or vectors.shape[0] != 3:
-        raise RuntimeError(f"vectors must be (3,X,Y,Z), got {tuple(vectors.shape)}")
-    if vectors.dtype not in (torch.float16, torch.bfloat16, torch.float32):
-        vectors = vectors.float()
-    vectors = vectors.contiguous()
-    shape = tuple(vectors.shape[1:])
-    eligible = split_eligible(shape, vectors, N, crop, overlap)
-    if fused is False and not eligible:
-        raise L.SkootsB200Error("the stream/resolve split needs N = 1, one whole-volume crop, Z % 64 == 0 and V % 256 == 0")
-    if fused is None:
-        fused = True
-    if not fused:
+    if fused is False:  # the opt-in split; the default path below stays as lean as it was (small volumes are launch-bound)
+        dev = L.require_cuda(mask, vectors)
+        if vectors.ndim != 4 or vectors.shape[0] != 3:
+            raise RuntimeError(f"vectors must be (3,X,Y,Z), got {tuple(vectors.shape)}")
+        if vectors.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            vectors = vectors.float()
+        vectors = vectors.contiguous()
+        shape = tuple(vectors.shape[1:])
+        if not split_eligible(shape, vectors, N, crop, overlap):
+            raise L.SkootsB200Error("the stream/resolve split needs N = 1, one whole-volume crop, Z % 64 == 0 and V % 256 == 0")
         mask = _as_mask(mask)
         sparse = new_sparse(shape, dev, None, workspace)
         if out is None:

@@ -99,6 +99,9 @@ def test_patch_skoots_rebinds_reference_modules():
         assert ("skoots.lib.flood_fill", "efficient_flood_fill") in done
         assert skoots.lib.flood_fill.efficient_flood_fill is ff.efficient_flood_fill
         assert skoots.lib.vector_to_embedding.vector_to_embedding.__module__ == "skoots_b200.lib.vector_to_embedding"
+        import skoots.validate.lib
+        assert ("skoots.validate.lib", "mask_iou") in done
+        assert skoots.validate.lib.mask_iou.__module__ == "skoots_b200.validate"
     finally:
         skoots_b200.patch.unpatch_skoots()
     assert skoots.lib.flood_fill.efficient_flood_fill is before

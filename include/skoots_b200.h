@@ -207,9 +207,12 @@ int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offset
  *   ranks.  Call order per rank (the two exchanges are NCCL send/recv and all-gather, driven by the
  *   caller — skoots_b200/sharded.py):
  *     skb_shard_label_local -> skb_shard_emit_runs (low / high H planes) -> [send/recv with the
- *     Z-neighbours] -> skb_shard_ingest_runs (into zeroed per-row halo words) ->
- *     skb_shard_boundary_pairs (packs [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]]) ->
- *     [all-gather] -> skb_shard_merge -> skb_assemble_slab.
+ *     Z-neighbours] -> skb_shard_boundary_pairs (halo_hi = NULL: zeroes the counters of
+ *     [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]] and packs my roots) ->
+ *     skb_shard_ingest_runs (into zeroed per-row halo words; the upper neighbour's call also appends the
+ *     (my root, its root) pairs of my last plane) -> [all-gather] -> skb_shard_merge -> skb_assemble_slab.
+ *     (skb_shard_boundary_pairs with halo_hi != NULL, called AFTER the ingests, finds the pairs by scanning
+ *     the halo words instead — the older, slower order; kept for callers that ingest without `exchange`.)
  *   Numbering after the merge is the single-GPU numbering (label_base + 1 + raster rank).
  *   runs buffers hold 3*(cap+1) int32: [count,_,_] then (start voxel, length, root id) triples.
  * ------------------------------------------------------------------------------------------- */
@@ -220,8 +223,15 @@ int skb_shard_label_local(const void* mask, int mask_dtype, int64_t X, int64_t Y
 int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
                         int face_is_high, int64_t halo, int32_t* runs, int64_t cap, uint32_t* status,
                         void* stream);
-int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs,
-                          int64_t cap, uint64_t* halo_words_zeroed, void* stream);
+/* exchange != NULL (the UPPER neighbour's runs): also appends the (my root, neighbour root) pairs of runs that touch
+ * my last plane to the exchange buffer — call skb_shard_boundary_pairs(halo_hi = NULL) BEFORE it, which zeroes the
+ * buffer's counters and packs my roots */
+int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                          const int32_t* runs, int64_t cap, uint64_t* halo_words_zeroed, int32_t* exchange,
+                          int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream);
+/* instead of re-zeroing all X*Y halo words before every ingest: zero exactly the words the previous pass's ingest
+ * set, from that pass's run list (prev_runs = the receive buffer, before the next exchange overwrites it) */
+int skb_shard_clear_halo(int64_t Z, const int32_t* prev_runs, int64_t cap, uint64_t* halo_words, void* stream);
 int skb_shard_boundary_pairs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                              int64_t Zl, int64_t capacity, const uint64_t* halo_hi, int32_t* exchange,
                              int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream);
@@ -261,7 +271,7 @@ int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, i
  *   HBM.  A flag that does not arrive within ~8 s sets SKB_STATUS_PEER_TIMEOUT instead of hanging.
  *   Call order per rank and pass (skoots_b200/sharded.py, transport "peer"):
  *     skb_shard_begin -> skb_shard_label_local -> skb_shard_emit_runs_peer (low / high face)
- *     -> skb_shard_ingest_runs_peer (from the low / high neighbour) -> skb_shard_boundary_pairs
+ *     -> skb_shard_boundary_pairs (halo_hi = NULL) -> skb_shard_ingest_runs_peer (from the low / high neighbour)
  *     -> skb_shard_push -> skb_shard_merge_peer -> skb_assemble_slab.
  *   The skb_peer_* calls are set-up / tear-down only: they are the one place the library allocates
  *   (cudaMalloc: legacy CUDA IPC cannot export a caching allocator's sub-allocations).
@@ -279,6 +289,9 @@ size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t cap_roots, i
 /* starts pass k+1: bumps the mailbox's pass counter, clears its run counters */
 int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
                     void* stream);
+/* skb_shard_clear_halo on the mailbox's receive-buffer copy of the PREVIOUS pass; call after skb_shard_begin */
+int skb_shard_clear_halo_peer(int64_t Z, void* mailbox, int from_high, int world, int64_t cap_runs,
+                              int64_t cap_roots, int64_t cap_pairs, uint64_t* halo_words, void* stream);
 /* like skb_shard_emit_runs for BOTH faces of the slab with one launch (`halo` planes each): the triples
  * are stored into the neighbours' mailboxes (NULL = no neighbour on that side) and their flags released */
 int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
@@ -286,10 +299,10 @@ int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, i
                              void* hi_neighbour_mailbox, int world, int64_t cap_runs, int64_t cap_roots,
                              int64_t cap_pairs, uint32_t* status, void* stream);
 /* waits for the neighbour's flag, then skb_shard_ingest_runs on the mailbox's receive buffer */
-int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, void* mailbox,
-                               int from_high, int world, int64_t cap_runs, int64_t cap_roots,
-                               int64_t cap_pairs, uint64_t* halo_words_zeroed, uint32_t* status,
-                               void* stream);
+int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                               void* mailbox, int from_high, int world, int64_t cap_runs, int64_t cap_roots,
+                               int64_t cap_pairs, uint64_t* halo_words_zeroed, int32_t* exchange,
+                               uint32_t* status, void* stream);
 /* the all-gather: stores the used part of `exchange` (written by skb_shard_boundary_pairs) into slot
  * `rank` of every rank's mailbox (peer_mailboxes: HOST array of `world` device pointers, own included)
  * and releases the flags */

@@ -57,7 +57,9 @@ SIGNATURES = {
     "skb_stamp_disks": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_label_local": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_int, _c_vp]),
     "skb_shard_emit_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
-    "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "skb_shard_ingest_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
+    "skb_shard_clear_halo": (_c_int, [_c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),
+    "skb_shard_clear_halo_peer": (_c_int, [_c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_boundary_pairs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_merge": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_stream": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
@@ -78,7 +80,7 @@ SIGNATURES = {
     "skb_shard_mailbox_bytes": (_c_sz, [_c_int, _c_i64, _c_i64, _c_i64]),
     "skb_shard_begin": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
     "skb_shard_emit_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
-    "skb_shard_ingest_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "skb_shard_ingest_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_shard_push": (_c_int, [_c_vp, _c_vp, ctypes.POINTER(ctypes.c_uint64), _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
     "skb_shard_merge_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_slab": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),

@@ -1282,8 +1282,18 @@ __global__ void shard_signal_runs_kernel(SignalRuns s0, SignalRuns s1, long long
 }
 
 // flag != NULL (peer transport): every CTA first waits until the neighbour's runs of this pass have landed
+// where the (my root, neighbour root) pairs found while ingesting the UPPER neighbour's runs go: a run that starts in
+// the neighbour's first plane z1 touches my last plane iff my voxel below it is foreground
+struct PairSink {
+    int* exch;  // NULL: no pairing (lower neighbour's runs) — [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]]
+    int cap_roots, cap_pairs;
+    int z1;     // first plane of the upper neighbour
+    int nk;     // words per row of my compact bit mask
+};
+
 __global__ void __launch_bounds__(256) shard_ingest_runs_kernel(CclView v, const int* runs, int cap, ull* __restrict__ halo,
-                                                               const int* flag, const int* epoch, long long parity_stride) {
+                                                               const int* flag, const int* epoch, long long parity_stride,
+                                                               PairSink ps) {
     if (flag) {
         const int e = *epoch;
         if (threadIdx.x == 0) spin_until(flag, e, v.status);
@@ -1299,6 +1309,16 @@ __global__ void __launch_bounds__(256) shard_ingest_runs_kernel(CclView v, const
         atomicOr(&halo[rowi], m);
         for (int j = 0; j < len; ++j) v.parent[s + j] = root;
         v.parent[root] = root;  // the neighbour's root becomes a node of my union-find (idempotent)
+        if (ps.exch && z == ps.z1 && (v.bits[(size_t)rowi * ps.nk + (ps.nk - 1)] >> 63)) {
+            const int a = gfind(v.parent, s - 1);  // my voxel right below the run's first voxel
+            const int slot = atomicAdd(ps.exch + 1, 1);
+            if (slot < ps.cap_pairs) {
+                ps.exch[2 + ps.cap_roots + 2 * slot] = a;
+                ps.exch[3 + ps.cap_roots + 2 * slot] = root;
+            } else {
+                atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            }
+        }
     }
 }
 
@@ -1507,15 +1527,41 @@ extern "C" int skb_shard_emit_runs(void* workspace, int64_t X, int64_t Y, int64_
     return SKB_OK;
 }
 
-extern "C" int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* runs, int64_t cap,
-                                     uint64_t* halo_words_zeroed, void* stream) {
-    int rc = skb_check_volume(X, Y, Z, "skb_shard_ingest_runs");
+// Zeroes exactly the halo words the PREVIOUS pass's ingest set, by walking that pass's run list (still intact in
+// the receive buffer) — instead of a 33 MB memset of all X*Y words per face and pass.
+__global__ void __launch_bounds__(256) shard_clear_halo_kernel(const int* runs, int cap, ull* __restrict__ halo, unsigned Z,
+                                                              const int* epoch, long long parity_stride) {
+    if (epoch) runs += (long long)((*epoch + 1) & 1) * parity_stride;  // the copy the previous pass used
+    const int n = min(runs[0], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        halo[(unsigned)runs[3 + 3 * i] / Z] = 0ull;
+}
+
+extern "C" int skb_shard_clear_halo(int64_t Z, const int32_t* prev_runs, int64_t cap, uint64_t* halo_words, void* stream) {
+    SKB_REQUIRE(Z > 0 && prev_runs && halo_words && cap > 0, "skb_shard_clear_halo: bad argument");
+    shard_clear_halo_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(prev_runs, (int)cap, reinterpret_cast<ull*>(halo_words),
+                                                                                (unsigned)Z, nullptr, 0);
+    SKB_LAUNCH_CHECK("shard_clear_halo_kernel");
+    return SKB_OK;
+}
+
+static PairSink pair_sink(int32_t* exchange, int64_t cap_roots, int64_t cap_pairs, int64_t z_off, int64_t Zl) {
+    PairSink ps = {exchange, (int)cap_roots, (int)cap_pairs, (int)(z_off + Zl), (int)(Zl / 64)};
+    return ps;
+}
+
+extern "C" int skb_shard_ingest_runs(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                     const int32_t* runs, int64_t cap, uint64_t* halo_words_zeroed, int32_t* exchange,
+                                     int64_t cap_roots, int64_t cap_pairs, uint32_t* status, void* stream) {
+    int rc = shard_common("skb_shard_ingest_runs", X, Y, Z, z_off, Zl);
     if (rc) return rc;
-    SKB_REQUIRE(workspace && runs && halo_words_zeroed && cap > 0, "skb_shard_ingest_runs: bad argument");
+    SKB_REQUIRE(workspace && runs && halo_words_zeroed && status && cap > 0, "skb_shard_ingest_runs: bad argument");
+    SKB_REQUIRE(!exchange || (cap_roots > 0 && cap_pairs > 0), "skb_shard_ingest_runs: bad exchange capacities");
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
-    CclView v = make_view(L, workspace, 0, 1, nullptr, nullptr);
+    CclView v = make_view(L, workspace, 0, 1, status, nullptr);
     shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        v, runs, (int)cap, reinterpret_cast<ull*>(halo_words_zeroed), nullptr, nullptr, 0);
+        v, runs, (int)cap, reinterpret_cast<ull*>(halo_words_zeroed), nullptr, nullptr, 0,
+        pair_sink(exchange, cap_roots, cap_pairs, z_off, Zl));
     SKB_LAUNCH_CHECK("shard_ingest_runs_kernel");
     return SKB_OK;
 }
@@ -1637,6 +1683,19 @@ extern "C" int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64
     return SKB_OK;
 }
 
+extern "C" int skb_shard_clear_halo_peer(int64_t Z, void* mailbox, int from_high, int world, int64_t cap_runs,
+                                         int64_t cap_roots, int64_t cap_pairs, uint64_t* halo_words, void* stream) {
+    int rc = mailbox_args("skb_shard_clear_halo_peer", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(Z > 0 && mailbox && halo_words && (from_high == 0 || from_high == 1), "skb_shard_clear_halo_peer: bad argument");
+    Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
+    shard_clear_halo_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(me.recv(from_high), (int)cap_runs,
+                                                                                reinterpret_cast<ull*>(halo_words), (unsigned)Z,
+                                                                                me.epoch(), me.M.runs_ints);
+    SKB_LAUNCH_CHECK("shard_clear_halo_kernel (peer)");
+    return SKB_OK;
+}
+
 extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
                                         int64_t halo, void* mailbox, void* lo_neighbour_mailbox,
                                         void* hi_neighbour_mailbox, int world, int64_t cap_runs, int64_t cap_roots,
@@ -1677,21 +1736,23 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
     return SKB_OK;
 }
 
-extern "C" int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, void* mailbox, int from_high,
-                                          int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
-                                          uint64_t* halo_words_zeroed, uint32_t* status, void* stream) {
-    int rc = skb_check_volume(X, Y, Z, "skb_shard_ingest_runs_peer");
+extern "C" int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                          void* mailbox, int from_high, int world, int64_t cap_runs, int64_t cap_roots,
+                                          int64_t cap_pairs, uint64_t* halo_words_zeroed, int32_t* exchange,
+                                          uint32_t* status, void* stream) {
+    int rc = shard_common("skb_shard_ingest_runs_peer", X, Y, Z, z_off, Zl);
     if (rc) return rc;
     rc = mailbox_args("skb_shard_ingest_runs_peer", world, cap_runs, cap_roots, cap_pairs);
     if (rc) return rc;
     SKB_REQUIRE(workspace && mailbox && halo_words_zeroed && status, "skb_shard_ingest_runs_peer: NULL pointer");
     SKB_REQUIRE(from_high == 0 || from_high == 1, "skb_shard_ingest_runs_peer: from_high must be 0 or 1");
+    SKB_REQUIRE(!exchange || from_high == 1, "skb_shard_ingest_runs_peer: pairs are found in the upper neighbour's runs only");
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     CclView v = make_view(L, workspace, 0, 1, status, nullptr);
     Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
     shard_ingest_runs_kernel<<<148 * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         v, me.recv(from_high), (int)cap_runs, reinterpret_cast<ull*>(halo_words_zeroed), me.flag(from_high), me.epoch(),
-        me.M.runs_ints);
+        me.M.runs_ints, pair_sink(exchange, cap_roots, cap_pairs, z_off, Zl));
     SKB_LAUNCH_CHECK("shard_ingest_runs_kernel (peer)");
     return SKB_OK;
 }

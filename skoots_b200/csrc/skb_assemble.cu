@@ -815,7 +815,9 @@ static void launch_assemble_t(const AsmParams& P, OutT* out, long long v_begin, 
     const long long c_begin = v_begin / 256, c_end = P.vec_aligned ? v_end / 256 : c_begin;
     if (c_end > c_begin) {
         long long blocks = (c_end - c_begin + ASM_WARPS - 1) / ASM_WARPS;
-        if (blocks > 148 * 4) blocks = 148 * 4;  // 4 resident CTAs per SM; warps stride over the chunks
+        // 4 resident CTAs per SM; warps stride over the chunks.  Measured at 2048x2048x512 (ms per launch):
+        // 2 CTAs/SM 4.94, 3: 3.98, 4: 3.59, 5 (48 registers): 3.80 — more streams in flight than this hurt.
+        if (blocks > 148 * 4) blocks = 148 * 4;
         const char* mode = getenv("SKB_GATHER_STAGING");  // experiments: "bulk" | "ldgsts" | unset = register prefetch
         const bool eligible = P.fast_ok && !P.dense && P.flat_bits;
         const int smem = ASM_WARPS * StageCfg<VecT>::WARP_BYTES;

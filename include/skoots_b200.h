@@ -99,6 +99,11 @@ size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity
  * mask -> bit-mask pack; PHASE_LABEL = everything after it.  Neither bit = the whole labelling. */
 #define SKB_CCL_PHASE_PACK 2
 #define SKB_CCL_PHASE_LABEL 4
+/* how the tile kernel hands tiles to its persistent warps: by default batches are claimed dynamically when
+ * there are >= 32 tiles per warp and tiles are assigned statically otherwise; these force one or the other
+ * (same labels either way — for tests and measurements) */
+#define SKB_CCL_TILES_DYNAMIC 8
+#define SKB_CCL_TILES_STATIC 16
 int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                          int planar, int32_t label_base, int64_t capacity, void* workspace,
                          size_t workspace_bytes, int32_t* ncomp, uint32_t* status, int flags,

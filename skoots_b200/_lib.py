@@ -24,6 +24,8 @@ MAX_WORLD = 16
 CCL_WORKSPACE_CLEAN = 1
 CCL_PHASE_PACK = 2
 CCL_PHASE_LABEL = 4
+CCL_TILES_DYNAMIC = 8
+CCL_TILES_STATIC = 16
 
 _DTYPES = {
     torch.uint8: SKB_U8, torch.bool: SKB_U8, torch.int16: SKB_I16, torch.int32: SKB_I32,

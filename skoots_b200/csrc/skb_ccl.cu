@@ -997,13 +997,15 @@ static void launch_pack(const void* mask, const CclView& v, cudaStream_t st) {
     }
 }
 
-static void launch_tile(const CclView& v, cudaStream_t st) {
+static void launch_tile(const CclView& v, int flags, cudaStream_t st) {
     const int nk_shift = shift_of(v.nk);
     const long long xt = (v.X + 7) / 8, n_yk = (long long)((v.Y + 7) / 8) * v.nk;
     const long long n_tiles = xt * n_yk;
     long long blocks = (n_tiles + CCL_TILE_WARPS - 1) / CCL_TILE_WARPS;
     if (blocks > 148 * 5) blocks = 148 * 5;  // 5 resident CTAs per SM (40 KB of shared memory each), persistent warps
-    const int dynamic = n_tiles >= 32 * blocks * CCL_TILE_WARPS ? 1 : 0;
+    int dynamic = n_tiles >= 32 * blocks * CCL_TILE_WARPS ? 1 : 0;
+    if (flags & SKB_CCL_TILES_DYNAMIC) dynamic = 1;
+    if (flags & SKB_CCL_TILES_STATIC) dynamic = 0;
     ccl_tile_kernel<<<(unsigned)blocks, 32 * CCL_TILE_WARPS, 0, st>>>(v, (unsigned)n_tiles, (unsigned)n_yk, nk_shift,
                                                                     n_yk < (1LL << 30) ? shift_of((int)n_yk) : -1, dynamic);
 }
@@ -1020,7 +1022,7 @@ static void launch_pack_and_tile(const void* mask, int mask_dtype, const CclView
         if (mask_dtype == SKB_U8) launch_pack<uint8_t>(mask, v, st);
         else launch_pack<int16_t>(mask, v, st);
     }
-    if (all || (flags & SKB_CCL_PHASE_LABEL)) launch_tile(v, st);
+    if (all || (flags & SKB_CCL_PHASE_LABEL)) launch_tile(v, flags, st);
 }
 
 static void launch_boundary(const CclView& v, const SkbCclLayout& L, int TX, int TY, cudaStream_t st) {

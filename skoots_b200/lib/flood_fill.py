@@ -48,13 +48,14 @@ def _workspace_for(shape, cap: int, workspace: Optional[Tensor], dev) -> Tensor:
     return workspace
 
 
-def launch_label(mask: Tensor, sparse: "SparseLabels", planar: bool, label_base: int, phase: int = 0) -> None:
+def launch_label(mask: Tensor, sparse: "SparseLabels", planar: bool, label_base: int, phase: int = 0, tiles: int = 0) -> None:
     """enqueues the labelling of `mask` into sparse.workspace on the current stream.  phase = 0 (all),
-    L.CCL_PHASE_PACK (header + bit mask only) or L.CCL_PHASE_LABEL (everything after the pack)."""
+    L.CCL_PHASE_PACK (header + bit mask only) or L.CCL_PHASE_LABEL (everything after the pack);
+    tiles = 0 | L.CCL_TILES_DYNAMIC | L.CCL_TILES_STATIC forces the tile kernel's work distribution."""
     dev = mask.device
     X, Y, Z = sparse.shape
     ws = sparse.workspace
-    flags = phase
+    flags = phase | tiles
     if phase != L.CCL_PHASE_LABEL:
         # a workspace that already went through a pass of this shape has its root bitmap zeroed (see the C header)
         key = (X, Y, Z, sparse.capacity, ws.data_ptr())

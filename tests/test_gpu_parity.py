@@ -326,3 +326,23 @@ def test_segment_volume_matches_eval_replay():
                          overlap=(5, 5, 3), device=DEV, autocast=False)
     assert got.dtype == torch.int16 and torch.equal(got.cpu(), want)
     assert int(want.max()) > 2
+
+
+@pytest.mark.parametrize("shape,density", [((40, 40, 128), 0.02), ((33, 70, 96), 0.3), ((64, 64, 64), 0.6), ((17, 9, 130), 1.0)])
+def test_ccl_tile_distribution_modes_agree(shape, density):
+    """the tile kernel claims batches dynamically (interleaved cursors + stealing) only on large volumes; forcing that
+    mode on small ones must give scipy's labelling too, as must the static mode."""
+    import skoots_b200._lib as L
+    from skoots_b200.lib.flood_fill import launch_label, new_sparse, write_dense
+    rng = np.random.default_rng(hash((shape, density)) % (2**32))
+    mask_np = rng.random(shape) < density
+    want, n_want = orc.label_components(mask_np)
+    mask = torch.from_numpy(mask_np.astype(np.uint8)).to(DEV)
+    for mode in (L.CCL_TILES_DYNAMIC, L.CCL_TILES_STATIC):
+        sp = new_sparse(shape, torch.device(DEV), capacity=mask.numel() // 2 + 1)
+        for _ in range(2):  # second pass: cursors and root bitmap are reused
+            launch_label(mask, sp, False, 0, tiles=mode)
+        out = torch.empty(shape, dtype=torch.int32, device=DEV)
+        write_dense(sp, out)
+        assert sp.num_components == n_want and np.array_equal(out.cpu().numpy(), want), mode
+

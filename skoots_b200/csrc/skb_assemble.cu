@@ -760,6 +760,48 @@ __global__ void __launch_bounds__(256) vec_embed2d_kernel(const VecT* __restrict
     out[at + plane] = __fadd_rn((float)y, __fmul_rn(skb_to_float<VecT>(vec[at + plane]), s1));
 }
 
+// N = 1 forms, 8 consecutive elements of the fastest axis per thread: one 16-byte load (two for fp32) per channel and
+// two 16-byte stores per channel, instead of a 2-byte load and a 4-byte store per thread.  `inner` = length of the
+// fastest axis (a multiple of 8), `mid` = length of the axis before it; C = 3 (x, y, z) or 2 (x, y).
+template <typename VecT, int C>
+__global__ void __launch_bounds__(256) vec_embed_n1_vec8_kernel(const void* __restrict__ vec, float* __restrict__ out,
+                                                                long long per_channel, unsigned inner, unsigned mid,
+                                                                float s0, float s1, float s2, long long groups_per_batch,
+                                                                long long total_groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_groups) return;
+    const long long b = g / groups_per_batch;
+    const long long i0 = (g - b * groups_per_batch) * 8;  // element index inside one channel of batch b
+    const unsigned q = (unsigned)(i0 / inner);
+    const unsigned last = (unsigned)(i0 - (long long)q * inner);
+    float idx[3];
+    if (C == 3) { idx[0] = (float)(q / mid); idx[1] = (float)(q - (q / mid) * mid); idx[2] = (float)last; }
+    else { idx[0] = (float)q; idx[1] = (float)last; idx[2] = 0.f; }
+    const float sc[3] = {s0, s1, s2};
+    const long long base = b * C * per_channel + i0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const Raw8<VecT> r = load_raw8<VecT, true>(vec, base + (long long)c * per_channel, 8);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float coord = c == C - 1 ? __fadd_rn(idx[c], (float)j) : idx[c];  // exact: small integers
+            o[j] = __fadd_rn(coord, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(r.w, j)), sc[c]));
+        }
+        float* dst = out + base + (long long)c * per_channel;
+        skb_st_stream16(dst, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+        skb_st_stream16(dst + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+    }
+}
+
+template <typename VecT, int C>
+static void launch_vec_embed_n1_vec8(const void* vec, float* out, long long B, long long per_channel, unsigned inner, unsigned mid,
+                                     const float* scale, cudaStream_t st) {
+    const long long gpb = per_channel / 8, total = B * gpb;
+    vec_embed_n1_vec8_kernel<VecT, C><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(vec, out, per_channel, inner, mid, scale[0], scale[1],
+                                                                                       C == 3 ? scale[2] : 0.f, gpb, total);
+}
+
 template <typename VecT>
 __global__ void __launch_bounds__(256) vec_embed_bwd_kernel(const float* __restrict__ go, VecT* __restrict__ gv,
                                                            long long inner, int C, float s0, float s1, float s2,
@@ -1045,6 +1087,13 @@ extern "C" int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_
     const long long V = X * Y * Z;
     const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
     const int es = elem_size(vec_dtype);
+    if (N == 1 && Z % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) && B * V / 8 < (1LL << 31) * 256) {
+        if (vec_dtype == SKB_F16) launch_vec_embed_n1_vec8<__half, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
+        else if (vec_dtype == SKB_BF16) launch_vec_embed_n1_vec8<__nv_bfloat16, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
+        else launch_vec_embed_n1_vec8<float, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
+        SKB_LAUNCH_CHECK("vec_embed_n1_vec8_kernel");
+        return SKB_OK;
+    }
     for (int64_t b = 0; b < B; ++b) {
         AsmParams P = {};
         P.vec = static_cast<const char*>(vec) + (size_t)b * 3 * V * es;
@@ -1072,6 +1121,14 @@ extern "C" int skb_vec_embed2d(const void* vec, int vec_dtype, int64_t B, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long total = B * X * Y;
     unsigned nb = (unsigned)((total + 255) / 256);
+    if (Y % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) &&
+        (vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32)) {
+        if (vec_dtype == SKB_F16) launch_vec_embed_n1_vec8<__half, 2>(vec, out, B, X * Y, (unsigned)Y, 1u, scale, st);
+        else if (vec_dtype == SKB_BF16) launch_vec_embed_n1_vec8<__nv_bfloat16, 2>(vec, out, B, X * Y, (unsigned)Y, 1u, scale, st);
+        else launch_vec_embed_n1_vec8<float, 2>(vec, out, B, X * Y, (unsigned)Y, 1u, scale, st);
+        SKB_LAUNCH_CHECK("vec_embed_n1_vec8_kernel (2-D)");
+        return SKB_OK;
+    }
     if (vec_dtype == SKB_F16)
         vec_embed2d_kernel<__half><<<nb, 256, 0, st>>>(static_cast<const __half*>(vec), (int)X, (int)Y, scale[0], scale[1], out, total);
     else if (vec_dtype == SKB_BF16)

@@ -346,3 +346,23 @@ def test_ccl_tile_distribution_modes_agree(shape, density):
         write_dense(sp, out)
         assert sp.num_components == n_want and np.array_equal(out.cpu().numpy(), want), mode
 
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+def test_vector_to_embedding_vectorised_n1_paths(dt):
+    """Z % 8 == 0 (3-D) / Y % 8 == 0 (2-D) take the 8-elements-per-thread N = 1 kernels: same bits as the oracle,
+    batches included; an unaligned view falls back to the scalar kernel with the same result."""
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    g = torch.Generator().manual_seed(17)
+    vec = ((torch.rand((2, 3, 19, 12, 24), generator=g) * 2 - 1) * 3).to(dt)
+    scale = torch.tensor((60, 60, 12))
+    want = orc.vector_to_embedding(scale, vec)
+    got = vector_to_embedding(scale, vec.to(DEV))
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+    v2 = ((torch.rand((3, 2, 37, 64), generator=g) * 2 - 1)).to(dt)
+    s2 = torch.tensor((60.0, 7.5))
+    assert torch.equal(vector_to_embedding(s2, v2.to(DEV)).cpu(), orc.vector_to_embedding(s2, v2))
+    # storage offset of one element: not 16-byte aligned any more
+    flat = torch.zeros(vec.numel() + 1, dtype=dt, device=DEV)
+    flat[1:] = vec.reshape(-1).to(DEV)
+    assert torch.equal(vector_to_embedding(scale, flat[1:].view(vec.shape)).cpu(), want)

@@ -78,3 +78,18 @@ def test_training_ops(ref):
     assert torch.equal(orc.binary_dilation(img), ref.dil(img))
     assert torch.equal(orc.binary_dilation_2d(img), ref.dil2d(img))
     assert torch.equal(orc.binary_erosion(img), ref.ero(img))
+
+
+def test_validation_metrics_live(ref):
+    """row f2: the oracle's contingency-table restatement against skoots.validate.lib run live."""
+    import skoots.validate.lib as vl
+    g = torch.Generator().manual_seed(33)
+    gt = (torch.randint(0, 9, (14, 12, 10), generator=g) * 3).to(torch.int32)
+    pred = torch.roll(gt, shifts=(1, 1, 0), dims=(0, 1, 2)).clone()
+    pred[pred == 6] = 21
+    pred[:3] = 0
+    iou = quiet(vl.mask_iou, gt, pred)
+    assert torch.equal(orc.mask_iou(gt.numpy(), pred.numpy()), iou)
+    assert torch.equal(orc.mask_dice(gt.numpy(), pred.numpy()), quiet(vl.mask_dice, gt, pred))
+    for thr in (0.05, 0.2, 0.6):
+        assert orc.accuracies_from_iou(iou, thr) == tuple(vl.accuracies_from_iou(iou, thr))

@@ -401,7 +401,9 @@ def run_b200(args):
             "path_roofline": {"bytes_per_voxel": ALGO_BYTES_PATH, "achieved": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
-            "roofline": {"kernel": f"{dominant}<half,int>", "bound": "hbm", "timed": "alone, CUDA events, right after the timed region", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"kernel": f"{dominant}<half,int>", "bound": "hbm",
+                         "timed": ("CUDA events around single launches on the same buffers right after the timed region"
+                                   if (world > 1 or split) else "CUDA events around the kernel inside every timed step"), "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": measured_traffic(dominant, V / world),
                          "traffic_source": "profiles/r01_traffic.json (ncu --set full dram bytes per voxel x voxels per launch)",
                          "algorithmic_bytes": gather_bytes, "peak_source": peak_src,

@@ -915,28 +915,51 @@ __global__ void __launch_bounds__(256) ccl_publish_kernel(CclView v) {
 // ------------------------------------------------------------------------------------------
 // dense writer: 8 voxels (one byte of the bit mask) per thread
 // ------------------------------------------------------------------------------------------
-template <typename OutT>
+// 8 voxels (one byte of the bit mask) per thread.  FLAT (Z % 64 == 0: no row padding, bit index == voxel index):
+// the byte is bits[gi] and the voxels are 8 gi .. 8 gi + 7 — no division at all (the 64-bit div/mod per thread
+// of the general form made this store-bound kernel run at half of HBM speed on a 64 x 4096 x 4096 stack).
+template <typename OutT, bool FLAT>
 __global__ void __launch_bounds__(256) ccl_dense_kernel(const ull* __restrict__ bits, const int* __restrict__ parent,
-                                                       int Z, int ZW, int Z8, long long n_groups,
+                                                       int Z, int ZW, int Z8, unsigned n_groups,
                                                        OutT* __restrict__ out, int vec_ok) {
-    long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_groups) return;
-    long long rowi = gi / Z8;
-    int z = (int)(gi % Z8) * 8;
-    unsigned byte = (unsigned)(bits[rowi * ZW + (z >> 6)] >> (z & 63)) & 0xFFu;
-    long long vox = rowi * Z + z;
-    __align__(16) OutT lab[8];
+    unsigned byte;
+    size_t vox;
+    int z = 0;
+    if (FLAT) {
+        byte = __ldg(reinterpret_cast<const unsigned char*>(bits) + gi);
+        vox = (size_t)gi * 8;
+    } else {
+        const unsigned rowi = gi / (unsigned)Z8;
+        z = (int)(gi - rowi * (unsigned)Z8) * 8;
+        byte = (unsigned)(bits[(size_t)rowi * ZW + (z >> 6)] >> (z & 63)) & 0xFFu;
+        vox = (size_t)rowi * Z + z;
+    }
+    unsigned lab[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lab[j] = (byte >> j) & 1u ? (OutT)skb_sparse_label(parent, (int)(vox + j)) : (OutT)0;
+    for (int j = 0; j < 8; ++j) lab[j] = 0u;
+    if (byte) {
+        // two dependent loads per foreground voxel, issued stage by stage for all 8 (index 0 stands in for background)
+        int p1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p1[j] = __ldg(parent + (((byte >> j) & 1u) ? vox + j : vox + (__ffs((int)byte) - 1)));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p2 = p1[j] < 0 ? p1[j] : __ldg(parent + p1[j]);
+            lab[j] = ((byte >> j) & 1u) ? (unsigned)(-p2) : 0u;
+        }
+    }
     if (vec_ok) {
         if (sizeof(OutT) == 2) {
-            *reinterpret_cast<uint4*>(out + vox) = *reinterpret_cast<uint4*>(lab);
+            skb_st_stream16(out + vox, make_uint4((lab[0] & 0xffffu) | (lab[1] << 16), (lab[2] & 0xffffu) | (lab[3] << 16),
+                                                  (lab[4] & 0xffffu) | (lab[5] << 16), (lab[6] & 0xffffu) | (lab[7] << 16)));
         } else {
-            reinterpret_cast<uint4*>(out + vox)[0] = reinterpret_cast<uint4*>(lab)[0];
-            reinterpret_cast<uint4*>(out + vox)[1] = reinterpret_cast<uint4*>(lab)[1];
+            skb_st_stream16(out + vox, make_uint4(lab[0], lab[1], lab[2], lab[3]));
+            skb_st_stream16(out + vox + 4, make_uint4(lab[4], lab[5], lab[6], lab[7]));
         }
     } else {
-        for (int j = 0; j < 8 && z + j < Z; ++j) out[vox + j] = lab[j];
+        for (int j = 0; j < 8 && z + j < Z; ++j) out[vox + j] = (OutT)lab[j];
     }
 }
 
@@ -1080,14 +1103,18 @@ extern "C" int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, 
     const ull* bits = reinterpret_cast<const ull*>(base + L.off_bits);
     const int* parent = reinterpret_cast<const int*>(base + L.off_parent);
     int Z8 = (int)((Z + 7) / 8);
-    long long groups = (long long)X * Y * Z8;
-    unsigned nb = (unsigned)((groups + 255) / 256);
+    const unsigned groups = (unsigned)((long long)X * Y * Z8);  // <= 2^28
+    unsigned nb = (groups + 255u) / 256u;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int vec_ok = (Z % 8 == 0) && skb_aligned16(out) ? 1 : 0;
-    if (out_dtype == SKB_I16)
-        ccl_dense_kernel<int16_t><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
-    else
-        ccl_dense_kernel<int32_t><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
+    const bool flat = Z % 64 == 0 && vec_ok;
+    if (out_dtype == SKB_I16) {
+        if (flat) ccl_dense_kernel<int16_t, true><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
+        else ccl_dense_kernel<int16_t, false><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
+    } else {
+        if (flat) ccl_dense_kernel<int32_t, true><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
+        else ccl_dense_kernel<int32_t, false><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
+    }
     SKB_LAUNCH_CHECK("ccl_dense_kernel");
     return SKB_OK;
 }

@@ -218,10 +218,18 @@ def run_b200(args):
 
     if world > 1:
         from skoots_b200.sharded import PeerComm, ShardedAssembler, TorchDistComm
+        import skoots_b200._lib as L_err
         transport = os.environ.get("SKB_TRANSPORT", "peer")
-        comm = PeerComm() if transport == "peer" else TorchDistComm()
-        runner = ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops, comm=comm,
-                                  split=bool(os.environ.get("SKB_SPLIT")))
+        make = lambda comm: ShardedAssembler(shape, world, rank, dev, scale=SCALE, hops=args.hops, comm=comm,
+                                             split=bool(os.environ.get("SKB_SPLIT")))
+        try:
+            runner = make(PeerComm() if transport == "peer" else TorchDistComm())
+        except L_err.SkootsB200Error as exc:  # collective failure (every rank raises): CUDA IPC is not usable on this box
+            if transport != "peer":
+                raise
+            if rank == 0:
+                print(f"bench.py: {exc}; falling back to the NCCL transport", file=sys.stderr, flush=True)
+            runner = make(TorchDistComm())
         z0, z1 = runner.z_range
         tv = make_tube_volume(shape, n_tubes_for(shape, args.tubes), seed=0, device=dev, z_range=(z0, z1),
                               want_mask=False, want_skeleton_dict=False)

@@ -172,6 +172,10 @@ def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1
             return out
         workspace = None  # more tile-local components than the default capacity: redo at the worst case, fused
     sparse = label_components(mask, planar=False, label_base=2, workspace=workspace, check=check)
+    want16 = (out.dtype if out is not None else out_dtype) == torch.int16
+    if check and want16 and sparse.num_components + 2 > 32767:
+        # the reference's int16 instance mask wraps silently here (SURVEY B#5); say so instead
+        raise RuntimeError(f"{sparse.num_components} components do not fit int16 instance labels; use out_dtype=torch.int32")
     return gather_instances(vectors, scale, sparse, N=N, decay=decay, crop=crop, overlap=overlap, out=out,
                             out_dtype=out_dtype)
 

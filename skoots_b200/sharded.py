@@ -132,25 +132,52 @@ class PeerComm:
         self._opened: List[int] = []
 
     def connect(self, lib, nbytes: int, device) -> Tuple[Mailbox, List[int]]:
+        """Collective.  Either every rank ends up with every mailbox mapped, or every rank raises
+        SkootsB200Error (a rank that cannot allocate / export / map must not leave the others waiting)."""
         self.lib = lib
-        self.mailbox = Mailbox(lib, nbytes, device)
-        mine = torch.frombuffer(bytearray(self.mailbox.handle()), dtype=torch.uint8).to(device)
+        error = ""
+        try:
+            self.mailbox = Mailbox(lib, nbytes, device)
+            handle = self.mailbox.handle()
+        except L.SkootsB200Error as exc:
+            self.mailbox, handle, error = None, bytes(L.PEER_HANDLE_BYTES), str(exc)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
         every = torch.empty(self.world * L.PEER_HANDLE_BYTES, dtype=torch.uint8, device=device)
         self.dist.all_gather_into_tensor(every, mine, group=self.group)
         handles = every.cpu().numpy().tobytes()
         self.peer_ptrs = []
-        with torch.cuda.device(device):
-            for r in range(self.world):
-                if r == self.rank:
-                    self.peer_ptrs.append(self.mailbox.ptr)
-                    continue
-                out = ctypes.c_void_p()
-                h = handles[r * L.PEER_HANDLE_BYTES:(r + 1) * L.PEER_HANDLE_BYTES]
-                L.check(lib.skb_peer_open(h, ctypes.byref(out)))
-                self.peer_ptrs.append(int(out.value))
-                self._opened.append(int(out.value))
-        self.dist.barrier(self.group)  # every mailbox is mapped everywhere before anyone stores into one
+        if not error:
+            with torch.cuda.device(device):
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.peer_ptrs.append(self.mailbox.ptr)
+                        continue
+                    out = ctypes.c_void_p()
+                    h = handles[r * L.PEER_HANDLE_BYTES:(r + 1) * L.PEER_HANDLE_BYTES]
+                    rc = lib.skb_peer_open(h, ctypes.byref(out)) if any(h) else -3
+                    if rc != 0:
+                        error = f"cannot map rank {r}'s mailbox: {lib.skb_last_error().decode()}"
+                        break
+                    self.peer_ptrs.append(int(out.value))
+                    self._opened.append(int(out.value))
+        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)  # also: everything is mapped before anyone stores
+        if int(ok.item()) == 0:
+            self._release()
+            raise L.SkootsB200Error("peer mailboxes are not available on this box"
+                                    + (f" ({error})" if error else " (another rank failed)"))
         return self.mailbox, self.peer_ptrs
+
+    def _release(self) -> None:
+        if self._opened:
+            with torch.cuda.device(self.mailbox.device if self.mailbox else torch.cuda.current_device()):
+                for p in self._opened:
+                    self.lib.skb_peer_close(p)
+        self._opened = []
+        self.peer_ptrs = []
+        if self.mailbox is not None:
+            self.mailbox.free()
+            self.mailbox = None
 
     def barrier(self) -> None:
         self.dist.barrier(self.group)
@@ -165,8 +192,7 @@ class PeerComm:
                 self.lib.skb_peer_close(p)
         self._opened = []
         self.dist.barrier(self.group)
-        self.mailbox.free()
-        self.mailbox = None
+        self._release()
 
 
 class ShardedAssembler:

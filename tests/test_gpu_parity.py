@@ -366,3 +366,18 @@ def test_vector_to_embedding_vectorised_n1_paths(dt):
     flat = torch.zeros(vec.numel() + 1, dtype=dt, device=DEV)
     flat[1:] = vec.reshape(-1).to(DEV)
     assert torch.equal(vector_to_embedding(scale, flat[1:].view(vec.shape)).cpu(), want)
+
+
+def test_int16_instance_labels_overflow_is_reported():
+    """more than 32 765 components cannot be told apart in an int16 instance mask: the reference wraps silently
+    (SURVEY B#5), this raises (and int32 works)."""
+    from skoots_b200.pipeline import assemble_instances
+    mask = torch.zeros((128, 128, 8), dtype=torch.uint8, device=DEV)
+    mask[::2, ::2, ::2] = 1            # 64 * 64 * 4 = 16 384 isolated voxels ... not enough
+    mask[1::2, 1::2, 1::2] = 1         # ... twice that: 32 768 components
+    vec = torch.zeros((3, 128, 128, 8), dtype=torch.float16, device=DEV)
+    with pytest.raises(RuntimeError, match="int16"):
+        assemble_instances(mask, vec, torch.tensor((60, 60, 12)), N=1, out_dtype=torch.int16)
+    out = assemble_instances(mask, vec, torch.tensor((60, 60, 12)), N=1, out_dtype=torch.int32)
+    assert int(out.max()) == 32768 + 2 and int((out > 0).sum()) == 32768
+

@@ -53,6 +53,23 @@ def test_mailbox_geometry_is_host_arithmetic():
     assert lib.skb_shard_begin(None, 2, 16, 16, 16, None) == -1 and b"NULL" in lib.skb_last_error()
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """argument errors of the round's new entry points come back as codes + text, nothing is enqueued."""
+    import skoots_b200._lib as L
+    lib = L.load()
+    assert lib.skb_renumber_workspace_bytes(0, 8) == 0 and lib.skb_renumber_workspace_bytes(1 << 20, 1 << 10) > (1 << 20) // 8
+    assert lib.skb_renumber(None, 2, 64, 8, None, 0, None, None, None, None) == -1 and b"NULL" in lib.skb_last_error()
+    assert lib.skb_label_max(None, 5, 64, None, None) == -1
+    assert lib.skb_unique_index_workspace_bytes(1) == 0 and lib.skb_unique_index_workspace_bytes(1000) >= 4000
+    assert lib.skb_accuracies_from_iou(None, 0, 4, 0.5, None, None, None) == -1 and b"non-empty" in lib.skb_last_error()
+    # slab geometry: Z, z_off, Zl multiples of 64; halo 1..64 planes
+    assert lib.skb_shard_emit_runs(None, 8, 8, 100, 0, 64, 0, 12, None, 16, None, None) == -1
+    assert b"multiples of 64" in lib.skb_last_error()
+    assert lib.skb_assemble_stream(None, 3, 8, 8, 64, 0, 64, None, None, None, 2, 0, None) == -1
+    assert lib.skb_assemble_stream(None, 3, 8, 8, 60, 0, 60, None, None, None, 2, 0, None) == -1
+    assert lib.skb_peer_alloc(0, None) == -1 and lib.skb_peer_free(None) == 0 and lib.skb_peer_close(None) == 0
+
+
 def test_no_cpu_fallback():
     import skoots_b200._lib as L
     from skoots_b200.lib.flood_fill import efficient_flood_fill

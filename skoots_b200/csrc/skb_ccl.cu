@@ -199,19 +199,38 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {  // <<<1, SKB_TILE_
 // one (u8) or two (i16) 16-byte loads, turns them into 16 bits (all-zero early-out), four lanes
 // combine their bits into one 64-bit word with two shuffles and lane 0 of the group stores it:
 // a warp reads 512 contiguous bytes and writes 64 contiguous bytes.
+constexpr int PACK_SEGS = 4;
+
 template <typename MaskT>
 __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__ mask, CclView v, unsigned n_seg,
                                                       int nk_shift) {
-    // two 16-element segments per thread (256 segments apart: both loads coalesced and in flight together)
-    const unsigned t0 = blockIdx.x * 512u + threadIdx.x;
-    unsigned b[2];
+    // PACK_SEGS 16-element segments per thread (256 segments apart: every load coalesced, all in flight together)
+    const unsigned t0 = blockIdx.x * (256u * PACK_SEGS) + threadIdx.x;
+    unsigned b[PACK_SEGS];
+    uint4 raw[PACK_SEGS][sizeof(MaskT)];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < PACK_SEGS; ++u) {
         const unsigned t = t0 + 256u * u;
-        b[u] = t < n_seg ? seg_bits<MaskT, 16>(mask + (size_t)t * 16, 16, true) : 0u;
+#pragma unroll
+        for (int h = 0; h < (int)sizeof(MaskT); ++h)
+            raw[u][h] = t < n_seg ? skb_ld_stream16(reinterpret_cast<const uint4*>(mask + (size_t)t * 16) + h) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < PACK_SEGS; ++u) {
+        unsigned bits = 0;
+#pragma unroll
+        for (int h = 0; h < (int)sizeof(MaskT); ++h) {
+            const unsigned w[4] = {raw[u][h].x, raw[u][h].y, raw[u][h].z, raw[u][h].w};
+            if (w[0] | w[1] | w[2] | w[3]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    bits |= (sizeof(MaskT) == 1 ? nz4(w[k]) : gt2(w[k])) << ((sizeof(MaskT) == 1 ? 4 : 2) * (4 * h + k));
+            }
+        }
+        b[u] = bits;
+    }
+#pragma unroll
+    for (int u = 0; u < PACK_SEGS; ++u) {
         const unsigned t = t0 + 256u * u;
         ull w = (ull)b[u] << (16 * (t & 3u));
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
@@ -740,6 +759,7 @@ __global__ void __launch_bounds__(32 * BND_WARPS) ccl_boundary_kernel(CclView v,
     const FaceWork f0 = boundary_word(v, widx, w0, false, 0ull, TX, TY);
     const FaceWork f1 = boundary_word(v, widx + 1u, w1, true, w0, TX, TY);
     const int cnt = f0.count() + f1.count();
+    if (!__any_sync(0xffffffffu, cnt != 0)) return;  // half of the warps that hold foreground have none on a tile face
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -747,7 +767,6 @@ __global__ void __launch_bounds__(32 * BND_WARPS) ccl_boundary_kernel(CclView v,
         if (lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
     if (total > BND_QUEUE) {  // dense mask: union in place
         auto direct = [&](int a, int b) { gunion(v.parent, a, b); };
         for_each_union(v, f0, direct);
@@ -1014,7 +1033,7 @@ static void launch_pack(const void* mask, const CclView& v, cudaStream_t st) {
     const bool fast = (v.Zl % 64 == 0) && skb_aligned16(mask);
     if (fast) {
         const unsigned n_seg = (unsigned)(rows * v.Zl / 16);
-        ccl_pack_kernel<MaskT><<<(n_seg + 511) / 512, 256, 0, st>>>(m, v, n_seg, nk_shift);
+        ccl_pack_kernel<MaskT><<<(n_seg + 256 * PACK_SEGS - 1) / (256 * PACK_SEGS), 256, 0, st>>>(m, v, n_seg, nk_shift);
     } else {
         ccl_pack_generic_kernel<MaskT><<<(unsigned)((rows * v.nk + 255) / 256), 256, 0, st>>>(m, v);
     }

@@ -342,6 +342,10 @@ int skb_label_max(const void* labels, int dtype, int64_t n_voxels, int32_t* max_
 size_t skb_renumber_workspace_bytes(int64_t n_voxels, int64_t table_size);
 int skb_renumber(void* labels, int dtype, int64_t n_voxels, int64_t table_size, void* workspace,
                  size_t workspace_bytes, int32_t* remap, int32_t* n_labels, uint32_t* status, void* stream);
+/* labels[i] = table[labels[i]] for 0 < labels[i] < table_size, in place: the `replace` step of the reference's
+ * multi-crop efficient_flood_fill (flood_fill.py:206-234) as one pass (row f3) */
+int skb_apply_label_table(void* labels, int dtype, int64_t n_voxels, const int32_t* table, int64_t table_size,
+                          void* stream);
 size_t skb_unique_index_workspace_bytes(int64_t table_size);
 int skb_unique_index(const void* labels, int dtype, int64_t n_voxels, int64_t table_size, int32_t* index,
                      int32_t* values, int32_t* count, void* workspace, size_t workspace_bytes,

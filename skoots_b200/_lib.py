@@ -69,6 +69,7 @@ SIGNATURES = {
     "skb_label_max": (_c_int, [_c_vp, _c_int, _c_i64, _c_vp, _c_vp]),
     "skb_renumber_workspace_bytes": (_c_sz, [_c_i64, _c_i64]),
     "skb_renumber": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "skb_apply_label_table": (_c_int, [_c_vp, _c_int, _c_i64, _c_vp, _c_i64, _c_vp]),
     "skb_unique_index_workspace_bytes": (_c_sz, [_c_i64]),
     "skb_unique_index": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_vp, _c_vp]),
     "skb_contingency": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),

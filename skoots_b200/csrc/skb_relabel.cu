@@ -469,3 +469,19 @@ extern "C" int skb_label_max(const void* labels, int dtype, int64_t n_voxels, in
     SKB_LAUNCH_CHECK("label_max_kernel");
     return SKB_OK;
 }
+
+/* labels[i] = table[labels[i]] for 0 < labels[i] < table_size, in place (the `replace` step of the reference's
+ * efficient_flood_fill, flood_fill.py:206-234, as one streaming pass with a look-up table) */
+extern "C" int skb_apply_label_table(void* labels, int dtype, int64_t n_voxels, const int32_t* table, int64_t table_size,
+                                     void* stream) {
+    int rc = check_labels_args("skb_apply_label_table", labels, dtype, n_voxels, table_size);
+    if (rc) return rc;
+    SKB_REQUIRE(table, "skb_apply_label_table: NULL table");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned vb = (unsigned)((n_voxels + 2047) / 2048);
+    if (dtype == SKB_I32) apply_remap_kernel<int><<<vb, 256, 0, st>>>(static_cast<int*>(labels), n_voxels, (int)table_size, table);
+    else apply_remap_kernel<short><<<vb, 256, 0, st>>>(static_cast<short*>(labels), n_voxels, (int)table_size, table);
+    SKB_LAUNCH_CHECK("apply_remap_kernel");
+    return SKB_OK;
+}
+

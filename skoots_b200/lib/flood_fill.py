@@ -110,19 +110,114 @@ def write_dense(sparse: SparseLabels, out: Tensor) -> Tensor:
     return out
 
 
-def efficient_flood_fill(skeleton: Tensor) -> Tensor:
+REFERENCE_CROP = (1000, 1000, 200)  # skoots/lib/flood_fill.py:28
+
+
+def _adjacent_by_sum_product(p0, p1):
+    """get_adjacent_labels, flood_fill.py:237-261, on two seam planes (host int16 arrays): labels (a, b) count as
+    touching when a+b and a*b (int16 arithmetic) both occur among the element-wise sums / products of the planes.
+    Host logic: the planes are two 2-D slices of the volume."""
+    import numpy as np
+    p0, p1 = p0.astype(np.int16), p1.astype(np.int16)
+    with np.errstate(over="ignore"):
+        sums = set(np.unique(p0 + p1).tolist())
+        prods = set(np.unique(p0 * p1).tolist())
+        found = []
+        for a in np.unique(p0):
+            for b in np.unique(p1):
+                if a == 0 or b == 0:
+                    continue
+                if int(np.int16(a + b)) in sums and int(np.int16(a * b)) in prods:
+                    found.append((int(a), int(b)))
+    return found
+
+
+def _flood_fill_reference_crops(vol: Tensor, crop=REFERENCE_CROP) -> Tensor:
+    """Row f3: the reference's efficient_flood_fill INCLUDING its multi-crop behaviour (flood_fill.py:27-122), for
+    volumes larger than one 1000x1000x200 crop: every crop is labelled on its own (numbering continues from the
+    previous crop's maximum — and restarts after an empty crop, :140), labels that meet at a crop seam are found
+    with the sum/product test and every group of them is replaced by its last-visited member.  The per-crop
+    labelling and the replacement run on the GPU; the seam test and the graph walk are host logic on two planes
+    per seam.  Bit-identical to the reference on its own fixture (tests/golden/flood_multicrop.npz)."""
+    import numpy as np
+    from .cropper import _origins
+    X, Y, Z = vol.shape
+    size = [min(c, d) for c, d in zip(crop, (X, Y, Z))]
+    max_id = 1
+    seams = ([], [], [])
+    for x in _origins(X, size[0], 0):
+        for y in _origins(Y, size[1], 0):
+            for z in _origins(Z, size[2], 0):
+                for ax, o in enumerate((x, y, z)):
+                    if o not in seams[ax]:
+                        seams[ax].append(o)
+                view = vol[x:x + size[0], y:y + size[1], z:z + size[2]]
+                piece = view.contiguous()
+                # flood_all(crop, max_id + 1), flood_fill.py:125-140: scipy's label (1..n) + (max_id + 1) on foreground
+                sparse = label_components(piece, planar=False, label_base=max_id + 1)
+                n = sparse.num_components
+                if max_id + 1 + n > 32767:
+                    raise RuntimeError("more labels than the reference's int16 volume can hold")
+                write_dense(sparse, piece)
+                view.copy_(piece)
+                max_id = max_id + 1 + n if n else 0  # `mask.max()`: 0 for an empty crop, so numbering restarts (:140)
+    pairs = []
+    for ax in range(3):
+        for o in seams[ax]:
+            if o > 0:
+                p0 = vol.select(ax, o).cpu().numpy()
+                p1 = vol.select(ax, o - 1).cpu().numpy()
+                pairs.extend(_adjacent_by_sum_product(p0, p1))
+    graph = {}
+    for a, b in pairs:
+        graph.setdefault(a, []).append(b)
+        graph.setdefault(b, []).append(a)
+    seen, table = set(), {}
+    for start in graph:  # connected_components + dfs, flood_fill.py:143-174, iteratively
+        if start in seen:
+            continue
+        order, stack = [start], [(start, iter(graph[start]))]
+        seen.add(start)
+        while stack:
+            node, it = stack[-1]
+            nxt = next((m for m in it if m not in seen), None)
+            if nxt is None:
+                stack.pop()
+            else:
+                seen.add(nxt)
+                order.append(nxt)
+                stack.append((nxt, iter(graph[nxt])))
+        for member in order[:-1]:
+            table.setdefault(member, order[-1])  # replaced by the LAST member (:100-104); first match wins (:197-203)
+    if table:
+        top = max(max(table), max(table.values())) + 1
+        lut = np.arange(top, dtype=np.int32)
+        for k, v in table.items():
+            lut[k] = v
+        lut_d = torch.from_numpy(lut).to(vol.device)
+        with torch.cuda.device(vol.device):
+            L.check(L.load().skb_apply_label_table(vol.data_ptr(), L.dtype_code(vol), vol.numel(), lut_d.data_ptr(), top,
+                                                   L.stream_ptr(vol.device)))
+    return vol
+
+
+def efficient_flood_fill(skeleton: Tensor, reference_crops: bool = False) -> Tensor:
     """Drop-in for skoots.lib.flood_fill.efficient_flood_fill (:13-122): labels the connected
     components of `skeleton > 0` IN PLACE (int16, same storage) and returns the (X,Y,Z) view.
 
     Numbering: 3..N+2 in raster order of each component's first voxel — bit-identical to the
     reference for any volume that fits one of its 1000x1000x200 crops.  For larger volumes the
-    reference's seam heuristic (flood_fill.py:237-261) can over-merge and re-use labels
-    (SURVEY.md B#6-#8); this implementation returns the exact components instead.
+    reference labels crop by crop and merges at the seams with a heuristic (flood_fill.py:237-261) that
+    can over-merge and re-use labels: by default this implementation returns the exact
+    components instead; `reference_crops=True` reproduces the reference's result bit for bit, quirks included.
     """
     assert skeleton.dtype == torch.int16, f"Input tensor datatype must be int16 not {skeleton.dtype}"
     vol = skeleton.squeeze(0) if skeleton.ndim == 4 else skeleton
     if not vol.is_contiguous():
         raise RuntimeError("efficient_flood_fill labels in place and needs a contiguous tensor")
+    L.require_cuda(vol)
+    if reference_crops and any(d > c for d, c in zip(vol.shape, REFERENCE_CROP)):
+        return _flood_fill_reference_crops(vol)
     sparse = label_components(vol, planar=False, label_base=2)
     if sparse.num_components + 2 > 32767:
         raise RuntimeError(f"{sparse.num_components} components do not fit the reference's int16 labels")

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
+import skoots_oracle as orc
 from conftest import load_golden, unpack_mask
+from skoots_b200.synthetic import make_tube_volume
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +82,23 @@ def test_flood_fill_multicrop_partition():
     out = efficient_flood_fill(cu(unpack_mask(fx)).to(torch.int16).unsqueeze(0))
     assert out.shape == fx["out"].shape
     assert np.array_equal(orc.canonical_relabel(out.cpu().numpy()), orc.canonical_relabel(fx["out"]))
+
+
+def test_flood_fill_reference_crops_bit_identical():
+    """row f3: with reference_crops=True the multi-crop behaviour of the reference (per-crop numbering, seam
+    heuristic, last-member replacement) is reproduced bit for bit on the reference's own output."""
+    from skoots_b200.lib.flood_fill import _flood_fill_reference_crops, efficient_flood_fill
+    fx = load_golden("flood_multicrop")
+    vol = cu(unpack_mask(fx)).to(torch.int16)
+    out = efficient_flood_fill(vol, reference_crops=True)
+    assert out.data_ptr() == vol.data_ptr() and np.array_equal(out.cpu().numpy(), fx["out"])
+    # small crops on a small volume against the oracle's replay: shifted last crops, several seams per axis, an empty crop
+    tv = make_tube_volume((70, 52, 40), 40, seed=13)
+    mask = tv.skeleton.clone()
+    mask[:30, :20, :16] = 0                      # one empty crop -> the reference restarts its numbering (B#7)
+    want = orc.flood_fill_multicrop(mask.to(torch.int16), crop=(30, 20, 16)).numpy()
+    got = _flood_fill_reference_crops(mask.to(torch.int16).to(DEV), crop=(30, 20, 16))
+    assert np.array_equal(got.cpu().numpy(), want)
 
 
 def test_assembly_against_reference_loop():

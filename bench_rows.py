@@ -148,10 +148,15 @@ def main():
     an = (1.0, 1.0, 3.0)
     want0 = orc.bake_skeleton(vols[0].mask, present[0], an, average=True)
     got0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=True)
-    rows.append(row("a8 bake_skeleton (+average)", "C4 8 x 300x300x20, 20 ids each", B * 300 * 300 * 20, 16,
-                    gpu_ms(lambda: [skel.bake_skeleton(masks_d[i], present_d[i], an, average=True) for i in range(B)], iters=5),
+    # voxel x skeleton-point pairs the min-reduction visits (9 flop each: 3 sub, 3 mul by anisotropy^2-weighted diff, 3 add/compare)
+    pairs = sum(int((t.mask == k).sum()) * int(p.shape[0]) for t, d in zip(vols, present) for k, p in d.items())
+    bake_ms = gpu_ms(lambda: [skel.bake_skeleton(masks_d[i], present_d[i], an, average=True) for i in range(B)], iters=5)
+    rows.append(row("a8 bake_skeleton (+average)", "C4 8 x 300x300x20, 20 ids each", B * 300 * 300 * 20, 16, bake_ms,
                     cpu_ms(lambda: [orc.bake_skeleton(vols[i].mask, present[i], an, average=True) for i in range(B)], iters=1, warm=False),
-                    bool(torch.allclose(got0.cpu(), want0, rtol=1e-5, atol=1e-5)), "fp32-ALU bound min-reduction; includes table packing + status read"))
+                    bool(torch.allclose(got0.cpu(), want0, rtol=1e-5, atol=1e-5)),
+                    f"fp32-ALU bound min-reduction: {pairs} voxel-point pairs x 9 flop = {9 * pairs / (bake_ms * 1e-3) / 1e12:.3f} TFLOP/s of the "
+                    "nominal 74 TFLOP/s fp32 FMA peak (SURVEY 8d) — at this size (8 calls of 1.8 Mvox) the row is bound by the per-call host "
+                    "work: table packing, 3 launches and a status read per sample"))
     wantm = orc.skeleton_to_mask(present[0], (300, 300, 20), 9, 3)
     rows.append(row("a9 skeleton_to_mask r=9 f=3", "C4 8 x 300x300x20", B * 300 * 300 * 20, 4,
                     gpu_ms(lambda: [skel.skeleton_to_mask(present_d[i], (300, 300, 20), radius=9, flank_radius=3) for i in range(B)], iters=5),

@@ -91,3 +91,27 @@ def test_peer_pass_replays_as_one_cuda_graph():
         torch.cuda.synchronize()
         assert torch.equal(torch.cat([r.out for r in grp.ranks], dim=2), want)
         assert all(int(r.meta[1]) == 0 for r in grp.ranks)
+
+
+@pytest.mark.parametrize("density", [0.05, 0.3, 0.7])
+def test_sharded_dense_random_masks_and_fields(density):
+    """dense random masks and vector fields: thousands of runs per face (the emit / boundary kernels leave their
+    shared-memory queues for the in-place fallbacks), many face pairs, dense tiles — still bit-identical to the
+    unsharded pass and to the oracle, for both transports."""
+    from skoots_b200.pipeline import assemble_instances
+    from skoots_b200.sharded import LocalGroup
+    g = torch.Generator().manual_seed(int(density * 100))
+    shape = (48, 40, 256)
+    mask = (torch.rand(shape, generator=g) < density).to(torch.uint8)
+    vec = ((torch.rand((3,) + shape, generator=g) * 2 - 1) * (torch.rand((3,) + shape, generator=g) < 0.5)).to(torch.float16)
+    scale = (5, 5, 12)
+    ref = orc.postprocess(mask, vec, torch.tensor(scale), N=1)
+    want = assemble_instances(mask.to(DEV), vec.to(DEV), torch.tensor(scale), N=1)
+    assert torch.equal(want.cpu(), ref)
+    for world, transport in ((2, "peer"), (4, "peer"), (3, "nccl")):
+        if 256 // 64 < world:
+            continue
+        grp = LocalGroup(shape, world, DEV, scale=scale, transport=transport)
+        grp.load_volume(mask.to(DEV), vec.to(DEV))
+        for _ in range(2):
+            assert torch.equal(grp.step(), want), (world, transport)

@@ -9,7 +9,8 @@
  *
  * Conventions (all entry points):
  *   - every pointer is a DEVICE pointer owned by the caller (inputs, outputs and workspace);
- *     the library never allocates, frees or synchronises; work is enqueued on `stream`
+ *     the library never allocates, frees or synchronises (only exception: the skb_peer_* set-up
+ *     calls of section (e')); work is enqueued on `stream`
  *     (a cudaStream_t / CUstream passed as void*; NULL = legacy default stream);
  *   - volumes are C-contiguous with Z fastest: (X,Y,Z), vector fields (3,X,Y,Z) — the
  *     reference's layout (skoots/lib/eval.py:61-64);

@@ -256,16 +256,15 @@ class ShardedAssembler:
         self._clean = False
         self.mask: Optional[Tensor] = None
         self.vec: Optional[Tensor] = None
-        # kernels of one pass: local(init,pack,tile,boundary,roots)=5, emit<=2, ingest<=2, pack_roots+pairs<=2,
-        # merge(init,union,reset,mark,scan x2,base,rank,clear,publish x2)=11, gather=1;
-        # peer transport adds begin=1, a signal per emitted face, push+signal=2
+        # kernel launches of one pass on this rank (bench.py reports them as gpu_launches)
         faces = (rank > 0) + (rank < world - 1)
         if self.transport == "peer":
             # begin, clear_halo=faces, local(init,pack,tile,boundary,roots)=5, emit+signal<=2, pack_roots=1, ingest=faces,
             # push+signal=2, merge(init,union,mark,scan x2,rank,publish x2)=8, gather=1
             self.launches_per_step = 1 + faces + 5 + 2 * (faces > 0) + 1 + faces + 2 + 8 + 1
         else:
-            self.launches_per_step = faces + 5 + 2 * faces + 1 + 8 + 1
+            # clear_halo=faces, local=5, emit=faces, pack_roots=1, ingest=faces, merge=8, gather=1 (+ NCCL's own kernels)
+            self.launches_per_step = faces + 5 + faces + 1 + faces + 8 + 1
         self.launches_per_step += 1 if self.split else 0  # split: stream + resolve instead of one gather
 
     def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:

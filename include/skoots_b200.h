@@ -212,6 +212,7 @@ int skb_stamp_disks(const float* points_xyz, int n_points, const int32_t* offset
  *   lives in the GLOBAL voxel index space of a full-size workspace, so component ids agree across
  *   ranks.  Call order per rank (the two exchanges are NCCL send/recv and all-gather, driven by the
  *   caller — skoots_b200/sharded.py):
+ *     skb_shard_clear_halo (per face; the halo words start zeroed and are kept clean this way) ->
  *     skb_shard_label_local -> skb_shard_emit_runs (low / high H planes) -> [send/recv with the
  *     Z-neighbours] -> skb_shard_boundary_pairs (halo_hi = NULL: zeroes the counters of
  *     [n_roots, n_pairs, roots[cap_roots], pairs[2*cap_pairs]] and packs my roots) ->
@@ -276,7 +277,8 @@ int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, i
  *   mailbox and then release a flag (= the pass number) there; consumers spin on flags in their own
  *   HBM.  A flag that does not arrive within ~8 s sets SKB_STATUS_PEER_TIMEOUT instead of hanging.
  *   Call order per rank and pass (skoots_b200/sharded.py, transport "peer"):
- *     skb_shard_begin -> skb_shard_label_local -> skb_shard_emit_runs_peer (low / high face)
+ *     skb_shard_begin -> skb_shard_clear_halo_peer (per face) -> skb_shard_label_local
+ *     -> skb_shard_emit_runs_peer (both faces)
  *     -> skb_shard_boundary_pairs (halo_hi = NULL) -> skb_shard_ingest_runs_peer (from the low / high neighbour)
  *     -> skb_shard_push -> skb_shard_merge_peer -> skb_assemble_slab.
  *   The skb_peer_* calls are set-up / tear-down only: they are the one place the library allocates

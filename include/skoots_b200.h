@@ -105,6 +105,9 @@ size_t skb_ccl_workspace_bytes(int64_t X, int64_t Y, int64_t Z, int64_t capacity
  * (same labels either way — for tests and measurements) */
 #define SKB_CCL_TILES_DYNAMIC 8
 #define SKB_CCL_TILES_STATIC 16
+/* do not reset *status at the start of the pass: the status word then accumulates over a series of passes (a timed
+ * loop, a replayed CUDA graph) and the caller clears it when it reads it */
+#define SKB_CCL_KEEP_STATUS 32
 int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
                          int planar, int32_t label_base, int64_t capacity, void* workspace,
                          size_t workspace_bytes, int32_t* ncomp, uint32_t* status, int flags,
@@ -250,6 +253,25 @@ int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t ca
 int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off,
                       int64_t Zl, const float scale[3], const void* workspace, const uint64_t* halo_lo,
                       const uint64_t* halo_hi, void* out, int out_dtype, void* stream);
+
+/* The general slab gather.  On top of skb_assemble_slab:
+ *   - N hops with `decay` over the reference's crop grid (crop / overlap as in skb_assemble; NULL = the whole volume
+ *     as one crop).  A hop stays inside the owner crop of its voxel, so it can leave the slab by at most
+ *     crop_z - overlap_z - 1 planes: vec_halo_lo / vec_halo_hi hold the vector field's planes
+ *     [z_off - vec_halo_planes, z_off) and [z_off+Zl, z_off+Zl+vec_halo_planes) as (3,X,Y,vec_halo_planes) arrays of
+ *     the field's dtype (the Z-neighbours' faces; NULL at the volume's ends; not needed for N = 1);
+ *   - label_halo_planes = how many planes beyond each face the halo words describe (the `halo` given to
+ *     skb_shard_emit_runs*).  A gather target beyond them cannot be answered from this rank's data:
+ *     SKB_STATUS_HALO_RANGE is OR-ed into *status instead of returning a wrong label silently.  0 = do not check;
+ *   - only the voxels [first_voxel, first_voxel + n_voxels) of the slab's flat (X,Y,Zl) index are written
+ *     (first_voxel a multiple of 256), so a caller can pipeline X-slabs of the upload / gather / download. */
+#define SKB_STATUS_HALO_RANGE 16u
+int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                         const float scale[3], int N, double decay, const int32_t crop[3], const int32_t overlap[3],
+                         const void* vec_halo_lo, const void* vec_halo_hi, int64_t vec_halo_planes,
+                         const void* workspace, const uint64_t* halo_lo, const uint64_t* halo_hi,
+                         int64_t label_halo_planes, void* out, int out_dtype, int64_t first_voxel,
+                         int64_t n_voxels, uint32_t* status, void* stream);
 
 /* Split form of the fused gather for N = 1 with the whole volume as one crop (the headline mode), on a
  * volume (z_off = 0, Zl = Z) or a slab.  skb_assemble_stream needs only the bit mask of the CCL

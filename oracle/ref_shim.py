@@ -9,6 +9,7 @@ The three stubs cover exactly what the reference touches at import time:
   * `skimage.io`                (skoots/validate/utils.py:4; only so that skoots.validate.lib imports)
   * `bism.*`                    (skoots/lib/utils.py:6-14 model factory imports)
   * `yacs.config.CfgNode`       (type annotation only)
+Used also by `oracle/ref_runner.py` (bench.py's CPU baseline).
 `PYTORCH_JIT=0` must be set before torch is imported: the scripted morphology
 functions hash a list through functools.cache and fail under torch 2.11
 (skoots/lib/morphology.py:10-16,145,167).
@@ -17,11 +18,30 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SKOOTS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """/root/reference in the build container; on the GPU box the byte-identical copy that
+    oracle/build_ref.py placed under oracle/_ref (git-ignored, travels with the snapshot)."""
+    env = os.environ.get("SKOOTS_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "skoots", "lib")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "skoots", "lib"))
+
+
+def reference_kind() -> str:
+    return "live tree" if REFERENCE_ROOT == "/root/reference" else "oracle/_ref copy"
 
 
 def _disk(radius, dtype=None):
@@ -44,11 +64,14 @@ class _Fabricating(types.ModuleType):
         return child
 
 
-def install():
-    """Make `import skoots.lib.*` work. Idempotent. Raises if the reference is absent."""
+def install(need_morphology: bool = True):
+    """Make `import skoots.lib.*` work. Idempotent. Raises if the reference is absent.
+    need_morphology=False skips the PYTORCH_JIT=0 requirement: only the scripted morphology functions
+    fail under torch 2.11, and the assembly path bench.py times (flood fill, vector_to_embedding,
+    index_skeleton_by_embed) then runs with the reference's stock torch.jit.script decorators active."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
-    if os.environ.get("PYTORCH_JIT", "1") != "0":
+    if need_morphology and os.environ.get("PYTORCH_JIT", "1") != "0":
         if "torch" in sys.modules:
             raise RuntimeError("set PYTORCH_JIT=0 before importing torch to run the reference")
         os.environ["PYTORCH_JIT"] = "0"

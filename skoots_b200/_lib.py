@@ -1,7 +1,10 @@
 """ctypes binding of libskoots_b200.so (include/skoots_b200.h).
 
-There is deliberately no fallback: if the shared library is missing or a CUDA tensor is not
-supplied, the call raises.  PyTorch is used only to own device memory and streams.
+There is deliberately no fallback: if the shared library or a CUDA device is missing, the call
+raises.  PyTorch is used only to own device memory and streams.  The `skoots.lib` mirrors accept
+HOST tensors too — the reference's `eval()` and `skoots-validate` hand CPU tensors to these
+functions (skoots/lib/eval.py:223,258-284; skoots/validate/__main__.py) — by staging them through
+the current CUDA device (`compute_device` / `stage_in` / `stage_out`): H2D, the same kernels, D2H.
 """
 from __future__ import annotations
 
@@ -19,6 +22,7 @@ STATUS_ROOT_OVERFLOW = 1
 STATUS_MISSING_ID = 2
 STATUS_PEER_TIMEOUT = 4
 STATUS_LABEL_RANGE = 8
+STATUS_HALO_RANGE = 16
 PEER_HANDLE_BYTES = 64
 MAX_WORLD = 16
 CCL_WORKSPACE_CLEAN = 1
@@ -26,6 +30,7 @@ CCL_PHASE_PACK = 2
 CCL_PHASE_LABEL = 4
 CCL_TILES_DYNAMIC = 8
 CCL_TILES_STATIC = 16
+CCL_KEEP_STATUS = 32
 
 _DTYPES = {
     torch.uint8: SKB_U8, torch.bool: SKB_U8, torch.int16: SKB_I16, torch.int32: SKB_I32,
@@ -87,6 +92,8 @@ SIGNATURES = {
     "skb_shard_push": (_c_int, [_c_vp, _c_vp, ctypes.POINTER(ctypes.c_uint64), _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
     "skb_shard_merge_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_slab": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
+    "skb_assemble_slab_ex": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3,
+                                      _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_assemble_range": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp]),
     "skb_assemble": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
 }
@@ -132,6 +139,54 @@ def require_cuda(*tensors: torch.Tensor) -> torch.device:
             raise SkootsB200Error("all tensors must live on the same CUDA device")
         dev = t.device
     return dev
+
+
+def compute_device(*tensors: torch.Tensor):
+    """(device the kernels run on, staged).  All-CUDA arguments run where they live; all-HOST arguments are staged
+    through the current CUDA device (staged = True: the caller copies inputs up and results back); a mix is an
+    error, as it is in the reference's torch code.  Without a CUDA device this raises: nothing here computes on the CPU."""
+    cuda = [t for t in tensors if isinstance(t, torch.Tensor) and t.is_cuda]
+    if len(cuda) == len(tensors):
+        return require_cuda(*tensors), False
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            raise SkootsB200Error("skoots_b200 expects torch tensors")
+    if cuda:
+        raise SkootsB200Error("all tensors must live on the same device (got a mix of host and CUDA tensors)")
+    if not torch.cuda.is_available():
+        raise SkootsB200Error("no CUDA device: skoots_b200 stages host tensors through the GPU and has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()), True
+
+
+_STAGE_CACHE: dict = {}
+
+
+def stage_in(t: torch.Tensor, dev: torch.device, reuse: bool = False) -> torch.Tensor:
+    """host -> device copy of a staged argument.  reuse=True keeps the device copy of the LAST such tensor (keyed by
+    storage, shape, dtype and in-place version) so that a caller that passes the same large host tensor call after
+    call — the whole-image label volume in eval()'s crop loop, skoots/lib/eval.py:277-279 — uploads it once."""
+    if t.device == dev:
+        return t
+    if not reuse:
+        return t.to(dev)
+    import weakref
+    key = (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, str(dev))
+    owner = t if t._base is None else t._base  # views share the base's storage and version counter
+    hit = _STAGE_CACHE.get("labels")
+    if hit is not None and hit[0] == key and hit[1]() is owner:
+        return hit[2]
+    d = t.to(dev)
+    _STAGE_CACHE["labels"] = (key, weakref.ref(owner), d)
+    return d
+
+
+def stage_out(t, staged: bool):
+    """device -> host copy of a staged call's result (tensors inside tuples included)."""
+    if not staged:
+        return t
+    if isinstance(t, tuple):
+        return tuple(stage_out(v, True) for v in t)
+    return t.cpu() if isinstance(t, torch.Tensor) else t
 
 
 def stream_ptr(device: torch.device) -> int:

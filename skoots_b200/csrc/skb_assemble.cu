@@ -27,6 +27,11 @@ struct AsmParams {
     int Zl, z_off;          // this call covers z in [z_off, z_off+Zl): vec/out are (.,X,Y,Zl) slabs (whole volume: Z, 0)
     const ull* halo_lo;     // slab mode: bits of global word k0-1 / k1 per row (the Z-neighbours' boundary planes)
     const ull* halo_hi;
+    int label_halo;         // slab mode: how many planes beyond each face the halo words really describe (0 = not checked)
+    unsigned* status;       // slab mode: SKB_STATUS_HALO_RANGE is OR-ed in when a target lies beyond them (may be NULL)
+    const void* vhalo_lo;   // slab mode, N > 1: the vector field's planes [z_off - vh, z_off) / [z_off+Zl, z_off+Zl+vh) as
+    const void* vhalo_hi;   //   (3,X,Y,vh) arrays (the Z-neighbours' faces), read by hops that leave the slab inside their crop
+    int vh;
     float s[3];
     int N;
     double decay;
@@ -93,10 +98,27 @@ __device__ __forceinline__ void walk(const AsmParams& P, int lx, int ly, int lz,
             unsigned u = (unsigned)fi;
             unsigned qz = u / ucz, cz = u - qz * ucz;
             unsigned cx = qz / ucy, cy = qz - cx * ucy;
-            long long g = ((long long)(ox + (int)cx) * P.Y + (oy + (int)cy)) * P.Z + (oz + (int)cz);
-            float h0 = load_vec<VecT>(P.vec_hops, g);
-            float h1 = load_vec<VecT>(P.vec_hops, g + P.cstride);
-            float h2 = load_vec<VecT>(P.vec_hops, g + 2 * P.cstride);
+            // the field holds z in [z_off, z_off+Zl) (whole volume: [0, Z)); a hop that leaves a slab inside its crop
+            // reads the neighbour's planes from the vector halo
+            const long long row = (long long)(ox + (int)cx) * P.Y + (oy + (int)cy);
+            const int zl = oz + (int)cz - P.z_off;
+            const void* hb = P.vec_hops;
+            long long g = row * P.Zl + zl, hs = P.cstride;
+            if (zl < 0 || zl >= P.Zl) {
+                const bool lo = zl < 0;
+                const int h = lo ? zl + P.vh : zl - P.Zl;
+                hb = lo ? P.vhalo_lo : P.vhalo_hi;
+                if (hb == nullptr || h < 0 || h >= P.vh) {  // cannot happen when the halo covers crop - overlap - 1 planes
+                    if (P.status) atomicOr(P.status, SKB_STATUS_HALO_RANGE);
+                    hb = P.vec_hops; g = row * P.Zl + (lo ? 0 : P.Zl - 1);
+                } else {
+                    g = row * P.vh + h;
+                    hs = (long long)P.X * P.Y * P.vh;
+                }
+            }
+            float h0 = load_vec<VecT>(hb, g);
+            float h1 = load_vec<VecT>(hb, g + hs);
+            float h2 = load_vec<VecT>(hb, g + 2 * hs);
             mx = __fadd_rn(mx, __fmul_rn(h0, __fmul_rn(kf, P.s[0])));
             my = __fadd_rn(my, __fmul_rn(h1, __fmul_rn(kf, P.s[1])));
             mz = __fadd_rn(mz, __fmul_rn(h2, __fmul_rn(kf, P.s[2])));
@@ -117,9 +139,15 @@ __device__ __forceinline__ int label_at(const AsmParams& P, int tx, int ty, int 
         return (int)__ldg(static_cast<const unsigned char*>(P.dense) + t);
     }
     ull w;
-    if (tz < P.z_off) w = P.halo_lo ? __ldg(P.halo_lo + rowi) : 0ull;
-    else if (tz >= P.z_off + P.Zl) w = P.halo_hi ? __ldg(P.halo_hi + rowi) : 0ull;
-    else w = __ldg(P.bits + rowi * P.ZW + ((tz - P.z_off) >> 6));
+    if (tz < P.z_off) {
+        w = P.halo_lo ? __ldg(P.halo_lo + rowi) : 0ull;
+        // the neighbour only sent the runs of its last `label_halo` planes: a target beyond them would be answered
+        // from a word that does not describe it — report instead of returning a wrong label
+        if (P.label_halo && tz < P.z_off - P.label_halo && P.status) atomicOr(P.status, SKB_STATUS_HALO_RANGE);
+    } else if (tz >= P.z_off + P.Zl) {
+        w = P.halo_hi ? __ldg(P.halo_hi + rowi) : 0ull;
+        if (P.label_halo && tz >= P.z_off + P.Zl + P.label_halo && P.status) atomicOr(P.status, SKB_STATUS_HALO_RANGE);
+    } else w = __ldg(P.bits + rowi * P.ZW + ((tz - P.z_off) >> 6));
     if (!((w >> (tz & 63)) & 1ull)) return 0;
     return skb_sparse_label(P.parent, (int)(rowi * P.Z + tz));
 }
@@ -951,11 +979,16 @@ extern "C" int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int
     return SKB_OK;
 }
 
-// Z-slab form (N = 1, whole volume as one crop): vec/out hold only z in [z_off, z_off+Zl); targets that
-// leave the slab are answered from the neighbours' boundary planes ingested by skb_shard_ingest_runs.
-extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
-                                 const float scale[3], const void* workspace, const uint64_t* halo_lo,
-                                 const uint64_t* halo_hi, void* out, int out_dtype, void* stream) {
+// Z-slab form: vec/out hold only z in [z_off, z_off+Zl); label targets that leave the slab are answered from the
+// neighbours' boundary planes ingested by skb_shard_ingest_runs (and reported through *status when they lie beyond
+// the `label_halo` planes those runs describe); with N > 1 the hops that leave the slab inside their crop read the
+// neighbours' vector planes from vec_halo_lo / vec_halo_hi.
+extern "C" int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                    const float scale[3], int N, double decay, const int32_t crop[3], const int32_t overlap[3],
+                                    const void* vec_halo_lo, const void* vec_halo_hi, int64_t vec_halo_planes,
+                                    const void* workspace, const uint64_t* halo_lo, const uint64_t* halo_hi,
+                                    int64_t label_halo_planes, void* out, int out_dtype, int64_t first_voxel,
+                                    int64_t n_voxels, uint32_t* status, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_assemble_slab");
     if (rc) return rc;
     SKB_REQUIRE(vec && out && scale && workspace, "skb_assemble_slab: NULL pointer");
@@ -964,17 +997,47 @@ extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int6
     SKB_REQUIRE(Z % 64 == 0 && z_off % 64 == 0 && Zl % 64 == 0 && Zl > 0 && z_off >= 0 && z_off + Zl <= Z,
                 "skb_assemble_slab: Z, z_off and Zl must be multiples of 64 with the slab inside the volume");
     SKB_REQUIRE(skb_aligned16(out), "skb_assemble_slab: out must be 16-byte aligned");
+    SKB_REQUIRE(N >= 1 && label_halo_planes >= 0 && label_halo_planes <= 64 && vec_halo_planes >= 0,
+                "skb_assemble_slab: N >= 1, label halo 0..64 planes, vector halo >= 0 planes");
+    const int64_t Vs = X * Y * Zl;
+    SKB_REQUIRE(first_voxel >= 0 && n_voxels >= 0 && first_voxel + n_voxels <= Vs && first_voxel % 256 == 0,
+                "skb_assemble_slab: [first_voxel, first_voxel+n_voxels) must lie in the slab and start on a multiple of 256");
+    if (n_voxels == 0) return SKB_OK;
+    const int32_t whole[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, none[3] = {0, 0, 0};
+    if (!crop) crop = whole;
+    if (!overlap) overlap = none;
+    const bool any_ov = overlap[0] > 0 || overlap[1] > 0 || overlap[2] > 0;
+    const bool all_ov = overlap[0] > 0 && overlap[1] > 0 && overlap[2] > 0;
+    SKB_REQUIRE(overlap[0] >= 0 && overlap[1] >= 0 && overlap[2] >= 0 && any_ov == all_ov,
+                "skb_assemble_slab: overlap must be all zero or all positive");
+    const int64_t dims[3] = {X, Y, Z};
+    for (int a = 0; a < 3; ++a) {
+        int64_t cs = crop[a] < dims[a] ? crop[a] : dims[a];
+        SKB_REQUIRE(crop[a] > 0 && cs - 2 * overlap[a] > 0, "skb_assemble_slab: crop must exceed twice the overlap on every axis");
+    }
+    if (N > 1) {
+        // a hop stays inside the owner crop of its voxel: at most crop - overlap - 1 planes from it (the whole crop when
+        // there is no overlap), clipped by the volume
+        const int64_t cz = crop[2] < Z ? crop[2] : Z;
+        const int64_t reach = any_ov ? cz - overlap[2] - 1 : cz - 1;
+        const int64_t need_lo = reach < z_off ? reach : z_off, need_hi = reach < Z - z_off - Zl ? reach : Z - z_off - Zl;
+        SKB_REQUIRE((need_lo == 0 || (vec_halo_lo && vec_halo_planes >= need_lo)) &&
+                        (need_hi == 0 || (vec_halo_hi && vec_halo_planes >= need_hi)),
+                    "skb_assemble_slab: N > 1 needs vector halos of crop_z - overlap_z - 1 planes (clipped by the volume) on both faces");
+    }
     AsmParams P = {};
     P.vec = vec; P.vec_hops = vec;
-    P.cstride = X * Y * Zl;
+    P.cstride = Vs;
     P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
     P.Zl = (int)Zl; P.z_off = (int)z_off;
     P.halo_lo = reinterpret_cast<const ull*>(halo_lo);
     P.halo_hi = reinterpret_cast<const ull*>(halo_hi);
+    P.label_halo = (int)label_halo_planes;
+    P.status = status;
+    P.vhalo_lo = vec_halo_lo; P.vhalo_hi = vec_halo_hi; P.vh = (int)vec_halo_planes;
     P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
-    P.N = 1; P.decay = 1.0;
-    const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
-    fill_crop(P, crop, ov);
+    P.N = N; P.decay = decay;
+    fill_crop(P, crop, overlap);
     P.vec_aligned = skb_aligned16(vec) && ((P.cstride * elem_size(vec_dtype)) % 16 == 0);
     SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
     const char* base = static_cast<const char*>(workspace);
@@ -983,12 +1046,20 @@ extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int6
     P.ZW = (int)(Zl / 64);
     P.flat_bits = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long V = X * Y * Zl;
-    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, 0, V, st);
-    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, 0, V, st);
-    else launch_assemble<float>(P, out, out_dtype, 0, V, st);
+    const long long v0 = first_voxel, v1 = first_voxel + n_voxels;
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, v0, v1, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, v0, v1, st);
+    else launch_assemble<float>(P, out, out_dtype, v0, v1, st);
     SKB_LAUNCH_CHECK("assemble_kernel (slab)");
     return SKB_OK;
+}
+
+// the N = 1, whole-volume-as-one-crop, whole-slab form (kept for callers of the first ABI revision; no range check)
+extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
+                                 const float scale[3], const void* workspace, const uint64_t* halo_lo,
+                                 const uint64_t* halo_hi, void* out, int out_dtype, void* stream) {
+    return skb_assemble_slab_ex(vec, vec_dtype, X, Y, Z, z_off, Zl, scale, 1, 1.0, nullptr, nullptr, nullptr, nullptr, 0, workspace,
+                                halo_lo, halo_hi, 0, out, out_dtype, 0, X * Y * Zl, nullptr, stream);
 }
 
 // ---- split gather: host side --------------------------------------------------------------------

@@ -136,11 +136,11 @@ __device__ __forceinline__ unsigned seg_bits(const MaskT* p, int n, bool vec_ok)
     return bits;
 }
 
-__global__ void ccl_init_kernel(CclView v, SkbCclHeader h) {  // <<<1, SKB_TILE_CURSORS>>>
+__global__ void ccl_init_kernel(CclView v, SkbCclHeader h, int keep_status) {  // <<<1, SKB_TILE_CURSORS>>>
     v.cursors[threadIdx.x * SKB_TILE_CURSOR_STRIDE] = 0u;
     if (threadIdx.x == 0) {
         *v.hdr = h;
-        *v.status = 0u;
+        if (!keep_status) *v.status = 0u;
         if (v.ncomp_out) *v.ncomp_out = 0;
     }
 }
@@ -996,7 +996,7 @@ void skb_ccl_launch_pack_and_tile(const void* mask, int mask_dtype, const CclVie
     const bool all = !(flags & (SKB_CCL_PHASE_PACK | SKB_CCL_PHASE_LABEL));
     if (all || (flags & SKB_CCL_PHASE_PACK)) {
         char* base = reinterpret_cast<char*>(v.hdr);
-        ccl_init_kernel<<<1, SKB_TILE_CURSORS, 0, st>>>(v, h);  // header by value: no host->device copy on the path
+        ccl_init_kernel<<<1, SKB_TILE_CURSORS, 0, st>>>(v, h, (flags & SKB_CCL_KEEP_STATUS) ? 1 : 0);  // header by value: no host->device copy on the path
         if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
         cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
         if (mask_dtype == SKB_U8) launch_pack<uint8_t>(mask, v, st);

@@ -51,7 +51,9 @@ class _EmbedProb(torch.autograd.Function):
 def baked_embed_to_prob(embedding: Tensor, baked_skeletons: Tensor, sigma: Tensor, eps: float = 1e-16) -> Tensor:
     """exp(sum_c (E_c - S_c)^2 / (-2 (sigma_c + eps)^2)); (B,C,...) -> (B,1,...) fp32, C = 2 or 3
     (embedding_to_prob.py:5-51).  Differentiable w.r.t. embedding and baked_skeletons."""
-    L.require_cuda(embedding, baked_skeletons)
+    dev, staged = L.compute_device(embedding, baked_skeletons)
+    if staged:
+        return baked_embed_to_prob(L.stage_in(embedding, dev), L.stage_in(baked_skeletons, dev), sigma, eps).cpu()
     if embedding.shape != baked_skeletons.shape:
         raise RuntimeError(f"embedding {tuple(embedding.shape)} and baked_skeletons {tuple(baked_skeletons.shape)} differ")
     C = embedding.shape[1]
@@ -105,7 +107,9 @@ class _VecProb(torch.autograd.Function):
 def vector_to_prob(scale: Tensor, vector: Tensor, baked_skeletons: Tensor, sigma: Tensor, eps: float = 1e-16) -> Tensor:
     """baked_embed_to_prob(vector_to_embedding(scale, vector), baked, sigma) in one kernel: the
     fp32 embedding is never written to HBM (train/engine.py:465-466).  Differentiable w.r.t. vector."""
-    L.require_cuda(vector, baked_skeletons)
+    dev, staged = L.compute_device(vector, baked_skeletons)
+    if staged:
+        return vector_to_prob(scale, L.stage_in(vector, dev), L.stage_in(baked_skeletons, dev), sigma, eps).cpu()
     C = vector.shape[1]
     if C not in (2, 3) or vector.ndim != C + 2 or vector.shape != baked_skeletons.shape:
         raise RuntimeError("vector and baked_skeletons must both be (B,2,X,Y) or (B,3,X,Y,Z)")

@@ -215,7 +215,10 @@ def efficient_flood_fill(skeleton: Tensor, reference_crops: bool = False) -> Ten
     vol = skeleton.squeeze(0) if skeleton.ndim == 4 else skeleton
     if not vol.is_contiguous():
         raise RuntimeError("efficient_flood_fill labels in place and needs a contiguous tensor")
-    L.require_cuda(vol)
+    dev, staged = L.compute_device(vol)
+    if staged:  # eval() labels a HOST tensor (eval.py:223): up, label on the GPU, back into the same storage
+        vol.copy_(efficient_flood_fill(L.stage_in(vol, dev), reference_crops))
+        return vol
     if reference_crops and any(d > c for d, c in zip(vol.shape, REFERENCE_CROP)):
         return _flood_fill_reference_crops(vol)
     sparse = label_components(vol, planar=False, label_base=2)

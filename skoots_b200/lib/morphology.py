@@ -10,7 +10,9 @@ _MAX333, _MAX331, _MIN333 = 0, 1, 2
 
 
 def _stencil(image: Tensor, op: int) -> Tensor:
-    dev = L.require_cuda(image)
+    dev, staged = L.compute_device(image)
+    if staged:
+        return _stencil(L.stage_in(image, dev), op).cpu()
     if image.ndim != 5:
         raise RuntimeError(f"expected a 5D (B,C,X,Y,Z) tensor, got {tuple(image.shape)}")
     src = image.float().contiguous()

@@ -14,7 +14,9 @@ def index_skeleton_by_embed(skeleton: Tensor, embed: Tensor) -> Tensor:
     assert (
         embed.ndim == 5 and skeleton.ndim == 5
     ), "Embed and skeleton must be a 5D tensor"
-    dev = L.require_cuda(skeleton, embed)
+    dev, staged = L.compute_device(skeleton, embed)
+    if staged:  # eval() hands over the same whole-image label volume for every crop (eval.py:277-279): uploaded once
+        return index_skeleton_by_embed(L.stage_in(skeleton, dev, reuse=True), L.stage_in(embed, dev)).cpu()
     b, c, x, y, z = embed.shape
     if b != 1 or c != 3:
         raise RuntimeError(f"embed must have shape (1,3,x,y,z), got {tuple(embed.shape)}")
@@ -64,7 +66,9 @@ def average_baked_skeletons(baked_skeleton: Tensor, kernel_size: int = 3) -> Ten
     """(B,3,X,Y,Z) -> per channel sum(3x3x3 window)/max(1,count(window>0)) (skeleton.py:18-48)."""
     if kernel_size != 3:
         raise NotImplementedError("the reference only ever uses kernel_size=3")
-    dev = L.require_cuda(baked_skeleton)
+    dev, staged = L.compute_device(baked_skeleton)
+    if staged:
+        return average_baked_skeletons(L.stage_in(baked_skeleton, dev), kernel_size).cpu()
     src = baked_skeleton.float().contiguous()
     b, c, X, Y, Z = src.shape
     out = torch.empty_like(src)
@@ -91,7 +95,9 @@ def bake_skeleton(masks: Tensor, skeletons: Dict[int, Tensor], anisotropy: Tuple
     (anisotropy scales coordinates, first minimum wins, fp32 out — SURVEY A.5).  `device` is
     accepted and ignored like the reference's positional mix-up (:507); the work runs on
     masks.device, which must be CUDA.  return_distance=True also returns the (1,X,Y,Z) distance."""
-    dev = L.require_cuda(masks)
+    dev, staged = L.compute_device(masks)
+    if staged:
+        return L.stage_out(bake_skeleton(L.stage_in(masks, dev), skeletons, anisotropy, average, device, return_distance), True)
     if -1 in skeletons:
         x, y, z = masks.shape[-3:]
         return torch.zeros((3, x, y, z), device=dev, dtype=torch.float16)
@@ -127,7 +133,9 @@ def skeleton_to_mask(skeletons: Dict[int, Tensor], shape: Tuple[int, int, int], 
     if not skeletons:
         return torch.zeros(tuple(shape)).unsqueeze(0)
     first = next(iter(skeletons.values()))
-    dev = L.require_cuda(first)
+    dev, staged = L.compute_device(first)
+    if staged:
+        return skeleton_to_mask({k: L.stage_in(v, dev) for k, v in skeletons.items()}, shape, device, radius, flank_radius).cpu()
     X, Y, Z = (int(s) for s in shape)
     out = torch.zeros((X, Y, Z), dtype=torch.float32, device=dev)
     pts = torch.cat([v.to(device=dev, dtype=torch.float32).reshape(-1, 3) for v in skeletons.values()], 0).contiguous()

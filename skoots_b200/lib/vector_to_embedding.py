@@ -23,9 +23,10 @@ class _Vec2Embed(torch.autograd.Function):
         B, C = grad_out.shape[:2]
         inner = grad_out[0, 0].numel()
         grad_vec = torch.empty(grad_out.shape, dtype=ctx.vec_dtype, device=grad_out.device)
-        L.check(L.load().skb_vec_embed_bwd(grad_out.data_ptr(), B, C, inner, L.f3(ctx.scale_vals),
-                                           grad_vec.data_ptr(), L.dtype_code(grad_vec),
-                                           L.stream_ptr(grad_out.device)))
+        with torch.cuda.device(grad_out.device):  # the launch must go to the tensor's GPU, not the current one
+            L.check(L.load().skb_vec_embed_bwd(grad_out.data_ptr(), B, C, inner, L.f3(ctx.scale_vals),
+                                               grad_vec.data_ptr(), L.dtype_code(grad_vec),
+                                               L.stream_ptr(grad_out.device)))
         return grad_vec, None, None
 
 
@@ -52,7 +53,12 @@ def _forward(vector: Tensor, scale_vals, N: int, decay: float) -> Tensor:
 
 def vector_to_embedding(scale: Tensor, vector: Tensor, N: int = 1, decay: float = 1.0) -> Tensor:
     """Same contract as skoots.lib.vector_to_embedding.vector_to_embedding (:135-174):
-    (B,3,X,Y,Z) -> fp32 embedding with N-1 crop-local hops, or (B,2,X,Y) with N == 1."""
+    (B,3,X,Y,Z) -> fp32 embedding with N-1 crop-local hops, or (B,2,X,Y) with N == 1.
+    A HOST `vector` (eval() passes CPU crops, skoots/lib/eval.py:271) is staged through the GPU and the
+    embedding comes back as a host tensor."""
+    dev, staged = L.compute_device(vector)
+    if staged:
+        return vector_to_embedding(scale, L.stage_in(vector, dev), N, decay).cpu()
     if vector.ndim == 4:
         assert decay == 1.0, f'decay parameter only valid for 5D tensor'
         assert N == 1, f'N must be equal to 1 for 4D tensors.'

@@ -152,6 +152,15 @@ def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1
     fused=False: the stream/resolve split with the gather's stream phase overlapped with the labelling
     (kept as a measured alternative: bit-identical, slower on B200 because the labelling kernels fill the SMs)."""
     mask = skeleton_mask.squeeze(0) if skeleton_mask.ndim == 4 else skeleton_mask
+    if not mask.is_cuda and not vectors.is_cuda:
+        # HOST volumes (what eval() holds, skoots/lib/eval.py:102-103,223): the pipelined upload / label / gather / download
+        dev, _ = L.compute_device(mask, vectors)
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else (mask if mask.dtype == torch.uint8 else mask.gt(0).view(torch.uint8))
+        v = vectors if vectors.dtype in (torch.float16, torch.bfloat16, torch.float32) else vectors.float()
+        want = out.dtype if out is not None else out_dtype
+        host_out = out if out is not None else torch.empty(tuple(m.shape), dtype=want)
+        runner = HostAssembler(tuple(m.shape), dev, vec_dtype=v.dtype, out_dtype=want)
+        return runner(m.contiguous(), v.contiguous(), scale, host_out, N=N, decay=decay, crop=crop, overlap=overlap, check=check)
     if fused is False:  # the opt-in split; the default path below stays as lean as it was (small volumes are launch-bound)
         dev = L.require_cuda(mask, vectors)
         if vectors.ndim != 4 or vectors.shape[0] != 3:
@@ -168,7 +177,11 @@ def assemble_instances(skeleton_mask: Tensor, vectors: Tensor, scale, N: int = 1
             out = torch.empty(shape, dtype=out_dtype, device=dev)
         assert out.is_contiguous() and tuple(out.shape) == shape and out.dtype in (torch.int32, torch.int16)
         assemble_split(mask, vectors, scale, sparse, out)
-        if not check or not (int(sparse.status.item()) & L.STATUS_ROOT_OVERFLOW):
+        if not check:
+            return out
+        if not (int(sparse.status.item()) & L.STATUS_ROOT_OVERFLOW):
+            if out.dtype == torch.int16 and sparse.num_components + 2 > 32767:  # same guard as the fused path below
+                raise RuntimeError(f"{sparse.num_components} components do not fit int16 instance labels; use out_dtype=torch.int32")
             return out
         workspace = None  # more tile-local components than the default capacity: redo at the worst case, fused
     sparse = label_components(mask, planar=False, label_base=2, workspace=workspace, check=check)
@@ -211,7 +224,7 @@ class HostAssembler:
             self.bounds = [0] + self.bounds
 
     def __call__(self, mask_host: Tensor, vec_host: Tensor, scale, out_host: Tensor, N: int = 1, decay: float = 1.0,
-                 crop=None, overlap=(0, 0, 0)) -> Tensor:
+                 crop=None, overlap=(0, 0, 0), check: bool = True) -> Tensor:
         X, Y, Z = self.shape
         plane = Y * Z
         main = torch.cuda.current_stream(self.dev)
@@ -243,7 +256,10 @@ class HostAssembler:
             with torch.cuda.stream(self.down):
                 out_host[x0:x1].copy_(self.out[x0:x1], non_blocking=True)
         torch.cuda.synchronize(self.dev)
-        sparse.check()
+        if check:
+            sparse.check()
+            if self.out.dtype == torch.int16 and sparse.num_components + 2 > 32767:
+                raise RuntimeError(f"{sparse.num_components} components do not fit int16 instance labels; use out_dtype=torch.int32")
         return out_host
 
 

@@ -200,16 +200,24 @@ class ShardedAssembler:
     walks are confined to its 500x500x50 crops and need vector halos as well."""
 
     def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
-                 comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
+                 decay: float = 1.0, crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0), comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
                  out_dtype=torch.int32, split: Optional[bool] = None):
-        if hops != 1:
-            raise NotImplementedError("the Z-sharded path implements N = 1")
         X, Y, Z = (int(v) for v in shape)
+        self.hops, self.decay = int(hops), float(decay)
+        self._crop = L.i3(crop) if crop is not None else None
+        self._overlap = L.i3(overlap) if crop is not None else None
+        self.vhalo_lo = self.vhalo_hi = None
+        self.vh = 0
+        if self.hops != 1:
+            raise NotImplementedError("the Z-sharded path implements N = 1")
         self.shape, self.world, self.rank, self.dev = (X, Y, Z), world, rank, torch.device(device)
         self.scale = [float(s) for s in scale]
         self.z_range = slab_bounds(Z, world)[rank]
         self.Zl = self.z_range[1] - self.z_range[0]
-        self.halo = int(math.ceil(abs(self.scale[2])))  # |v| <= 1 -> a target is at most this many planes away
+        # label halo: how far beyond a face this rank can answer a gather target.  The network's vectors lie in [-1, 1]
+        # (vector_to_embedding.py:140), so ceil(scale_z) planes is the default; a field that exceeds it is DETECTED
+        # (STATUS_HALO_RANGE -> check_status() raises) and the caller can ask for up to 64 planes
+        self.halo = int(math.ceil(abs(self.scale[2]))) if halo is None else int(halo)
         if self.halo > 64 or self.halo > self.Zl:
             raise ValueError("halo deeper than one 64-plane word / than the slab is not supported")
         self.comm = comm
@@ -293,7 +301,8 @@ class ShardedAssembler:
 
     def _label_local(self, phase: int) -> None:
         X, Y, Z = self.shape
-        flags = phase | (L.CCL_WORKSPACE_CLEAN if self._clean and phase != L.CCL_PHASE_LABEL else 0)
+        # the status word is sticky across passes (graph replays included): check_status() reads and clears it
+        flags = phase | L.CCL_KEEP_STATUS | (L.CCL_WORKSPACE_CLEAN if self._clean and phase != L.CCL_PHASE_LABEL else 0)
         L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, self.z_range[0], self.Zl,
                                                self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
                                                self.meta[1:2].data_ptr(), flags, self._s()))
@@ -378,10 +387,9 @@ class ShardedAssembler:
                 L.check(self.lib.skb_shard_push(self.exch.data_ptr(), self.mailbox.ptr, self._peer_arr, self.world, self.rank,
                                                 self.cap_runs, self.cap_roots, self.cap_pairs, self._s()))
 
-    def phase_merge_and_gather(self, timers=None) -> Tensor:
-        """after the all-gather: `gathered` holds every rank's roots and pairs."""
+    def phase_merge(self) -> None:
+        """after the all-gather: `gathered` holds every rank's roots and pairs -> global numbering on this rank."""
         X, Y, Z = self.shape
-        z0, _ = self.z_range
         with torch.cuda.device(self.dev), self._chain():
             if self.transport == "peer":
                 L.check(self.lib.skb_shard_merge_peer(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.mailbox.ptr,
@@ -393,24 +401,38 @@ class ShardedAssembler:
                                                  self.meta[0:1].data_ptr(), self.meta[1:2].data_ptr(), self._s()))
             self._clean = True  # a completed merge leaves the root bitmap zeroed
             if self.split:
-                chain_done = torch.cuda.Event()
-                chain_done.record(torch.cuda.current_stream(self.dev))
+                self._chain_done = torch.cuda.Event()
+                self._chain_done.record(torch.cuda.current_stream(self.dev))
+
+    def gather(self, voxel_range: Optional[Tuple[int, int]] = None) -> Tensor:
+        """the fused slab gather (or, split, the resolve pass) over the slab or a stretch [first, first+count) of its
+        flat (X,Y,Zl) index.  A target beyond the planes the neighbours' runs describe sets STATUS_HALO_RANGE."""
+        X, Y, Z = self.shape
+        z0, _ = self.z_range
         with torch.cuda.device(self.dev):
             if self.split:
-                torch.cuda.current_stream(self.dev).wait_event(chain_done)
+                torch.cuda.current_stream(self.dev).wait_event(self._chain_done)
                 L.check(self.lib.skb_assemble_resolve(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
                                                       L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
                                                       L.ptr(self.halo_hi), self.flags.data_ptr(), self.out.data_ptr(),
                                                       L.dtype_code(self.out), self._s()))
                 return self.out
-            if timers is not None:
-                timers[0].record()
-            L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl,
-                                               L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
-                                               L.ptr(self.halo_hi), self.out.data_ptr(), L.dtype_code(self.out), self._s()))
-            if timers is not None:
-                timers[1].record()
+            first, count = (0, X * Y * self.Zl) if voxel_range is None else (int(voxel_range[0]), int(voxel_range[1]))
+            L.check(self.lib.skb_assemble_slab_ex(
+                self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl, L.f3(self.scale), self.hops, self.decay,
+                self._crop, self._overlap, L.ptr(self.vhalo_lo), L.ptr(self.vhalo_hi), self.vh, self.workspace.data_ptr(),
+                L.ptr(self.halo_lo), L.ptr(self.halo_hi), self.halo, self.out.data_ptr(), L.dtype_code(self.out), first, count,
+                self.meta[1:2].data_ptr(), self._s()))
         return self.out
+
+    def phase_merge_and_gather(self, timers=None) -> Tensor:
+        self.phase_merge()
+        if timers is not None and not self.split:
+            timers[0].record()
+        out = self.gather()
+        if timers is not None and not self.split:
+            timers[1].record()
+        return out
 
     # ---- one pass over torch.distributed ----------------------------------------------------------
     def capture(self) -> bool:
@@ -433,11 +455,32 @@ class ShardedAssembler:
             torch.cuda.synchronize(self.dev)
         return self.graph is not None
 
-    def step(self, timers=None) -> Tensor:
+    def step(self, timers=None, check: bool = True) -> Tensor:
+        """one pass over the loaded slab.  check=True (default) reads the 8-byte status word back before returning the
+        labels, so a peer that fell out of step (in-kernel waits are bounded, not infinite), an overflowed list or a
+        gather target beyond the halo raises here instead of returning labels built from partial data.  A caller that
+        times a loop of passes skips the read (check=False) and calls `check_status()` once after the loop."""
         if getattr(self, "graph", None) is not None and timers is None:
             self.graph.replay()
-            return self.out
-        return self._step_eager(timers)
+        else:
+            self._step_eager(timers)
+        if check:
+            self.check_status()
+        return self.out
+
+    def check_status(self) -> int:
+        """raises on any status bit of the last pass(es); returns the component count.  One small D2H read (synchronises)."""
+        ncomp, status = (int(v) for v in self.meta.tolist())
+        if status:
+            self.meta[1:2].zero_()
+        if status & L.STATUS_ROOT_OVERFLOW:
+            raise L.SkootsB200Error("sharded CCL: a list capacity (roots / runs / pairs) overflowed")
+        if status & L.STATUS_PEER_TIMEOUT:
+            raise L.SkootsB200Error("sharded pass: a peer's flag did not arrive (a rank fell out of step or died)")
+        if status & L.STATUS_HALO_RANGE:
+            raise L.SkootsB200Error(f"sharded gather: a vector points more than {self.halo} planes beyond this rank's slab "
+                                    "(|v_z * scale_z| exceeds the halo the neighbours sent); construct the assembler with a larger halo")
+        return ncomp
 
     def _step_eager(self, timers=None) -> Tensor:
         self.phase_local()
@@ -511,46 +554,119 @@ class ShardedAssembler:
 
     def check(self) -> Tuple[int, int]:
         """(n_components, labelled voxels over all ranks); raises on a capacity overflow."""
-        ncomp, status = (int(v) for v in self.meta.tolist())
-        if status & L.STATUS_ROOT_OVERFLOW:
-            raise L.SkootsB200Error("sharded CCL: a list capacity (roots / runs / pairs) overflowed")
-        if status & L.STATUS_PEER_TIMEOUT:
-            raise L.SkootsB200Error("sharded pass: a peer's flag did not arrive (a rank fell out of step or died)")
+        ncomp = self.check_status()
         labelled = (self.out > 0).sum().to(torch.int64)
         if self.comm is not None and self.world > 1:
             self.comm.dist.all_reduce(labelled, group=self.comm.group)
         return ncomp, int(labelled.item())
 
+    # ---- host buffers -----------------------------------------------------------------------------------
+    def _host_plan(self, n_slabs: int):
+        """X-ranges of the pipelined host pass; a range starts on a multiple of 256 slab voxels (skb_assemble_slab_ex)."""
+        X, Y, _ = self.shape
+        plane = Y * self.Zl
+        bounds = sorted({X * i // n_slabs for i in range(n_slabs + 1)})
+        bounds = [b for b in bounds if (b * plane) % 256 == 0 or b == X]
+        if bounds[0] != 0:
+            bounds = [0] + bounds
+        return list(zip(bounds[:-1], bounds[1:]))
+
+    def run_host(self, mask_host: Tensor, vec_host: Tensor, out_host: Tensor, n_slabs: int = 8, check: bool = True) -> Tensor:
+        """One pass with this rank's slab in HOST memory (pinned for full speed): mask (X,Y,Zl) u8, vectors (3,X,Y,Zl),
+        labels written to out_host (X,Y,Zl) int32 | int16 — the sharded form of `pipeline.HostAssembler`.
+
+        Pipelined on three streams: the mask goes up first and the whole labelling chain (local labelling, both
+        exchanges with the other ranks, merge) runs while the vector field follows X-range by X-range; each range is
+        gathered as soon as it has landed and its labels travel back while the next range is still arriving, so both
+        PCIe directions and the kernels overlap.  The pass ends with a device synchronisation and the status check."""
+        X, Y, Z = self.shape
+        if self.split:
+            raise L.SkootsB200Error("run_host pipelines the fused slab gather; construct the assembler without split=True")
+        if self.mask is None or self.mask.dtype != torch.uint8 or tuple(self.mask.shape) != (X, Y, self.Zl):
+            self.mask = torch.empty((X, Y, self.Zl), dtype=torch.uint8, device=self.dev)
+        if self.vec is None or self.vec.dtype != vec_host.dtype:
+            self.vec = torch.empty((3, X, Y, self.Zl), dtype=vec_host.dtype, device=self.dev)
+        if out_host.dtype != self.out.dtype:
+            self.graph = None  # a captured pass writes the old buffer
+            self.out = torch.empty((X, Y, self.Zl), dtype=out_host.dtype, device=self.dev)
+        if getattr(self, "_up", None) is None:
+            self._up, self._down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        mask_host, vec_host, out_host = mask_host.reshape(X, Y, self.Zl), vec_host.reshape(3, X, Y, self.Zl), out_host.reshape(X, Y, self.Zl)
+        plane = Y * self.Zl
+        main = torch.cuda.current_stream(self.dev)
+        self._up.wait_stream(main)
+        self._down.wait_stream(main)
+        ranges = self._host_plan(n_slabs) if self.hops == 1 else [(0, X)]  # N > 1: a walk may read any X-range of its crop
+        landed = []
+        with torch.cuda.stream(self._up):
+            self.mask.copy_(mask_host, non_blocking=True)
+            mask_ready = torch.cuda.Event()
+            mask_ready.record(self._up)
+            for x0, x1 in ranges:
+                for c in range(3):  # one contiguous block per channel and range: a plain DMA each
+                    self.vec[c, x0:x1].copy_(vec_host[c, x0:x1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._up)
+                landed.append(ev)
+        main.wait_event(mask_ready)
+        self.phase_local()
+        if self.transport != "peer":
+            self.comm.neighbour_exchange(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi)
+        self.phase_ingest()
+        if self.transport != "peer":
+            self.comm.all_gather(self.gathered, self.exch)
+        self.phase_merge()
+        for (x0, x1), ev in zip(ranges, landed):
+            main.wait_event(ev)
+            self.gather((x0 * plane, (x1 - x0) * plane))
+            done = torch.cuda.Event()
+            done.record(main)
+            self._down.wait_event(done)
+            with torch.cuda.stream(self._down):
+                out_host[x0:x1].copy_(self.out[x0:x1], non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+        if check:
+            self.check_status()
+        return out_host
+
     def e2e(self, steps: int, mask_host: Optional[Tensor] = None, vec_host: Optional[Tensor] = None,
-            out_host: Optional[Tensor] = None) -> dict:
-        """the same pass with this rank's slab in pinned HOST memory: H2D + pass + D2H per step."""
+            out_host: Optional[Tensor] = None, out_dtype=None, n_slabs: int = 8) -> dict:
+        """times `run_host` over `steps` passes (wall clock between barriers, max over ranks) with this rank's slab in
+        pinned HOST memory; returns the e2e record of bench.py plus this rank's PCIe rates."""
         import time
         X, Y, Z = self.shape
         if mask_host is None:
             mask_host = self.mask.cpu().pin_memory()
             vec_host = self.vec.cpu().pin_memory()
-            out_host = torch.empty(self.out.shape, dtype=self.out.dtype).pin_memory()
-
-        def once():
-            self.mask.copy_(mask_host, non_blocking=True)
-            self.vec.copy_(vec_host, non_blocking=True)
-            self.step()
-            out_host.copy_(self.out, non_blocking=True)
-            torch.cuda.synchronize(self.dev)
-        once()
+        if out_host is None:
+            out_host = torch.empty((X, Y, self.Zl), dtype=out_dtype or self.out.dtype).pin_memory()
+        self.run_host(mask_host, vec_host, out_host, n_slabs)
         self.comm.barrier()
         torch.cuda.synchronize(self.dev)
         t0 = time.perf_counter()
         for _ in range(steps):
-            once()
+            self.run_host(mask_host, vec_host, out_host, n_slabs, check=False)
+        mine = (time.perf_counter() - t0) / steps
         self.comm.barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=self.dev)
-        self.comm.dist.all_reduce(dt, op=self.comm.dist.ReduceOp.MAX, group=self.comm.group)
-        dt = float(dt.item())
-        return {"value": X * Y * Z / dt, "unit": "voxels/s",
-                "h2d_bytes_per_step": (mask_host.numel() + vec_host.numel() * 2) * self.world,
-                "d2h_bytes_per_step": out_host.numel() * out_host.element_size() * self.world,
-                "ms_per_step": dt * 1e3, "steps": steps, "api": "skoots_b200.sharded.ShardedAssembler.e2e"}
+        wall = (time.perf_counter() - t0) / steps
+        self.check_status()
+        h2d = mask_host.numel() * mask_host.element_size() + vec_host.numel() * vec_host.element_size()
+        d2h = out_host.numel() * out_host.element_size()
+        dist = self.comm.dist
+        t = torch.tensor([wall, mine], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.comm.group)
+        dt = float(t[0].item())
+        rates = torch.zeros(self.world, dtype=torch.float64, device=self.dev)
+        rates[self.rank] = (h2d + d2h) / mine / 1e9
+        dist.all_reduce(rates, group=self.comm.group)
+        self.host_out = out_host
+        return {"value": X * Y * Z / dt, "unit": "voxels/s", "h2d_bytes_per_step": h2d * self.world,
+                "d2h_bytes_per_step": d2h * self.world, "ms_per_step": dt * 1e3, "steps": steps,
+                "out_dtype": str(out_host.dtype).replace("torch.", ""),
+                "pcie_GBps_per_rank": [round(float(v), 1) for v in rates.tolist()],
+                "pipeline": f"mask up -> labelling chain + exchanges while {len(self._host_plan(n_slabs))} X-ranges of the vectors "
+                            "follow; each range gathered when landed, labels travel back meanwhile (3 streams)",
+                "api": "skoots_b200.sharded.ShardedAssembler.run_host"}
 
 
 class LocalGroup:
@@ -597,9 +713,5 @@ class LocalGroup:
                     r.gathered.copy_(allg)
         outs = [r.phase_merge_and_gather() for r in self.ranks]
         for r in self.ranks:
-            ncomp, status = (int(v) for v in r.meta.tolist())
-            if status & L.STATUS_ROOT_OVERFLOW:
-                raise L.SkootsB200Error("sharded CCL: a list capacity overflowed")
-            if status & L.STATUS_PEER_TIMEOUT:
-                raise L.SkootsB200Error("sharded pass: a flag did not arrive")
+            r.check_status()
         return torch.cat(outs, dim=2)

@@ -12,7 +12,7 @@ skoots/train/dataloader.py:111-115).  This module draws all of them from straigh
   skeleton dict   : rounded points along the segment, one per unit length
 
 Everything is torch, so the same code fills a 128x128x32 CPU fixture or one rank's Z-slab
-of a 2048x2048x512 volume directly in HBM (``z_range`` selects the slab; tubes are drawn
+of a 2048x2048x512 volume directly in HBM (``z_range`` selects the slab, ``xy_range`` a box; tubes are drawn
 for the whole volume from the seed so every rank sees the same objects).
 """
 from __future__ import annotations
@@ -56,20 +56,22 @@ def make_tube_volume(
     radius: float = 4.0,
     skel_radius: float = 1.5,
     z_range: Optional[Tuple[int, int]] = None,
+    xy_range: Optional[Tuple[Tuple[int, int], Tuple[int, int]]] = None,
     flat: bool = False,
     want_mask: bool = True,
     want_skeleton_dict: bool = True,
 ) -> TubeVolume:
     X, Y, Z = shape
     z0, z1 = (0, Z) if z_range is None else z_range
-    Zl = z1 - z0
+    (x0, x1), (y0, y1) = ((0, X), (0, Y)) if xy_range is None else xy_range  # only this box of the volume is filled
+    Zl, Xl, Yl = z1 - z0, x1 - x0, y1 - y0
     dev = torch.device(device)
     a_np, b_np = draw_tubes(shape, n_tubes, seed, flat)
 
-    best = torch.full((X, Y, Zl), float("inf"), dtype=torch.float32, device=dev)
-    mask = torch.zeros((X, Y, Zl), dtype=torch.int32, device=dev) if want_mask else None
-    skel = torch.zeros((X, Y, Zl), dtype=torch.uint8, device=dev)
-    vec = torch.zeros((3, X, Y, Zl), dtype=torch.float16, device=dev)
+    best = torch.full((Xl, Yl, Zl), float("inf"), dtype=torch.float32, device=dev)
+    mask = torch.zeros((Xl, Yl, Zl), dtype=torch.int32, device=dev) if want_mask else None
+    skel = torch.zeros((Xl, Yl, Zl), dtype=torch.uint8, device=dev)
+    vec = torch.zeros((3, Xl, Yl, Zl), dtype=torch.float16, device=dev)
     sc = torch.tensor(scale, dtype=torch.float32, device=dev)
 
     pad = radius + 1.0
@@ -77,8 +79,8 @@ def make_tube_volume(
         a, b = a_np[i], b_np[i]
         lo = np.floor(np.minimum(a, b) - pad).astype(np.int64)
         hi = np.ceil(np.maximum(a, b) + pad).astype(np.int64) + 1
-        lo = np.maximum(lo, [0, 0, z0])
-        hi = np.minimum(hi, [X, Y, z1])
+        lo = np.maximum(lo, [x0, y0, z0])
+        hi = np.minimum(hi, [x1, y1, z1])
         if np.any(hi <= lo):
             continue
         gx = torch.arange(lo[0], hi[0], device=dev, dtype=torch.float32)[:, None, None]
@@ -92,7 +94,7 @@ def make_tube_volume(
         dx, dy, dz = px - gx, py - gy, pz - gz
         dist = torch.sqrt(dx * dx + dy * dy + dz * dz)
 
-        sl = (slice(lo[0], hi[0]), slice(lo[1], hi[1]), slice(lo[2] - z0, hi[2] - z0))
+        sl = (slice(lo[0] - x0, hi[0] - x0), slice(lo[1] - y0, hi[1] - y0), slice(lo[2] - z0, hi[2] - z0))
         cur = best[sl]
         win = (dist < radius) & (dist < cur)
         best[sl] = torch.where(win, dist, cur)

@@ -1,6 +1,7 @@
 """What the reference does to an instance mask after assembly, on B200:
 `fastremap.renumber` (skoots/lib/eval.py:304) and the per-object validation metrics of
-`skoots/validate/lib.py` — same names, arguments and return conventions, CUDA tensors only.
+`skoots/validate/lib.py` — same names, arguments and return conventions.  CUDA tensors are
+processed where they live; host tensors (what `skoots-validate` reads from tif files) are staged through the GPU.
 
 The reference's `mask_iou` / `mask_dice` loop over every (gt object, predicted object) pair with full-volume
 boolean passes — O(N·M·V).  Here one pass over the two masks fills a contingency table (`skb_contingency`)
@@ -46,6 +47,13 @@ def renumber(arr: Tensor, in_place: bool = False, max_label: Optional[int] = Non
     1..N in order of first appearance in the C-order scan, 0 stays 0.  Returns (renumbered, remap) where
     remap[old] = new (0 for labels that do not occur) — fastremap returns the same mapping as a dict and may also
     shrink the dtype, which this does not."""
+    dev, staged = L.compute_device(arr)
+    if staged:  # eval.py:304 renumbers a host array: up, renumber, back (into the same storage when in_place)
+        out, remap = renumber(L.stage_in(arr, dev), in_place=False, max_label=max_label)
+        if in_place:
+            arr.copy_(out)
+            return arr, remap.cpu()
+        return out.cpu(), remap.cpu()
     src = _as_labels(arr)
     if src.numel() == 0:
         return (arr if in_place else arr.clone()), torch.zeros(1, dtype=torch.int32, device=arr.device)
@@ -72,6 +80,9 @@ class _Contingency:
     def __init__(self, gt: Tensor, pred: Tensor):
         assert gt.shape == pred.shape, "Input tensors must be the same shape"        # validate/lib.py:198
         assert gt.device == pred.device, "Input tensors must be on the same device"  # validate/lib.py:199
+        dev, self.staged = L.compute_device(gt, pred)  # skoots-validate passes host tensors read from tif files
+        if self.staged:
+            gt, pred = L.stage_in(gt, dev), L.stage_in(pred, dev)
         gt, pred = _as_labels(gt), _as_labels(pred)
         dev, lib, n = gt.device, L.load(), gt.numel()
         self.dev = dev
@@ -114,7 +125,8 @@ class _Contingency:
 def mask_iou(gt: Tensor, pred: Tensor) -> Tensor:
     """skoots/validate/lib.py:190-229 — N x M matrix of IoUs, rows = sorted gt labels > 0, columns = sorted
     predicted labels > 0, float32; 0 where two objects do not touch."""
-    return _Contingency(gt, pred).ratios(True, False)[0]
+    c = _Contingency(gt, pred)
+    return L.stage_out(c.ratios(True, False)[0], c.staged)
 
 
 def mask_dice(gt: Tensor, pred: Tensor) -> Tensor:
@@ -125,12 +137,14 @@ def mask_dice(gt: Tensor, pred: Tensor) -> Tensor:
     if dice.numel():
         both = c.area_gt[:c.N, None].to(torch.int64) + c.area_pred[None, :c.M].to(torch.int64)
         assert not bool((2 * c.inter.to(torch.int64) >= both).logical_and(c.inter > 0).any()), "numerator >= denominator"
-    return dice
+    return L.stage_out(dice, c.staged)
 
 
 def accuracies_from_iou(iou: Tensor, thr: float = 0.1) -> Tuple[int, int, int]:
     """skoots/validate/lib.py:170-187 — (true positives, false positives, false negatives) at an IoU threshold."""
-    L.require_cuda(iou)
+    dev, staged = L.compute_device(iou)
+    if staged:
+        iou = L.stage_in(iou, dev)
     if iou.ndim != 2 or iou.shape[0] == 0 or iou.shape[1] == 0:
         # the reference's iou.max(dim=1) raises on an empty dimension
         raise IndexError("accuracies_from_iou: the IoU matrix must have at least one row and one column")

@@ -32,7 +32,22 @@ def test_bench_line_has_the_contract_keys():
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
     assert r["traffic"] is None or r["traffic"] > 0
     c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "bit-exact: True" in c["sample"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0
+    assert d["config"]["cpu_sample"] in c["sample"]
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 256 * 256 * 128 * 7 and e["d2h_bytes_per_step"] == 256 * 256 * 128 * 4
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 256 * 256 * 128 * 7 and e["d2h_bytes_per_step"] == 256 * 256 * 128 * 2
     assert d["gpu_launches"] > 0 and e["value"] < d["value"]
+    p = d["parity"]
+    assert p["sample_vs_oracle"] == "bit-exact" and p["e2e_vs_device"] == "bit-exact"
+    assert d["parity_detail"]["sample_vs_oracle"]["labelled_compared"] > 0
+    x = d["extras"]
+    assert x["eval_N10"]["sample_vs_oracle"] == "bit-exact" and x["eval_N10"]["voxels_per_s"] > 0
+    assert len(x["density_sweep"]["rows"]) == 3 and all(r["sample_vs_oracle"] == "bit-exact" for r in x["density_sweep"]["rows"])
+    fr = [r["nonzero_vector_fraction"] for r in x["density_sweep"]["rows"]]
+    assert fr[0] < fr[1] < fr[2]
+
+
+def test_bench_eval_mode_line():
+    d = _run("--mode", "eval", "--hops", "10", "--no-extras")
+    assert d["parity"]["sample_vs_oracle"] == "bit-exact" and d["parity"]["e2e_vs_device"] == "bit-exact"
+    assert "eval()" in d["config"]["workload"] and d["e2e"]["out_dtype"] == "int16"

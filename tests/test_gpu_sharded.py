@@ -115,3 +115,48 @@ def test_sharded_dense_random_masks_and_fields(density):
         grp.load_volume(mask.to(DEV), vec.to(DEV))
         for _ in range(2):
             assert torch.equal(grp.step(), want), (world, transport)
+
+
+def test_vectors_beyond_the_halo_are_detected_not_mislabelled():
+    """nothing bounds the UNet's vectors; a target farther than the label halo from the slab used to be
+    answered from the wrong halo word.  It is now reported, and a deeper halo gives the unsharded result."""
+    import skoots_b200._lib as L
+    from skoots_b200.pipeline import assemble_instances
+    from skoots_b200.sharded import LocalGroup
+    X, Y, Z = 32, 32, 256
+    mask = torch.zeros((X, Y, Z), dtype=torch.uint8, device=DEV)
+    mask[8:10, 8:10, 90:100] = 1
+    mask[20, 20, 30:40] = 1
+    vec = torch.zeros((3, X, Y, Z), dtype=torch.float16, device=DEV)
+    vec[2, 8:10, 8:10, 50:64] = 3.0      # 36 planes up, across the face at z = 64, into the first blob
+    vec[2, 20, 20, 64:80] = -2.5          # 30 planes down, across the same face, into the second
+    scale = (60, 60, 12)
+    want = assemble_instances(mask, vec, torch.tensor(scale), N=1)
+    assert int(want[8, 8, 60]) == int(want[8, 8, 95]) > 0 and int(want[20, 20, 66]) == int(want[20, 20, 35]) > 0
+    for transport in ("peer", "nccl"):
+        grp = LocalGroup((X, Y, Z), 4, DEV, scale=scale, transport=transport)   # default halo = ceil(scale_z) = 12 planes
+        grp.load_volume(mask, vec)
+        with pytest.raises(L.SkootsB200Error, match="beyond this rank's slab"):
+            grp.step()
+        deep = LocalGroup((X, Y, Z), 4, DEV, scale=scale, transport=transport, halo=64)
+        deep.load_volume(mask, vec)
+        assert torch.equal(deep.step(), want)
+        assert torch.equal(deep.step(), want)
+
+
+def test_slab_gather_by_ranges_equals_whole_slab():
+    """skb_assemble_slab_ex over X-ranges (what the pipelined host pass issues) writes what one whole-slab launch writes."""
+    from skoots_b200.sharded import LocalGroup
+    shape = (64, 48, 128)
+    tv = make_tube_volume(shape, 60, seed=9, device=DEV)
+    grp = LocalGroup(shape, 2, DEV, transport="nccl")
+    grp.load_volume(tv.skeleton, tv.vectors)
+    want = grp.step()
+    for r in grp.ranks:
+        whole = r.out.clone()
+        r.out.fill_(-7)
+        plane = shape[1] * r.Zl
+        for x0, x1 in ((0, 8), (8, 40), (40, 64)):
+            r.gather((x0 * plane, (x1 - x0) * plane))
+        assert torch.equal(r.out, whole)
+    assert int(want.max()) > 3

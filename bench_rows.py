@@ -4,7 +4,7 @@ iterations), algorithmic GB/s against the measured HBM peak, and the CPU oracle 
 the same inputs (with a parity check).  Not the driver's benchmark (that is bench.py); this produces
 the per-row evidence table committed under profiles/.
 
-    python bench_rows.py > profiles/r01_rows.json
+    python bench_rows.py > profiles/r02_rows.json
 """
 from __future__ import annotations
 
@@ -150,13 +150,59 @@ def main():
     got0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=True)
     # voxel x skeleton-point pairs the min-reduction visits (9 flop each: 3 sub, 3 mul by anisotropy^2-weighted diff, 3 add/compare)
     pairs = sum(int((t.mask == k).sum()) * int(p.shape[0]) for t, d in zip(vols, present) for k, p in d.items())
+    cpu_bake = cpu_ms(lambda: [orc.bake_skeleton(vols[i].mask, present[i], an, average=True) for i in range(B)], iters=1, warm=False)
     bake_ms = gpu_ms(lambda: [skel.bake_skeleton(masks_d[i], present_d[i], an, average=True) for i in range(B)], iters=5)
-    rows.append(row("a8 bake_skeleton (+average)", "C4 8 x 300x300x20, 20 ids each", B * 300 * 300 * 20, 16, bake_ms,
-                    cpu_ms(lambda: [orc.bake_skeleton(vols[i].mask, present[i], an, average=True) for i in range(B)], iters=1, warm=False),
-                    bool(torch.allclose(got0.cpu(), want0, rtol=1e-5, atol=1e-5)),
-                    f"fp32-ALU bound min-reduction: {pairs} voxel-point pairs x 9 flop = {9 * pairs / (bake_ms * 1e-3) / 1e12:.3f} TFLOP/s of the "
-                    "nominal 74 TFLOP/s fp32 FMA peak (SURVEY 8d) — at this size (8 calls of 1.8 Mvox) the row is bound by the per-call host "
-                    "work: table packing, 3 launches and a status read per sample"))
+    rows.append(row("a8 bake_skeleton (+average), 8 per-sample calls (the reference's call pattern)", "C4 8 x 300x300x20, 20 ids each",
+                    B * 300 * 300 * 20, 16, bake_ms, cpu_bake, bool(torch.allclose(got0.cpu(), want0, rtol=1e-5, atol=1e-5)),
+                    "one fused launch + table upload + one status read per sample: host-bound"))
+    masks_b = torch.stack(masks_d)
+    gotb = skel.bake_skeletons_batch(masks_b, present_d, an, average=True)
+    batch_ms = gpu_ms(lambda: skel.bake_skeletons_batch(masks_b, present_d, an, average=True), iters=10)
+    nocheck_ms = gpu_ms(lambda: skel.bake_skeletons_batch(masks_b, present_d, an, average=True, check=False), iters=10)
+    # the kernel alone: tables packed once outside the timed region
+    ids_t, begin_t, off_t, pts_t, n_ids, n_pts = skel._pack_batch(present_d, DEV)
+    out_b = torch.empty((B, 3, 300, 300, 20), dtype=torch.float32, device=DEV)
+    st_b = torch.zeros(1, dtype=torch.int32, device=DEV)
+    from skoots_b200 import _lib as L_
+
+    def bake_kernel_only():
+        L_.check(L_.load().skb_bake_skeletons(masks_b.data_ptr(), L_.dtype_code(masks_b), B, 300, 300, 20, ids_t.data_ptr(), begin_t.data_ptr(),
+                                              off_t.data_ptr(), n_ids, pts_t.data_ptr(), n_pts, L_.f3(an), 1, out_b.data_ptr(), 0,
+                                              st_b.data_ptr(), L_.stream_ptr(DEV)))
+    kern_ms = gpu_ms(bake_kernel_only, iters=10)
+    rows.append(row("a8 bake_skeletons_batch (+average), ONE launch for the batch", "C4 8 x 300x300x20, 20 ids each",
+                    B * 300 * 300 * 20, 16, batch_ms, cpu_bake,
+                    bool(torch.allclose(gotb[0].cpu(), want0, rtol=1e-5, atol=1e-5) and torch.equal(out_b, gotb)),
+                    f"whole call incl. table packing and the status read; without the read {nocheck_ms:.4f} ms; the kernel alone "
+                    f"{kern_ms:.4f} ms = {16 * B * 1.8e6 / (kern_ms * 1e-3) / 1e9:.0f} GB/s of 16 B/voxel "
+                    f"({16 * B * 1.8e6 / (kern_ms * 1e-3) / 1e9 / hbm_peak():.2f} of HBM), {9 * pairs / (kern_ms * 1e-3) / 1e12:.3f} TFLOP/s "
+                    f"of the nominal 74 TFLOP/s fp32 peak over {pairs} voxel-point pairs: memory-bound, not ALU-bound"))
+    # the reference's only GPU kernel (Triton, skoots/lib/skeleton.py:51-367) on the same box and inputs.
+    # Its semantics differ from the CPU path (fp16 outputs, anisotropy on squared differences, per-axis max on
+    # ties), so it is raced, not compared bit for bit.
+    try:
+        import ref_shim
+        ref_shim.install()
+        import skoots.lib.skeleton as ref_skel
+        masks_i = [m.contiguous() for m in masks_d]
+        ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False)  # compile
+        tri_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=False) for i in range(B)], iters=3, warm=1)
+        ours_raw = gpu_ms(lambda: skel.bake_skeletons_batch(masks_b, present_d, an, average=False, check=False), iters=10)
+        tri0 = ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False).float()
+        mine0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=False)
+        agree = float((tri0 == mine0).float().mean().item())
+        try:
+            tri_avg_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=True) for i in range(B)], iters=3, warm=1)
+        except Exception as exc:  # scripted morphology helpers may not run under this torch
+            tri_avg_ms = None
+        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton _bake_skeleton_triton vs skb_bake_skeletons (average=False)",
+                     "config": "C4 8 x 300x300x20, 20 ids each, same B200, same inputs", "voxels": B * 300 * 300 * 20,
+                     "reference_triton_ms": round(tri_ms, 4), "reference_triton_with_average_ms": None if tri_avg_ms is None else round(tri_avg_ms, 4),
+                     "skoots_b200_ms": round(ours_raw, 4), "skoots_b200_with_average_ms": round(nocheck_ms, 4),
+                     "speedup": round(tri_ms / ours_raw, 1), "fraction_of_voxels_where_both_agree": round(agree, 4),
+                     "note": "the reference launches one Triton program per voxel, 8 launches + 8 synchronisations per batch, fp16 out"})
+    except Exception as exc:
+        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton kernel", "unavailable": repr(exc)[:300]})
     wantm = orc.skeleton_to_mask(present[0], (300, 300, 20), 9, 3)
     rows.append(row("a9 skeleton_to_mask r=9 f=3", "C4 8 x 300x300x20", B * 300 * 300 * 20, 4,
                     gpu_ms(lambda: [skel.skeleton_to_mask(present_d[i], (300, 300, 20), radius=9, flank_radius=3) for i in range(B)], iters=5),

@@ -186,18 +186,23 @@ int skb_vec_prob(const void* vec, int vec_dtype, const void* baked, int baked_dt
                  float* prob, const float* grad_out, void* grad_vec, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * a8  bake_skeleton (CPU/torch semantics)                     skoots/lib/skeleton.py:370-445
- *   mask (X,Y,Z) u8|i16|i32 object ids; ids: sorted object ids (device, n_ids); offsets: device
- *   prefix (n_ids+1) into points_xyzw (device, n_points x 4 floats, 16-byte rows);
- *   anisotropy: HOST array.  baked (3,X,Y,Z) f32 = nearest point of the voxel's own skeleton
- *   (first minimum), 0 on background; distance (X,Y,Z) f32 optional.  *status |= 2 when a mask
- *   id has no skeleton (the reference raises KeyError, skeleton.py:422).
+ * a8  bake_skeleton (CPU/torch semantics) + average_baked_skeletons     skoots/lib/skeleton.py:370-445, 18-48
+ *   One launch for a batch of B samples (the reference calls bake_skeleton once per sample inside the data
+ *   loader, dataloader.py:177; B = 1 is that call).  masks (B,X,Y,Z) u8|i16|i32 object ids.  Tables (device):
+ *   ids = every sample's SORTED object ids, concatenated; id_begin (B+1) = range of sample b in ids;
+ *   offsets (n_ids+1) = prefix of point counts over the whole batch into points_xyzw (n_points x 4 floats,
+ *   16-byte rows).  anisotropy: HOST array.  baked (B,3,X,Y,Z) f32 = nearest point of the voxel's own skeleton
+ *   (first minimum of the sqrt'ed distances), 0 on background; average != 0 fuses the masked 3x3x3 mean of
+ *   average_baked_skeletons (sum of the window / max(1, count of entries > 0), zero padded) so the un-averaged
+ *   field never reaches HBM.  distance (B,X,Y,Z) f32 optional.  *status |= SKB_STATUS_MISSING_ID when a mask id
+ *   has no skeleton (the reference raises KeyError, skeleton.py:422); the caller zeroes *status and may read it
+ *   once per batch.
  * ------------------------------------------------------------------------------------------- */
 #define SKB_STATUS_MISSING_ID 2u
-int skb_bake_skeleton(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z,
-                      const int32_t* ids, const int32_t* offsets, int n_ids,
-                      const float* points_xyzw, int n_points, const float anisotropy[3],
-                      float* baked, float* distance, uint32_t* status, void* stream);
+int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
+                       const int32_t* ids, const int32_t* id_begin, const int32_t* offsets, int n_ids,
+                       const float* points_xyzw, int n_points, const float anisotropy[3], int average,
+                       float* baked, float* distance, uint32_t* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a9  skeleton_to_mask                                         skoots/lib/skeleton.py:531-593

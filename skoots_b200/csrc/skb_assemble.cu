@@ -788,9 +788,11 @@ __global__ void __launch_bounds__(256) vec_embed2d_kernel(const VecT* __restrict
     out[at + plane] = __fadd_rn((float)y, __fmul_rn(skb_to_float<VecT>(vec[at + plane]), s1));
 }
 
-// N = 1 forms, 8 consecutive elements of the fastest axis per thread: one 16-byte load (two for fp32) per channel and
+// N = 1 forms, 8 consecutive elements of the flat index per thread: one 16-byte load (two for fp32) per channel and
 // two 16-byte stores per channel, instead of a 2-byte load and a 4-byte store per thread.  `inner` = length of the
-// fastest axis (a multiple of 8), `mid` = length of the axis before it; C = 3 (x, y, z) or 2 (x, y).
+// fastest axis, `mid` = length of the axis before it; C = 3 (x, y, z) or 2 (x, y).  The channel plane must be a
+// multiple of 8 elements (16-byte aligned planes); a group may run over a row end (Z = 20 in the training crops), so the
+// coordinates of the first element are decomposed once and carried for the other seven.
 template <typename VecT, int C>
 __global__ void __launch_bounds__(256) vec_embed_n1_vec8_kernel(const void* __restrict__ vec, float* __restrict__ out,
                                                                 long long per_channel, unsigned inner, unsigned mid,
@@ -800,11 +802,20 @@ __global__ void __launch_bounds__(256) vec_embed_n1_vec8_kernel(const void* __re
     if (g >= total_groups) return;
     const long long b = g / groups_per_batch;
     const long long i0 = (g - b * groups_per_batch) * 8;  // element index inside one channel of batch b
-    const unsigned q = (unsigned)(i0 / inner);
-    const unsigned last = (unsigned)(i0 - (long long)q * inner);
-    float idx[3];
-    if (C == 3) { idx[0] = (float)(q / mid); idx[1] = (float)(q - (q / mid) * mid); idx[2] = (float)last; }
-    else { idx[0] = (float)q; idx[1] = (float)last; idx[2] = 0.f; }
+    unsigned q = (unsigned)(i0 / inner);
+    unsigned last = (unsigned)(i0 - (long long)q * inner);
+    unsigned c0 = C == 3 ? q / mid : q, c1 = C == 3 ? q - (q / mid) * mid : 0u;
+    float idx[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (C == 3) { idx[0][j] = (float)c0; idx[1][j] = (float)c1; idx[2][j] = (float)last; }
+        else { idx[0][j] = (float)c0; idx[1][j] = (float)last; idx[2][j] = 0.f; }
+        if (++last == inner) {
+            last = 0;
+            if (C == 3) { if (++c1 == mid) { c1 = 0; ++c0; } }
+            else ++c0;
+        }
+    }
     const float sc[3] = {s0, s1, s2};
     const long long base = b * C * per_channel + i0;
 #pragma unroll
@@ -812,10 +823,8 @@ __global__ void __launch_bounds__(256) vec_embed_n1_vec8_kernel(const void* __re
         const Raw8<VecT> r = load_raw8<VecT, true>(vec, base + (long long)c * per_channel, 8);
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float coord = c == C - 1 ? __fadd_rn(idx[c], (float)j) : idx[c];  // exact: small integers
-            o[j] = __fadd_rn(coord, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(r.w, j)), sc[c]));
-        }
+        for (int j = 0; j < 8; ++j)
+            o[j] = __fadd_rn(idx[c][j], __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(r.w, j)), sc[c]));
         float* dst = out + base + (long long)c * per_channel;
         skb_st_stream16(dst, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
         skb_st_stream16(dst + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
@@ -1158,7 +1167,7 @@ extern "C" int skb_vec_embed3d(const void* vec, int vec_dtype, int64_t B, int64_
     const long long V = X * Y * Z;
     const int32_t crop[3] = {(int32_t)X, (int32_t)Y, (int32_t)Z}, ov[3] = {0, 0, 0};
     const int es = elem_size(vec_dtype);
-    if (N == 1 && Z % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) && B * V / 8 < (1LL << 31) * 256) {
+    if (N == 1 && V % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) && B * V / 8 < (1LL << 31) * 256) {
         if (vec_dtype == SKB_F16) launch_vec_embed_n1_vec8<__half, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
         else if (vec_dtype == SKB_BF16) launch_vec_embed_n1_vec8<__nv_bfloat16, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
         else launch_vec_embed_n1_vec8<float, 3>(vec, out, B, V, (unsigned)Z, (unsigned)Y, scale, st);
@@ -1192,7 +1201,7 @@ extern "C" int skb_vec_embed2d(const void* vec, int vec_dtype, int64_t B, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long total = B * X * Y;
     unsigned nb = (unsigned)((total + 255) / 256);
-    if (Y % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) &&
+    if ((X * Y) % 8 == 0 && skb_aligned16(vec) && skb_aligned16(out) &&
         (vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32)) {
         if (vec_dtype == SKB_F16) launch_vec_embed_n1_vec8<__half, 2>(vec, out, B, X * Y, (unsigned)Y, 1u, scale, st);
         else if (vec_dtype == SKB_BF16) launch_vec_embed_n1_vec8<__nv_bfloat16, 2>(vec, out, B, X * Y, (unsigned)Y, 1u, scale, st);

@@ -22,6 +22,23 @@ __device__ __forceinline__ float red(float a, float b) {
     return OP == OP_MIN333 ? fminf(a, b) : fmaxf(a, b);
 }
 
+// Six consecutive z inputs (z0-1 .. z0+4) of one row, zero outside the volume.  When the row is 16-byte aligned and the
+// four middle elements exist, they come in as one 16-byte load.
+__device__ __forceinline__ void load_row6(const float* __restrict__ row, int z0, int Z, bool aligned4, float (&v)[6]) {
+    if (aligned4 && z0 + 4 <= Z) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(row + z0));
+        v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+        v[0] = z0 > 0 ? __ldg(row + z0 - 1) : 0.f;
+        v[5] = z0 + 4 < Z ? __ldg(row + z0 + 4) : 0.f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int zz = z0 - 1 + k;
+            v[k] = (zz >= 0 && zz < Z) ? __ldg(row + zz) : 0.f;
+        }
+    }
+}
+
 // torch.max/min propagate NaN; fmaxf/fminf do not.  The reference's conv3d already turns NaN into
 // NaN for the whole window (0*NaN), so NaN inputs are outside the parity contract.
 template <int OP>
@@ -38,6 +55,7 @@ __global__ void __launch_bounds__(256) stencil3_kernel(const float* __restrict__
     const int z0 = zg * 4;
     const float* base = in + vol * (long long)X * Y * Z;
     constexpr int RZ = OP == OP_MAX331 ? 0 : 1;
+    const bool aligned4 = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
 
     float acc[4];
     bool first = true;
@@ -51,12 +69,7 @@ __global__ void __launch_bounds__(256) stencil3_kernel(const float* __restrict__
 #pragma unroll
                 for (int k = 0; k < 6; ++k) v[k] = 0.f;
             } else {
-                const float* row = base + ((long long)xx * Y + yy) * Z;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int zz = z0 - 1 + k;
-                    v[k] = (zz >= 0 && zz < Z) ? __ldg(row + zz) : 0.f;
-                }
+                load_row6(base + ((long long)xx * Y + yy) * Z, z0, Z, aligned4, v);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -68,34 +81,67 @@ __global__ void __launch_bounds__(256) stencil3_kernel(const float* __restrict__
         }
     }
     float* orow = out + vol * (long long)X * Y * Z + ((long long)x * Y + y) * Z;
+    if (aligned4 && z0 + 4 <= Z && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        *reinterpret_cast<float4*>(orow + z0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (z0 + j < Z) orow[z0 + j] = acc[j];
+        for (int j = 0; j < 4; ++j)
+            if (z0 + j < Z) orow[z0 + j] = acc[j];
+    }
 }
 
+// Round 1 issued 27 scalar loads per voxel.  Now one thread produces 4 consecutive z outputs from 9 rows of 6 inputs
+// (54 loads -> 13.5 per voxel, mostly 16-byte ones).  The reference sums the 27 conv channels in tap order
+// (dx, dy, dz ascending) with zeros at the border: the same order is kept per output.
 __global__ void __launch_bounds__(256) masked_mean27_kernel(const float* __restrict__ in, float* __restrict__ out, int X,
-                                                           int Y, int Z, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int z = (int)(i % Z);
-    long long r = i / Z;
+                                                           int Y, int Z, long long n_groups, int Z4) {
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    const int zg = (int)(gi % Z4);
+    long long r = gi / Z4;
     const int y = (int)(r % Y);
     r /= Y;
     const int x = (int)(r % X);
-    const float* base = in + (r / X) * (long long)X * Y * Z;
-    // the reference sums the 27 conv channels in tap order (dx,dy,dz ascending) with zeros at the border
-    float sum = 0.f, cnt = 0.f;
-    for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int xx = x + dx, yy = y + dy, zz = z + dz;
-                float v = 0.f;
-                if (xx >= 0 && xx < X && yy >= 0 && yy < Y && zz >= 0 && zz < Z)
-                    v = __ldg(base + ((long long)xx * Y + yy) * Z + zz);
-                sum = __fadd_rn(sum, v);
-                cnt += v > 0.f ? 1.f : 0.f;
+    const long long vol = r / X;
+    const int z0 = zg * 4;
+    const float* base = in + vol * (long long)X * Y * Z;
+    const bool aligned4 = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int xx = x + dx, yy = y + dy;
+            float v[6];
+            if (xx < 0 || xx >= X || yy < 0 || yy >= Y) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) v[k] = 0.f;
+            } else {
+                load_row6(base + ((long long)xx * Y + yy) * Z, z0, Z, aligned4, v);
             }
-    out[i] = __fdiv_rn(sum, cnt == 0.f ? 1.f : cnt);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    sum[j] = __fadd_rn(sum[j], v[j + dz]);
+                    cnt[j] += v[j + dz] > 0.f ? 1.f : 0.f;
+                }
+            }
+        }
+    }
+    float* orow = out + vol * (long long)X * Y * Z + ((long long)x * Y + y) * Z;
+    if (aligned4 && z0 + 4 <= Z && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        float4 o;
+        o.x = __fdiv_rn(sum[0], cnt[0] == 0.f ? 1.f : cnt[0]);
+        o.y = __fdiv_rn(sum[1], cnt[1] == 0.f ? 1.f : cnt[1]);
+        o.z = __fdiv_rn(sum[2], cnt[2] == 0.f ? 1.f : cnt[2]);
+        o.w = __fdiv_rn(sum[3], cnt[3] == 0.f ? 1.f : cnt[3]);
+        *reinterpret_cast<float4*>(orow + z0) = o;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (z0 + j < Z) orow[z0 + j] = __fdiv_rn(sum[j], cnt[j] == 0.f ? 1.f : cnt[j]);
+    }
 }
 
 // ---- tile epilogue -------------------------------------------------------------------------------
@@ -116,52 +162,82 @@ __device__ __forceinline__ float epi_load(const void* base, long long idx) {
     return skb_to_float<T>(static_cast<const T*>(base)[idx]);
 }
 
+// Round 1 took the 7 x 7 x 3 box max by brute force: 147 taps x 2 loads per output voxel (84 us per 300x300x20 tile).
+// A box max is separable: a CTA owns a 16 x 16 x bz block of interior outputs, stages the masked skeleton values of the
+// block plus its (3,3,1) apron in shared memory once (-inf outside the tile: it never wins), and reduces along z (3 taps),
+// y (7) and x (7) in shared memory — 2 global loads per staged voxel instead of 294 per output.
+constexpr int EPI_BX = 16, EPI_BY = 16, EPI_BZ = 16, EPI_RX = EPI_BX + 6, EPI_RY = EPI_BY + 6;
+
 template <typename T>
-__global__ void __launch_bounds__(256) tile_epilogue_kernel(EpiParams P, long long n_interior) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_interior) return;
-    const int iz = P.tz - 2 * P.mz, iy = P.ty - 2 * P.my;
-    const int lz = (int)(i % iz) + P.mz;
-    long long r = i / iz;
-    const int ly = (int)(r % iy) + P.my;
-    const int lx = (int)(r / iy) + P.mx;
+__global__ void __launch_bounds__(256) tile_epilogue_kernel(EpiParams P, int bz, int nby, int nbz) {
+    extern __shared__ float epi_smem[];
+    const int rz = bz + 2;
+    float* A = epi_smem;                          // [RX][RY][bz+2] staged values, later [RX][BY][bz] (after the y pass)
+    float* B = epi_smem + EPI_RX * EPI_RY * rz;   // [RX][RY][bz]   after the z pass
+    int t = blockIdx.x;
+    const int kz = t % nbz; t /= nbz;
+    const int ky = t % nby, kx = t / nby;
+    const int ix = P.tx - 2 * P.mx, iy = P.ty - 2 * P.my, iz = P.tz - 2 * P.mz;
+    // tile-local coordinates of the block's first output voxel
+    const int lx0 = P.mx + kx * EPI_BX, ly0 = P.my + ky * EPI_BY, lz0 = P.mz + kz * bz;
     const long long plane = (long long)P.tx * P.ty * P.tz;
-    const long long at = ((long long)lx * P.ty + ly) * P.tz + lz;
     const void* prob = static_cast<const char*>(P.unet) + (size_t)(P.C - 1) * plane * sizeof(T);
     const void* skel = static_cast<const char*>(P.unet) + (size_t)(P.C - 2) * plane * sizeof(T);
 
-    // vectors: v * (prob > thr) computed in the network dtype, then .half()  (eval.py:149,175)
-    const float keep = epi_load<T>(prob, at) > P.thr ? 1.f : 0.f;
-    const long long gx = P.ox + lx, gy = P.oy + ly, gz = P.oz + lz;
-    const long long gat = (gx * P.Y + gy) * P.Z + gz, V = (long long)P.X * P.Y * P.Z;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float v = epi_load<T>(P.unet, c * plane + at) * keep;
-        v = skb_to_float<T>(skb_from_float<T>(v));  // the product is rounded to the network dtype first
-        P.vectors[c * V + gat] = __float2half_rn(v);
+    // stage: (skel.float() * (prob > thr)) over the block + apron (eval.py:146-150)
+    const int n_stage = EPI_RX * EPI_RY * rz;
+    for (int i = threadIdx.x; i < n_stage; i += 256) {
+        const int z = i % rz, q = i / rz, y = q % EPI_RY, x = q / EPI_RY;
+        const int xx = lx0 - 3 + x, yy = ly0 - 3 + y, zz = lz0 - 1 + z;
+        float v = -INFINITY;
+        if (xx >= 0 && xx < P.tx && yy >= 0 && yy < P.ty && zz >= 0 && zz < P.tz) {
+            const long long at = ((long long)xx * P.ty + yy) * P.tz + zz;
+            v = epi_load<T>(skel, at) * (epi_load<T>(prob, at) > P.thr ? 1.f : 0.f);
+        }
+        A[i] = v;
     }
-
-    // skeleton: (skel.float() * (prob>thr)) dilated 3x3x3 then 3x3x1 twice == zero-padded max over
-    // |dx|,|dy| <= 3, |dz| <= 1; zero joins the max only where a stage's window leaves the tile
-    float m = 0.f;
-    bool have = (lx <= 2 || lx >= P.tx - 3 || ly <= 2 || ly >= P.ty - 3 || lz == 0 || lz == P.tz - 1);
-    for (int dx = -3; dx <= 3; ++dx) {
-        const int xx = lx + dx;
-        if (xx < 0 || xx >= P.tx) continue;
-        for (int dy = -3; dy <= 3; ++dy) {
-            const int yy = ly + dy;
-            if (yy < 0 || yy >= P.ty) continue;
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = lz + dz;
-                if (zz < 0 || zz >= P.tz) continue;
-                const long long q = ((long long)xx * P.ty + yy) * P.tz + zz;
-                const float s = epi_load<T>(skel, q) * (epi_load<T>(prob, q) > P.thr ? 1.f : 0.f);
-                m = have ? fmaxf(m, s) : s;
-                have = true;
-            }
+    __syncthreads();
+    const int n_z = EPI_RX * EPI_RY * bz;
+    for (int i = threadIdx.x; i < n_z; i += 256) {
+        const int z = i % bz, q = i / bz;
+        const float* a = A + q * rz + z;
+        B[i] = fmaxf(fmaxf(a[0], a[1]), a[2]);
+    }
+    __syncthreads();
+    const int n_y = EPI_RX * EPI_BY * bz;
+    for (int i = threadIdx.x; i < n_y; i += 256) {  // A is free again: [RX][BY][bz]
+        const int z = i % bz, q = i / bz, y = q % EPI_BY, x = q / EPI_BY;
+        const float* b0 = B + (x * EPI_RY + y) * bz + z;
+        float m = b0[0];
+#pragma unroll
+        for (int d = 1; d <= 6; ++d) m = fmaxf(m, b0[d * bz]);
+        A[i] = m;
+    }
+    __syncthreads();
+    const int n_out = EPI_BX * EPI_BY * bz;
+    const long long V = (long long)P.X * P.Y * P.Z;
+    for (int i = threadIdx.x; i < n_out; i += 256) {
+        const int z = i % bz, q = i / bz, y = q % EPI_BY, x = q / EPI_BY;
+        const int lx = lx0 + x, ly = ly0 + y, lz = lz0 + z;
+        if (lx >= P.mx + ix || ly >= P.my + iy || lz >= P.mz + iz) continue;
+        const float* c0 = A + (x * EPI_BY + y) * bz + z;
+        float m = c0[0];
+#pragma unroll
+        for (int d = 1; d <= 6; ++d) m = fmaxf(m, c0[d * EPI_BY * bz]);
+        // zero joins the max only where the window of one of the three zero-padded dilations leaves the tile
+        if (lx <= 2 || lx >= P.tx - 3 || ly <= 2 || ly >= P.ty - 3 || lz == 0 || lz == P.tz - 1) m = fmaxf(m, 0.f);
+        const long long at = ((long long)lx * P.ty + ly) * P.tz + lz;
+        const long long gat = ((long long)(P.ox + lx) * P.Y + (P.oy + ly)) * P.Z + (P.oz + lz);
+        P.skel[gat] = m > P.thr ? 1 : 0;
+        // vectors: v * (prob > thr) computed in the network dtype, then .half()  (eval.py:149,175)
+        const float keep = epi_load<T>(prob, at) > P.thr ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = epi_load<T>(P.unet, c * plane + at) * keep;
+            v = skb_to_float<T>(skb_from_float<T>(v));  // the product is rounded to the network dtype first
+            P.vectors[c * V + gat] = __float2half_rn(v);
         }
     }
-    P.skel[gat] = m > P.thr ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -187,9 +263,10 @@ extern "C" int skb_masked_mean27(const float* in, float* out, int64_t n_volumes,
     int rc = skb_check_volume(X, Y, Z, "skb_masked_mean27");
     if (rc) return rc;
     SKB_REQUIRE(in && out && in != out && n_volumes >= 1, "skb_masked_mean27: bad argument");
-    const long long total = n_volumes * X * Y * Z;
-    masked_mean27_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        in, out, (int)X, (int)Y, (int)Z, total);
+    const int Z4 = (int)((Z + 3) / 4);
+    const long long groups = n_volumes * X * Y * Z4;
+    masked_mean27_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, out, (int)X, (int)Y, (int)Z, groups, Z4);
     SKB_LAUNCH_CHECK("masked_mean27_kernel");
     return SKB_OK;
 }
@@ -215,12 +292,22 @@ extern "C" int skb_tile_epilogue(const void* unet, int in_dtype, int C, const in
     P.thr = threshold;
     P.vectors = static_cast<__half*>(vectors_f16); P.skel = skeleton_u8;
     P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
-    const long long n = (long long)(P.tx - 2 * P.mx) * (P.ty - 2 * P.my) * (P.tz - 2 * P.mz);
-    const unsigned nb = (unsigned)((n + 255) / 256);
+    const int ix = P.tx - 2 * P.mx, iy = P.ty - 2 * P.my, iz = P.tz - 2 * P.mz;
+    const int bz = iz < EPI_BZ ? iz : EPI_BZ;
+    const int nbx = (ix + EPI_BX - 1) / EPI_BX, nby = (iy + EPI_BY - 1) / EPI_BY, nbz = (iz + bz - 1) / bz;
+    const long long blocks = (long long)nbx * nby * nbz;
+    SKB_REQUIRE(blocks < (1LL << 31), "skb_tile_epilogue: tile too large");
+    const int smem = (int)sizeof(float) * EPI_RX * EPI_RY * (2 * bz + 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (in_dtype == SKB_F32) tile_epilogue_kernel<float><<<nb, 256, 0, st>>>(P, n);
-    else if (in_dtype == SKB_F16) tile_epilogue_kernel<__half><<<nb, 256, 0, st>>>(P, n);
-    else tile_epilogue_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(P, n);
+#define EPI_LAUNCH(T)                                                                                          \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(tile_epilogue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+        tile_epilogue_kernel<T><<<(unsigned)blocks, 256, smem, st>>>(P, bz, nby, nbz);                         \
+    } while (0)
+    if (in_dtype == SKB_F32) EPI_LAUNCH(float);
+    else if (in_dtype == SKB_F16) EPI_LAUNCH(__half);
+    else EPI_LAUNCH(__nv_bfloat16);
+#undef EPI_LAUNCH
     SKB_LAUNCH_CHECK("tile_epilogue_kernel");
     return SKB_OK;
 }

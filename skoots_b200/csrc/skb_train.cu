@@ -5,12 +5,15 @@
 //   skb_vec_prob_fwd/_bwd     the same with E = idx + v*s computed on the fly from the network's
 //                             vector head (vector_to_embedding N=1 fused in; train/engine.py:465-466),
 //                             so the fp32 embedding never goes to HBM.
-//   skb_bake_skeleton         skoots/lib/skeleton.py:370-445 (CPU/torch semantics): for every voxel of
+//   skb_bake_skeletons        skoots/lib/skeleton.py:370-445 (CPU/torch semantics) + :18-48: for every voxel of
 //                             object k the nearest point of skeleton k, anisotropy scaling the
-//                             coordinates, first minimum wins.  The point table is staged into shared
-//                             memory with one TMA bulk copy (cp.async.bulk + mbarrier); the search
-//                             is an fp32 min-reduction per voxel — no tensor cores, by design.
+//                             coordinates, first minimum wins; then the masked 3x3x3 mean.  A CTA stages only
+//                             the skeletons of the ids inside its tile into shared memory (one TMA bulk copy
+//                             per id, cp.async.bulk + mbarrier); the search is an fp32 min-reduction per
+//                             voxel — no tensor cores, by design.  One launch per batch.
 //   skb_stamp_disks           skoots/lib/skeleton.py:531-593 (skeleton_to_mask)
+#include <initializer_list>
+
 #include "skb_common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -24,6 +27,181 @@ struct ProbParams {
     float scale[3];      // fused form only
     int X, Y, Z;         // fused form only (Z = 1, Y = last dim for 2-D)
 };
+
+// ---- 8 consecutive elements per thread: 16-byte streaming loads / stores --------------------------------
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&o)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&o)[8]) {
+    const uint4 a = skb_ld_stream16(p), b = skb_ld_stream16(p + 4);
+    o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.y); o[2] = __uint_as_float(a.z); o[3] = __uint_as_float(a.w);
+    o[4] = __uint_as_float(b.x); o[5] = __uint_as_float(b.y); o[6] = __uint_as_float(b.z); o[7] = __uint_as_float(b.w);
+}
+template <> __device__ __forceinline__ void ld8<__half>(const __half* p, float (&o)[8]) {
+    const uint4 a = skb_ld_stream16(p);
+    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o[2 * k] = __half2float(__ushort_as_half((unsigned short)(w[k] & 0xffffu)));
+        o[2 * k + 1] = __half2float(__ushort_as_half((unsigned short)(w[k] >> 16)));
+    }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[8]) {
+    const uint4 a = skb_ld_stream16(p);
+    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o[2 * k] = __uint_as_float(w[k] << 16);
+        o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+    skb_st_stream16(p, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+    skb_st_stream16(p + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+}
+template <> __device__ __forceinline__ void st8<__half>(__half* p, const float (&v)[8]) {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        w[k] = (unsigned)__half_as_ushort(__float2half_rn(v[2 * k])) | ((unsigned)__half_as_ushort(__float2half_rn(v[2 * k + 1])) << 16);
+    skb_st_stream16(p, make_uint4(w[0], w[1], w[2], w[3]));
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        w[k] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * k])) |
+               ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * k + 1])) << 16);
+    skb_st_stream16(p, make_uint4(w[0], w[1], w[2], w[3]));
+}
+
+// One thread = 8 consecutive voxels of one batch entry (inner % 8 == 0, every plane 16-byte aligned): the C planes of E
+// and S come in as 16-byte loads, the probability leaves as two 16-byte stores.  Same fp32 operation sequence as the
+// scalar kernels below, which remain for ragged shapes.
+template <typename ST, int NC>
+__global__ void __launch_bounds__(256) embed_prob_fwd_vec8_kernel(const float* __restrict__ E, const ST* __restrict__ S,
+                                                                 float* __restrict__ out, ProbParams P, long long gpb,
+                                                                 long long groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const long long b = g / gpb, r = (g - b * gpb) * 8;
+    const long long base = b * NC * P.inner + r;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float e[8], s[8];
+        ld8<float>(E + base + c * P.inner, e);
+        ld8<ST>(S + base + c * P.inner, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = __fsub_rn(e[j], s[j]);
+            acc[j] = __fadd_rn(acc[j], __fdiv_rn(__fmul_rn(d, d), P.neg2sig2[c]));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = expf(acc[j]);
+    st8<float>(out + b * P.inner + r, acc);
+}
+
+template <typename ST, int NC>
+__global__ void __launch_bounds__(256) embed_prob_bwd_vec8_kernel(const float* __restrict__ E, const ST* __restrict__ S,
+                                                                 const float* __restrict__ prob, const float* __restrict__ go,
+                                                                 float* __restrict__ gE, ST* __restrict__ gS, ProbParams P,
+                                                                 long long gpb, long long groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const long long b = g / gpb, r = (g - b * gpb) * 8;
+    const long long base = b * NC * P.inner + r;
+    float gp[8], p8[8];
+    ld8<float>(go + b * P.inner + r, gp);
+    ld8<float>(prob + b * P.inner + r, p8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gp[j] = gp[j] * p8[j];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float e[8], s[8], ge[8], gs[8];
+        ld8<float>(E + base + c * P.inner, e);
+        ld8<ST>(S + base + c * P.inner, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = e[j] - s[j];
+            ge[j] = gp[j] * 2.f * d / P.neg2sig2[c];
+            gs[j] = -ge[j];
+        }
+        if (gE) st8<float>(gE + base + c * P.inner, ge);
+        if (gS) st8<ST>(gS + base + c * P.inner, gs);
+    }
+}
+
+template <typename VT, typename ST, bool BWD, int NC>
+__global__ void __launch_bounds__(256) vec_prob_vec8_kernel(const VT* __restrict__ vec, const ST* __restrict__ S,
+                                                           float* __restrict__ prob, const float* __restrict__ go,
+                                                           VT* __restrict__ gvec, ProbParams P, long long gpb, long long groups) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const long long b = g / gpb, r = (g - b * gpb) * 8;
+    const long long base = b * NC * P.inner + r;
+    // coordinates of the 8 voxels: decompose the first, carry for the rest (a group may run over a row end: Z = 20)
+    int c0[8], c1[8], c2[8];
+    {
+        const unsigned ur = (unsigned)r;  // inner < 2^31 (checked by the host)
+        int x, y, z;
+        if (NC == 3) {
+            const unsigned q = ur / (unsigned)P.Z;
+            z = (int)(ur - q * (unsigned)P.Z);
+            x = (int)(q / (unsigned)P.Y);
+            y = (int)(q - (unsigned)x * (unsigned)P.Y);
+        } else {
+            x = (int)(ur / (unsigned)P.Y);
+            y = (int)(ur - (unsigned)x * (unsigned)P.Y);
+            z = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c0[j] = x; c1[j] = y; c2[j] = z;
+            if (NC == 3) {
+                if (++z == P.Z) { z = 0; if (++y == P.Y) { y = 0; ++x; } }
+            } else {
+                if (++y == P.Y) { y = 0; ++x; }
+            }
+        }
+    }
+    float d[3][8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float v[8], s[8];
+        ld8<VT>(vec + base + c * P.inner, v);
+        ld8<ST>(S + base + c * P.inner, s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = c == 0 ? c0[j] : (c == 1 ? c1[j] : c2[j]);
+            const float e = __fadd_rn((float)idx, __fmul_rn(v[j], P.scale[c]));
+            d[c][j] = __fsub_rn(e, s[j]);
+            acc[j] = __fadd_rn(acc[j], __fdiv_rn(__fmul_rn(d[c][j], d[c][j]), P.neg2sig2[c]));
+        }
+    }
+    float p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = expf(acc[j]);
+    if (!BWD) {
+        st8<float>(prob + b * P.inner + r, p);
+    } else {
+        float gp[8];
+        ld8<float>(go + b * P.inner + r, gp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gp[j] = gp[j] * p[j];
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+            float gv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = gp[j] * 2.f * d[c][j] / P.neg2sig2[c] * P.scale[c];
+            st8<VT>(gvec + base + c * P.inner, gv);
+        }
+    }
+}
 
 template <typename ST>
 __global__ void __launch_bounds__(256) embed_prob_fwd_kernel(const float* __restrict__ E, const ST* __restrict__ S,
@@ -113,6 +291,14 @@ static int fill_prob(ProbParams& P, int64_t B, int C, int64_t inner, const float
     else if (dtype == SKB_BF16) { using ST = __nv_bfloat16; FN; }          \
     else { skb_set_error("unsupported dtype %d", dtype); return SKB_E_ARG; }
 
+// the 8-per-thread kernels need whole groups per plane and 16-byte aligned planes
+static bool vec8_ok(int64_t inner, std::initializer_list<const void*> ptrs) {
+    if (inner % 8 != 0 || inner >= (1LL << 31)) return false;
+    for (const void* p : ptrs)
+        if (p && !skb_aligned16(p)) return false;
+    return true;
+}
+
 extern "C" int skb_embed_prob_fwd(const float* embedding, const void* baked, int baked_dtype, int64_t B, int C,
                                   int64_t inner, const float* sigma, float eps, float* out, void* stream) {
     ProbParams P = {};
@@ -120,8 +306,15 @@ extern "C" int skb_embed_prob_fwd(const float* embedding, const void* baked, int
     if (rc) return rc;
     SKB_REQUIRE(embedding && baked && out, "skb_embed_prob_fwd: NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned nb = (unsigned)((P.total + 255) / 256);
-    DISPATCH_S(baked_dtype, (embed_prob_fwd_kernel<ST><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), out, P)));
+    if (vec8_ok(inner, {embedding, baked, out})) {
+        const long long gpb = inner / 8, groups = B * gpb;
+        const unsigned nb = (unsigned)((groups + 255) / 256);
+        if (C == 3) { DISPATCH_S(baked_dtype, (embed_prob_fwd_vec8_kernel<ST, 3><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), out, P, gpb, groups))); }
+        else { DISPATCH_S(baked_dtype, (embed_prob_fwd_vec8_kernel<ST, 2><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), out, P, gpb, groups))); }
+    } else {
+        const unsigned nb = (unsigned)((P.total + 255) / 256);
+        DISPATCH_S(baked_dtype, (embed_prob_fwd_kernel<ST><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), out, P)));
+    }
     SKB_LAUNCH_CHECK("embed_prob_fwd_kernel");
     return SKB_OK;
 }
@@ -134,10 +327,19 @@ extern "C" int skb_embed_prob_bwd(const float* embedding, const void* baked, int
     if (rc) return rc;
     SKB_REQUIRE(embedding && baked && prob && grad_out && (grad_embedding || grad_baked), "skb_embed_prob_bwd: NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned nb = (unsigned)((P.total + 255) / 256);
-    DISPATCH_S(baked_dtype, (embed_prob_bwd_kernel<ST><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), prob,
-                                                                          grad_out, grad_embedding,
-                                                                          static_cast<ST*>(grad_baked), P)));
+    if (vec8_ok(inner, {embedding, baked, prob, grad_out, grad_embedding, grad_baked})) {
+        const long long gpb = inner / 8, groups = B * gpb;
+        const unsigned nb = (unsigned)((groups + 255) / 256);
+        if (C == 3) { DISPATCH_S(baked_dtype, (embed_prob_bwd_vec8_kernel<ST, 3><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), prob, grad_out,
+                                                                                      grad_embedding, static_cast<ST*>(grad_baked), P, gpb, groups))); }
+        else { DISPATCH_S(baked_dtype, (embed_prob_bwd_vec8_kernel<ST, 2><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), prob, grad_out,
+                                                                                      grad_embedding, static_cast<ST*>(grad_baked), P, gpb, groups))); }
+    } else {
+        const unsigned nb = (unsigned)((P.total + 255) / 256);
+        DISPATCH_S(baked_dtype, (embed_prob_bwd_kernel<ST><<<nb, 256, 0, st>>>(embedding, static_cast<const ST*>(baked), prob,
+                                                                              grad_out, grad_embedding,
+                                                                              static_cast<ST*>(grad_baked), P)));
+    }
     SKB_LAUNCH_CHECK("embed_prob_bwd_kernel");
     return SKB_OK;
 }
@@ -145,9 +347,18 @@ extern "C" int skb_embed_prob_bwd(const float* embedding, const void* baked, int
 template <typename VT>
 static int launch_vec_prob(const void* vec, const void* baked, int baked_dtype, float* prob, const float* go, void* gvec,
                            const ProbParams& P, cudaStream_t st) {
-    const unsigned nb = (unsigned)((P.total + 255) / 256);
     const VT* v = static_cast<const VT*>(vec);
     VT* gv = static_cast<VT*>(gvec);
+    if (vec8_ok(P.inner, {vec, baked, prob, go, gvec})) {
+        const long long gpb = P.inner / 8, groups = (P.total / P.inner) * gpb;
+        const unsigned nb = (unsigned)((groups + 255) / 256);
+#define VP8(BWD_, NC_) DISPATCH_S(baked_dtype, (vec_prob_vec8_kernel<VT, ST, BWD_, NC_><<<nb, 256, 0, st>>>(v, static_cast<const ST*>(baked), prob, go, gv, P, gpb, groups)))
+        if (go) { if (P.C == 3) { VP8(true, 3); } else { VP8(true, 2); } }
+        else { if (P.C == 3) { VP8(false, 3); } else { VP8(false, 2); } }
+#undef VP8
+        return SKB_OK;
+    }
+    const unsigned nb = (unsigned)((P.total + 255) / 256);
     if (go) {
         DISPATCH_S(baked_dtype, (vec_prob_kernel<VT, ST, true><<<nb, 256, 0, st>>>(v, static_cast<const ST*>(baked), prob, go, gv, P)));
     } else {
@@ -180,21 +391,21 @@ extern "C" int skb_vec_prob(const void* vec, int vec_dtype, const void* baked, i
 }
 
 // ------------------------------------------------------------------------------------------
-// bake_skeleton: nearest skeleton point per voxel (min-reduction; TMA-staged point table)
+// bake_skeleton: nearest skeleton point per voxel (min-reduction) + the masked 3x3x3 mean, one launch per batch
 // ------------------------------------------------------------------------------------------
+// Round 1 staged the WHOLE point table (up to 160 KB) into every 256-voxel CTA: ~250 B/voxel of L2 -> shared traffic for
+// 16 algorithmic, occupancy capped by shared memory, one launch + one averaging launch + a blocking status read per
+// sample (profiles/r01_rows.json: 1.73 ms for C4, 2 % of HBM).  Now:
+//   * one launch covers the whole batch (grid.y = sample);
+//   * a CTA owns an 8 x 8 x TZ tile of one sample plus, when the mean is fused, a one-voxel halo around it;
+//   * it looks up the object ids that actually occur in that region (usually 0-3), and stages ONLY their skeletons into
+//     shared memory with one TMA bulk copy per id (cp.async.bulk + mbarrier); ids that do not fit the arena are read
+//     through the read-only cache instead — same arithmetic either way;
+//   * the nearest point of every region voxel goes to shared memory, and the masked 27-mean of
+//     average_baked_skeletons (skeleton.py:18-48: sum of the window / count of its entries > 0, zero padded, taps in
+//     (dx,dy,dz) order) is taken from there, so the un-averaged field never reaches HBM.
+// HBM traffic: the mask (+ ~1.7x halo re-reads that hit L2) in, 12 B/voxel out.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-// one elected thread: stage `bytes` (multiple of 16) from global to shared with a TMA bulk copy
-__device__ __forceinline__ void tma_stage(void* smem_dst, const void* gsrc, unsigned bytes, ull* bar) {
-    const unsigned b = smem_u32(bar), d = smem_u32(smem_dst);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
-                 "l"(gsrc), "r"(bytes), "r"(b)
-                 : "memory");
-}
 
 __device__ __forceinline__ void mbar_wait(ull* bar, unsigned phase) {
     const unsigned b = smem_u32(bar);
@@ -211,99 +422,206 @@ __device__ __forceinline__ void mbar_wait(ull* bar, unsigned phase) {
         : "memory");
 }
 
+constexpr int BAKE_T = 8;          // tile edge in x and y
+constexpr int BAKE_MAXU = 24;      // distinct ids a CTA tracks in shared memory (more: read from global)
+constexpr int BAKE_ARENA = 1536;   // skeleton points staged per CTA (24 KB)
+
 struct BakeParams {
-    int X, Y, Z;
-    int n_ids;
-    int n_points;
-    int staged_points;   // how many points fit the shared-memory stage
+    int X, Y, Z, TZ, H;    // H = 1 when the 27-mean is fused (halo), else 0
+    int tiles_y, tiles_z;
     float an[3];
-    const int* ids;      // sorted object ids
-    const int* offsets;  // n_ids + 1 prefix of point counts
-    const float* points; // (n_points, 4) xyz + pad, 16-byte rows
-    unsigned* status;    // bit 1: a mask id has no skeleton (reference raises KeyError)
+    const int* ids;        // every sample's sorted object ids, concatenated
+    const int* id_begin;   // (B + 1) range of sample b in `ids`
+    const int* offsets;    // (n_ids + 1) prefix of point counts, global over the batch
+    const float* points;   // (n_points, 4) xyz + pad, 16-byte rows
+    unsigned* status;      // SKB_STATUS_MISSING_ID: a mask id has no skeleton (the reference raises KeyError)
+    long long V;           // voxels per sample
 };
 
 template <typename MT>
-__global__ void __launch_bounds__(256) bake_kernel(const MT* __restrict__ mask, float* __restrict__ baked,
-                                                  float* __restrict__ dist_out, BakeParams P, long long V) {
+__global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ masks, float* __restrict__ baked,
+                                                       float* __restrict__ dist_out, BakeParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_pts = reinterpret_cast<float4*>(smem_raw);
+    const int RX = BAKE_T + 2 * P.H, RY = BAKE_T + 2 * P.H, RZ = P.TZ + 2 * P.H, RN = RX * RY * RZ;
+    float4* s_arena = reinterpret_cast<float4*>(smem_raw);                 // BAKE_ARENA points
+    float* s_b = reinterpret_cast<float*>(s_arena + BAKE_ARENA);           // 4 x RN: x, y, z, distance
+    int* s_slot = reinterpret_cast<int*>(s_b + 4 * RN);                    // RN
+    __shared__ int s_present[BAKE_MAXU], s_lo[BAKE_MAXU], s_cnt[BAKE_MAXU], s_at[BAKE_MAXU];
     __shared__ __align__(8) ull bar;
-    if (threadIdx.x == 0 && P.staged_points > 0) tma_stage(s_pts, P.points, (unsigned)P.staged_points * 16u, &bar);
-    __syncthreads();  // barrier init visible to everyone before they wait on it
 
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int id = 0;
-    int x = 0, y = 0, z = 0;
-    if (i < V) {
-        id = (int)mask[i];
-        z = (int)(i % P.Z);
-        const long long q = i / P.Z;
-        y = (int)(q % P.Y);
-        x = (int)(q / P.Y);
+    const int b = blockIdx.y;
+    int t = blockIdx.x;
+    const int tz = t % P.tiles_z; t /= P.tiles_z;
+    const int ty = t % P.tiles_y, tx = t / P.tiles_y;
+    const int x0 = tx * BAKE_T - P.H, y0 = ty * BAKE_T - P.H, z0 = tz * P.TZ - P.H;  // region origin (may be -1)
+    const MT* mask = masks + (long long)b * P.V;
+    const int id_lo = __ldg(P.id_begin + b), id_hi = __ldg(P.id_begin + b + 1);
+
+    if (threadIdx.x < BAKE_MAXU) s_present[threadIdx.x] = -1;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    int lo = 0, hi = 0;
-    if (id != 0) {
-        int a = 0, b = P.n_ids - 1, found = -1;
-        while (a <= b) {
-            int m = (a + b) >> 1, v = __ldg(P.ids + m);
-            if (v == id) { found = m; break; }
-            if (v < id) a = m + 1; else b = m - 1;
+    __syncthreads();
+
+    // A. region voxels -> slot of their object in the CTA's id list (-1 background, <= -2: id index -2-v, list full)
+    for (int i = threadIdx.x; i < RN; i += 256) {
+        const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
+        const int gx = x0 + rx, gy = y0 + ry, gz = z0 + rz;
+        int slot = -1;
+        if (gx >= 0 && gx < P.X && gy >= 0 && gy < P.Y && gz >= 0 && gz < P.Z) {
+            const int id = (int)mask[((long long)gx * P.Y + gy) * P.Z + gz];
+            if (id != 0) {
+                int a = id_lo, e = id_hi - 1, found = -1;
+                while (a <= e) {
+                    const int m = (a + e) >> 1, v = __ldg(P.ids + m);
+                    if (v == id) { found = m; break; }
+                    if (v < id) a = m + 1; else e = m - 1;
+                }
+                if (found < 0) {
+                    atomicOr(P.status, SKB_STATUS_MISSING_ID);
+                } else {
+                    slot = -2 - found;
+                    for (int k = 0; k < BAKE_MAXU; ++k) {
+                        int cur = *reinterpret_cast<volatile int*>(&s_present[k]);
+                        if (cur == -1) cur = atomicCAS(&s_present[k], -1, found);
+                        if (cur == -1 || cur == found) { slot = k; break; }
+                    }
+                }
+            }
         }
-        if (found < 0) atomicOr(P.status, 2u);
-        else { lo = __ldg(P.offsets + found); hi = __ldg(P.offsets + found + 1); }
+        s_slot[i] = slot;
     }
-    if (P.staged_points > 0) mbar_wait(&bar, 0);
+    __syncthreads();
 
-    if (i >= V) return;
-    float bx = 0.f, by = 0.f, bz = 0.f, best = INFINITY;
-    const float ax = __fmul_rn(P.an[0], (float)x), ay = __fmul_rn(P.an[1], (float)y), az = __fmul_rn(P.an[2], (float)z);
-    for (int k = lo; k < hi; ++k) {
-        const float4 p = k < P.staged_points ? s_pts[k] : __ldg(reinterpret_cast<const float4*>(P.points) + k);
-        const float dx = __fsub_rn(__fmul_rn(p.x, P.an[0]), ax);
-        const float dy = __fsub_rn(__fmul_rn(p.y, P.an[1]), ay);
-        const float dz = __fsub_rn(__fmul_rn(p.z, P.an[2]), az);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float d = sqrtf(d2);  // the reference compares cdist's sqrt'ed values (first argmin)
-        if (d < best) { best = d; bx = p.x; by = p.y; bz = p.z; }
+    // B. one thread lays the present skeletons out in the arena and starts one bulk copy per skeleton
+    if (threadIdx.x == 0) {
+        int at = 0;
+        unsigned bytes = 0;
+        for (int k = 0; k < BAKE_MAXU && s_present[k] >= 0; ++k) {
+            const int f = s_present[k];
+            const int lo = __ldg(P.offsets + f), cnt = __ldg(P.offsets + f + 1) - lo;
+            s_lo[k] = lo; s_cnt[k] = cnt;
+            if (cnt > 0 && at + cnt <= BAKE_ARENA) { s_at[k] = at; at += cnt; bytes += (unsigned)cnt * 16u; }
+            else s_at[k] = -1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        for (int k = 0; k < BAKE_MAXU && s_present[k] >= 0; ++k)
+            if (s_at[k] >= 0)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(s_arena + s_at[k])),
+                             "l"(P.points + 4ll * s_lo[k]), "r"((unsigned)s_cnt[k] * 16u), "r"(smem_u32(&bar))
+                             : "memory");
     }
-    baked[i] = bx;
-    baked[i + V] = by;
-    baked[i + 2 * V] = bz;
-    if (dist_out) dist_out[i] = (lo < hi) ? best : 0.f;
+    __syncthreads();          // s_lo / s_cnt / s_at visible
+    mbar_wait(&bar, 0);       // the staged skeletons have landed
+
+    // C. nearest point of every region voxel (first minimum of the sqrt'ed distances, like cdist + argmin)
+    const float4* gpts = reinterpret_cast<const float4*>(P.points);
+    for (int i = threadIdx.x; i < RN; i += 256) {
+        const int slot = s_slot[i];
+        float bx = 0.f, by = 0.f, bz = 0.f, best = INFINITY;
+        if (slot != -1) {
+            const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
+            const float ax = __fmul_rn(P.an[0], (float)(x0 + rx)), ay = __fmul_rn(P.an[1], (float)(y0 + ry)),
+                        az = __fmul_rn(P.an[2], (float)(z0 + rz));
+            int lo, cnt;
+            const float4* src;
+            if (slot >= 0) {
+                lo = s_lo[slot]; cnt = s_cnt[slot];
+                src = s_at[slot] >= 0 ? s_arena + s_at[slot] : gpts + lo;
+            } else {
+                const int f = -2 - slot;
+                lo = __ldg(P.offsets + f); cnt = __ldg(P.offsets + f + 1) - lo;
+                src = gpts + lo;
+            }
+            for (int k = 0; k < cnt; ++k) {
+                const float4 p = src[k];
+                const float dx = __fsub_rn(__fmul_rn(p.x, P.an[0]), ax);
+                const float dy = __fsub_rn(__fmul_rn(p.y, P.an[1]), ay);
+                const float dz = __fsub_rn(__fmul_rn(p.z, P.an[2]), az);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                const float d = sqrtf(d2);
+                if (d < best) { best = d; bx = p.x; by = p.y; bz = p.z; }
+            }
+            if (cnt <= 0) best = 0.f;
+        } else {
+            best = 0.f;
+        }
+        s_b[i] = bx; s_b[RN + i] = by; s_b[2 * RN + i] = bz; s_b[3 * RN + i] = best;
+    }
+    __syncthreads();
+
+    // D. outputs of the tile: the nearest point itself, or its masked 27-mean
+    const int TN = BAKE_T * BAKE_T * P.TZ;
+    float* out = baked + (long long)b * 3 * P.V;
+    for (int i = threadIdx.x; i < TN; i += 256) {
+        const int lz = i % P.TZ, q = i / P.TZ, ly = q % BAKE_T, lx = q / BAKE_T;
+        const int gx = tx * BAKE_T + lx, gy = ty * BAKE_T + ly, gz = tz * P.TZ + lz;
+        if (gx >= P.X || gy >= P.Y || gz >= P.Z) continue;
+        const long long g = ((long long)gx * P.Y + gy) * P.Z + gz;
+        const int c = ((lx + P.H) * RY + (ly + P.H)) * RZ + (lz + P.H);
+        if (P.H == 0) {
+            out[g] = s_b[c]; out[g + P.V] = s_b[RN + c]; out[g + 2 * P.V] = s_b[2 * RN + c];
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* sb = s_b + ch * RN;
+                float sum = 0.f, cnt = 0.f;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dz = -1; dz <= 1; ++dz) {
+                            const float v = sb[c + (dx * RY + dy) * RZ + dz];  // 0 outside the volume, as zero padding
+                            sum = __fadd_rn(sum, v);
+                            cnt += v > 0.f ? 1.f : 0.f;
+                        }
+                out[g + ch * P.V] = __fdiv_rn(sum, cnt == 0.f ? 1.f : cnt);
+            }
+        }
+        if (dist_out) dist_out[(long long)b * P.V + g] = s_b[3 * RN + c];
+    }
 }
 
-extern "C" int skb_bake_skeleton(const void* mask, int mask_dtype, int64_t X, int64_t Y, int64_t Z, const int32_t* ids,
-                                 const int32_t* offsets, int n_ids, const float* points_xyzw, int n_points,
-                                 const float anisotropy[3], float* baked, float* distance, uint32_t* status,
-                                 void* stream) {
-    int rc = skb_check_volume(X, Y, Z, "skb_bake_skeleton");
+extern "C" int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
+                                  const int32_t* ids, const int32_t* id_begin, const int32_t* offsets, int n_ids,
+                                  const float* points_xyzw, int n_points, const float anisotropy[3], int average,
+                                  float* baked, float* distance, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_bake_skeletons");
     if (rc) return rc;
-    SKB_REQUIRE(mask && baked && status && anisotropy && n_ids >= 0 && n_points >= 0, "skb_bake_skeleton: bad argument");
-    SKB_REQUIRE(n_ids == 0 || (ids && offsets && points_xyzw), "skb_bake_skeleton: NULL tables");
-    SKB_REQUIRE(n_points == 0 || skb_aligned16(points_xyzw), "skb_bake_skeleton: point table must be 16-byte aligned");
+    SKB_REQUIRE(masks && baked && status && anisotropy && id_begin && B >= 1 && B <= 65535 && n_ids >= 0 && n_points >= 0,
+                "skb_bake_skeletons: bad argument");
+    SKB_REQUIRE(n_ids == 0 || (ids && offsets), "skb_bake_skeletons: NULL id tables");
+    SKB_REQUIRE(n_points == 0 || (points_xyzw && skb_aligned16(points_xyzw)), "skb_bake_skeletons: point table must be 16-byte aligned");
+    SKB_REQUIRE(mask_dtype == SKB_I32 || mask_dtype == SKB_I16 || mask_dtype == SKB_U8, "skb_bake_skeletons: mask dtype must be u8, i16 or i32");
     BakeParams P;
     P.X = (int)X; P.Y = (int)Y; P.Z = (int)Z;
-    P.n_ids = n_ids; P.n_points = n_points;
-    const int max_stage = (160 * 1024) / 16;  // 160 KB of the 227 KB: leaves room for two CTAs of small tables
-    P.staged_points = n_points < max_stage ? n_points : max_stage;
+    P.H = average ? 1 : 0;
+    P.TZ = Z < 32 ? (int)Z : 32;
+    const int tiles_x = (int)((X + BAKE_T - 1) / BAKE_T);
+    P.tiles_y = (int)((Y + BAKE_T - 1) / BAKE_T);
+    P.tiles_z = (int)((Z + P.TZ - 1) / P.TZ);
     P.an[0] = anisotropy[0]; P.an[1] = anisotropy[1]; P.an[2] = anisotropy[2];
-    P.ids = ids; P.offsets = offsets; P.points = points_xyzw; P.status = status;
-    const long long V = X * Y * Z;
-    const size_t smem = (size_t)P.staged_points * 16;
+    P.ids = ids; P.id_begin = id_begin; P.offsets = offsets; P.points = points_xyzw; P.status = status;
+    P.V = X * Y * Z;
+    const long long tiles = (long long)tiles_x * P.tiles_y * P.tiles_z;
+    SKB_REQUIRE(tiles < (1LL << 31), "skb_bake_skeletons: too many tiles");
+    const int RN = (BAKE_T + 2 * P.H) * (BAKE_T + 2 * P.H) * (P.TZ + 2 * P.H);
+    const size_t smem = (size_t)BAKE_ARENA * 16 + (size_t)RN * 5 * 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaMemsetAsync(status, 0, sizeof(uint32_t), st);
-    const unsigned nb = (unsigned)((V + 255) / 256);
-#define BAKE_LAUNCH(MT)                                                                                             \
-    do {                                                                                                            \
-        cudaFuncSetAttribute(bake_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-        bake_kernel<MT><<<nb, 256, smem, st>>>(static_cast<const MT*>(mask), baked, distance, P, V);                \
+    const dim3 grid((unsigned)tiles, (unsigned)B);
+#define BAKE_LAUNCH(MT)                                                                                               \
+    do {                                                                                                              \
+        cudaFuncSetAttribute(bake_tile_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        bake_tile_kernel<MT><<<grid, 256, smem, st>>>(static_cast<const MT*>(masks), baked, distance, P);             \
     } while (0)
     if (mask_dtype == SKB_I32) BAKE_LAUNCH(int32_t);
     else if (mask_dtype == SKB_I16) BAKE_LAUNCH(int16_t);
-    else if (mask_dtype == SKB_U8) BAKE_LAUNCH(uint8_t);
-    else SKB_REQUIRE(false, "skb_bake_skeleton: mask dtype must be u8, i16 or i32");
-    SKB_LAUNCH_CHECK("bake_kernel");
+    else BAKE_LAUNCH(uint8_t);
+    SKB_LAUNCH_CHECK("bake_tile_kernel");
     return SKB_OK;
 }
 

@@ -77,16 +77,61 @@ def average_baked_skeletons(baked_skeleton: Tensor, kernel_size: int = 3) -> Ten
     return out
 
 
-def _pack_skeletons(skeletons: Dict[int, Tensor], device):
-    ids = sorted(int(k) for k in skeletons.keys())
-    lens = [int(skeletons[k].shape[0]) for k in ids]
-    offsets = np.zeros(len(ids) + 1, dtype=np.int32)
-    offsets[1:] = np.cumsum(lens)
-    n = int(offsets[-1])
-    pts = torch.zeros((max(n, 1), 4), dtype=torch.float32, device=device)
-    if n:
-        pts[:n, :3] = torch.cat([skeletons[k].to(device=device, dtype=torch.float32).reshape(-1, 3) for k in ids], 0)
-    return (torch.tensor(ids, dtype=torch.int32, device=device), torch.from_numpy(offsets).to(device), pts, n)
+def _pack_batch(skeletons_list, device):
+    """id / offset tables of a batch of skeleton dicts: built on the host from the dicts' keys and the tensors' SHAPES
+    (no device read), sent up as ONE small int32 array; the points of all samples are concatenated on the device."""
+    ids, lens, begin, tensors = [], [], [0], []
+    for sk in skeletons_list:
+        keys = sorted(int(k) for k in sk.keys())
+        for k in keys:
+            t = sk[k]
+            ids.append(k)
+            lens.append(int(t.shape[0]))
+            if t.shape[0]:
+                tensors.append(t)
+        begin.append(len(ids))
+    n_ids, n_pts = len(ids), int(sum(lens))
+    table = np.zeros(n_ids + len(begin) + n_ids + 1, dtype=np.int32)
+    table[:n_ids] = ids
+    table[n_ids:n_ids + len(begin)] = begin
+    if n_ids:
+        np.cumsum(lens, out=table[n_ids + len(begin) + 1:])
+    table_d = torch.from_numpy(table).to(device, non_blocking=True)
+    pts = torch.zeros((max(n_pts, 1), 4), dtype=torch.float32, device=device)
+    if n_pts:
+        pts[:n_pts, :3].copy_(torch.cat([t.to(device=device, dtype=torch.float32).reshape(-1, 3) for t in tensors], 0))
+    return table_d[:n_ids], table_d[n_ids:n_ids + len(begin)], table_d[n_ids + len(begin):], pts, n_ids, n_pts
+
+
+def bake_skeletons_batch(masks, skeletons_list, anisotropy: Tuple[float, float, float] = (1.0, 1.0, 1.0), average: bool = True,
+                         return_distance: bool = False, check: bool = True):
+    """`bake_skeleton` for a whole batch in ONE launch: masks (B,X,Y,Z) tensor (or a list of (X,Y,Z) / (1,X,Y,Z) tensors of
+    one shape), skeletons_list = one `Dict[int, Tensor[M,3]]` per sample.  Returns (B,3,X,Y,Z) fp32 (and (B,1,X,Y,Z)
+    distances).  The status word is read ONCE for the batch (check=False: not at all; the caller owns the check).
+    Semantics per sample = the reference's CPU path (skeleton.py:370-445) followed by average_baked_skeletons."""
+    if not isinstance(masks, torch.Tensor):
+        masks = torch.stack([m.squeeze(0) if m.ndim == 4 else m for m in masks])
+    dev = L.require_cuda(masks)
+    assert masks.ndim == 4 and masks.shape[0] == len(skeletons_list), "one skeleton dict per sample"
+    m = masks if masks.dtype in (torch.int32, torch.int16, torch.uint8) else masks.to(torch.int32)
+    m = m.contiguous()
+    B, X, Y, Z = m.shape
+    ids, begin, offsets, pts, n_ids, n_pts = _pack_batch(skeletons_list, dev)
+    baked = torch.empty((B, 3, X, Y, Z), dtype=torch.float32, device=dev)
+    dist = torch.empty((B, 1, X, Y, Z), dtype=torch.float32, device=dev) if return_distance else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().skb_bake_skeletons(m.data_ptr(), L.dtype_code(m), B, X, Y, Z, ids.data_ptr(), begin.data_ptr(),
+                                            offsets.data_ptr(), n_ids, pts.data_ptr(), n_pts, L.f3(anisotropy), int(bool(average)),
+                                            baked.data_ptr(), L.ptr(dist), status.data_ptr(), L.stream_ptr(dev)))
+    if check and int(status.item()) & L.STATUS_MISSING_ID:
+        for b in range(B):
+            present = set(torch.unique(m[b]).tolist()) - {0}
+            missing = sorted(present - set(int(k) for k in skeletons_list[b]))
+            if missing:
+                raise KeyError(missing[0])
+        raise KeyError("mask id without a skeleton")
+    return (baked, dist) if return_distance else baked
 
 
 def bake_skeleton(masks: Tensor, skeletons: Dict[int, Tensor], anisotropy: Tuple[float, float, float] = (1.0, 1.0, 1.0),
@@ -94,7 +139,10 @@ def bake_skeleton(masks: Tensor, skeletons: Dict[int, Tensor], anisotropy: Tuple
     """Drop-in for skoots.lib.skeleton.bake_skeleton (:448-528) with the CPU/torch semantics
     (anisotropy scales coordinates, first minimum wins, fp32 out — SURVEY A.5).  `device` is
     accepted and ignored like the reference's positional mix-up (:507); the work runs on
-    masks.device, which must be CUDA.  return_distance=True also returns the (1,X,Y,Z) distance."""
+    masks.device (host tensors are staged through the GPU).  return_distance=True also returns the (1,X,Y,Z)
+    distance.  One kernel launch (nearest point + the masked 27-mean fused) and one status read — the reference raises
+    KeyError synchronously for a mask id without a skeleton (:422), so does this; `bake_skeletons_batch` does a whole
+    batch with one launch and one read."""
     dev, staged = L.compute_device(masks)
     if staged:
         return L.stage_out(bake_skeleton(L.stage_in(masks, dev), skeletons, anisotropy, average, device, return_distance), True)
@@ -104,24 +152,8 @@ def bake_skeleton(masks: Tensor, skeletons: Dict[int, Tensor], anisotropy: Tuple
     if masks.ndim == 4 and masks.shape[0] == 1:
         masks = masks.squeeze(0)
     assert masks.ndim == 3, f"masks must be 3d with no batch. not {masks.shape=}"
-    m = masks if masks.dtype in (torch.int32, torch.int16, torch.uint8) else masks.to(torch.int32)
-    m = m.contiguous()
-    X, Y, Z = m.shape
-    ids, offsets, pts, n_pts = _pack_skeletons(skeletons, dev)
-    baked = torch.empty((3, X, Y, Z), dtype=torch.float32, device=dev)
-    dist = torch.empty((1, X, Y, Z), dtype=torch.float32, device=dev) if return_distance else None
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        L.check(L.load().skb_bake_skeleton(m.data_ptr(), L.dtype_code(m), X, Y, Z, ids.data_ptr(), offsets.data_ptr(),
-                                           ids.numel(), pts.data_ptr(), n_pts, L.f3(anisotropy), baked.data_ptr(),
-                                           L.ptr(dist), status.data_ptr(), L.stream_ptr(dev)))
-    if int(status.item()) & L.STATUS_MISSING_ID:
-        present = set(torch.unique(m).tolist()) - {0}
-        missing = sorted(present - set(int(k) for k in skeletons))
-        raise KeyError(missing[0] if missing else "mask id without a skeleton")
-    if average:
-        baked = average_baked_skeletons(baked.unsqueeze(0)).squeeze(0)
-    return (baked, dist) if return_distance else baked
+    out = bake_skeletons_batch(masks.unsqueeze(0), [skeletons], anisotropy, average, return_distance)
+    return (out[0][0], out[1][0]) if return_distance else out[0]
 
 
 def skeleton_to_mask(skeletons: Dict[int, Tensor], shape: Tuple[int, int, int], device=None, radius: int = 7,
@@ -139,7 +171,10 @@ def skeleton_to_mask(skeletons: Dict[int, Tensor], shape: Tuple[int, int, int], 
     X, Y, Z = (int(s) for s in shape)
     out = torch.zeros((X, Y, Z), dtype=torch.float32, device=dev)
     pts = torch.cat([v.to(device=dev, dtype=torch.float32).reshape(-1, 3) for v in skeletons.values()], 0).contiguous()
-    off = get_cached_disk_coords(dev, radius, flank_radius).T.to(torch.int32).contiguous()
+    key = ("i32", str(dev), int(radius), int(flank_radius))
+    off = _DISK_CACHE.get(key)
+    if off is None:  # (S,3) int32 form of the cached stamp, built once per (device, radius, flank)
+        off = _DISK_CACHE[key] = get_cached_disk_coords(dev, radius, flank_radius).T.to(torch.int32).contiguous()
     with torch.cuda.device(dev):
         L.check(L.load().skb_stamp_disks(pts.data_ptr(), pts.shape[0], off.data_ptr(), off.shape[0], X, Y, Z,
                                          out.data_ptr(), L.stream_ptr(dev)))

@@ -200,7 +200,8 @@ class ShardedAssembler:
     walks are confined to its 500x500x50 crops and need vector halos as well."""
 
     def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
-                 decay: float = 1.0, crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0), comm=None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
+                 decay: float = 1.0, crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0), comm=None,
+                 halo: Optional[int] = None, cap_roots: int = 1 << 18, cap_pairs: int = 1 << 17, cap_runs: Optional[int] = None,
                  out_dtype=torch.int32, split: Optional[bool] = None):
         X, Y, Z = (int(v) for v in shape)
         self.hops, self.decay = int(hops), float(decay)

@@ -381,3 +381,103 @@ def test_int16_instance_labels_overflow_is_reported():
     out = assemble_instances(mask, vec, torch.tensor((60, 60, 12)), N=1, out_dtype=torch.int32)
     assert int(out.max()) == 32768 + 2 and int((out > 0).sum()) == 32768
 
+
+
+# ---- round 2 kernels: batched bake, vectorised probability / embedding kernels on ragged rows, separable epilogue ----
+@pytest.mark.parametrize("shape", [(40, 36, 20), (21, 19, 70)])
+def test_bake_skeletons_batch_matches_oracle(shape):
+    """one launch for a batch: nearest point + fused masked 27-mean per sample == the oracle per sample (bit-exact points,
+    1e-5 averaged), distances, uneven tiles, and Z > 32 (more than one tile along z)."""
+    from skoots_b200.lib.skeleton import bake_skeleton, bake_skeletons_batch
+    vols = [make_tube_volume(shape, 10, seed=s, radius=3.0) for s in range(3)]
+    present = [{int(k): t.skeletons[int(k)] for k in torch.unique(t.mask).tolist() if k != 0} for t in vols]
+    masks = torch.stack([t.mask for t in vols]).to(DEV)
+    sk_d = [{k: v.to(DEV) for k, v in d.items()} for d in present]
+    an = (1.0, 1.0, 3.0)
+    raw, dist = bake_skeletons_batch(masks, sk_d, an, average=False, return_distance=True)
+    avg = bake_skeletons_batch(masks, sk_d, an, average=True)
+    assert raw.shape == (3, 3) + shape and dist.shape == (3, 1) + shape
+    for b in range(3):
+        want = orc.bake_skeleton(vols[b].mask, present[b], an, average=False)
+        assert torch.equal(raw[b].cpu(), want), b
+        d = ((want - torch.stack(torch.meshgrid(*[torch.arange(n, dtype=torch.float32) for n in shape], indexing="ij")))
+             * torch.tensor(an).view(3, 1, 1, 1)).pow(2).sum(0).sqrt() * (vols[b].mask != 0)
+        np.testing.assert_allclose(dist[b, 0].cpu().numpy(), d.numpy(), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(avg[b].cpu().numpy(), orc.bake_skeleton(vols[b].mask, present[b], an, average=True).numpy(),
+                                   rtol=1e-5, atol=1e-6)
+        assert torch.equal(bake_skeleton(masks[b], sk_d[b], an, average=False), raw[b])     # the per-sample call is B = 1 of the same kernel
+    with pytest.raises(KeyError):
+        bake_skeletons_batch(masks, [sk_d[0], {k: v for k, v in list(sk_d[1].items())[1:]}, sk_d[2]], an)
+
+
+def test_bake_many_ids_per_tile_and_long_skeletons():
+    """more distinct ids in one 8x8 tile than the CTA's shared-memory list holds, and skeletons longer than its arena:
+    both fall back to reading the table through the cache — same result."""
+    from skoots_b200.lib.skeleton import bake_skeletons_batch
+    g = torch.Generator().manual_seed(5)
+    shape = (24, 24, 20)
+    mask = torch.randint(0, 120, shape, generator=g, dtype=torch.int32)          # confetti: ~100 ids per tile
+    sk = {k: torch.randint(0, 24, (int(torch.randint(1, 6, (1,), generator=g)), 3), generator=g).float() for k in range(1, 120)}
+    sk[7] = torch.randint(0, 24, (2000, 3), generator=g).float()                 # longer than the 1536-point arena
+    sk[8] = torch.zeros((0, 3))                                                   # an id with an empty skeleton bakes to 0
+    mask[mask == 8] = 0
+    got = bake_skeletons_batch(mask[None].to(DEV), [{k: v.to(DEV) for k, v in sk.items()}], (1.0, 2.0, 3.0), average=False)
+    want = orc.bake_skeleton(mask, {k: v for k, v in sk.items() if v.shape[0]}, (1.0, 2.0, 3.0), average=False)
+    assert torch.equal(got[0].cpu(), want)
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
+def test_vectorised_kernels_on_rows_that_are_not_multiples_of_8(dt):
+    """Z = 20 (the training crop): an 8-element group runs over row ends; the 16-byte kernels must give what the
+    scalar kernels give (Z = 21: plane not a multiple of 8 -> scalar path) and what the oracle gives."""
+    from skoots_b200.lib.embedding_to_prob import baked_embed_to_prob, vector_to_prob
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    g = torch.Generator().manual_seed(11)
+    scale, sigma = torch.tensor((60.0, 60.0, 12.0)), torch.tensor((20.0, 15.0, 6.0))
+    for shape in ((2, 3, 14, 6, 20), (2, 3, 7, 5, 21)):
+        vec = (torch.rand(shape, generator=g) * 2 - 1).to(dt)
+        baked = (torch.rand(shape, generator=g) * 30).to(dt)
+        emb_want = orc.vector_to_embedding(scale, vec)
+        emb = vector_to_embedding(scale, vec.to(DEV))
+        assert torch.equal(emb.cpu(), emb_want), shape
+        want = orc.baked_embed_to_prob(emb_want, baked, sigma)
+        got = baked_embed_to_prob(emb, baked.to(DEV), sigma)
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-30)
+        assert torch.equal(vector_to_prob(scale, vec.to(DEV), baked.to(DEV), sigma), got)
+    # gradients of the 8-wide kernels against autograd through the oracle formula (fp32)
+    vec = (torch.rand((2, 3, 14, 6, 20), generator=g) * 2 - 1)
+    baked = torch.rand((2, 3, 14, 6, 20), generator=g) * 30
+    w = torch.rand((2, 1, 14, 6, 20), generator=g)
+    v_ref = vec.clone().requires_grad_(True)
+    (orc.baked_embed_to_prob(orc.vector_to_embedding(scale, v_ref), baked, sigma) * w).sum().backward()
+    v_cu = vec.to(DEV).requires_grad_(True)
+    (vector_to_prob(scale, v_cu, baked.to(DEV), sigma) * w.to(DEV)).sum().backward()
+    np.testing.assert_allclose(v_cu.grad.cpu().numpy(), v_ref.grad.numpy(), rtol=2e-5, atol=1e-12)
+    e_cu = orc.vector_to_embedding(scale, vec).to(DEV).requires_grad_(True)
+    b_cu = baked.to(DEV).requires_grad_(True)
+    (baked_embed_to_prob(e_cu, b_cu, sigma) * w.to(DEV)).sum().backward()
+    e_ref = orc.vector_to_embedding(scale, vec).requires_grad_(True)
+    b_ref = baked.clone().requires_grad_(True)
+    (orc.baked_embed_to_prob(e_ref, b_ref, sigma) * w).sum().backward()
+    np.testing.assert_allclose(e_cu.grad.cpu().numpy(), e_ref.grad.numpy(), rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose(b_cu.grad.cpu().numpy(), b_ref.grad.numpy(), rtol=2e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("tile,origin,ov", [((40, 37, 12), (3, 2, 1), (6, 5, 2)), ((20, 20, 40), (0, 0, 0), (3, 3, 1)),
+                                            ((33, 18, 7), (1, 0, 2), (1, 1, 1))])
+def test_separable_tile_epilogue_random_tiles(tile, origin, ov):
+    """the shared-memory separable box max against the oracle's replay of eval.py:145-176: negative values (zero joins the
+    max only at the tile border), blocks cut by the interior's end, several z blocks."""
+    from skoots_b200.pipeline import tile_epilogue
+    g = torch.Generator().manual_seed(sum(tile))
+    for dt in (torch.float32, torch.float16):
+        unet = torch.rand((1, 6) + tile, generator=g)
+        unet[:, 0:3] = unet[:, 0:3] * 2 - 1
+        unet[:, -2] = unet[:, -2] * 2 - 0.7            # skeleton channel with negatives
+        unet = unet.to(dt)
+        X, Y, Z = (origin[a] + tile[a] + 2 for a in range(3))
+        wv, ws = torch.zeros((3, X, Y, Z), dtype=torch.float16), torch.zeros((1, X, Y, Z), dtype=torch.uint8)
+        orc.tile_epilogue(unet, wv, ws, origin, ov)
+        gv, gs = torch.zeros_like(wv, device=DEV), torch.zeros_like(ws, device=DEV)
+        tile_epilogue(unet.to(DEV), gv, gs, origin, ov)
+        assert torch.equal(gs.cpu(), ws) and torch.equal(gv.cpu(), wv), (tile, dt)

@@ -182,7 +182,7 @@ def main():
     # ties), so it is raced, not compared bit for bit.
     try:
         import ref_shim
-        ref_shim.install()
+        ref_shim.install(need_morphology=False)
         import skoots.lib.skeleton as ref_skel
         masks_i = [m.contiguous() for m in masks_d]
         ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False)  # compile

@@ -142,6 +142,17 @@ int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int64_t Y, int
                        int label_dtype, void* out, int out_dtype, int64_t first_voxel,
                        int64_t n_voxels, void* stream);
 
+/* a10  2-D mode (BASELINE.json configs[4]): a stack of S independent images.  The reference has no 2-D gather of
+ *   its own (index_skeleton_by_embed asserts 5-D input, skoots/lib/skeleton.py:671-673): the 2-D gather is its 3-D
+ *   function applied per slice with Z = 1, on _vec2embed2D's embedding (vector_to_embedding.py:50-76):
+ *   out[s,x,y] = labels[s, clamp(rint(x + v[s,0,x,y]*scale0), 0, X-1), clamp(rint(y + v[s,1,x,y]*scale1), 0, Y-1)].
+ *   vec (S,2,X,Y) f16|bf16|f32; labels = the workspace of skb_ccl_label_sparse(planar = 1) over the (S,X,Y) stack
+ *   (4-connectivity, numbering restarts per slice — utils/flood_and_stitch.py:63-69) or a dense (S,X,Y) volume;
+ *   out (S,X,Y) i32|i16. */
+int skb_assemble_planar(const void* vec, int vec_dtype, int64_t S, int64_t X, int64_t Y, const float scale[2],
+                        const void* workspace, const void* labels_dense, int label_dtype, void* out,
+                        int out_dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a4  binary_dilation / binary_dilation_2d / binary_erosion     skoots/lib/morphology.py:130-199
  *   zero-padded 3x3x3 max (op 0), 3x3x1 max (op 1), 3x3x3 min (op 2) over n_volumes = B*C

@@ -95,6 +95,28 @@ def ref_tile_epilogue(out, vectors, skeleton, origin, overlap, cropsize):
     skeleton[dst] = skel[src].gt(0.8).to(torch.uint8)
 
 
+def gen_2d(g=None):
+    """a10, 2-D mode (BASELINE configs[4]): per-slice scipy label (utils/flood_and_stitch.py:63-69), the reference's
+    2-D vector_to_embedding and — it has no 2-D gather — its index_skeleton_by_embed applied per slice with Z = 1."""
+    from scipy.ndimage import label as ndi_label
+    g = g or torch.Generator().manual_seed(4321)
+    tv = make_tube_volume((3, 72, 64), 30, seed=9, flat=True, scale=(1.0, 12.0, 12.0))
+    noise = (torch.rand((3, 72, 64), generator=g) < 0.03).to(torch.uint8)
+    masks = torch.maximum(tv.skeleton, noise)
+    vec = tv.vectors[1:3].permute(1, 0, 2, 3).contiguous().float()     # (S,2,X,Y): the in-plane components
+    vec[0, :, :8] *= 6.0                                                 # targets far outside the image: clamp to the border
+    scale = torch.tensor((12.0, 12.0))
+    out = np.zeros((3, 72, 64), dtype=np.int32)
+    for s_ in range(3):
+        plane = (masks[s_].numpy() > 0).astype(np.int32)
+        ndi_label(plane, output=plane)                                   # flood_and_stitch.py:66-69
+        emb2 = ref_v2e(scale, vec[s_][None])
+        emb3 = torch.cat([emb2, torch.zeros((1, 1, 72, 64))], dim=1).unsqueeze(-1)
+        lab5 = torch.from_numpy(plane)[None, None, :, :, None]
+        out[s_] = ref_index(lab5, emb3)[0, 0, :, :, 0].numpy()
+    save("assembly_2d", masks=np.packbits(masks.numpy()), shape=np.array(masks.shape), vectors=vec.numpy(), scale=scale.numpy(), out=out)
+
+
 def main():
     g = torch.Generator().manual_seed(1234)
 
@@ -179,6 +201,8 @@ def main():
     emb = ref_v2e(scale, tva.vectors[None], N=4)
     pack["inst_whole_N4"] = ref_index(labels[None, None], emb)[0, 0].numpy()
     save("assembly", **pack)
+
+    gen_2d(g)
 
     # ---- a7: baked_embed_to_prob ------------------------------------------------------------------------
     E = torch.rand((2, 3, 9, 8, 7), generator=g) * 30

@@ -339,6 +339,22 @@ def postprocess(skeleton_mask: torch.Tensor, vectors: torch.Tensor, scale, N: in
                               crop=dims if crop is None else crop, overlap=overlap, out_dtype=out_dtype)
 
 
+def postprocess_2d(skeleton_masks: torch.Tensor, vectors: torch.Tensor, scale, label_base: int = 0) -> torch.Tensor:
+    """2-D mode (BASELINE configs[4]) slice by slice: `scipy.ndimage.label` of the plane (4-connectivity,
+    utils/flood_and_stitch.py:63-69), `_vec2embed2D` (vector_to_embedding.py:50-76), and — the reference has no 2-D
+    gather (skeleton.py:671-673 asserts 5-D) — `index_skeleton_by_embed` with Z = 1.  masks (S,X,Y), vectors (S,2,X,Y)."""
+    S, X, Y = skeleton_masks.shape
+    out = torch.zeros((S, X, Y), dtype=torch.int32)
+    for s in range(S):
+        lab, _ = label_components(skeleton_masks[s].numpy())
+        lab = torch.from_numpy(lab.astype(np.int32))
+        lab = torch.where(lab > 0, lab + label_base, lab)
+        emb2 = vector_to_embedding(scale, vectors[s][None])                              # (1,2,X,Y)
+        emb3 = torch.cat([emb2, torch.zeros((1, 1, X, Y))], dim=1).unsqueeze(-1)         # (1,3,X,Y,1)
+        out[s] = index_skeleton_by_embed(lab[None, None, :, :, None], emb3)[0, 0, :, :, 0]
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # a7: embedding -> probability                        skoots/lib/embedding_to_prob.py
 # --------------------------------------------------------------------------------------

@@ -29,6 +29,8 @@ struct AsmParams {
     const ull* halo_hi;
     int label_halo;         // slab mode: how many planes beyond each face the halo words really describe (0 = not checked)
     unsigned* status;       // slab mode: SKB_STATUS_HALO_RANGE is OR-ed in when a target lies beyond them (may be NULL)
+    int planar;             // 2-D mode: the volume is a stack (X = slices, Y, Z = image axes) and `vec` is (slices, 2, Y, Z):
+    long long plane;        //   two channels per slice, `plane` = Y * Z elements each; the slice axis never moves
     const void* vhalo_lo;   // slab mode, N > 1: the vector field's planes [z_off - vh, z_off) / [z_off+Zl, z_off+Zl+vh) as
     const void* vhalo_hi;   //   (3,X,Y,vh) arrays (the Z-neighbours' faces), read by hops that leave the slab inside their crop
     int vh;
@@ -260,9 +262,34 @@ __device__ __forceinline__ ChunkRegs<VecT> load_chunk(const AsmParams& P, long l
     const unsigned uz = (unsigned)P.Zl;
     ChunkRegs<VecT> c;
     // every independent load is issued before anything waits on one of them
-    c.r0 = load_raw8<VecT, FULL>(P.vec, i0, nvalid);
-    c.r1 = load_raw8<VecT, FULL>(P.vec, i0 + P.cstride, nvalid);
-    c.r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
+    if (P.planar) {
+        // (slices, 2, Y, Z): the slice's two channels are the y / z components; the x (slice) component is zero
+#pragma unroll
+        for (int k = 0; k < Raw8<VecT>::NW; ++k) c.r0.w[k] = 0u;
+        if (FULL) {  // plane % 8 == 0: the 8 voxels share a slice
+            const long long sl = i0 / P.plane, a0 = sl * 2 * P.plane + (i0 - sl * P.plane);
+            c.r1 = load_raw8<VecT, true>(P.vec, a0, 8);
+            c.r2 = load_raw8<VecT, true>(P.vec, a0 + P.plane, 8);
+        } else {
+            typedef typename RawOf<VecT>::type raw_t;
+#pragma unroll
+            for (int k = 0; k < Raw8<VecT>::NW; ++k) { c.r1.w[k] = 0u; c.r2.w[k] = 0u; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < nvalid) {
+                    const long long i = i0 + j, sl = i / P.plane, a = sl * 2 * P.plane + (i - sl * P.plane);
+                    const unsigned e1 = (unsigned)__ldg(static_cast<const raw_t*>(P.vec) + a);
+                    const unsigned e2 = (unsigned)__ldg(static_cast<const raw_t*>(P.vec) + a + P.plane);
+                    if (sizeof(raw_t) == 2) { c.r1.w[j >> 1] |= e1 << (16 * (j & 1)); c.r2.w[j >> 1] |= e2 << (16 * (j & 1)); }
+                    else { c.r1.w[j] = e1; c.r2.w[j] = e2; }
+                }
+            }
+        }
+    } else {
+        c.r0 = load_raw8<VecT, FULL>(P.vec, i0, nvalid);
+        c.r1 = load_raw8<VecT, FULL>(P.vec, i0 + P.cstride, nvalid);
+        c.r2 = load_raw8<VecT, FULL>(P.vec, i0 + 2 * P.cstride, nvalid);
+    }
     c.self = 0;
     if (P.fast_ok && !P.dense && nvalid > 0) {
         if (P.flat_bits) {  // no row padding: bit index == (slab-local) voxel index
@@ -898,7 +925,7 @@ static void launch_assemble_t(const AsmParams& P, OutT* out, long long v_begin, 
         // 2 CTAs/SM 4.94, 3: 3.98, 4: 3.59, 5 (48 registers): 3.80 — more streams in flight than this hurt.
         if (blocks > 148 * 4) blocks = 148 * 4;
         const char* mode = getenv("SKB_GATHER_STAGING");  // experiments: "bulk" | "ldgsts" | unset = register prefetch
-        const bool eligible = P.fast_ok && !P.dense && P.flat_bits;
+        const bool eligible = P.fast_ok && !P.dense && P.flat_bits && !P.planar;
         const int smem = ASM_WARPS * StageCfg<VecT>::WARP_BYTES;
         if (eligible && mode && mode[0] == 'b') {
             // > 48 KB of dynamic shared memory is opt-in per function (and per device): cheap, so set it every time
@@ -985,6 +1012,53 @@ extern "C" int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int
     else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, v0, v1, st);
     else launch_assemble<float>(P, out, out_dtype, v0, v1, st);
     SKB_LAUNCH_CHECK("assemble_kernel");
+    return SKB_OK;
+}
+
+// 2-D mode (BASELINE config 5): a stack of S independent images.  The reference has no 2-D gather of its own —
+// index_skeleton_by_embed asserts 5-D input (skeleton.py:671-673) — so the 2-D gather is its 3-D function applied to
+// each slice with Z = 1: out[s,x,y] = labels[s, clamp(rint(x + v0*s0)), clamp(rint(y + v1*s1))] with
+// _vec2embed2D's embedding (vector_to_embedding.py:50-76).  vec (S,2,X,Y) f16|bf16|f32, labels = the planar CCL
+// workspace of the (S,X,Y) stack (skb_ccl_label_sparse with planar = 1; per-slice numbering) or a dense (S,X,Y) volume.
+extern "C" int skb_assemble_planar(const void* vec, int vec_dtype, int64_t S, int64_t X, int64_t Y, const float scale[2],
+                                   const void* workspace, const void* labels_dense, int label_dtype, void* out,
+                                   int out_dtype, void* stream) {
+    int rc = skb_check_volume(S, X, Y, "skb_assemble_planar");
+    if (rc) return rc;
+    SKB_REQUIRE(vec && out && scale, "skb_assemble_planar: NULL pointer");
+    SKB_REQUIRE(workspace || labels_dense, "skb_assemble_planar: need a planar CCL workspace or a dense label stack");
+    SKB_REQUIRE(vec_dtype == SKB_F16 || vec_dtype == SKB_BF16 || vec_dtype == SKB_F32, "skb_assemble_planar: vec dtype");
+    SKB_REQUIRE(out_dtype == SKB_I32 || out_dtype == SKB_I16, "skb_assemble_planar: out dtype must be i32 or i16");
+    SKB_REQUIRE(skb_aligned16(out), "skb_assemble_planar: out must be 16-byte aligned");
+    if (labels_dense)
+        SKB_REQUIRE(label_dtype == SKB_I16 || label_dtype == SKB_I32 || label_dtype == SKB_U8, "skb_assemble_planar: label dtype");
+    AsmParams P = {};
+    P.vec = vec; P.vec_hops = vec;
+    P.planar = 1; P.plane = X * Y;
+    P.cstride = X * Y;
+    P.X = (int)S; P.Y = (int)X; P.Z = (int)Y;
+    P.Zl = (int)Y; P.z_off = 0;
+    P.s[0] = 0.f; P.s[1] = scale[0]; P.s[2] = scale[1];
+    P.N = 1; P.decay = 1.0;
+    const int32_t crop[3] = {(int32_t)S, (int32_t)X, (int32_t)Y}, ov[3] = {0, 0, 0};
+    fill_crop(P, crop, ov);
+    P.vec_aligned = skb_aligned16(vec) && (P.plane % 8 == 0) && ((P.plane * elem_size(vec_dtype)) % 16 == 0);
+    if (labels_dense) {
+        P.dense = labels_dense; P.dense_dtype = label_dtype;
+    } else {
+        SkbCclLayout L = skb_ccl_layout(S, X, Y, 1);
+        const char* base = static_cast<const char*>(workspace);
+        P.bits = reinterpret_cast<const ull*>(base + L.off_bits);
+        P.parent = reinterpret_cast<const int*>(base + L.off_parent);
+        P.ZW = L.ZW;
+        P.flat_bits = (Y % 64 == 0) ? 1 : 0;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long V = S * X * Y;
+    if (vec_dtype == SKB_F16) launch_assemble<__half>(P, out, out_dtype, 0, V, st);
+    else if (vec_dtype == SKB_BF16) launch_assemble<__nv_bfloat16>(P, out, out_dtype, 0, V, st);
+    else launch_assemble<float>(P, out, out_dtype, 0, V, st);
+    SKB_LAUNCH_CHECK("assemble_kernel (planar)");
     return SKB_OK;
 }
 

@@ -165,15 +165,15 @@ __device__ __forceinline__ float epi_load(const void* base, long long idx) {
 // Round 1 took the 7 x 7 x 3 box max by brute force: 147 taps x 2 loads per output voxel (84 us per 300x300x20 tile).
 // A box max is separable: a CTA owns a 16 x 16 x bz block of interior outputs, stages the masked skeleton values of the
 // block plus its (3,3,1) apron in shared memory once (-inf outside the tile: it never wins), and reduces along z (3 taps),
-// y (7) and x (7) in shared memory — 2 global loads per staged voxel instead of 294 per output.
+// y (7) and x (7) — the z pass in registers while staging, y and x in shared memory — 2 global loads per staged voxel
+// instead of 294 per output.
 constexpr int EPI_BX = 16, EPI_BY = 16, EPI_BZ = 16, EPI_RX = EPI_BX + 6, EPI_RY = EPI_BY + 6;
 
 template <typename T>
 __global__ void __launch_bounds__(256) tile_epilogue_kernel(EpiParams P, int bz, int nby, int nbz) {
     extern __shared__ float epi_smem[];
-    const int rz = bz + 2;
-    float* A = epi_smem;                          // [RX][RY][bz+2] staged values, later [RX][BY][bz] (after the y pass)
-    float* B = epi_smem + EPI_RX * EPI_RY * rz;   // [RX][RY][bz]   after the z pass
+    float* B = epi_smem;                          // [RX][RY][bz]  masked skeleton after the z pass
+    float* A = epi_smem + EPI_RX * EPI_RY * bz;   // [RX][BY][bz]  after the y pass
     int t = blockIdx.x;
     const int kz = t % nbz; t /= nbz;
     const int ky = t % nby, kx = t / nby;
@@ -184,28 +184,30 @@ __global__ void __launch_bounds__(256) tile_epilogue_kernel(EpiParams P, int bz,
     const void* prob = static_cast<const char*>(P.unet) + (size_t)(P.C - 1) * plane * sizeof(T);
     const void* skel = static_cast<const char*>(P.unet) + (size_t)(P.C - 2) * plane * sizeof(T);
 
-    // stage: (skel.float() * (prob > thr)) over the block + apron (eval.py:146-150)
-    const int n_stage = EPI_RX * EPI_RY * rz;
-    for (int i = threadIdx.x; i < n_stage; i += 256) {
-        const int z = i % rz, q = i / rz, y = q % EPI_RY, x = q / EPI_RY;
-        const int xx = lx0 - 3 + x, yy = ly0 - 3 + y, zz = lz0 - 1 + z;
-        float v = -INFINITY;
-        if (xx >= 0 && xx < P.tx && yy >= 0 && yy < P.ty && zz >= 0 && zz < P.tz) {
-            const long long at = ((long long)xx * P.ty + yy) * P.tz + zz;
-            v = epi_load<T>(skel, at) * (epi_load<T>(prob, at) > P.thr ? 1.f : 0.f);
+    // stage + z pass: one thread per (x, y) row of the block + apron.  It reads the row's bz + 2 values of
+    // (skel.float() * (prob > thr)) (eval.py:146-150; -inf outside the tile: never wins) — all loads of a row are
+    // independent and issued together — and stores the 3-tap z maxima.
+    for (int row = threadIdx.x; row < EPI_RX * EPI_RY; row += 256) {
+        const int y = row % EPI_RY, x = row / EPI_RY;
+        const int xx = lx0 - 3 + x, yy = ly0 - 3 + y;
+        float v[EPI_BZ + 2];
+        const bool inside = xx >= 0 && xx < P.tx && yy >= 0 && yy < P.ty;
+        const long long at0 = ((long long)xx * P.ty + yy) * P.tz;
+#pragma unroll
+        for (int k = 0; k < EPI_BZ + 2; ++k) {
+            const int zz = lz0 - 1 + k;
+            float s_ = 0.f, p_ = 0.f;
+            const bool ok = inside && k < bz + 2 && zz >= 0 && zz < P.tz;
+            if (ok) { s_ = epi_load<T>(skel, at0 + zz); p_ = epi_load<T>(prob, at0 + zz); }
+            v[k] = ok ? s_ * (p_ > P.thr ? 1.f : 0.f) : -INFINITY;
         }
-        A[i] = v;
-    }
-    __syncthreads();
-    const int n_z = EPI_RX * EPI_RY * bz;
-    for (int i = threadIdx.x; i < n_z; i += 256) {
-        const int z = i % bz, q = i / bz;
-        const float* a = A + q * rz + z;
-        B[i] = fmaxf(fmaxf(a[0], a[1]), a[2]);
+#pragma unroll
+        for (int k = 0; k < EPI_BZ; ++k)
+            if (k < bz) B[row * bz + k] = fmaxf(fmaxf(v[k], v[k + 1]), v[k + 2]);
     }
     __syncthreads();
     const int n_y = EPI_RX * EPI_BY * bz;
-    for (int i = threadIdx.x; i < n_y; i += 256) {  // A is free again: [RX][BY][bz]
+    for (int i = threadIdx.x; i < n_y; i += 256) {
         const int z = i % bz, q = i / bz, y = q % EPI_BY, x = q / EPI_BY;
         const float* b0 = B + (x * EPI_RY + y) * bz + z;
         float m = b0[0];
@@ -297,7 +299,7 @@ extern "C" int skb_tile_epilogue(const void* unet, int in_dtype, int C, const in
     const int nbx = (ix + EPI_BX - 1) / EPI_BX, nby = (iy + EPI_BY - 1) / EPI_BY, nbz = (iz + bz - 1) / bz;
     const long long blocks = (long long)nbx * nby * nbz;
     SKB_REQUIRE(blocks < (1LL << 31), "skb_tile_epilogue: tile too large");
-    const int smem = (int)sizeof(float) * EPI_RX * EPI_RY * (2 * bz + 2);
+    const int smem = (int)sizeof(float) * (EPI_RX * EPI_RY + EPI_RX * EPI_BY) * bz;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define EPI_LAUNCH(T)                                                                                          \
     do {                                                                                                       \

@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
     __syncthreads();
 
     // A. region voxels -> slot of their object in the CTA's id list (-1 background, <= -2: id index -2-v, list full)
+    int any_fg = 0;
     for (int i = threadIdx.x; i < RN; i += 256) {
         const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
         const int gx = x0 + rx, gy = y0 + ry, gz = z0 + rz;
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
                 if (found < 0) {
                     atomicOr(P.status, SKB_STATUS_MISSING_ID);
                 } else {
+                    any_fg = 1;
                     slot = -2 - found;
                     for (int k = 0; k < BAKE_MAXU; ++k) {
                         int cur = *reinterpret_cast<volatile int*>(&s_present[k]);
@@ -492,29 +494,47 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
         }
         s_slot[i] = slot;
     }
-    __syncthreads();
+    // most tiles of an instance mask hold no object at all (and neither does their halo): their output is zero
+    if (!__syncthreads_or(any_fg)) {
+        const int TN0 = BAKE_T * BAKE_T * P.TZ;
+        float* out0 = baked + (long long)b * 3 * P.V;
+        for (int i = threadIdx.x; i < TN0; i += 256) {
+            const int lz = i % P.TZ, q = i / P.TZ, ly = q % BAKE_T, lx = q / BAKE_T;
+            const int gx = tx * BAKE_T + lx, gy = ty * BAKE_T + ly, gz = tz * P.TZ + lz;
+            if (gx >= P.X || gy >= P.Y || gz >= P.Z) continue;
+            const long long g = ((long long)gx * P.Y + gy) * P.Z + gz;
+            out0[g] = 0.f; out0[g + P.V] = 0.f; out0[g + 2 * P.V] = 0.f;
+            if (dist_out) dist_out[(long long)b * P.V + g] = 0.f;
+        }
+        return;
+    }
 
-    // B. one thread lays the present skeletons out in the arena and starts one bulk copy per skeleton
+    // B. the present skeletons are laid out in the arena (one lane per id reads its range, thread 0 assigns the
+    //    offsets and announces the byte count), then one TMA bulk copy per skeleton
+    if (threadIdx.x < BAKE_MAXU && s_present[threadIdx.x] >= 0) {
+        const int f = s_present[threadIdx.x];
+        const int lo = __ldg(P.offsets + f);
+        s_lo[threadIdx.x] = lo;
+        s_cnt[threadIdx.x] = __ldg(P.offsets + f + 1) - lo;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         int at = 0;
         unsigned bytes = 0;
         for (int k = 0; k < BAKE_MAXU && s_present[k] >= 0; ++k) {
-            const int f = s_present[k];
-            const int lo = __ldg(P.offsets + f), cnt = __ldg(P.offsets + f + 1) - lo;
-            s_lo[k] = lo; s_cnt[k] = cnt;
+            const int cnt = s_cnt[k];
             if (cnt > 0 && at + cnt <= BAKE_ARENA) { s_at[k] = at; at += cnt; bytes += (unsigned)cnt * 16u; }
             else s_at[k] = -1;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-        for (int k = 0; k < BAKE_MAXU && s_present[k] >= 0; ++k)
-            if (s_at[k] >= 0)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 smem_u32(s_arena + s_at[k])),
-                             "l"(P.points + 4ll * s_lo[k]), "r"((unsigned)s_cnt[k] * 16u), "r"(smem_u32(&bar))
-                             : "memory");
     }
-    __syncthreads();          // s_lo / s_cnt / s_at visible
+    __syncthreads();          // s_at visible, the byte count announced
+    if (threadIdx.x < BAKE_MAXU && s_present[threadIdx.x] >= 0 && s_at[threadIdx.x] >= 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(s_arena + s_at[threadIdx.x])),
+                     "l"(P.points + 4ll * s_lo[threadIdx.x]), "r"((unsigned)s_cnt[threadIdx.x] * 16u), "r"(smem_u32(&bar))
+                     : "memory");
     mbar_wait(&bar, 0);       // the staged skeletons have landed
 
     // C. nearest point of every region voxel (first minimum of the sqrt'ed distances, like cdist + argmin)
@@ -565,6 +585,19 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
         if (P.H == 0) {
             out[g] = s_b[c]; out[g + P.V] = s_b[RN + c]; out[g + 2 * P.V] = s_b[2 * RN + c];
         } else {
+            // a window without any object voxel averages to zero (slots: -1 = background)
+            int any = 0;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dz = -1; dz <= 1; ++dz) any |= (s_slot[c + (dx * RY + dy) * RZ + dz] != -1);
+            if (!any) {
+                out[g] = 0.f; out[g + P.V] = 0.f; out[g + 2 * P.V] = 0.f;
+                if (dist_out) dist_out[(long long)b * P.V + g] = 0.f;
+                continue;
+            }
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 const float* sb = s_b + ch * RN;

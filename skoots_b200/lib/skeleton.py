@@ -99,7 +99,9 @@ def _pack_batch(skeletons_list, device):
     table_d = torch.from_numpy(table).to(device, non_blocking=True)
     pts = torch.zeros((max(n_pts, 1), 4), dtype=torch.float32, device=device)
     if n_pts:
-        pts[:n_pts, :3].copy_(torch.cat([t.to(device=device, dtype=torch.float32).reshape(-1, 3) for t in tensors], 0))
+        ready = all(t.device == device and t.dtype == torch.float32 and t.ndim == 2 for t in tensors)  # the usual case: no per-tensor work
+        pts[:n_pts, :3].copy_(torch.cat(tensors if ready else
+                                        [t.to(device=device, dtype=torch.float32).reshape(-1, 3) for t in tensors], 0))
     return table_d[:n_ids], table_d[n_ids:n_ids + len(begin)], table_d[n_ids + len(begin):], pts, n_ids, n_pts
 
 

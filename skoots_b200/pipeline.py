@@ -57,6 +57,47 @@ def gather_instances(vectors: Tensor, scale, labels, N: int = 1, decay: float = 
     return out
 
 
+def gather_instances_2d(vectors: Tensor, scale, labels, out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.int32) -> Tensor:
+    """2-D mode (BASELINE configs[4]): vectors (S,2,X,Y) f16/bf16/f32 of S independent images; labels = planar
+    SparseLabels of the (S,X,Y) stack or a dense (S,X,Y) label stack -> (S,X,Y) labels.  The reference's 2-D gather is
+    `index_skeleton_by_embed` per slice with Z = 1 on `_vec2embed2D`'s embedding (skeleton.py:656-695,
+    vector_to_embedding.py:50-76)."""
+    dev = L.require_cuda(vectors)
+    if vectors.ndim != 4 or vectors.shape[1] != 2:
+        raise RuntimeError(f"vectors must be (S,2,X,Y), got {tuple(vectors.shape)}")
+    if vectors.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+        vectors = vectors.float()
+    vectors = vectors.contiguous()
+    S, _, X, Y = vectors.shape
+    if out is None:
+        out = torch.empty((S, X, Y), dtype=out_dtype, device=dev)
+    assert out.is_contiguous() and tuple(out.shape) == (S, X, Y) and out.dtype in (torch.int32, torch.int16)
+    ws_ptr, dense_ptr, dense_code = 0, 0, 0
+    if isinstance(labels, SparseLabels):
+        assert labels.shape == (S, X, Y), "label workspace was built for another stack"
+        ws_ptr = labels.workspace.data_ptr()
+    else:
+        L.require_cuda(labels)
+        dense = labels.reshape(S, X, Y).contiguous()
+        if dense.dtype not in (torch.int16, torch.int32, torch.uint8):
+            dense = dense.to(torch.int32)
+        dense_ptr, dense_code = dense.data_ptr(), L.dtype_code(dense)
+    with torch.cuda.device(dev):
+        L.check(L.load().skb_assemble_planar(vectors.data_ptr(), L.dtype_code(vectors), S, X, Y, L.f3(as_floats(scale, 2)), ws_ptr,
+                                             dense_ptr, dense_code, out.data_ptr(), L.dtype_code(out), L.stream_ptr(dev)))
+    return out
+
+
+def assemble_instances_2d(skeleton_masks: Tensor, vectors: Tensor, scale, out_dtype: torch.dtype = torch.int32,
+                          workspace: Optional[Tensor] = None, out: Optional[Tensor] = None, check: bool = True,
+                          label_base: int = 0) -> Tensor:
+    """2-D mode end to end: per-slice connected components (4-connectivity, numbering restarting per slice at
+    label_base + 1 — `scipy.ndimage.label` on each plane, utils/flood_and_stitch.py:63-69) of the (S,X,Y) u8 stack,
+    then the fused 2-D gather.  Returns (S,X,Y) labels."""
+    sparse = label_components(skeleton_masks, planar=True, label_base=label_base, workspace=workspace, check=check)
+    return gather_instances_2d(vectors, scale, sparse, out=out, out_dtype=out_dtype)
+
+
 _CHAIN_STREAMS = {}
 
 

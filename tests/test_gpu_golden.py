@@ -189,3 +189,29 @@ def test_skeleton_to_mask():
         assert np.array_equal(get_cached_disk_coords(DEV, r, f).cpu().numpy(), fx[f"offsets_r{r}_f{f}"])
         got = skeleton_to_mask(sk, (40, 36, 8), radius=r, flank_radius=f)
         assert np.array_equal(got.cpu().numpy(), fx[f"mask_r{r}_f{f}"])
+
+
+def test_2d_mode_fused_gather_matches_reference_fixture():
+    """a10 / BASELINE configs[4]: planar CCL + the fused 2-D gather against the reference-generated fixture, then
+    ragged image sizes (no 16-byte alignment, plane not a multiple of 8) and 16-bit output against the oracle."""
+    from skoots_b200.lib.flood_fill import label_components, write_dense
+    from skoots_b200.pipeline import assemble_instances_2d, gather_instances_2d
+    fx = load_golden("assembly_2d")
+    masks = cu(unpack_mask(fx, "masks"))
+    for dt in (torch.float32, torch.float16):
+        vec = cu(fx["vectors"]).to(dt)
+        want = fx["out"] if dt == torch.float32 else orc.postprocess_2d(masks.cpu(), vec.cpu(), torch.from_numpy(fx["scale"])).numpy()
+        got = assemble_instances_2d(masks, vec, torch.from_numpy(fx["scale"]))
+        assert got.dtype == torch.int32 and np.array_equal(got.cpu().numpy(), want), dt
+    sp = label_components(masks, planar=True, label_base=0)
+    dense = torch.empty(masks.shape, dtype=torch.int32, device=DEV)
+    write_dense(sp, dense)
+    assert np.array_equal(gather_instances_2d(cu(fx["vectors"]), torch.from_numpy(fx["scale"]), dense).cpu().numpy(), fx["out"])
+    g = torch.Generator().manual_seed(2)
+    for shape in ((2, 37, 29), (5, 64, 128), (1, 8, 8)):
+        m = (torch.rand(shape, generator=g) < 0.2).to(torch.uint8)
+        v = ((torch.rand((shape[0], 2) + shape[1:], generator=g) * 2 - 1) * (torch.rand((shape[0], 2) + shape[1:], generator=g) < 0.6)).to(torch.float16)
+        scale = torch.tensor((7.0, 5.0))
+        want = orc.postprocess_2d(m, v, scale)
+        got = assemble_instances_2d(m.to(DEV), v.to(DEV), scale, out_dtype=torch.int16)
+        assert np.array_equal(got.cpu().numpy(), want.numpy().astype(np.int16)), shape

@@ -179,3 +179,11 @@ def test_renumber_restatement():
     assert remap == {0: 0, 7: 1, 3: 2, 9: 3}
     with pytest.raises(AssertionError):
         orc.mask_dice(a, a)  # identical objects: the reference's own assert fires (validate/lib.py:266-268)
+
+
+def test_2d_mode_against_reference_fixture():
+    """a10: per-slice scipy label + the reference's 2-D embedding + its gather with Z = 1 (tests/golden/assembly_2d.npz)."""
+    fx = load_golden("assembly_2d")
+    masks = torch.from_numpy(unpack_mask(fx, "masks"))
+    got = orc.postprocess_2d(masks, torch.from_numpy(fx["vectors"]), torch.from_numpy(fx["scale"]))
+    assert np.array_equal(got.numpy(), fx["out"])

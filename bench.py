@@ -400,7 +400,7 @@ def run_b200(args):
     timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     graphed = False
-    if world > 1 and not os.environ.get("SKB_NO_GRAPH"):
+    if world > 1 and not os.environ.get("SKB_NO_GRAPH") and args.hops == 1:  # N > 1 passes start with an NCCL exchange: eager
         # all ranks must agree: a rank replaying a graph and a rank issuing eagerly would still match
         # collectives, but keep the measurement uniform
         ok = torch.tensor([1 if runner.capture() else 0], device=dev)

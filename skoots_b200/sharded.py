@@ -196,8 +196,14 @@ class PeerComm:
 
 
 class ShardedAssembler:
-    """Per-rank state + the phases of one pass.  N = 1 (the headline mode): with N > 1 the reference's
-    walks are confined to its 500x500x50 crops and need vector halos as well."""
+    """Per-rank state + the phases of one pass.
+
+    N = 1 (the headline mode) needs only the label halo.  With N > 1 — `eval()` runs N = 10 over its 500x500x50 crop
+    grid, skoots/lib/eval.py:245-284 — a walk stays inside the crop that owns its voxel, so its hops can leave the slab by
+    up to crop_z - overlap_z - 1 planes (44 for eval()): every pass starts by swapping that many planes of the vector
+    field with the two Z-neighbours ("vector halo"; one NCCL send/recv pair per face, or plain copies in
+    the single-process emulation), and the label halo defaults to a whole 64-plane word because a ten-hop walk is not
+    bounded by scale_z."""
 
     def __init__(self, shape: Sequence[int], world: int, rank: int, device, scale=(60, 60, 12), hops: int = 1,
                  decay: float = 1.0, crop: Optional[Sequence[int]] = None, overlap: Sequence[int] = (0, 0, 0), comm=None,
@@ -209,12 +215,22 @@ class ShardedAssembler:
         self._overlap = L.i3(overlap) if crop is not None else None
         self.vhalo_lo = self.vhalo_hi = None
         self.vh = 0
-        if self.hops != 1:
-            raise NotImplementedError("the Z-sharded path implements N = 1")
         self.shape, self.world, self.rank, self.dev = (X, Y, Z), world, rank, torch.device(device)
         self.scale = [float(s) for s in scale]
-        self.z_range = slab_bounds(Z, world)[rank]
+        bounds = slab_bounds(Z, world)
+        self.z_range = bounds[rank]
         self.Zl = self.z_range[1] - self.z_range[0]
+        if self.hops > 1:
+            if split:
+                raise ValueError("the stream/resolve split covers N = 1 only")
+            cz = min(int(crop[2]), Z) if crop is not None else Z
+            ov_z = int(overlap[2]) if crop is not None else 0
+            self.vh = cz - ov_z - 1 if ov_z > 0 else cz - 1   # how far a hop can be from its voxel along z (it stays in the owner crop)
+            if world > 1 and self.vh > min(b[1] - b[0] for b in bounds):
+                raise ValueError(f"N > 1 over crops {cz} planes deep needs {self.vh} planes of the neighbour's vector field, "
+                                 f"more than the thinnest slab holds: use fewer ranks or the whole-volume pass")
+            if halo is None:
+                halo = min(64, self.Zl)
         # label halo: how far beyond a face this rank can answer a gather target.  The network's vectors lie in [-1, 1]
         # (vector_to_embedding.py:140), so ceil(scale_z) planes is the default; a field that exceeds it is DETECTED
         # (STATUS_HALO_RANGE -> check_status() raises) and the caller can ask for up to 64 planes
@@ -253,6 +269,7 @@ class ShardedAssembler:
             self.gathered = mk(world * exchange_layout(cap_roots, cap_pairs))
         self.meta = mk(2)  # [n_components, status]
         self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
+        self._vec_dtype = None  # vector halos are allocated when the field's dtype is known (load / run_host)
         # stream/resolve split of the gather (pipeline.assemble_split): the slab's stream phase runs on the current
         # stream while the labelling chain AND both exchanges run on a high-priority side stream
         can_split = (X * Y * self.Zl) % 256 == 0
@@ -289,6 +306,41 @@ class ShardedAssembler:
         L.require_cuda(mask_slab, vec_slab)
         self.mask = (mask_slab.view(torch.uint8) if mask_slab.dtype == torch.bool else mask_slab).contiguous()
         self.vec = vec_slab.contiguous()
+        self._alloc_vector_halos(self.vec.dtype)
+
+    def _alloc_vector_halos(self, dtype) -> None:
+        if self.hops == 1 or self.world == 1 or self._vec_dtype == dtype:
+            return
+        X, Y, _ = self.shape
+        self._vec_dtype = dtype
+        mk = lambda: torch.zeros((3, X, Y, self.vh), dtype=dtype, device=self.dev)
+        self.vhalo_lo = mk() if self.rank > 0 else None                    # planes [z0 - vh, z0) of the lower neighbour
+        self.vhalo_hi = mk() if self.rank < self.world - 1 else None       # planes [z1, z1 + vh) of the upper neighbour
+        self.vsend_lo = mk() if self.rank > 0 else None                    # contiguous copies of my own faces, as they travel
+        self.vsend_hi = mk() if self.rank < self.world - 1 else None
+
+    def pack_vector_faces(self) -> None:
+        """my first / last vh planes of the vector field as contiguous (3,X,Y,vh) blocks (one strided copy each)."""
+        if self.vsend_lo is not None:
+            self.vsend_lo.copy_(self.vec[:, :, :, :self.vh])
+        if self.vsend_hi is not None:
+            self.vsend_hi.copy_(self.vec[:, :, :, self.Zl - self.vh:])
+
+    def exchange_vector_halos(self) -> None:
+        """N > 1: swap vh planes of the vector field with both Z-neighbours (my low face -> the lower rank's high halo, my
+        high face -> the upper rank's low halo).  NCCL send/recv for both transports: 2 x 3 x X x Y x vh elements per face."""
+        if self.hops == 1 or self.world == 1:
+            return
+        self.pack_vector_faces()
+        d, ops = self.comm.dist, []
+        if self.rank > 0:
+            ops.append(d.P2POp(d.isend, self.vsend_lo, self.rank - 1, self.comm.group))
+            ops.append(d.P2POp(d.irecv, self.vhalo_lo, self.rank - 1, self.comm.group))
+        if self.rank < self.world - 1:
+            ops.append(d.P2POp(d.isend, self.vsend_hi, self.rank + 1, self.comm.group))
+            ops.append(d.P2POp(d.irecv, self.vhalo_hi, self.rank + 1, self.comm.group))
+        for req in d.batch_isend_irecv(ops):
+            req.wait()
 
     def _s(self):
         return L.stream_ptr(self.dev)
@@ -484,6 +536,7 @@ class ShardedAssembler:
         return ncomp
 
     def _step_eager(self, timers=None) -> Tensor:
+        self.exchange_vector_halos()  # N > 1 only; first in the pass on every rank, before any kernel waits on a peer's flag
         self.phase_local()
         if self.transport != "peer":
             with self._chain():
@@ -507,9 +560,7 @@ class ShardedAssembler:
                 if self.split:
                     self._stream_phase()
                 else:
-                    L.check(self.lib.skb_assemble_slab(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0],
-                                                       self.Zl, L.f3(self.scale), self.workspace.data_ptr(), L.ptr(self.halo_lo),
-                                                       L.ptr(self.halo_hi), self.out.data_ptr(), L.dtype_code(self.out), self._s()))
+                    self.gather()
                 b.record()
                 torch.cuda.synchronize(self.dev)
                 if _:
@@ -587,6 +638,7 @@ class ShardedAssembler:
             self.mask = torch.empty((X, Y, self.Zl), dtype=torch.uint8, device=self.dev)
         if self.vec is None or self.vec.dtype != vec_host.dtype:
             self.vec = torch.empty((3, X, Y, self.Zl), dtype=vec_host.dtype, device=self.dev)
+        self._alloc_vector_halos(self.vec.dtype)
         if out_host.dtype != self.out.dtype:
             self.graph = None  # a captured pass writes the old buffer
             self.out = torch.empty((X, Y, self.Zl), dtype=out_host.dtype, device=self.dev)
@@ -617,6 +669,9 @@ class ShardedAssembler:
         if self.transport != "peer":
             self.comm.all_gather(self.gathered, self.exch)
         self.phase_merge()
+        if self.hops > 1:  # the walks read the neighbours' vectors: swap the faces once the field has landed (every rank
+            main.wait_event(landed[-1])  # issues it at this point of its pass, after the chain's in-kernel waits)
+            self.exchange_vector_halos()
         for (x0, x1), ev in zip(ranges, landed):
             main.wait_event(ev)
             self.gather((x0 * plane, (x1 - x0) * plane))
@@ -696,6 +751,14 @@ class LocalGroup:
             r.load(mask[:, :, z0:z1].contiguous(), vec[:, :, :, z0:z1].contiguous())
 
     def step(self) -> Tensor:
+        if self.ranks[0].hops > 1 and self.world > 1:  # stand-in for exchange_vector_halos(): plain copies
+            for r in self.ranks:
+                r.pack_vector_faces()
+            for i, r in enumerate(self.ranks):
+                if i > 0:
+                    r.vhalo_lo.copy_(self.ranks[i - 1].vsend_hi)
+                if i < self.world - 1:
+                    r.vhalo_hi.copy_(self.ranks[i + 1].vsend_lo)
         for r in self.ranks:
             r.phase_local()
         if self.transport != "peer":

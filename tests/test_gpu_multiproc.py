@@ -66,6 +66,18 @@ def _worker(rank: int, world: int, port: int, transport: str, shape):
             run.run_host(mask_h, vec_h, out_h, n_slabs=4)
             assert torch.equal(out_h, want.cpu().to(dt)), f"rank {rank}: host pass ({dt}) differs"
     dist.barrier()
+    # eval()'s configuration Z-sharded: crop grid, N = 6 hops, the vector halos travel over NCCL send/recv
+    crop, ov = (48, 40, 50), (4, 4, 5)
+    want_eval = assemble_instances(mask, vec, torch.tensor(scale), N=6, crop=crop, overlap=ov, out_dtype=torch.int16)[:, :, z0:z1].contiguous()
+    comm2 = run.comm if transport != "peer" else TorchDistComm()
+    ev = ShardedAssembler(shape, world, rank, dev, scale=scale, hops=6, crop=crop, overlap=ov, comm=comm2, out_dtype=torch.int16)
+    ev.load(run.mask, run.vec)
+    for _ in range(2):
+        assert torch.equal(ev.step(), want_eval), f"rank {rank}: sharded eval-mode pass differs from the unsharded one"
+    out_h = torch.empty(want_eval.shape, dtype=torch.int16).pin_memory()
+    ev.run_host(mask_h, vec_h, out_h)
+    assert torch.equal(out_h, want_eval.cpu()), f"rank {rank}: eval-mode host pass differs"
+    dist.barrier()
     if hasattr(run.comm, "close"):
         run.comm.close()
     dist.destroy_process_group()

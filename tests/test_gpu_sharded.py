@@ -160,3 +160,30 @@ def test_slab_gather_by_ranges_equals_whole_slab():
             r.gather((x0 * plane, (x1 - x0) * plane))
         assert torch.equal(r.out, whole)
     assert int(want.max()) > 3
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("world,crop,ov,N,decay", [(2, (48, 40, 50), (4, 4, 5), 10, 1.0), (4, (48, 40, 50), (4, 4, 5), 4, 0.95),
+                                                   (4, (40, 40, 16), (5, 5, 2), 6, 1.0), (2, None, (0, 0, 0), 3, 1.0)])
+def test_sharded_multi_hop_walks_equal_unsharded(world, crop, ov, N, decay, transport):
+    """eval()'s configuration (crop grid, N = 10) Z-sharded.  Hops that leave the slab inside their crop read
+    the neighbour's vector planes from the vector halo; the result must equal the unsharded crop-grid pass bit for bit."""
+    from skoots_b200.pipeline import assemble_instances
+    from skoots_b200.sharded import LocalGroup
+    shape = (96, 80, 256) if crop is not None else (48, 40, 128)
+    tv = make_tube_volume(shape, 150, seed=8, device=DEV, scale=(20.0, 20.0, 8.0))
+    tv.skeleton[40:43, 30:33, 20:shape[2] - 16] = 1
+    tv.vectors[2, 30:50, 26:37, :] = 0.6     # walks that run along z, across crop seams and slab faces
+    scale = (20, 20, 8)
+    want = assemble_instances(tv.skeleton, tv.vectors, torch.tensor(scale), N=N, decay=decay, crop=crop, overlap=ov, out_dtype=torch.int16)
+    if crop is None and world > 1:
+        # one crop = the whole volume: a hop may land anywhere, which no neighbour halo can cover
+        with pytest.raises(ValueError):
+            LocalGroup(shape, world, DEV, scale=scale, transport=transport, hops=N, out_dtype=torch.int16)
+        return
+    grp = LocalGroup(shape, world, DEV, scale=scale, transport=transport, hops=N, decay=decay, crop=crop, overlap=ov, out_dtype=torch.int16)
+    grp.load_volume(tv.skeleton, tv.vectors)
+    for _ in range(2):
+        got = grp.step()
+        assert got.dtype == torch.int16 and torch.equal(got, want), (world, crop, N)
+    assert int((want > 0).sum()) > 1000

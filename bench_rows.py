@@ -177,32 +177,6 @@ def main():
                     f"{kern_ms:.4f} ms = {16 * B * 1.8e6 / (kern_ms * 1e-3) / 1e9:.0f} GB/s of 16 B/voxel "
                     f"({16 * B * 1.8e6 / (kern_ms * 1e-3) / 1e9 / hbm_peak():.2f} of HBM), {9 * pairs / (kern_ms * 1e-3) / 1e12:.3f} TFLOP/s "
                     f"of the nominal 74 TFLOP/s fp32 peak over {pairs} voxel-point pairs: memory-bound, not ALU-bound"))
-    # the reference's only GPU kernel (Triton, skoots/lib/skeleton.py:51-367) on the same box and inputs (SURVEY 2.3 G1).
-    # Its semantics differ from the CPU path (SURVEY A.5: fp16 outputs, anisotropy on squared differences, per-axis max on
-    # ties), so it is raced, not compared bit for bit.
-    try:
-        import ref_shim
-        ref_shim.install(need_morphology=False)
-        import skoots.lib.skeleton as ref_skel
-        masks_i = [m.contiguous() for m in masks_d]
-        ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False)  # compile
-        tri_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=False) for i in range(B)], iters=3, warm=1)
-        ours_raw = gpu_ms(lambda: skel.bake_skeletons_batch(masks_b, present_d, an, average=False, check=False), iters=10)
-        tri0 = ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False).float()
-        mine0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=False)
-        agree = float((tri0 == mine0).float().mean().item())
-        try:
-            tri_avg_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=True) for i in range(B)], iters=3, warm=1)
-        except Exception as exc:  # scripted morphology helpers may not run under this torch
-            tri_avg_ms = None
-        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton _bake_skeleton_triton vs skb_bake_skeletons (average=False)",
-                     "config": "C4 8 x 300x300x20, 20 ids each, same B200, same inputs", "voxels": B * 300 * 300 * 20,
-                     "reference_triton_ms": round(tri_ms, 4), "reference_triton_with_average_ms": None if tri_avg_ms is None else round(tri_avg_ms, 4),
-                     "skoots_b200_ms": round(ours_raw, 4), "skoots_b200_with_average_ms": round(nocheck_ms, 4),
-                     "speedup": round(tri_ms / ours_raw, 1), "fraction_of_voxels_where_both_agree": round(agree, 4),
-                     "note": "the reference launches one Triton program per voxel, 8 launches + 8 synchronisations per batch, fp16 out"})
-    except Exception as exc:
-        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton kernel", "unavailable": repr(exc)[:300]})
     wantm = orc.skeleton_to_mask(present[0], (300, 300, 20), 9, 3)
     rows.append(row("a9 skeleton_to_mask r=9 f=3", "C4 8 x 300x300x20", B * 300 * 300 * 20, 4,
                     gpu_ms(lambda: [skel.skeleton_to_mask(present_d[i], (300, 300, 20), radius=9, flank_radius=3) for i in range(B)], iters=5),
@@ -258,6 +232,22 @@ def main():
                         cpu_ms(lambda: [orc.label_components(host[i]) for i in range(n_cpu)], iters=1) * (S / n_cpu),
                         bool((out[0].cpu().numpy() == want0).all() and (out[S - 1].cpu().numpy() == orc.label_components(host[(S - 1) % 8])[0]).all()),
                         "1 B mask in + 4 B int32 labels out" + ("" if S <= 8 else "; CPU time = 8 slices x 8")))
+        # the whole 2-D path: per-slice CCL + the fused planar gather (vectors = the tubes' in-plane components)
+        from skoots_b200.pipeline import assemble_instances_2d
+        vt = tv.vectors[1:3].permute(1, 0, 2, 3).contiguous()
+        vstack = vt if S <= 8 else vt.repeat(S // 8, 1, 1, 1).contiguous()
+        s2d = torch.tensor((60.0, 60.0))
+        out2 = torch.empty(stack.shape, dtype=torch.int32, device=DEV)
+        assemble_instances_2d(stack, vstack, s2d, workspace=sp.workspace, out=out2)
+        want2 = orc.postprocess_2d(stack[:1].cpu(), vstack[:1].cpu(), s2d)
+        t0 = time.perf_counter()
+        orc.postprocess_2d(stack[:1].cpu(), vstack[:1].cpu(), s2d)
+        cpu_one = (time.perf_counter() - t0) * 1e3
+        rows.append(row(f"a10 2-D path: per-slice CCL + fused planar gather, {S} slices", f"C5 {S} x 4096x4096", S * 4096 * 4096, 9,
+                        gpu_ms(lambda: assemble_instances_2d(stack, vstack, s2d, workspace=sp.workspace, out=out2, check=False)),
+                        cpu_one * S, bool(torch.equal(out2[0].cpu(), want2[0]) and torch.equal(out2[S - 1].cpu(), out2[(S - 1) % 8].cpu())),
+                        "1 B mask + 4 B fp16 vectors in, 4 B labels out; CPU time = one slice x S"))
+        del vt, vstack, out2
         v2 = (torch.rand((min(S, 8), 2, 4096, 4096), device=DEV) * 2 - 1).half()
         if S > 8:
             v2 = v2.repeat(S // 8, 1, 1, 1).contiguous()
@@ -294,6 +284,33 @@ def main():
                     "4 B gt + 4 B prediction per voxel; the CPU figure is the oracle's contingency restatement, "
                     "not the reference's O(N*M*V) loop"))
     del tv, inst, gt, scratch
+
+    # the reference's only GPU kernel (Triton, skoots/lib/skeleton.py:51-367) on the same box and inputs (SURVEY 2.3 G1).
+    # Its semantics differ from the CPU path (SURVEY A.5: fp16 outputs, anisotropy on squared differences, per-axis max on
+    # ties), so it is raced, not compared bit for bit.
+    try:
+        import ref_shim
+        ref_shim.install(need_morphology=False)
+        import skoots.lib.skeleton as ref_skel
+        masks_i = [m.contiguous() for m in masks_d]
+        ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False)  # compile
+        tri_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=False) for i in range(B)], iters=3, warm=1)
+        ours_raw = gpu_ms(lambda: skel.bake_skeletons_batch(masks_b, present_d, an, average=False, check=False), iters=10)
+        tri0 = ref_skel.bake_skeleton(masks_i[0], present_d[0], an, average=False).float()
+        mine0 = skel.bake_skeleton(masks_d[0], present_d[0], an, average=False)
+        agree = float((tri0 == mine0).float().mean().item())
+        try:
+            tri_avg_ms = gpu_ms(lambda: [ref_skel.bake_skeleton(masks_i[i], present_d[i], an, average=True) for i in range(B)], iters=3, warm=1)
+        except Exception as exc:  # scripted morphology helpers may not run under this torch
+            tri_avg_ms = None
+        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton _bake_skeleton_triton vs skb_bake_skeletons (average=False)",
+                     "config": "C4 8 x 300x300x20, 20 ids each, same B200, same inputs", "voxels": B * 300 * 300 * 20,
+                     "reference_triton_ms": round(tri_ms, 4), "reference_triton_with_average_ms": None if tri_avg_ms is None else round(tri_avg_ms, 4),
+                     "skoots_b200_ms": round(ours_raw, 4), "skoots_b200_with_average_ms": round(nocheck_ms, 4),
+                     "speedup": round(tri_ms / ours_raw, 1), "fraction_of_voxels_where_both_agree": round(agree, 4),
+                     "note": "the reference launches one Triton program per voxel, 8 launches + 8 synchronisations per batch, fp16 out"})
+    except Exception as exc:
+        rows.append({"row": "a8 HEAD-TO-HEAD: reference Triton kernel", "unavailable": repr(exc)[:300]})
 
     print(json.dumps({"hbm_peak_GBps": hbm_peak(), "rows": rows}, indent=1))
 

@@ -28,6 +28,19 @@ void skb_set_error(const char* fmt, ...);
         }                                                                        \
     } while (0)
 
+// > 48 KB of dynamic shared memory is an opt-in per function AND per device: raise it the first time a kernel is launched
+// on a device instead of on every launch (the call costs a few microseconds of host time on launch-bound paths).
+#define SKB_RAISE_SMEM_ONCE(kernel, bytes)                                                                     \
+    do {                                                                                                       \
+        static bool raised__[64] = {};                                                                         \
+        int dev__ = 0;                                                                                         \
+        cudaGetDevice(&dev__);                                                                                 \
+        if (dev__ < 0 || dev__ >= 64 || !raised__[dev__]) {                                                    \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));           \
+            if (dev__ >= 0 && dev__ < 64) raised__[dev__] = true;                                              \
+        }                                                                                                      \
+    } while (0)
+
 static inline size_t skb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline bool skb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

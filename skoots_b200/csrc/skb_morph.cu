@@ -303,7 +303,7 @@ extern "C" int skb_tile_epilogue(const void* unet, int in_dtype, int C, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define EPI_LAUNCH(T)                                                                                          \
     do {                                                                                                       \
-        cudaFuncSetAttribute(tile_epilogue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
+        SKB_RAISE_SMEM_ONCE(tile_epilogue_kernel<T>, 96 * 1024);                                               \
         tile_epilogue_kernel<T><<<(unsigned)blocks, 256, smem, st>>>(P, bz, nby, nbz);                         \
     } while (0)
     if (in_dtype == SKB_F32) EPI_LAUNCH(float);

@@ -428,6 +428,7 @@ constexpr int BAKE_ARENA = 1536;   // skeleton points staged per CTA (24 KB)
 
 struct BakeParams {
     int X, Y, Z, TZ, H;    // H = 1 when the 27-mean is fused (halo), else 0
+    int fast_rows;         // one tile along z, rows are whole 16-byte chunks of mask and 4-float chunks of output
     int tiles_y, tiles_z;
     float an[3];
     const int* ids;        // every sample's sorted object ids, concatenated
@@ -463,6 +464,38 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // 0. most tiles of an instance mask hold no object at all (and neither does their halo).  When a region row is the
+    //    whole z row and 16-byte chunks are legal, test it with vector loads and, if empty, store the zeros as vectors.
+    if (P.fast_rows) {
+        constexpr int PER = 16 / (int)sizeof(MT);
+        const int chunks = P.Z / PER;
+        int any = 0;
+        for (int i = threadIdx.x; i < RX * RY * chunks; i += 256) {
+            const int ch = i % chunks, row = i / chunks, ry = row % RY, rx = row / RY;
+            const int gx = x0 + rx, gy = y0 + ry;
+            if (gx >= 0 && gx < P.X && gy >= 0 && gy < P.Y) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(mask + ((long long)gx * P.Y + gy) * P.Z) + ch);
+                any |= (q.x | q.y | q.z | q.w) != 0u;
+            }
+        }
+        if (!__syncthreads_or(any)) {
+            const int c4 = P.Z / 4;
+            float* out0 = baked + (long long)b * 3 * P.V;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = threadIdx.x; i < BAKE_T * BAKE_T * c4; i += 256) {
+                const int ch = i % c4, row = i / c4, ly = row % BAKE_T, lx = row / BAKE_T;
+                const int gx = tx * BAKE_T + lx, gy = ty * BAKE_T + ly;
+                if (gx >= P.X || gy >= P.Y) continue;
+                const long long g = ((long long)gx * P.Y + gy) * P.Z + 4 * ch;
+                *reinterpret_cast<float4*>(out0 + g) = zero;
+                *reinterpret_cast<float4*>(out0 + g + P.V) = zero;
+                *reinterpret_cast<float4*>(out0 + g + 2 * P.V) = zero;
+                if (dist_out) *reinterpret_cast<float4*>(dist_out + (long long)b * P.V + g) = zero;
+            }
+            return;
+        }
+    }
 
     // A. region voxels -> slot of their object in the CTA's id list (-1 background, <= -2: id index -2-v, list full)
     int any_fg = 0;
@@ -642,13 +675,16 @@ extern "C" int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, 
     P.V = X * Y * Z;
     const long long tiles = (long long)tiles_x * P.tiles_y * P.tiles_z;
     SKB_REQUIRE(tiles < (1LL << 31), "skb_bake_skeletons: too many tiles");
+    const int msize = mask_dtype == SKB_I32 ? 4 : (mask_dtype == SKB_I16 ? 2 : 1);
+    P.fast_rows = (P.tiles_z == 1 && (Z * msize) % 16 == 0 && Z % 4 == 0 && skb_aligned16(masks) && skb_aligned16(baked) &&
+                   (!distance || skb_aligned16(distance))) ? 1 : 0;
     const int RN = (BAKE_T + 2 * P.H) * (BAKE_T + 2 * P.H) * (P.TZ + 2 * P.H);
     const size_t smem = (size_t)BAKE_ARENA * 16 + (size_t)RN * 5 * 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid((unsigned)tiles, (unsigned)B);
 #define BAKE_LAUNCH(MT)                                                                                               \
     do {                                                                                                              \
-        cudaFuncSetAttribute(bake_tile_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        SKB_RAISE_SMEM_ONCE(bake_tile_kernel<MT>, 200 * 1024);                                                        \
         bake_tile_kernel<MT><<<grid, 256, smem, st>>>(static_cast<const MT*>(masks), baked, distance, P);             \
     } while (0)
     if (mask_dtype == SKB_I32) BAKE_LAUNCH(int32_t);

@@ -400,6 +400,25 @@ int skb_iou_dice(const int32_t* inter, const int32_t* area_gt, const int32_t* ar
 int skb_accuracies_from_iou(const float* iou, int64_t N, int64_t M, float thr, int32_t* hits_scratch,
                             int32_t* out3, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f4)  the elastic deformation of the training augmentation     skoots/train/merged_transform.py:75-188, 43-72
+ *   noise (3,D,H,W) f32 device = the coarse random field the reference draws with torch.rand (D along X, H along Y,
+ *   W along Z); magnitude_rev = displacement_magnitude reversed (HOST array).  Neither of the reference's two dense
+ *   (X,Y,Z,3) grids is built: the trilinear displacement is evaluated per voxel / per point from the coarse field.
+ *   skb_elastic_resample  F.grid_sample(mode="nearest", align_corners=True, zeros padding) of n_volumes volumes
+ *                         (X,Y,Z) f32 through grid = identity + displacement.  Out of place.
+ *   skb_elastic_points    new position of every skeleton point (n,3), int64 (points_are_int64 != 0: results truncated
+ *                         toward zero like the reference's in-place assignment) or f32; points outside the volume are
+ *                         copied unchanged.
+ *   Parity is stated with a tolerance (ATen's own CPU and CUDA upsampling kernels differ in the last bit): see DESIGN.md.
+ * ------------------------------------------------------------------------------------------- */
+int skb_elastic_resample(const float* noise, int64_t D, int64_t H, int64_t W, const float magnitude_rev[3],
+                         const float* in, float* out, int64_t n_volumes, int64_t X, int64_t Y, int64_t Z,
+                         void* stream);
+int skb_elastic_points(const float* noise, int64_t D, int64_t H, int64_t W, const float magnitude_rev[3],
+                       const void* points, int points_are_int64, int64_t n_points, int64_t X, int64_t Y,
+                       int64_t Z, void* out_points, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -515,3 +515,34 @@ def accuracies_from_iou(iou: torch.Tensor, thr: float = 0.1) -> Tuple[int, int, 
     pred_hit = iou.max(dim=0)[0].gt(thr)
     return int(gt_hit.sum()), int((~pred_hit).sum()), int((~gt_hit).sum())
 
+
+
+# --------------------------------------------------------------------------------------
+# f4: elastic deformation of the augmentation     skoots/train/merged_transform.py:75-188, 43-72
+# --------------------------------------------------------------------------------------
+
+
+def elastic_deform(noise: torch.Tensor, *args: torch.Tensor, skeleton: Dict[int, torch.Tensor],
+                   displacement_magnitude=(0.05, 0.05, 0.01)):
+    """The reference's operations with the random field injected: `noise` is what its
+    `torch.rand((1, 3, ds[2], ds[1], ds[0]))` (:140) returns.  Trilinear upsampling to the crop, identity grid from
+    three linspaces, nearest grid_sample of every argument, then the second grid ((base - offset + 1)/2 * size) looked
+    up at every in-volume skeleton point, components reversed, assigned into the (integer) point tensor."""
+    import torch.nn.functional as F
+    b, c, x, y, z = args[0].shape
+    mag = torch.tensor(tuple(reversed(displacement_magnitude)), dtype=torch.float32)
+    offset = F.interpolate(noise.float(), (x, y, z), mode="trilinear").permute((0, 2, 3, 4, 1)).mul(mag.view(1, 1, 1, 1, 3))
+    d1, d2, d3 = torch.linspace(-1, 1, x), torch.linspace(-1, 1, y), torch.linspace(-1, 1, z)
+    meshx, meshy, meshz = torch.meshgrid((d1, d2, d3), indexing="ij")
+    base = torch.stack((meshz, meshy, meshx), 3).unsqueeze(0)
+    grid = (base + offset).float()
+    out = [F.grid_sample(a.float(), grid, align_corners=True, mode="nearest") for a in args]
+    grid = (base - offset).float().add(1).div(2).mul(torch.tensor((z, y, x)).view(1, 1, 1, 1, 3))
+    new = {}
+    for k, skel in skeleton.items():
+        skel = skel.clone()
+        sx, sy, sz = skel[:, 0], skel[:, 1], skel[:, 2]
+        ind = (sx >= 0) & (sx < x) & (sy >= 0) & (sy < y) & (sz >= 0) & (sz < z)
+        skel[ind, :] = grid[0, sx[ind].long(), sy[ind].long(), sz[ind].long(), :][:, [2, 1, 0]].to(skel.dtype)
+        new[k] = skel
+    return (*out, new)

@@ -81,6 +81,8 @@ SIGNATURES = {
     "skb_contingency": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_iou_dice": (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp]),
     "skb_accuracies_from_iou": (_c_int, [_c_vp, _c_i64, _c_i64, ctypes.c_float, _c_vp, _c_vp, _c_vp]),
+    "skb_elastic_resample": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp]),
+    "skb_elastic_points": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_peer_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
     "skb_peer_free": (_c_int, [_c_vp]),
     "skb_peer_export": (_c_int, [_c_vp, ctypes.c_char_p]),

@@ -215,3 +215,33 @@ def test_2d_mode_fused_gather_matches_reference_fixture():
         want = orc.postprocess_2d(m, v, scale)
         got = assemble_instances_2d(m.to(DEV), v.to(DEV), scale, out_dtype=torch.int16)
         assert np.array_equal(got.cpu().numpy(), want.numpy().astype(np.int16)), shape
+
+
+def test_elastic_deform_f4():
+    """elastic_deform without the dense grids.  Parity bar: the displacement is a chain of fp32
+    lerps that ATen itself evaluates differently on CPU and CUDA, so samples may differ where a coordinate lies within
+    ~1e-4 of a rounding boundary: at most 0.1 % of the voxels may differ from the reference's output, and a skeleton
+    coordinate (integer after truncation) by at most 1."""
+    from skoots_b200.train.merged_transform import elastic_deform
+    fx = load_golden("elastic")
+    for tag in ("a", "b"):
+        sk = {1: cu(fx[f"{tag}_sk1"]), 2: cu(fx[f"{tag}_sk2"])}
+        ds = tuple(int(v) for v in fx[f"{tag}_ds"])
+        img, mask, new = elastic_deform(cu(fx[f"{tag}_image"]), cu(fx[f"{tag}_mask"]), skeleton=sk, displacement_shape=ds,
+                                        displacement_magnitude=tuple(float(v) for v in fx[f"{tag}_mag"]), noise=cu(fx[f"{tag}_noise"]))
+        for got, key in ((img, "image"), (mask, "mask")):
+            want = fx[f"{tag}_out_{key}"]
+            assert got.shape == want.shape
+            assert float((got.cpu().numpy() != want).mean()) <= 1e-3, (tag, key)
+        for k in (1, 2):
+            want = fx[f"{tag}_out_sk{k}"]
+            assert new[k].dtype == torch.int64 and int(np.abs(new[k].cpu().numpy() - want).max()) <= 1, (tag, k)
+            assert float((new[k].cpu().numpy() != want).mean()) <= 0.05
+        assert np.array_equal(new[2].cpu().numpy()[2:4], fx[f"{tag}_sk2"][2:4])   # outside the volume: unchanged
+    # a seeded call draws the field exactly like the reference does (torch.rand of the same shape on the same device)
+    a = cu(fx["a_image"])
+    torch.manual_seed(3)
+    one = elastic_deform(a, skeleton={})[0]
+    torch.manual_seed(3)
+    two = elastic_deform(a, skeleton={}, noise=torch.rand((1, 3, 2, 6, 6), device=DEV))[0]
+    assert torch.equal(one, two)

@@ -187,3 +187,18 @@ def test_2d_mode_against_reference_fixture():
     masks = torch.from_numpy(unpack_mask(fx, "masks"))
     got = orc.postprocess_2d(masks, torch.from_numpy(fx["vectors"]), torch.from_numpy(fx["scale"]))
     assert np.array_equal(got.numpy(), fx["out"])
+
+
+def test_elastic_deform_against_reference_fixture():
+    """f4: the oracle's elastic_deform against tests/golden/elastic.npz — volumes produced by the unmodified reference
+    (pinned); skeleton points restated (UNPINNED: the reference's skeleton loop cannot run under this torch, see
+    oracle/gen_golden_elastic.py)."""
+    fx = load_golden("elastic")
+    for tag in ("a", "b"):
+        sk = {1: torch.from_numpy(fx[f"{tag}_sk1"]), 2: torch.from_numpy(fx[f"{tag}_sk2"])}
+        img, mask, new = orc.elastic_deform(torch.from_numpy(fx[f"{tag}_noise"]), torch.from_numpy(fx[f"{tag}_image"]),
+                                            torch.from_numpy(fx[f"{tag}_mask"]), skeleton=sk,
+                                            displacement_magnitude=tuple(float(v) for v in fx[f"{tag}_mag"]))
+        assert np.array_equal(img.numpy(), fx[f"{tag}_out_image"]) and np.array_equal(mask.numpy(), fx[f"{tag}_out_mask"])
+        assert np.array_equal(new[1].numpy(), fx[f"{tag}_out_sk1"]) and np.array_equal(new[2].numpy(), fx[f"{tag}_out_sk2"])
+        assert np.array_equal(new[2].numpy()[2:4], fx[f"{tag}_sk2"][2:4])   # points outside the volume are left alone

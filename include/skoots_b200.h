@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SKB_VERSION 100
+#define SKB_VERSION 200
 
 /* element types */
 enum { SKB_U8 = 0, SKB_I16 = 1, SKB_I32 = 2, SKB_F16 = 3, SKB_BF16 = 4, SKB_F32 = 5 };
@@ -315,10 +315,12 @@ int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, i
  *   mailbox and then release a flag (= the pass number) there; consumers spin on flags in their own
  *   HBM.  A flag that does not arrive within ~8 s sets SKB_STATUS_PEER_TIMEOUT instead of hanging.
  *   Call order per rank and pass (skoots_b200/sharded.py, transport "peer"):
- *     skb_shard_begin -> skb_shard_clear_halo_peer (per face) -> skb_shard_label_local
- *     -> skb_shard_emit_runs_peer (both faces)
- *     -> skb_shard_boundary_pairs (halo_hi = NULL) -> skb_shard_ingest_runs_peer (from the low / high neighbour)
- *     -> skb_shard_push -> skb_shard_merge_peer -> skb_assemble_slab.
+ *     skb_shard_begin_pass (pass counter, halo words of the previous pass cleared, pair counter zeroed)
+ *     -> skb_shard_label_local -> skb_shard_emit_runs_peer (both faces; the kernel's last CTA per face signals)
+ *     -> skb_shard_ingest_runs_peer (from the low / high neighbour; the latter appends the face pairs)
+ *     -> skb_shard_push (roots + pairs to every rank; last CTA signals) -> skb_shard_merge_peer (one cooperative
+ *     kernel: eight phases separated by grid barriers) -> skb_assemble_slab[_ex].
+ *     13 kernel launches per pass on a rank with two neighbours (round 1: 24 + 3 memsets).
  *   The skb_peer_* calls are set-up / tear-down only: they are the one place the library allocates
  *   (cudaMalloc: legacy CUDA IPC cannot export a caching allocator's sub-allocations).
  * ------------------------------------------------------------------------------------------- */
@@ -335,6 +337,11 @@ size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t cap_roots, i
 /* starts pass k+1: bumps the mailbox's pass counter, clears its run counters */
 int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
                     void* stream);
+/* the same plus, in the same call: skb_shard_clear_halo_peer for both faces with ONE launch (halo_lo / halo_hi: the
+ * X*Y halo words of each face, NULL where there is no neighbour) and the zeroing of the exchange buffer's counters
+ * (exchange may be NULL) — the prologue of a pass as two launches instead of five nodes */
+int skb_shard_begin_pass(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, int64_t Z,
+                         uint64_t* halo_lo, uint64_t* halo_hi, int32_t* exchange, void* stream);
 /* skb_shard_clear_halo on the mailbox's receive-buffer copy of the PREVIOUS pass; call after skb_shard_begin */
 int skb_shard_clear_halo_peer(int64_t Z, void* mailbox, int from_high, int world, int64_t cap_runs,
                               int64_t cap_roots, int64_t cap_pairs, uint64_t* halo_words, void* stream);
@@ -349,11 +356,13 @@ int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z,
                                void* mailbox, int from_high, int world, int64_t cap_runs, int64_t cap_roots,
                                int64_t cap_pairs, uint64_t* halo_words_zeroed, int32_t* exchange,
                                uint32_t* status, void* stream);
-/* the all-gather: stores the used part of `exchange` (written by skb_shard_boundary_pairs) into slot
- * `rank` of every rank's mailbox (peer_mailboxes: HOST array of `world` device pointers, own included)
- * and releases the flags */
-int skb_shard_push(const int32_t* exchange, void* mailbox, const uint64_t* peer_mailboxes, int world,
-                   int rank, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, void* stream);
+/* the all-gather: stores my payload — the slab's root list straight from the workspace, the face pairs the upper
+ * neighbour's ingest appended to `exchange` (counters zeroed by skb_shard_begin_pass) — into slot `rank` of every
+ * rank's mailbox (peer_mailboxes: HOST array of `world` device pointers, own included); the last CTA of the kernel
+ * releases the flags.  No skb_shard_boundary_pairs call is needed on this transport. */
+int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* exchange, void* mailbox,
+                   const uint64_t* peer_mailboxes, int world, int rank, int64_t cap_runs, int64_t cap_roots,
+                   int64_t cap_pairs, uint32_t* status, void* stream);
 /* waits for every rank's flag, then skb_shard_merge on the mailbox's gather buffer */
 int skb_shard_merge_peer(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity,
                          void* mailbox, int world, int rank, int64_t cap_runs, int64_t cap_roots,

@@ -766,96 +766,24 @@ __global__ void __launch_bounds__(256) ccl_flatten_kernel(CclView v) {
 // K4: exclusive scan of the chunk histogram — one CTA per 8192-entry tile, then one CTA over the
 // (<= 4096) tile totals.  The rank kernel adds the two levels, so there is no third pass.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_exclusive_scan_1024(int sum, int* warp_sums, int* total) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        int ws = warp_sums[lane], wi = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += t;
-        }
-        warp_sums[lane] = wi - ws;
-        if (lane == 31) *total = wi;
-    }
-    __syncthreads();
-    return warp_sums[wid] + incl - sum;
-}
-
 __global__ void __launch_bounds__(1024) ccl_scan_tiles_kernel(CclView v) {
     __shared__ int warp_sums[32];
     __shared__ int total;
-    constexpr int PER = SKB_SCAN_TILE / 1024;
-    const long long at = (long long)blockIdx.x * SKB_SCAN_TILE + (long long)threadIdx.x * PER;
-    int vals[PER], sum = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        vals[j] = (at + j < v.n_chunks) ? v.chunks[at + j] : 0;
-        sum += vals[j];
-    }
-    int run = block_exclusive_scan_1024(sum, warp_sums, &total);
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        if (at + j < v.n_chunks) v.chunks[at + j] = run;
-        run += vals[j];
-    }
-    if (threadIdx.x == 0) v.scan_tiles[blockIdx.x] = total;
+    ccl_scan_tile_body(v, blockIdx.x, warp_sums, &total);
 }
 
 __global__ void __launch_bounds__(1024) ccl_scan_top_kernel(CclView v) {
     __shared__ int warp_sums[32];
     __shared__ int total;
-    constexpr int PER = 4;  // n_scan_tiles <= 4096 for any volume the library accepts
-    const long long at = (long long)threadIdx.x * PER;
-    int vals[PER], sum = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        vals[j] = (at + j < v.n_scan_tiles) ? v.scan_tiles[at + j] : 0;
-        sum += vals[j];
-    }
-    int run = block_exclusive_scan_1024(sum, warp_sums, &total);
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        if (at + j < v.n_scan_tiles) v.scan_tiles[at + j] = run;
-        run += vals[j];
-    }
-    if (threadIdx.x == 0) {
-        v.hdr->n_components = total;
-        if (v.ncomp_out) *v.ncomp_out = total;
-    }
+    ccl_scan_top_body(v, warp_sums, &total);
 }
 
 // ------------------------------------------------------------------------------------------
 // K5: raster-order rank of each global root -> label code
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int roots_before_word(const CclView& v, long long wi) {
-    long long c = wi >> 6;
-    int r = v.chunks[c] + v.scan_tiles[c / SKB_SCAN_TILE];
-    for (long long j = c << 6; j < wi; ++j) r += __popcll(v.rootbits[j]);
-    return r;
-}
-
 __global__ void __launch_bounds__(256) ccl_rank_kernel(CclView v) {
     unsigned n = v.hdr->n_global_roots;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int r = v.groots[i];
-        int bit;
-        long long wi = word_of_voxel(v, r, &bit);
-        int rank = roots_before_word(v, wi) + __popcll(v.rootbits[wi] & ((1ull << bit) - 1ull));
-        if (!v.connect_x) {  // planar: numbering restarts in every x-plane
-            long long plane_words = (long long)v.Y * v.ZW;
-            rank -= roots_before_word(v, (wi / plane_words) * plane_words);
-        }
-        v.parent[r] = -(v.hdr->label_base + 1 + rank);
-    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ccl_rank_root(v, v.groots[i]);
 }
 
 // leaves the root bitmap all-zero again (only the words the global roots touched), so the next pass over

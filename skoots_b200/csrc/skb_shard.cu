@@ -1,7 +1,12 @@
 // Z-sharded connected-component labelling and its two exchanges: the kernels a rank
 // runs around the single-GPU labelling kernels of skb_ccl.cu, for both transports (NCCL between the phases, or
 // stores into peer mailboxes over NVLink with release/acquire flags).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "skb_ccl.cuh"
+
+namespace cg = cooperative_groups;
 
 // ==========================================================================================
 // Z-sharded labelling.
@@ -83,6 +88,11 @@ struct EmitFace {
     const ull* face;  // compact copy of that word of every row
     int z_lo, z_hi;
     RunsDst dst;
+    // peer transport: the LAST CTA of the face to finish publishes the run count in the neighbour's buffer and releases
+    // its flag (round 1 used a second, one-warp kernel for this: one more launch on the latency chain).  NULL: no signal.
+    int* done;         // local counter of finished CTAs (zero between passes)
+    int* remote_runs;  // the neighbour's receive buffer, copy 0 ([count,_,_] + triples)
+    int* remote_flag;
 };
 
 // counter = count, then (start voxel, length, root id) triples.  blockIdx.y picks the face (the peer
@@ -92,8 +102,8 @@ struct EmitFace {
 constexpr int EMIT_ROWS = 4;
 constexpr int EMIT_QUEUE = 96;  // runs a warp can queue
 
-__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFace f0, EmitFace f1, int cap, unsigned* status) {
-    const EmitFace& f = blockIdx.y ? f1 : f0;
+// returns whether this thread stored any triple
+__device__ __forceinline__ bool emit_face_rows(const CclView& v, const EmitFace& f, int cap, unsigned* status, int2 (*s_runs)[EMIT_QUEUE]) {
     const RunsDst& dst = f.dst;
     const int z_lo = f.z_lo, z_hi = f.z_hi;
     int* const runs = dst.counter;
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
     ull any = 0ull;
 #pragma unroll
     for (int r = 0; r < EMIT_ROWS; ++r) { w[r] &= range; any |= w[r]; }
-    if (!__any_sync(0xffffffffu, any != 0ull)) return;
+    if (!__any_sync(0xffffffffu, any != 0ull)) return false;
     // one atomicAdd per warp (a per-run atomic on the single counter would serialise in L2)
     int cnt = 0;
 #pragma unroll
@@ -134,7 +144,6 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
     // The root of a run is a 3-load pointer chase in global memory.  Runs are first queued in shared memory
     // (start voxel, length), then taken one per lane, so a warp's chases overlap instead of following the
     // row-by-row order in which they were found (a warp of 128 rows holds ~1.5 runs, in different rows).
-    __shared__ int2 s_runs[8][EMIT_QUEUE];
     int2* queue = s_runs[threadIdx.x >> 5];
     const bool queued = total <= EMIT_QUEUE;
     int at = incl - cnt;
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
             }
         }
     }
-    if (!queued) return;
+    if (!queued) return cnt > 0;
     __syncwarp();
     for (int i = lane; i < total; i += 32) {
         const int2 e = queue[i];
@@ -173,23 +182,26 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
             atomicOr(status, SKB_STATUS_ROOT_OVERFLOW);
         }
     }
+    return lane < total;
 }
 
-// peer transport: publishes my face's run count in the neighbour's buffer, then releases its flag.  The
-// triples were stored by the previous kernel on this stream, so they are ordered before the flag.
-struct SignalRuns {
-    const int* local_cnt;  // NULL: no such face
-    int* remote_runs;
-    int* remote_flag;
-};
-__global__ void shard_signal_runs_kernel(SignalRuns s0, SignalRuns s1, long long parity_stride, const int* epoch) {
-    if (threadIdx.x < 2) {
-        const SignalRuns& s = threadIdx.x ? s1 : s0;
-        if (s.local_cnt) {
-            const int e = *epoch;
-            s.remote_runs[(long long)(e & 1) * parity_stride] = *s.local_cnt;
+__global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFace f0, EmitFace f1, int cap, unsigned* status) {
+    __shared__ int2 s_runs[8][EMIT_QUEUE];
+    const EmitFace& f = blockIdx.y ? f1 : f0;
+    const bool stored = emit_face_rows(v, f, cap, status, s_runs);
+    if (f.done == nullptr) return;
+    // my triples (stored into the neighbour's memory) become visible system-wide before my CTA counts itself as finished
+    if (stored) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int finished = atomicAdd(f.done, 1);
+        if (finished == (int)gridDim.x - 1) {  // every CTA of this face has counted itself: the run count is final
+            __threadfence();
+            *f.done = 0;
+            const int e = *f.dst.epoch;
+            f.remote_runs[(long long)(e & 1) * f.dst.parity_stride] = *reinterpret_cast<volatile int*>(f.dst.counter);
             __threadfence_system();
-            st_release_sys(s.remote_flag, e);
+            st_release_sys(f.remote_flag, e);
         }
     }
 }
@@ -370,6 +382,96 @@ __global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, Mer
     }
 }
 
+// ---- the merge as ONE cooperative kernel --------------------------------------------------------------------
+// Round 1 ran the merge as eight dependent launches (init, union, mark, scan x2, rank, publish x2): 56 us of an 8-GPU
+// pass for a few thousand roots and pairs — almost all of it launch-to-launch latency.  Here the same phases run
+// inside one cooperatively launched grid (one 1024-thread CTA per SM, every CTA resident), separated by grid-wide
+// barriers (~1.5 us each).  The phases are the kernels above, verbatim, with the (block, rank-row) indices of their
+// grids mapped onto this grid's CTAs.
+constexpr int MERGE_FUSED_THREADS = 1024;
+
+template <typename F>
+__device__ __forceinline__ void merge_for_each(const MergeView& m, const int* base, bool pairs, bool skip_own, F&& f) {
+    const int per = gridDim.x / m.world > 0 ? gridDim.x / m.world : 1;  // CTAs per rank-row
+    for (int row = blockIdx.x / per; row < m.world; row += (gridDim.x + per - 1) / per) {
+        if (skip_own && row == m.rank) continue;
+        const int* e = base + (size_t)row * m.stride;
+        const int n = min(pairs ? e[1] : e[0], pairs ? m.cap_pairs : m.cap_roots);
+        const int* items = e + 2 + (pairs ? m.cap_roots : 0);
+        for (int i = (blockIdx.x % per) * blockDim.x + threadIdx.x; i < n; i += per * blockDim.x) f(items, i);
+    }
+}
+
+__global__ void __launch_bounds__(MERGE_FUSED_THREADS, 1) shard_merge_fused_kernel(CclView v, MergeView m, int label_base) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int warp_sums[32];
+    __shared__ int total;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    // phase 0: wait for every rank's payload of this pass (peer transport), reset the header fields the phases append to
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            v.hdr->n_global_roots = 0u;
+            v.hdr->label_base = label_base;
+        }
+        if (m.flags && (int)threadIdx.x < m.world) spin_until(m.flags + threadIdx.x * SKB_FLAG_STRIDE, *m.epoch, v.status);
+        __threadfence();
+    }
+    grid.sync();
+    const int* base = merge_base(m);
+    // phase 1: foreign roots join my union-find as singletons
+    merge_for_each(m, base, false, true, [&](const int* items, int i) { v.parent[items[i]] = items[i]; });
+    grid.sync();
+    // phase 2: every rank's face pairs
+    merge_for_each(m, base, true, false, [&](const int* items, int i) { gunion(v.parent, items[2 * i], items[2 * i + 1]); });
+    grid.sync();
+    // phase 3: global roots among all ranks' roots -> list + bitmap + chunk histogram
+    merge_for_each(m, base, false, false, [&](const int* items, int i) {
+        const int root = items[i];
+        if (gfind(v.parent, root) != root) return;
+        unsigned slot = atomicAdd(&v.hdr->n_global_roots, 1u);
+        if (slot >= (unsigned)v.capacity) {
+            atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+            return;
+        }
+        v.groots[slot] = root;
+        int bit;
+        long long wi = word_of_voxel(v, root, &bit);
+        atomicOr(&v.rootbits[wi], 1ull << bit);
+        atomicAdd(&v.chunks[wi >> 6], 1);
+    });
+    grid.sync();
+    // phase 4 / 5: two-level exclusive scan of the chunk histogram
+    for (long long t = blockIdx.x; t < v.n_scan_tiles; t += gridDim.x) {
+        ccl_scan_tile_body(v, t, warp_sums, &total);
+        __syncthreads();
+    }
+    grid.sync();
+    if (blockIdx.x == 0) ccl_scan_top_body(v, warp_sums, &total);
+    grid.sync();
+    // phase 6: raster rank of every global root -> label code
+    const unsigned n_g = min(v.hdr->n_global_roots, (unsigned)v.capacity);
+    for (unsigned i = tid; i < n_g; i += nthr) ccl_rank_root(v, v.groots[i]);
+    grid.sync();
+    // phase 7: every listed root takes the code of its global root; the root bitmap is left zeroed for the next pass
+    for (unsigned i = tid; i < n_g; i += nthr) {
+        int bit;
+        v.rootbits[word_of_voxel(v, v.groots[i], &bit)] = 0ull;
+    }
+    merge_for_each(m, base, false, false, [&](const int* items, int i) {
+        const int root = items[i];
+        int a = root, p = gload(v.parent + a);
+        while (p >= 0 && p != a) { a = p; p = gload(v.parent + a); }
+        if (p < 0 && a != root) v.parent[root] = p;
+    });
+    grid.sync();
+    // phase 8: tile roots that are not slab roots take the code of their root
+    const unsigned n_t = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
+    for (unsigned i = tid; i < n_t; i += nthr) {
+        const int r = v.tile_roots[i], g = v.flat[i];
+        if (g != r) v.parent[r] = v.parent[g];
+    }
+}
+
 static int shard_common(const char* who, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl) {
     int rc = skb_check_volume(X, Y, Z, who);
     if (rc) return rc;
@@ -526,6 +628,29 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
 }
 
 static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st) {
+    static int fused_ok = -1;  // -1 unknown; SKB_SHARD_FUSED=0 keeps the eight-launch form (measurements)
+    if (fused_ok < 0) {
+        const char* e = getenv("SKB_SHARD_FUSED");
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_merge_fused_kernel, MERGE_FUSED_THREADS, 0);
+        fused_ok = (!(e && e[0] == '0') && coop && per_sm >= 1) ? 1 : 0;
+    }
+    if (fused_ok) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        CclView vv = v;
+        MergeView mm = m;
+        int lb = label_base;
+        void* args[] = {&vv, &mm, &lb};
+        cudaError_t rc = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(shard_merge_fused_kernel), dim3((unsigned)sms),
+                                                     dim3(MERGE_FUSED_THREADS), args, 0, st);
+        if (rc == cudaSuccess) return SKB_OK;
+        (void)cudaGetLastError();
+        fused_ok = 0;  // not launchable here: the eight-launch form from now on
+    }
     const dim3 per_rank(MERGE_BLOCKS, m.world);
     shard_merge_init_kernel<<<per_rank, 256, 0, st>>>(v, m, label_base);
     shard_merge_union_kernel<<<per_rank, 256, 0, st>>>(v, m);
@@ -574,21 +699,44 @@ extern "C" size_t skb_shard_mailbox_bytes(int world, int64_t cap_runs, int64_t c
     return skb_mailbox_layout(world, cap_runs, cap_roots, cap_pairs).total;
 }
 
-__global__ void shard_begin_kernel(int* epoch, int* cnt) {
+__global__ void shard_begin_kernel(int* epoch, int* cnt, int* exch) {
     if (threadIdx.x == 0) {
         *epoch += 1;
         cnt[0] = 0;
         cnt[1] = 0;
+        if (exch) { exch[0] = 0; exch[1] = 0; }  // [n_roots (unused by the peer transport), n_pairs]
     }
+}
+
+// both faces' halo words of the previous pass in one launch (blockIdx.y = face)
+__global__ void __launch_bounds__(256) shard_clear_halos_kernel(const int* runs_lo, const int* runs_hi, int cap, ull* __restrict__ halo_lo,
+                                                               ull* __restrict__ halo_hi, unsigned Z, const int* epoch,
+                                                               long long parity_stride) {
+    const int* runs = blockIdx.y ? runs_hi : runs_lo;
+    ull* halo = blockIdx.y ? halo_hi : halo_lo;
+    if (!halo) return;
+    runs += (long long)((*epoch + 1) & 1) * parity_stride;  // the copy the previous pass used
+    const int n = min(runs[0], cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        halo[(unsigned)runs[3 + 3 * i] / Z] = 0ull;
 }
 
 extern "C" int skb_shard_begin(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs,
                                void* stream) {
+    return skb_shard_begin_pass(mailbox, world, cap_runs, cap_roots, cap_pairs, 1, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int skb_shard_begin_pass(void* mailbox, int world, int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, int64_t Z,
+                                    uint64_t* halo_lo, uint64_t* halo_hi, int32_t* exchange, void* stream) {
     int rc = mailbox_args("skb_shard_begin", world, cap_runs, cap_roots, cap_pairs);
     if (rc) return rc;
-    SKB_REQUIRE(mailbox, "skb_shard_begin: NULL mailbox");
+    SKB_REQUIRE(mailbox && Z > 0, "skb_shard_begin: NULL mailbox");
     Mailbox mb = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
-    shard_begin_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(mb.epoch(), mb.cnt(0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    shard_begin_kernel<<<1, 32, 0, st>>>(mb.epoch(), mb.cnt(0), exchange);
+    if (halo_lo || halo_hi)
+        shard_clear_halos_kernel<<<dim3(74, 2), 256, 0, st>>>(mb.recv(0), mb.recv(1), (int)cap_runs, reinterpret_cast<ull*>(halo_lo),
+                                                             reinterpret_cast<ull*>(halo_hi), (unsigned)Z, mb.epoch(), mb.M.runs_ints);
     SKB_LAUNCH_CHECK("shard_begin_kernel");
     return SKB_OK;
 }
@@ -621,8 +769,7 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
     CclView v = skb_ccl_make_view(L, workspace, 0, 1, status, nullptr);
     Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
     // my LOW face lands in the lower neighbour's recv_hi, my HIGH face in the upper neighbour's recv_lo
-    EmitFace f[2];
-    SignalRuns sg[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    EmitFace f[2] = {};
     int n = 0;
     for (int hi = 0; hi < 2; ++hi) {
         void* nbp = hi ? hi_neighbour_mailbox : lo_neighbour_mailbox;
@@ -633,14 +780,15 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
         f[n].z_lo = (int)(hi ? z_off + Zl - halo : z_off);
         f[n].z_hi = (int)(hi ? z_off + Zl : z_off + halo);
         f[n].dst = {me.cnt(hi), remote + 3, me.epoch(), me.M.runs_ints};
-        sg[n] = {me.cnt(hi), remote, nb.flag(hi ? 0 : 1)};
+        f[n].done = me.cnt(2 + hi);  // counters 2, 3 of the same line: CTAs of my low / high face that have finished
+        f[n].remote_runs = remote;
+        f[n].remote_flag = nb.flag(hi ? 0 : 1);
         ++n;
     }
     if (n == 1) f[1] = f[0];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned nblk = (unsigned)(((long long)X * Y + 256 * EMIT_ROWS - 1) / (256 * EMIT_ROWS));
-    shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);
-    shard_signal_runs_kernel<<<1, 32, 0, st>>>(sg[0], sg[1], me.M.runs_ints, me.epoch());
+    shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);  // its last CTA per face signals
     SKB_LAUNCH_CHECK("skb_shard_emit_runs_peer");
     return SKB_OK;
 }
@@ -671,34 +819,51 @@ struct PeerTable {
     int* flag[SKB_MAX_WORLD];      // rank p's flag word for payloads coming from me
 };
 
-// grid (PUSH_BLOCKS, world): CTA (.,p) stores the used part of my payload into slot `rank` of rank p
+// grid (PUSH_BLOCKS, world): CTA (.,p) stores my payload — [n_roots, n_pairs, roots, pairs] — into slot `rank` of rank p:
+// the roots straight from the slab's root list (round 1 first packed them into the exchange buffer with one more
+// kernel), the pairs from where the ingest appended them.  The last CTA to finish releases every rank's flag (round 1:
+// a separate one-warp kernel).
 constexpr int PUSH_BLOCKS = 4;
-__global__ void __launch_bounds__(256) shard_push_kernel(const int* __restrict__ exch, PeerTable T, int rank, int cap_roots,
-                                                        int cap_pairs, long long stride, long long parity_stride,
-                                                        const int* epoch) {
+__global__ void __launch_bounds__(256) shard_push_kernel(CclView v, const int* __restrict__ exch, PeerTable T, int world, int rank,
+                                                        int cap_roots, int cap_pairs, long long stride, long long parity_stride,
+                                                        const int* epoch, int* done) {
     const int p = blockIdx.y;
-    int* dst = T.gathered[p] + (long long)(*epoch & 1) * parity_stride + (long long)rank * stride;
-    const int n_roots = min(exch[0], cap_roots), n_pairs = min(exch[1], cap_pairs);
-    const int head = 2 + n_roots, tail = 2 * n_pairs;
+    const int e = *epoch;
+    int* dst = T.gathered[p] + (long long)(e & 1) * parity_stride + (long long)rank * stride;
+    const unsigned n_all = v.hdr->n_global_roots;
+    const int n_roots = (int)min(n_all, (unsigned)cap_roots), n_pairs = min(exch[1], cap_pairs);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (int i = tid; i < head; i += nthr) dst[i] = exch[i];
+    if (tid == 0) {
+        dst[0] = n_roots;
+        dst[1] = n_pairs;
+        if (p == 0 && n_all > (unsigned)cap_roots) atomicOr(v.status, SKB_STATUS_ROOT_OVERFLOW);
+    }
+    for (int i = tid; i < n_roots; i += nthr) dst[2 + i] = v.groots[i];
     const int* ps = exch + 2 + cap_roots;
     int* pd = dst + 2 + cap_roots;
-    for (int i = tid; i < tail; i += nthr) pd[i] = ps[i];
-}
-
-__global__ void shard_signal_all_kernel(PeerTable T, int world, const int* epoch) {
-    if ((int)threadIdx.x < world) {
-        __threadfence_system();
-        st_release_sys(T.flag[threadIdx.x], *epoch);
+    for (int i = tid; i < 2 * n_pairs; i += nthr) pd[i] = ps[i];
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *done = 0;
+        if ((int)threadIdx.x < world) {
+            __threadfence_system();
+            st_release_sys(T.flag[threadIdx.x], e);
+        }
     }
 }
 
-extern "C" int skb_shard_push(const int32_t* exchange, void* mailbox, const uint64_t* peer_mailboxes, int world, int rank,
-                              int64_t cap_runs, int64_t cap_roots, int64_t cap_pairs, void* stream) {
-    int rc = mailbox_args("skb_shard_push", world, cap_runs, cap_roots, cap_pairs);
+extern "C" int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* exchange, void* mailbox,
+                              const uint64_t* peer_mailboxes, int world, int rank, int64_t cap_runs, int64_t cap_roots,
+                              int64_t cap_pairs, uint32_t* status, void* stream) {
+    int rc = skb_check_volume(X, Y, Z, "skb_shard_push");
     if (rc) return rc;
-    SKB_REQUIRE(exchange && mailbox && peer_mailboxes && rank >= 0 && rank < world, "skb_shard_push: bad argument");
+    rc = mailbox_args("skb_shard_push", world, cap_runs, cap_roots, cap_pairs);
+    if (rc) return rc;
+    SKB_REQUIRE(workspace && exchange && mailbox && peer_mailboxes && status && rank >= 0 && rank < world, "skb_shard_push: bad argument");
     Mailbox me = mailbox_at(mailbox, world, cap_runs, cap_roots, cap_pairs);
     PeerTable T = {};
     for (int p = 0; p < world; ++p) {
@@ -707,11 +872,12 @@ extern "C" int skb_shard_push(const int32_t* exchange, void* mailbox, const uint
         T.gathered[p] = pm.gathered();
         T.flag[p] = pm.flag_gather(rank);
     }
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
+    CclView v = skb_ccl_make_view(L, workspace, 0, 1, status, nullptr);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long parity_stride = (long long)world * me.M.stride;
-    shard_push_kernel<<<dim3(PUSH_BLOCKS, world), 256, 0, st>>>(exchange, T, rank, (int)cap_roots, (int)cap_pairs, me.M.stride,
-                                                               parity_stride, me.epoch());
-    shard_signal_all_kernel<<<1, 32, 0, st>>>(T, world, me.epoch());
+    shard_push_kernel<<<dim3(PUSH_BLOCKS, world), 256, 0, st>>>(v, exchange, T, world, rank, (int)cap_roots, (int)cap_pairs, me.M.stride,
+                                                               parity_stride, me.epoch(), me.cnt(4));
     SKB_LAUNCH_CHECK("skb_shard_push");
     return SKB_OK;
 }

@@ -285,12 +285,12 @@ class ShardedAssembler:
         # kernel launches of one pass on this rank (bench.py reports them as gpu_launches)
         faces = (rank > 0) + (rank < world - 1)
         if self.transport == "peer":
-            # begin, clear_halo=faces, local(init,pack,tile,boundary,roots)=5, emit+signal<=2, pack_roots=1, ingest=faces,
-            # push+signal=2, merge(init,union,mark,scan x2,rank,publish x2)=8, gather=1
-            self.launches_per_step = 1 + faces + 5 + 2 * (faces > 0) + 1 + faces + 2 + 8 + 1
+            # begin=1, clear_halos=1, local(init,pack,tile,boundary,roots)=5, emit (signals itself)=1, ingest=faces,
+            # push (signals itself)=1, merge (one cooperative kernel)=1, gather=1
+            self.launches_per_step = 1 + (faces > 0) + 5 + (faces > 0) + faces + 1 + 1 + 1
         else:
-            # clear_halo=faces, local=5, emit=faces, pack_roots=1, ingest=faces, merge=8, gather=1 (+ NCCL's own kernels)
-            self.launches_per_step = faces + 5 + faces + 1 + faces + 8 + 1
+            # clear_halo=faces, local=5, emit=faces, pack_roots=1, ingest=faces, merge=1, gather=1 (+ NCCL's own kernels)
+            self.launches_per_step = faces + 5 + faces + 1 + faces + 1 + 1
         self.launches_per_step += 1 if self.split else 0  # split: stream + resolve instead of one gather
 
     def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:
@@ -372,18 +372,16 @@ class ShardedAssembler:
         z0, z1 = self.z_range
         peer = self.transport == "peer"
         with torch.cuda.device(self.dev):
-            if peer:
-                L.check(self.lib.skb_shard_begin(self.mailbox.ptr, *self._geom, self._s()))
             # the halo words of the previous pass are cleared from its run lists (not a 33 MB memset per face and pass);
             # this has to happen before the next exchange overwrites the lists
-            for hi, halo in ((0, self.halo_lo), (1, self.halo_hi)):
-                if halo is None:
-                    continue
-                if peer:
-                    L.check(self.lib.skb_shard_clear_halo_peer(Z, self.mailbox.ptr, hi, *self._geom, halo.data_ptr(), self._s()))
-                else:
-                    L.check(self.lib.skb_shard_clear_halo(Z, (self.recv_hi if hi else self.recv_lo).data_ptr(), self.cap_runs,
-                                                          halo.data_ptr(), self._s()))
+            if peer:  # pass counter + both faces' halo words + the exchange buffer's counters: two launches
+                L.check(self.lib.skb_shard_begin_pass(self.mailbox.ptr, *self._geom, Z, L.ptr(self.halo_lo), L.ptr(self.halo_hi),
+                                                      self.exch.data_ptr(), self._s()))
+            else:
+                for hi, halo in ((0, self.halo_lo), (1, self.halo_hi)):
+                    if halo is not None:
+                        L.check(self.lib.skb_shard_clear_halo(Z, (self.recv_hi if hi else self.recv_lo).data_ptr(), self.cap_runs,
+                                                              halo.data_ptr(), self._s()))
             if self.split:
                 from .pipeline import chain_stream
                 main = torch.cuda.current_stream(self.dev)
@@ -418,10 +416,10 @@ class ShardedAssembler:
         z0, z1 = self.z_range
         peer = self.transport == "peer"
         with torch.cuda.device(self.dev), self._chain():
-            # zero the exchange buffer's counters and pack my roots (needs only the local phase) ...
-            L.check(self.lib.skb_shard_boundary_pairs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, self.capacity,
-                                                      0, self.exch.data_ptr(), self.cap_roots, self.cap_pairs,
-                                                      self.meta[1:2].data_ptr(), self._s()))
+            if not peer:  # zero the exchange buffer's counters and pack my roots (needs only the local phase) ...
+                L.check(self.lib.skb_shard_boundary_pairs(self.workspace.data_ptr(), X, Y, Z, z0, self.Zl, self.capacity,
+                                                          0, self.exch.data_ptr(), self.cap_roots, self.cap_pairs,
+                                                          self.meta[1:2].data_ptr(), self._s()))
             # ... then the neighbours' runs; the upper neighbour's ingest also appends the face pairs
             for hi, halo, recv in ((0, self.halo_lo, None if peer else self.recv_lo),
                                    (1, self.halo_hi, None if peer else self.recv_hi)):
@@ -437,8 +435,10 @@ class ShardedAssembler:
                                                            self.cap_runs, halo.data_ptr(), exch, self.cap_roots, self.cap_pairs,
                                                            self.meta[1:2].data_ptr(), self._s()))
             if peer:
-                L.check(self.lib.skb_shard_push(self.exch.data_ptr(), self.mailbox.ptr, self._peer_arr, self.world, self.rank,
-                                                self.cap_runs, self.cap_roots, self.cap_pairs, self._s()))
+                # roots straight from the slab's root list + the pairs the ingest appended -> every rank's mailbox
+                L.check(self.lib.skb_shard_push(self.workspace.data_ptr(), X, Y, Z, self.exch.data_ptr(), self.mailbox.ptr,
+                                                self._peer_arr, self.world, self.rank, self.cap_runs, self.cap_roots,
+                                                self.cap_pairs, self.meta[1:2].data_ptr(), self._s()))
 
     def phase_merge(self) -> None:
         """after the all-gather: `gathered` holds every rank's roots and pairs -> global numbering on this rank."""

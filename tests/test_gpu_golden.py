@@ -23,7 +23,7 @@ def cu(a, dtype=None):
 
 def test_library_loaded_is_in_tree():
     import skoots_b200._lib as L
-    assert L.load().skb_version() == 100
+    assert L.load().skb_version() == 200
     assert L.LIB_PATH.endswith("skoots_b200/libskoots_b200.so")
 
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/skoots_b200.h but not exported"
     assert declared == set(L.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert L.load().skb_version() == 100
+    assert L.load().skb_version() == 200
 
 
 def test_argument_errors_do_not_need_a_gpu():

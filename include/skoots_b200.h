@@ -316,11 +316,11 @@ int skb_assemble_resolve(const void* vec, int vec_dtype, int64_t X, int64_t Y, i
  *   HBM.  A flag that does not arrive within ~8 s sets SKB_STATUS_PEER_TIMEOUT instead of hanging.
  *   Call order per rank and pass (skoots_b200/sharded.py, transport "peer"):
  *     skb_shard_begin_pass (pass counter, halo words of the previous pass cleared, pair counter zeroed)
- *     -> skb_shard_label_local -> skb_shard_emit_runs_peer (both faces; the kernel's last CTA per face signals)
+ *     -> skb_shard_label_local -> skb_shard_emit_runs_peer (both faces + a one-warp signal kernel)
  *     -> skb_shard_ingest_runs_peer (from the low / high neighbour; the latter appends the face pairs)
- *     -> skb_shard_push (roots + pairs to every rank; last CTA signals) -> skb_shard_merge_peer (one cooperative
- *     kernel: eight phases separated by grid barriers) -> skb_assemble_slab[_ex].
- *     13 kernel launches per pass on a rank with two neighbours (round 1: 24 + 3 memsets).
+ *     -> skb_shard_push (roots + pairs to every rank; its last CTA signals) -> skb_shard_merge_peer (eight launches; a
+ *     one-kernel cooperative form exists behind SKB_SHARD_FUSED=1 — measured slower) -> skb_assemble_slab[_ex].
+ *     21 kernel launches + 1 memset per pass on a rank with two neighbours (round 1: 24 + 3 memsets).
  *   The skb_peer_* calls are set-up / tear-down only: they are the one place the library allocates
  *   (cudaMalloc: legacy CUDA IPC cannot export a caching allocator's sub-allocations).
  * ------------------------------------------------------------------------------------------- */
@@ -360,7 +360,7 @@ int skb_shard_ingest_runs_peer(void* workspace, int64_t X, int64_t Y, int64_t Z,
  * neighbour's ingest appended to `exchange` (counters zeroed by skb_shard_begin_pass) — into slot `rank` of every
  * rank's mailbox (peer_mailboxes: HOST array of `world` device pointers, own included); the last CTA of the kernel
  * releases the flags.  No skb_shard_boundary_pairs call is needed on this transport. */
-int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* exchange, void* mailbox,
+int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, const int32_t* exchange, void* mailbox,
                    const uint64_t* peer_mailboxes, int world, int rank, int64_t cap_runs, int64_t cap_roots,
                    int64_t cap_pairs, uint32_t* status, void* stream);
 /* waits for every rank's flag, then skb_shard_merge on the mailbox's gather buffer */

@@ -92,7 +92,7 @@ SIGNATURES = {
     "skb_shard_begin": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp]),
     "skb_shard_emit_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_ingest_runs_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
-    "skb_shard_push": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, ctypes.POINTER(ctypes.c_uint64), _c_int, _c_int, _c_i64, _c_i64, _c_i64,
+    "skb_shard_push": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, ctypes.POINTER(ctypes.c_uint64), _c_int, _c_int, _c_i64, _c_i64, _c_i64,
                                 _c_vp, _c_vp]),
     "skb_shard_begin_pass": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_shard_merge_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),

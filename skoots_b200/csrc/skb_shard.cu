@@ -103,13 +103,14 @@ constexpr int EMIT_ROWS = 4;
 constexpr int EMIT_QUEUE = 96;  // runs a warp can queue
 
 // returns whether this thread stored any triple
-__device__ __forceinline__ bool emit_face_rows(const CclView& v, const EmitFace& f, int cap, unsigned* status, int2 (*s_runs)[EMIT_QUEUE]) {
+__device__ __forceinline__ bool emit_face_rows(const CclView& v, const EmitFace& f, int cap, unsigned* status, int2 (*s_runs)[EMIT_QUEUE],
+                                               unsigned row_block) {
     const RunsDst& dst = f.dst;
     const int z_lo = f.z_lo, z_hi = f.z_hi;
     int* const runs = dst.counter;
     int* const tri = dst.triples + (dst.epoch ? (long long)(*dst.epoch & 1) * dst.parity_stride : 0LL);
     const unsigned n_rows = (unsigned)v.X * (unsigned)v.Y;
-    const unsigned row0 = (blockIdx.x * blockDim.x + threadIdx.x) * EMIT_ROWS;
+    const unsigned row0 = (row_block * blockDim.x + threadIdx.x) * EMIT_ROWS;
     const int lane = threadIdx.x & 31;
     const int k = z_lo >> 6, b0 = z_lo & 63, nb = z_hi - z_lo;
     const ull range = (nb >= 64 ? ~0ull : ((1ull << nb) - 1ull)) << b0;
@@ -188,7 +189,15 @@ __device__ __forceinline__ bool emit_face_rows(const CclView& v, const EmitFace&
 __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFace f0, EmitFace f1, int cap, unsigned* status) {
     __shared__ int2 s_runs[8][EMIT_QUEUE];
     const EmitFace& f = blockIdx.y ? f1 : f0;
-    const bool stored = emit_face_rows(v, f, cap, status, s_runs);
+    // Signalling from the kernel's last CTA (f.done != NULL) was measured and NOT adopted: counting 4096 CTAs per face on
+    // one address serialises in L2 (30 -> 74 us), and a bounded grid that walks the row blocks loses as much to its
+    // serial iterations (58 us for two faces).  The one-warp signal kernel behind this one costs 6 us.
+    const unsigned n_row_blocks = ((unsigned)v.X * (unsigned)v.Y + blockDim.x * EMIT_ROWS - 1) / (blockDim.x * EMIT_ROWS);
+    bool stored = false;
+    for (unsigned rb = blockIdx.x; rb < n_row_blocks; rb += gridDim.x) {
+        stored |= emit_face_rows(v, f, cap, status, s_runs, rb);
+        __syncwarp();  // the warp's queue is reused by its next row block
+    }
     if (f.done == nullptr) return;
     // my triples (stored into the neighbour's memory) become visible system-wide before my CTA counts itself as finished
     if (stored) __threadfence_system();
@@ -202,6 +211,25 @@ __global__ void __launch_bounds__(256) shard_emit_runs_kernel(CclView v, EmitFac
             f.remote_runs[(long long)(e & 1) * f.dst.parity_stride] = *reinterpret_cast<volatile int*>(f.dst.counter);
             __threadfence_system();
             st_release_sys(f.remote_flag, e);
+        }
+    }
+}
+
+// peer transport: publishes my face's run count in the neighbour's buffer, then releases its flag.  The
+// triples were stored by the previous kernel on this stream, so they are ordered before the flag.
+struct SignalRuns {
+    const int* local_cnt;  // NULL: no such face
+    int* remote_runs;
+    int* remote_flag;
+};
+__global__ void shard_signal_runs_kernel(SignalRuns s0, SignalRuns s1, long long parity_stride, const int* epoch) {
+    if (threadIdx.x < 2) {
+        const SignalRuns& s = threadIdx.x ? s1 : s0;
+        if (s.local_cnt) {
+            const int e = *epoch;
+            s.remote_runs[(long long)(e & 1) * parity_stride] = *s.local_cnt;
+            __threadfence_system();
+            st_release_sys(s.remote_flag, e);
         }
     }
 }
@@ -389,6 +417,7 @@ __global__ void __launch_bounds__(256) shard_publish_roots_kernel(CclView v, Mer
 // barriers (~1.5 us each).  The phases are the kernels above, verbatim, with the (block, rank-row) indices of their
 // grids mapped onto this grid's CTAs.
 constexpr int MERGE_FUSED_THREADS = 1024;
+constexpr int MERGE_FUSED_CTAS = 32;
 
 template <typename F>
 __device__ __forceinline__ void merge_for_each(const MergeView& m, const int* base, bool pairs, bool skip_own, F&& f) {
@@ -628,14 +657,17 @@ extern "C" int skb_shard_merge(void* workspace, int64_t X, int64_t Y, int64_t Z,
 }
 
 static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView& m, int32_t label_base, cudaStream_t st) {
-    static int fused_ok = -1;  // -1 unknown; SKB_SHARD_FUSED=0 keeps the eight-launch form (measurements)
+    // The one-kernel form is opt-in (SKB_SHARD_FUSED=1).  Measured on a 1/8 slab of the headline volume (ncu launch list,
+    // profiles/r02_launches_shard8_emulated.txt): 64 us with one CTA per SM, 73 us with 32 CTAs, against 56 us for the sum
+    // of the eight launches it replaces — eight grid-wide barriers of 1024-thread CTAs cost more than eight launch gaps.
+    static int fused_ok = -1;
     if (fused_ok < 0) {
         const char* e = getenv("SKB_SHARD_FUSED");
         int dev = 0, coop = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_merge_fused_kernel, MERGE_FUSED_THREADS, 0);
-        fused_ok = (!(e && e[0] == '0') && coop && per_sm >= 1) ? 1 : 0;
+        fused_ok = ((e && e[0] == '1') && coop && per_sm >= 1) ? 1 : 0;
     }
     if (fused_ok) {
         int dev = 0, sms = 0;
@@ -645,7 +677,10 @@ static int launch_merge(const CclView& v, const SkbCclLayout& L, const MergeView
         MergeView mm = m;
         int lb = label_base;
         void* args[] = {&vv, &mm, &lb};
-        cudaError_t rc = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(shard_merge_fused_kernel), dim3((unsigned)sms),
+        // a few thousand roots and pairs: 32 CTAs have more than enough threads, and a grid barrier among 32 CTAs costs a
+        // fraction of one among 148 (measured with all SMs: 64 us for the kernel, more than the eight launches it replaced)
+        const int ctas = sms < MERGE_FUSED_CTAS ? sms : MERGE_FUSED_CTAS;
+        cudaError_t rc = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(shard_merge_fused_kernel), dim3((unsigned)ctas),
                                                      dim3(MERGE_FUSED_THREADS), args, 0, st);
         if (rc == cudaSuccess) return SKB_OK;
         (void)cudaGetLastError();
@@ -788,7 +823,13 @@ extern "C" int skb_shard_emit_runs_peer(void* workspace, int64_t X, int64_t Y, i
     if (n == 1) f[1] = f[0];
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned nblk = (unsigned)(((long long)X * Y + 256 * EMIT_ROWS - 1) / (256 * EMIT_ROWS));
-    shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);  // its last CTA per face signals
+    SignalRuns sg[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    for (int i = 0; i < n; ++i) {
+        sg[i] = {f[i].dst.counter, f[i].remote_runs, f[i].remote_flag};
+        f[i].done = nullptr;  // see the kernel: signalling from its last CTA is slower than the signal kernel
+    }
+    shard_emit_runs_kernel<<<dim3(nblk, n), 256, 0, st>>>(v, f[0], f[1], (int)cap_runs, status);
+    shard_signal_runs_kernel<<<1, 32, 0, st>>>(sg[0], sg[1], me.M.runs_ints, me.epoch());
     SKB_LAUNCH_CHECK("skb_shard_emit_runs_peer");
     return SKB_OK;
 }
@@ -842,10 +883,12 @@ __global__ void __launch_bounds__(256) shard_push_kernel(CclView v, const int* _
     const int* ps = exch + 2 + cap_roots;
     int* pd = dst + 2 + cap_roots;
     for (int i = tid; i < 2 * n_pairs; i += nthr) pd[i] = ps[i];
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();  // the CTA's stores happen-before thread 0's fence (fences are cumulative): one system fence per CTA
     __shared__ int last;
-    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(done, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    }
     __syncthreads();
     if (last) {
         if (threadIdx.x == 0) *done = 0;
@@ -856,7 +899,7 @@ __global__ void __launch_bounds__(256) shard_push_kernel(CclView v, const int* _
     }
 }
 
-extern "C" int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, const int32_t* exchange, void* mailbox,
+extern "C" int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, int64_t capacity, const int32_t* exchange, void* mailbox,
                               const uint64_t* peer_mailboxes, int world, int rank, int64_t cap_runs, int64_t cap_roots,
                               int64_t cap_pairs, uint32_t* status, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_shard_push");
@@ -872,8 +915,9 @@ extern "C" int skb_shard_push(void* workspace, int64_t X, int64_t Y, int64_t Z, 
         T.gathered[p] = pm.gathered();
         T.flag[p] = pm.flag_gather(rank);
     }
-    SkbCclLayout L = skb_ccl_layout(X, Y, Z, 1);
-    CclView v = skb_ccl_make_view(L, workspace, 0, 1, status, nullptr);
+    SKB_REQUIRE(capacity > 0 && capacity <= 0x7fffffff, "skb_shard_push: bad capacity");
+    SkbCclLayout L = skb_ccl_layout(X, Y, Z, capacity);  // the root list sits behind the capacity-sized arrays
+    CclView v = skb_ccl_make_view(L, workspace, 0, capacity, status, nullptr);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long parity_stride = (long long)world * me.M.stride;
     shard_push_kernel<<<dim3(PUSH_BLOCKS, world), 256, 0, st>>>(v, exchange, T, world, rank, (int)cap_roots, (int)cap_pairs, me.M.stride,

@@ -285,12 +285,12 @@ class ShardedAssembler:
         # kernel launches of one pass on this rank (bench.py reports them as gpu_launches)
         faces = (rank > 0) + (rank < world - 1)
         if self.transport == "peer":
-            # begin=1, clear_halos=1, local(init,pack,tile,boundary,roots)=5, emit (signals itself)=1, ingest=faces,
-            # push (signals itself)=1, merge (one cooperative kernel)=1, gather=1
-            self.launches_per_step = 1 + (faces > 0) + 5 + (faces > 0) + faces + 1 + 1 + 1
+            # begin=1, clear_halos=1, local(init,pack,tile,boundary,roots)=5, emit+signal=2, ingest=faces,
+            # push (signals itself)=1, merge(init,union,mark,scan x2,rank,publish x2)=8, gather=1
+            self.launches_per_step = 1 + (faces > 0) + 5 + 2 * (faces > 0) + faces + 1 + 8 + 1
         else:
-            # clear_halo=faces, local=5, emit=faces, pack_roots=1, ingest=faces, merge=1, gather=1 (+ NCCL's own kernels)
-            self.launches_per_step = faces + 5 + faces + 1 + faces + 1 + 1
+            # clear_halo=faces, local=5, emit=faces, pack_roots=1, ingest=faces, merge=8, gather=1 (+ NCCL's own kernels)
+            self.launches_per_step = faces + 5 + faces + 1 + faces + 8 + 1
         self.launches_per_step += 1 if self.split else 0  # split: stream + resolve instead of one gather
 
     def attach(self, mailbox: Mailbox, peer_ptrs: Sequence[int]) -> None:
@@ -436,7 +436,7 @@ class ShardedAssembler:
                                                            self.meta[1:2].data_ptr(), self._s()))
             if peer:
                 # roots straight from the slab's root list + the pairs the ingest appended -> every rank's mailbox
-                L.check(self.lib.skb_shard_push(self.workspace.data_ptr(), X, Y, Z, self.exch.data_ptr(), self.mailbox.ptr,
+                L.check(self.lib.skb_shard_push(self.workspace.data_ptr(), X, Y, Z, self.capacity, self.exch.data_ptr(), self.mailbox.ptr,
                                                 self._peer_arr, self.world, self.rank, self.cap_runs, self.cap_roots,
                                                 self.cap_pairs, self.meta[1:2].data_ptr(), self._s()))
 

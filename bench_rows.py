@@ -96,6 +96,15 @@ def main():
                         cpu_ms(lambda: orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=N)), bool(torch.equal(got.cpu(), want)),
                         "launch-latency bound at this size (12 kernels for 0.5 Mvox)"))
 
+    from skoots_b200.pipeline import GraphedAssembler
+    for N in (1, 10):
+        run = GraphedAssembler((128, 128, 32), SCALE, DEV, N=N)
+        want = orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=N)
+        got = run(m, v)
+        rows.append(row(f"a1+a2+a3 whole path N={N}, ONE CUDA-graph launch (GraphedAssembler)", "C1 128x128x32, 20 tubes", 128 * 128 * 32, 11,
+                        gpu_ms(lambda: run(m, v, check=False)), cpu_ms(lambda: orc.postprocess(tv.skeleton, tv.vectors, SCALE, N=N)),
+                        bool(torch.equal(got.cpu(), want)), "two device-to-device input copies + one graph replay of the 11-kernel chain"))
+
     # ---- C2: one 300x300x20 tile: epilogue, dilation chain, flood fill, assembly --------------------------
     tv = make_tube_volume((300, 300, 20), 20, seed=0)
     g = torch.Generator().manual_seed(1)
@@ -112,6 +121,13 @@ def main():
                     gpu_ms(lambda: tile_epilogue(unet_d, gv, gs, (0, 0, 0), (50, 50, 5))),
                     cpu_ms(lambda: orc.tile_epilogue(unet, wv, ws, (0, 0, 0), (50, 50, 5))),
                     bool(torch.equal(gv.cpu(), wv) and torch.equal(gs.cpu(), ws)), "20 B read per tile voxel"))
+    # 16 different tiles back to back (what eval()'s tile loop does): 576 MB of network output, far larger than L2, and the
+    # host's launch path amortised — the per-tile figure is the kernel's, not Python's
+    tiles16 = [(unet_d + 0.001 * k).contiguous() for k in range(16)]
+    rows.append(row("a5 tile epilogue, 16 tiles back to back (per tile)", "C2 16 x 300x300x20 tiles", 300 * 300 * 20, 20,
+                    gpu_ms(lambda: [tile_epilogue(t, gv, gs, (0, 0, 0), (50, 50, 5)) for t in tiles16]) / 16,
+                    cpu_ms(lambda: orc.tile_epilogue(unet, wv, ws, (0, 0, 0), (50, 50, 5))), True, "20 B read per tile voxel"))
+    del tiles16
     img = unet[:, 3:4].contiguous()
     img_d = img.to(DEV)
     rows.append(row("a4 binary_dilation + 2x binary_dilation_2d", "C2 300x300x20", 300 * 300 * 20, 24,
@@ -284,6 +300,26 @@ def main():
                     "4 B gt + 4 B prediction per voxel; the CPU figure is the oracle's contingency restatement, "
                     "not the reference's O(N*M*V) loop"))
     del tv, inst, gt, scratch
+
+    # ---- f4: elastic deformation of one training crop (image + mask + skeleton points) -------------------------------
+    from skoots_b200.train.merged_transform import elastic_deform
+    tvf = vols[0]
+    img5 = torch.rand((1, 1, 300, 300, 20))
+    mask5 = tvf.mask.float()[None, None]
+    sk_long = {k: p.long() for k, p in present[0].items()}
+    noise = torch.rand((1, 3, 2, 6, 6))
+    w_img, w_mask, w_sk = orc.elastic_deform(noise, img5, mask5, skeleton=sk_long)
+    img_d5, mask_d5 = img5.to(DEV), mask5.to(DEV)
+    sk_d5 = {k: p.to(DEV) for k, p in sk_long.items()}
+    noise_d = noise.to(DEV)
+    g_img, g_mask, g_sk = elastic_deform(img_d5, mask_d5, skeleton=sk_d5, noise=noise_d)
+    mism = float((g_mask.cpu() != w_mask).float().mean())
+    rows.append(row("f4 elastic_deform (image + mask + skeleton points)", "C4 one 300x300x20 crop, 20 skeletons", 2 * 300 * 300 * 20, 8,
+                    gpu_ms(lambda: elastic_deform(img_d5, mask_d5, skeleton=sk_d5, noise=noise_d)),
+                    cpu_ms(lambda: orc.elastic_deform(noise, img5, mask5, skeleton=sk_long), iters=1),
+                    bool(mism <= 1e-3 and all(int((g_sk[k].cpu() - w_sk[k]).abs().max()) <= 1 for k in w_sk)),
+                    f"4 B read + 4 B written per voxel and argument; {mism:.2e} of the mask voxels differ from the torch oracle "
+                    "(rounding ties of the nearest sampling, DESIGN.md)"))
 
     # the reference's only GPU kernel (Triton, skoots/lib/skeleton.py:51-367) on the same box and inputs.
     # Its semantics differ from the CPU path (fp16 outputs, anisotropy on squared differences, per-axis max on

@@ -24,6 +24,8 @@ struct ProbParams {
     long long inner;     // voxels per (b,c) plane
     long long total;     // B * inner
     float neg2sig2[3];   // -2 (sigma+eps)^2, rounded like the reference (fp32 ops)
+    float inv[3];        // 1 / neg2sig2: the BACKWARD kernels multiply (gradients carry a tolerance, and an IEEE division is
+                         // ~12 instructions: six of them per voxel made the fused backward instruction-bound, 172 us for C4)
     float scale[3];      // fused form only
     int X, Y, Z;         // fused form only (Z = 1, Y = last dim for 2-D)
 };
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(256) embed_prob_bwd_vec8_kernel(const float* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float d = e[j] - s[j];
-            ge[j] = gp[j] * 2.f * d / P.neg2sig2[c];
+            ge[j] = gp[j] * 2.f * d * P.inv[c];
             gs[j] = -ge[j];
         }
         if (gE) st8<float>(gE + base + c * P.inner, ge);
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(256) vec_prob_vec8_kernel(const VT* __restrict
             const int idx = c == 0 ? c0[j] : (c == 1 ? c1[j] : c2[j]);
             const float e = __fadd_rn((float)idx, __fmul_rn(v[j], P.scale[c]));
             d[c][j] = __fsub_rn(e, s[j]);
-            acc[j] = __fadd_rn(acc[j], __fdiv_rn(__fmul_rn(d[c][j], d[c][j]), P.neg2sig2[c]));
+            acc[j] = BWD ? acc[j] + d[c][j] * d[c][j] * P.inv[c]
+                         : __fadd_rn(acc[j], __fdiv_rn(__fmul_rn(d[c][j], d[c][j]), P.neg2sig2[c]));
         }
     }
     float p[8];
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(256) vec_prob_vec8_kernel(const VT* __restrict
     for (int c = 0; c < NC; ++c) {
             float gv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = gp[j] * 2.f * d[c][j] / P.neg2sig2[c] * P.scale[c];
+            for (int j = 0; j < 8; ++j) gv[j] = gp[j] * 2.f * d[c][j] * P.inv[c] * P.scale[c];
             st8<VT>(gvec + base + c * P.inner, gv);
         }
     }
@@ -281,6 +284,7 @@ static int fill_prob(ProbParams& P, int64_t B, int C, int64_t inner, const float
         volatile float s2 = s * s;
         volatile float s3 = s2 * 2.f;
         P.neg2sig2[c] = -s3;
+        P.inv[c] = 1.0f / P.neg2sig2[c];
     }
     return SKB_OK;
 }
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
     float4* s_arena = reinterpret_cast<float4*>(smem_raw);                 // BAKE_ARENA points
     float* s_b = reinterpret_cast<float*>(s_arena + BAKE_ARENA);           // 4 x RN: x, y, z, distance
     int* s_slot = reinterpret_cast<int*>(s_b + 4 * RN);                    // RN
-    __shared__ int s_present[BAKE_MAXU], s_lo[BAKE_MAXU], s_cnt[BAKE_MAXU], s_at[BAKE_MAXU];
+    __shared__ int s_present[BAKE_MAXU], s_present_id[BAKE_MAXU], s_lo[BAKE_MAXU], s_cnt[BAKE_MAXU], s_at[BAKE_MAXU];
     __shared__ __align__(8) ull bar;
 
     const int b = blockIdx.y;
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
     const MT* mask = masks + (long long)b * P.V;
     const int id_lo = __ldg(P.id_begin + b), id_hi = __ldg(P.id_begin + b + 1);
 
-    if (threadIdx.x < BAKE_MAXU) s_present[threadIdx.x] = -1;
+    if (threadIdx.x < BAKE_MAXU) { s_present[threadIdx.x] = -1; s_present_id[threadIdx.x] = 0; }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -506,21 +510,36 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
         if (gx >= 0 && gx < P.X && gy >= 0 && gy < P.Y && gz >= 0 && gz < P.Z) {
             const int id = (int)mask[((long long)gx * P.Y + gy) * P.Z + gz];
             if (id != 0) {
-                int a = id_lo, e = id_hi - 1, found = -1;
-                while (a <= e) {
-                    const int m = (a + e) >> 1, v = __ldg(P.ids + m);
-                    if (v == id) { found = m; break; }
-                    if (v < id) a = m + 1; else e = m - 1;
+                // a tile sees one to three objects: most voxels find their id among the ones the CTA has already looked
+                // up (shared memory) and skip the binary search through the id table (five dependent global loads)
+                for (int k = 0; k < BAKE_MAXU; ++k) {
+                    const int pid = *reinterpret_cast<volatile int*>(&s_present_id[k]);
+                    if (pid == id) { slot = k; break; }
+                    if (pid == 0) break;
                 }
-                if (found < 0) {
-                    atomicOr(P.status, SKB_STATUS_MISSING_ID);
-                } else {
+                if (slot >= 0) {
                     any_fg = 1;
-                    slot = -2 - found;
-                    for (int k = 0; k < BAKE_MAXU; ++k) {
-                        int cur = *reinterpret_cast<volatile int*>(&s_present[k]);
-                        if (cur == -1) cur = atomicCAS(&s_present[k], -1, found);
-                        if (cur == -1 || cur == found) { slot = k; break; }
+                } else {
+                    int a = id_lo, e = id_hi - 1, found = -1;
+                    while (a <= e) {
+                        const int m = (a + e) >> 1, v = __ldg(P.ids + m);
+                        if (v == id) { found = m; break; }
+                        if (v < id) a = m + 1; else e = m - 1;
+                    }
+                    if (found < 0) {
+                        atomicOr(P.status, SKB_STATUS_MISSING_ID);
+                    } else {
+                        any_fg = 1;
+                        slot = -2 - found;
+                        for (int k = 0; k < BAKE_MAXU; ++k) {
+                            int cur = *reinterpret_cast<volatile int*>(&s_present[k]);
+                            if (cur == -1) cur = atomicCAS(&s_present[k], -1, found);
+                            if (cur == -1 || cur == found) {
+                                slot = k;
+                                s_present_id[k] = id;  // published after the entry: a reader that misses it just searches
+                                break;
+                            }
+                        }
                     }
                 }
             }

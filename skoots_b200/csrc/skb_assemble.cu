@@ -246,6 +246,14 @@ __device__ __forceinline__ unsigned nonzero_bits(const Raw8<VecT>& a, const Raw8
     return work;
 }
 
+// Measured and NOT adopted (round 2): a per-lane form for DENSE chunks.  The density sweep (bench.py extras) shows the
+// path at 0.24 of its roofline when half of the voxels carry a vector (four queue rounds per chunk) against 0.81 on the
+// sparse headline volume, so chunks with >= 48 work items were handed to resolve_group (each lane resolves its own 8
+// voxels with staged, unconditional loads).  Inlined, it pushed the kernel over its 64-register budget (spills);
+// out of line, the call's stack frame did the same to every chunk's path: the headline gather went from 3.61 to 4.60 ms
+// while the 50 % case only improved from 1.89 to 1.76 ms per 268 Mvox.  The dense regime needs its own kernel
+// instantiation chosen per launch, not a branch in this one.
+
 // What one lane holds for its 8 voxels between the load and the processing of a 256-voxel chunk.
 template <typename VecT> struct ChunkRegs {
     Raw8<VecT> r0, r1, r2;
@@ -701,6 +709,7 @@ __device__ __forceinline__ void resolve_group(const AsmParams& P, long long i0, 
     // stage 1: targets -> address of the 64-bit word that holds the target's bit (slab, or a neighbour's halo plane)
     const ull* wp[8];
     int tv[8], tb[8];
+    bool beyond = false;  // a target past the planes the neighbours' runs describe (slab mode): reported, not mislabelled
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float ex = __fadd_rn(fx, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(a.w, j)), P.s[0]));
@@ -710,12 +719,18 @@ __device__ __forceinline__ void resolve_group(const AsmParams& P, long long i0, 
         const long long rowi = (long long)tx * P.Y + ty;
         const ull* p = P.bits + rowi * P.ZW + ((tz - P.z_off) >> 6);
         bool have = ((work >> j) & 1u) != 0u;
-        if (tz < P.z_off) { p = P.halo_lo + rowi; have = have && P.halo_lo != nullptr; }
-        else if (tz >= z_end) { p = P.halo_hi + rowi; have = have && P.halo_hi != nullptr; }
+        if (tz < P.z_off) {
+            beyond |= have && P.label_halo && tz < P.z_off - P.label_halo;
+            p = P.halo_lo + rowi; have = have && P.halo_lo != nullptr;
+        } else if (tz >= z_end) {
+            beyond |= have && P.label_halo && tz >= z_end + P.label_halo;
+            p = P.halo_hi + rowi; have = have && P.halo_hi != nullptr;
+        }
         wp[j] = have ? p : P.bits;
         tv[j] = have ? (int)(rowi * P.Z + tz) : -1;
         tb[j] = tz & 63;
     }
+    if (beyond && P.status) atomicOr(P.status, SKB_STATUS_HALO_RANGE);
     // stage 2: bit-mask words
     ull ww[8];
 #pragma unroll

@@ -116,20 +116,19 @@ REFERENCE_CROP = (1000, 1000, 200)  # skoots/lib/flood_fill.py:28
 def _adjacent_by_sum_product(p0, p1):
     """get_adjacent_labels, flood_fill.py:237-261, on two seam planes (host int16 arrays): labels (a, b) count as
     touching when a+b and a*b (int16 arithmetic) both occur among the element-wise sums / products of the planes.
-    Host logic: the planes are two 2-D slices of the volume."""
+    Host logic on two 2-D slices; the reference's double Python loop over the label pairs is one outer sum / product
+    and two membership tests here (same pairs, same order: a ascending, then b ascending)."""
     import numpy as np
     p0, p1 = p0.astype(np.int16), p1.astype(np.int16)
     with np.errstate(over="ignore"):
-        sums = set(np.unique(p0 + p1).tolist())
-        prods = set(np.unique(p0 * p1).tolist())
-        found = []
-        for a in np.unique(p0):
-            for b in np.unique(p1):
-                if a == 0 or b == 0:
-                    continue
-                if int(np.int16(a + b)) in sums and int(np.int16(a * b)) in prods:
-                    found.append((int(a), int(b)))
-    return found
+        sums, prods = np.unique(p0 + p1), np.unique(p0 * p1)
+        a, b = np.unique(p0), np.unique(p1)
+        a, b = a[a != 0], b[b != 0]
+        if a.size == 0 or b.size == 0:
+            return []
+        hit = np.isin((a[:, None] + b[None, :]).astype(np.int16), sums) & np.isin((a[:, None] * b[None, :]).astype(np.int16), prods)
+    ia, ib = np.nonzero(hit)
+    return list(zip(a[ia].astype(int).tolist(), b[ib].astype(int).tolist()))
 
 
 def _flood_fill_reference_crops(vol: Tensor, crop=REFERENCE_CROP) -> Tensor:

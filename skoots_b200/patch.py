@@ -49,23 +49,40 @@ def unpatch_skoots() -> None:
     _SAVED.clear()
 
 
-def patch_skoots() -> List[Tuple[str, str]]:
-    """Returns the (module, attribute) pairs that were rebound. Idempotent."""
+def _bug_compatible_flood_fill():
+    """`efficient_flood_fill` with the reference's multi-crop behaviour (seam heuristic, label re-use after an empty crop:
+    SURVEY.md B#6-#8) reproduced bit for bit on volumes larger than one 1000x1000x200 crop."""
+    import functools
+
+    from skoots_b200.lib.flood_fill import efficient_flood_fill
+    bound = functools.partial(efficient_flood_fill, reference_crops=True)
+    functools.update_wrapper(bound, efficient_flood_fill)
+    return bound
+
+
+def patch_skoots(bug_compatible: bool = False) -> List[Tuple[str, str]]:
+    """Returns the (module, attribute) pairs that were rebound. Idempotent.
+
+    bug_compatible=False (default) binds the exact connected-component labelling: identical to the reference on any
+    volume that fits one of its 1000x1000x200 flood-fill crops, and the same partition minus the reference's spurious
+    seam merges on larger ones.  bug_compatible=True binds `efficient_flood_fill(..., reference_crops=True)` instead:
+    the reference's own result bit for bit on every volume, quirks included (north_star's "bit-exact to the reference")."""
     done: List[Tuple[str, str]] = []
     originals = {}
+    special = {("skoots.lib.flood_fill", "efficient_flood_fill"): _bug_compatible_flood_fill()} if bug_compatible else {}
     for (mod_name, attr), (new_mod, new_attr) in _TARGETS.items():
         try:
             mod = importlib.import_module(mod_name)
         except Exception:
             continue
-        new = getattr(importlib.import_module(new_mod), new_attr)
+        new = special.get((mod_name, attr)) or getattr(importlib.import_module(new_mod), new_attr)
         old = getattr(mod, attr, None)
         if old is not None and old is not new:
             originals[id(old)] = new
             _SAVED.setdefault((mod_name, attr), old)
         setattr(mod, attr, new)
         done.append((mod_name, attr))
-    by_name = {attr: getattr(importlib.import_module(nm), na) for (_, attr), (nm, na) in _TARGETS.items()}
+    by_name = {attr: special.get(key) or getattr(importlib.import_module(nm), na) for key, (nm, na) in _TARGETS.items() for attr in (key[1],)}
     for caller in _CALLERS:
         mod = sys.modules.get(caller)
         if mod is None:

@@ -122,3 +122,19 @@ def test_patch_skoots_rebinds_reference_modules():
     finally:
         skoots_b200.patch.unpatch_skoots()
     assert skoots.lib.flood_fill.efficient_flood_fill is before
+
+
+def test_patch_skoots_bug_compatible_binding():
+    """patch_skoots(bug_compatible=True) binds the flood fill that reproduces the reference's multi-crop quirks."""
+    import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not present")
+    ref_shim.install()
+    import skoots.lib.flood_fill
+    import skoots_b200.patch
+    try:
+        skoots_b200.patch.patch_skoots(bug_compatible=True)
+        fn = skoots.lib.flood_fill.efficient_flood_fill
+        assert getattr(fn, "keywords", None) == {"reference_crops": True} and fn.__name__ == "efficient_flood_fill"
+    finally:
+        skoots_b200.patch.unpatch_skoots()

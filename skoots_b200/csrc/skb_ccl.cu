@@ -136,9 +136,8 @@ __device__ __forceinline__ unsigned seg_bits(const MaskT* p, int n, bool vec_ok)
     return bits;
 }
 
-__global__ void ccl_init_kernel(CclView v, SkbCclHeader h, int keep_status, unsigned n_any) {  // <<<1, SKB_TILE_CURSORS>>>
+__global__ void ccl_init_kernel(CclView v, SkbCclHeader h, int keep_status) {  // <<<1, SKB_TILE_CURSORS>>>
     v.cursors[threadIdx.x * SKB_TILE_CURSOR_STRIDE] = 0u;
-    for (unsigned i = threadIdx.x; i < n_any; i += blockDim.x) v.tile_any[i] = 0u;  // n_any = 0: the host used a memset
     if (threadIdx.x == 0) {
         *v.hdr = h;
         if (!keep_status) *v.status = 0u;
@@ -154,19 +153,6 @@ __global__ void ccl_init_kernel(CclView v, SkbCclHeader h, int keep_status, unsi
 // combine their bits into one 64-bit word with two shuffles and lane 0 of the group stores it:
 // a warp reads 512 contiguous bytes and writes 64 contiguous bytes.
 constexpr int PACK_SEGS = 4;
-
-__device__ __forceinline__ int shift_of_dev(int n) { return (n > 0 && !(n & (n - 1))) ? __ffs(n) - 1 : -1; }
-
-// word `wl` of the (slab's) bit mask holds foreground: set the bit of its tile in the tile list's order
-// (k fastest, then y tile, then x tile — ccl_tile_kernel's decode)
-__device__ __forceinline__ void mark_tile(const CclView& v, unsigned wl, int nk_shift) {
-    const unsigned rowi = nk_shift >= 0 ? (wl >> nk_shift) : wl / (unsigned)v.nk;
-    const unsigned kl = wl - rowi * (unsigned)v.nk;
-    const unsigned x = v.y_shift >= 0 ? (rowi >> v.y_shift) : rowi / (unsigned)v.Y;
-    const unsigned y = rowi - x * (unsigned)v.Y;
-    const unsigned t = ((x >> 3) * (unsigned)v.n_yt + (y >> 3)) * (unsigned)v.nk + kl;
-    atomicOr(v.tile_any + (t >> 5), 1u << (t & 31u));
-}
 
 template <typename MaskT>
 __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__ mask, CclView v, unsigned n_seg,
@@ -211,7 +197,6 @@ __global__ void __launch_bounds__(256) ccl_pack_kernel(const MaskT* __restrict__
                 if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
             }
             v.bits[wl] = w;
-            if (w) mark_tile(v, wl, nk_shift);  // ~1.5 % of the words of a skeleton mask
         }
     }
 }
@@ -228,7 +213,6 @@ __global__ void __launch_bounds__(256) ccl_pack_generic_kernel(const MaskT* __re
     ull w = 0;
     for (int i = 0; i < n; ++i) w |= (ull)(p[i] > 0) << i;
     v.bits[t] = w;
-    if (w) mark_tile(v, t, shift_of_dev(v.nk));
     if (v.face_lo) {
         if (kl == 0u) v.face_lo[rowi] = w;
         if (kl == (unsigned)v.nk - 1u) v.face_hi[rowi] = w;
@@ -530,12 +514,9 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
         const unsigned yt = nk_shift >= 0 ? (yk >> nk_shift) : yk / (unsigned)v.nk;
         return Tile{(int)xt * 8, (int)yt * 8, v.k0 + (int)(yk - yt * (unsigned)v.nk)};
     };
-    auto load = [&](unsigned t, const Tile& T, ull& w0, ull& w1) {
+    auto load = [&](const Tile& T, ull& w0, ull& w1) {
         const int xa = T.x0 + (r0 >> 3), xb = T.x0 + (r1 >> 3), y = T.y0 + (lane & 7);
         w0 = 0; w1 = 0;
-        // the pack kernel marked the tiles that hold foreground: the words of the others are not even loaded
-        // (consecutive tiles share a word of the list, so the test is an L1 hit)
-        if (!((__ldg(v.tile_any + (t >> 5)) >> (t & 31u)) & 1u)) return;
         if (y < v.Y) {
             if (xa < v.X) w0 = v.bits[((size_t)xa * v.Y + y) * v.nk + (T.k - v.k0)];
             if (xb < v.X) w1 = v.bits[((size_t)xb * v.Y + y) * v.nk + (T.k - v.k0)];
@@ -589,6 +570,10 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
         }
     };
 
+    // Measured and NOT adopted (round 2): a tile-occupancy bitmap written by the pack kernel so that this kernel would not load
+    // the words of empty tiles.  The tile kernel went from 244 to 202 us on the headline volume, but marking the tiles cost the
+    // pack kernel — a pure stream at the HBM roofline — far more: 340 -> ~440 us with one atomicOr per non-empty word (8 M
+    // atomics on 16 K words), 793 us with a read-before-atomic (profiles/r02_launches_ccl_tile_bitmap_experiment.txt).
     // One tile at a time, the next tile's two row words in flight while the current one is labelled (a
     // single copy of the labelling code: unrolling it over a batch quadrupled the kernel's time).
     unsigned batch;
@@ -596,7 +581,7 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
     unsigned t = batch * tile_batch, t_end = min(t + tile_batch, n_tiles);
     Tile cur = decode(t);
     ull w0, w1;
-    load(t, cur, w0, w1);
+    load(cur, w0, w1);
     for (;;) {
         unsigned tn = t + 1;
         bool more = true;
@@ -611,7 +596,7 @@ __global__ void __launch_bounds__(32 * CCL_TILE_WARPS, 5) ccl_tile_kernel(CclVie
         ull n0 = 0, n1 = 0;
         if (more) {
             nxt = decode(tn);
-            load(tn, nxt, n0, n1);
+            load(nxt, n0, n1);
         }
         if (__any_sync(0xffffffffu, (w0 | w1) != 0ull) &&
             !tile_sparse(v, srow, reinterpret_cast<SparseTileScratch*>(slab), sbuf, buf_n, lane, w0, w1, cur.x0, cur.y0, 64 * cur.k)) {
@@ -893,8 +878,6 @@ CclView skb_ccl_make_view(const SkbCclLayout& L, void* ws, int planar, int64_t c
     v.face_lo = nullptr; v.face_hi = nullptr;
     v.chunks = reinterpret_cast<int*>(base + L.off_chunks);
     v.cursors = reinterpret_cast<unsigned*>(base + L.off_cursors);
-    v.tile_any = reinterpret_cast<unsigned*>(base + L.off_tile_any);
-    v.n_yt = (L.Y + 7) / 8;
     v.scan_tiles = reinterpret_cast<int*>(base + L.off_scan_tiles);
     v.tile_roots = reinterpret_cast<int*>(base + L.off_tile_roots);
     v.flat = reinterpret_cast<int*>(base + L.off_flat);
@@ -945,12 +928,7 @@ void skb_ccl_launch_pack_and_tile(const void* mask, int mask_dtype, const CclVie
     const bool all = !(flags & (SKB_CCL_PHASE_PACK | SKB_CCL_PHASE_LABEL));
     if (all || (flags & SKB_CCL_PHASE_PACK)) {
         char* base = reinterpret_cast<char*>(v.hdr);
-        // the tile-occupancy words this pass will visit: zeroed by the init kernel when they are few (16 K words for
-        // 2048x2048x512), by a memset for extreme aspect ratios
-        const long long n_any = (((long long)((v.X + 7) / 8) * v.n_yt * v.nk) + 31) / 32;
-        if (n_any > 65536) cudaMemsetAsync(v.tile_any, 0, (size_t)n_any * 4, st);
-        ccl_init_kernel<<<1, SKB_TILE_CURSORS, 0, st>>>(v, h, (flags & SKB_CCL_KEEP_STATUS) ? 1 : 0,
-                                                        n_any > 65536 ? 0u : (unsigned)n_any);  // header by value: no host->device copy on the path
+        ccl_init_kernel<<<1, SKB_TILE_CURSORS, 0, st>>>(v, h, (flags & SKB_CCL_KEEP_STATUS) ? 1 : 0);  // header by value: no host->device copy on the path
         if (!(flags & SKB_CCL_WORKSPACE_CLEAN)) cudaMemsetAsync(base + L.off_rootbits, 0, (size_t)L.n_words * 8, st);
         cudaMemsetAsync(base + L.off_chunks, 0, (size_t)(L.n_chunks + 1) * 4, st);
         if (mask_dtype == SKB_U8) launch_pack<uint8_t>(mask, v, st);

@@ -20,8 +20,6 @@ struct CclView {
     ull* face_hi;
     int* chunks;
     unsigned* cursors;  // SKB_TILE_CURSORS work cursors, SKB_TILE_CURSOR_STRIDE ints apart
-    unsigned* tile_any; // one bit per tile of the (slab's) tile list: the tile holds foreground
-    int n_yt;           // tiles along y
     int* scan_tiles;
     int* tile_roots;
     int* flat;

@@ -92,8 +92,7 @@ struct SkbCclLayout {
     int X, Y, Z, ZW;      // ZW = 64-bit words per (x,y) row of the bit-packed mask
     int64_t V, n_words, n_chunks;
     int64_t n_scan_tiles;  // chunk histogram is scanned in tiles of SKB_SCAN_TILE entries
-    int64_t n_tiles;       // 8x8x64 tiles of the whole volume
-    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_face_lo, off_face_hi, off_cursors, off_tile_any,
+    size_t off_bits, off_parent, off_rootbits, off_chunks, off_scan_tiles, off_face_lo, off_face_hi, off_cursors,
         off_tile_roots, off_flat, off_groots, total;
 };
 
@@ -115,10 +114,6 @@ static inline SkbCclLayout skb_ccl_layout(int64_t X, int64_t Y, int64_t Z, int64
     L.off_face_lo = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
     L.off_face_hi = at;    at = skb_align_up(at + (size_t)X * Y * 8, 256);
     L.off_cursors = at;    at = skb_align_up(at + (size_t)SKB_TILE_CURSORS * SKB_TILE_CURSOR_STRIDE * 4, 256);
-    // one bit per 8x8x64 tile: set by the pack kernel where the tile holds foreground, so that the tile kernel does not even
-    // load the words of the (75-98 %) empty tiles
-    L.n_tiles = ((X + 7) / 8) * ((Y + 7) / 8) * (int64_t)L.ZW;
-    L.off_tile_any = at;   at = skb_align_up(at + (size_t)((L.n_tiles + 31) / 32) * 4, 256);
     L.off_tile_roots = at; at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_flat = at;       at = skb_align_up(at + (size_t)capacity * 4, 256);
     L.off_groots = at;     at = skb_align_up(at + (size_t)capacity * 4, 256);

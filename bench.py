@@ -400,7 +400,7 @@ def run_b200(args):
     timers = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     graphed = False
-    if world > 1 and not os.environ.get("SKB_NO_GRAPH") and args.hops == 1:  # N > 1 passes start with an NCCL exchange: eager
+    if world > 1 and not os.environ.get("SKB_NO_GRAPH") and runner.graphable:  # a pass with an NCCL exchange inside stays eager
         # all ranks must agree: a rank replaying a graph and a rank issuing eagerly would still match
         # collectives, but keep the measurement uniform
         ok = torch.tensor([1 if runner.capture() else 0], device=dev)
@@ -540,7 +540,10 @@ def run_b200(args):
         gather_bytes = ALGO_BYTES_GATHER * V / world
         achieved = gather_bytes / (gather_ms * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(dominant, V / world)
-        config.update({"components": n_components, "labelled_voxels": labelled,
+        # `config` stays what both arms agree on (workload, tube count, CPU sample box, input size); what only this arm
+        # knows goes next to it
+        details = {}
+        details.update({"components": n_components, "labelled_voxels": labelled,
                        "sharding": "none" if world == 1 else (
                            f"Z-slabs x{world}; halo-run exchange + root all-gather "
                            + ("stored by the kernels into peer mailboxes over NVLink (release/acquire flags, no NCCL in a pass)"
@@ -551,7 +554,7 @@ def run_b200(args):
         line = {
             "metric": "post-proc voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "details": details,
             "path_roofline": {"bytes_per_voxel": ALGO_BYTES_PATH, "achieved": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9,
                               "peak": hbm_peak, "unit": "GB/s",
                               "frac": ALGO_BYTES_PATH * V / world / (ms_per_step * 1e-3) / 1e9 / hbm_peak},

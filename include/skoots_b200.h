@@ -274,8 +274,11 @@ int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int6
  *   - N hops with `decay` over the reference's crop grid (crop / overlap as in skb_assemble; NULL = the whole volume
  *     as one crop).  A hop stays inside the owner crop of its voxel, so it can leave the slab by at most
  *     crop_z - overlap_z - 1 planes: vec_halo_lo / vec_halo_hi hold the vector field's planes
- *     [z_off - vec_halo_planes, z_off) and [z_off+Zl, z_off+Zl+vec_halo_planes) as (3,X,Y,vec_halo_planes) arrays of
- *     the field's dtype (the Z-neighbours' faces; NULL at the volume's ends; not needed for N = 1);
+ *     [z_off - vec_halo_planes, z_off) and [z_off+Zl, z_off+Zl+vec_halo_planes) of the field's dtype (NULL at the
+ *     volume's ends; not needed for N = 1), as the LAST / FIRST vec_halo_planes planes of (3,X,Y,depth) arrays:
+ *     vec_halo_*_depth = 0 or vec_halo_planes -> packed copies of the neighbours' faces; = the neighbour's slab depth ->
+ *     the neighbour's OWN slab, mapped into this process (CUDA IPC, skb_peer_*): the few hops that cross a face then read
+ *     the peer GPU's memory over NVLink directly and nothing is exchanged;
  *   - label_halo_planes = how many planes beyond each face the halo words describe (the `halo` given to
  *     skb_shard_emit_runs*).  A gather target beyond them cannot be answered from this rank's data:
  *     SKB_STATUS_HALO_RANGE is OR-ed into *status instead of returning a wrong label silently.  0 = do not check;
@@ -285,6 +288,7 @@ int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int6
 int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
                          const float scale[3], int N, double decay, const int32_t crop[3], const int32_t overlap[3],
                          const void* vec_halo_lo, const void* vec_halo_hi, int64_t vec_halo_planes,
+                         int64_t vec_halo_lo_depth, int64_t vec_halo_hi_depth,
                          const void* workspace, const uint64_t* halo_lo, const uint64_t* halo_hi,
                          int64_t label_halo_planes, void* out, int out_dtype, int64_t first_voxel,
                          int64_t n_voxels, uint32_t* status, void* stream);

@@ -98,7 +98,7 @@ SIGNATURES = {
     "skb_shard_merge_peer": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_int, _c_i64, _c_i64, _c_i64, ctypes.c_int32, _c_vp, _c_vp, _c_vp]),
     "skb_assemble_slab": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp]),
     "skb_assemble_slab_ex": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3,
-                                      _c_vp, _c_vp, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp]),
+                                      _c_vp, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_i64, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_assemble_planar": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
     "skb_assemble_range": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp]),
     "skb_assemble": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_int, ctypes.c_double, _c_i3, _c_i3, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),

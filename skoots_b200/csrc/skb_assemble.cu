@@ -31,9 +31,10 @@ struct AsmParams {
     unsigned* status;       // slab mode: SKB_STATUS_HALO_RANGE is OR-ed in when a target lies beyond them (may be NULL)
     int planar;             // 2-D mode: the volume is a stack (X = slices, Y, Z = image axes) and `vec` is (slices, 2, Y, Z):
     long long plane;        //   two channels per slice, `plane` = Y * Z elements each; the slice axis never moves
-    const void* vhalo_lo;   // slab mode, N > 1: the vector field's planes [z_off - vh, z_off) / [z_off+Zl, z_off+Zl+vh) as
-    const void* vhalo_hi;   //   (3,X,Y,vh) arrays (the Z-neighbours' faces), read by hops that leave the slab inside their crop
-    int vh;
+    const void* vhalo_lo;   // slab mode, N > 1: where hops that leave the slab inside their crop read the Z-neighbours' vectors:
+    const void* vhalo_hi;   //   (3,X,Y,depth) arrays whose LAST vh planes (lo) / FIRST vh planes (hi) are the planes
+    int vh;                 //   [z_off - vh, z_off) / [z_off+Zl, z_off+Zl+vh) of the field.  depth = vh: packed copies of the
+    int vdepth_lo, vdepth_hi;  // faces; depth = the neighbour's slab depth: the neighbour's own slab, mapped over NVLink
     float s[3];
     int N;
     double decay;
@@ -114,8 +115,9 @@ __device__ __forceinline__ void walk(const AsmParams& P, int lx, int ly, int lz,
                     if (P.status) atomicOr(P.status, SKB_STATUS_HALO_RANGE);
                     hb = P.vec_hops; g = row * P.Zl + (lo ? 0 : P.Zl - 1);
                 } else {
-                    g = row * P.vh + h;
-                    hs = (long long)P.X * P.Y * P.vh;
+                    const int depth = lo ? P.vdepth_lo : P.vdepth_hi;
+                    g = row * depth + (lo ? depth - P.vh + h : h);
+                    hs = (long long)P.X * P.Y * depth;
                 }
             }
             float h0 = load_vec<VecT>(hb, g);
@@ -1084,6 +1086,7 @@ extern "C" int skb_assemble_planar(const void* vec, int vec_dtype, int64_t S, in
 extern "C" int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
                                     const float scale[3], int N, double decay, const int32_t crop[3], const int32_t overlap[3],
                                     const void* vec_halo_lo, const void* vec_halo_hi, int64_t vec_halo_planes,
+                                    int64_t vec_halo_lo_depth, int64_t vec_halo_hi_depth,
                                     const void* workspace, const uint64_t* halo_lo, const uint64_t* halo_hi,
                                     int64_t label_halo_planes, void* out, int out_dtype, int64_t first_voxel,
                                     int64_t n_voxels, uint32_t* status, void* stream) {
@@ -1133,6 +1136,9 @@ extern "C" int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, i
     P.label_halo = (int)label_halo_planes;
     P.status = status;
     P.vhalo_lo = vec_halo_lo; P.vhalo_hi = vec_halo_hi; P.vh = (int)vec_halo_planes;
+    P.vdepth_lo = (int)(vec_halo_lo_depth > 0 ? vec_halo_lo_depth : vec_halo_planes);
+    P.vdepth_hi = (int)(vec_halo_hi_depth > 0 ? vec_halo_hi_depth : vec_halo_planes);
+    SKB_REQUIRE(P.vdepth_lo >= P.vh && P.vdepth_hi >= P.vh, "skb_assemble_slab: a vector halo array is shallower than the halo");
     P.s[0] = scale[0]; P.s[1] = scale[1]; P.s[2] = scale[2];
     P.N = N; P.decay = decay;
     fill_crop(P, crop, overlap);
@@ -1156,7 +1162,7 @@ extern "C" int skb_assemble_slab_ex(const void* vec, int vec_dtype, int64_t X, i
 extern "C" int skb_assemble_slab(const void* vec, int vec_dtype, int64_t X, int64_t Y, int64_t Z, int64_t z_off, int64_t Zl,
                                  const float scale[3], const void* workspace, const uint64_t* halo_lo,
                                  const uint64_t* halo_hi, void* out, int out_dtype, void* stream) {
-    return skb_assemble_slab_ex(vec, vec_dtype, X, Y, Z, z_off, Zl, scale, 1, 1.0, nullptr, nullptr, nullptr, nullptr, 0, workspace,
+    return skb_assemble_slab_ex(vec, vec_dtype, X, Y, Z, z_off, Zl, scale, 1, 1.0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, workspace,
                                 halo_lo, halo_hi, 0, out, out_dtype, 0, X * Y * Zl, nullptr, stream);
 }
 

@@ -117,6 +117,19 @@ class Mailbox:
             pass
 
 
+def _device_view(ptr: int, shape, dtype: torch.dtype, device) -> Tensor:
+    """a torch tensor over library-allocated device memory (CUDA array interface; the memory outlives the view's users)"""
+    typestr = {torch.float16: "<f2", torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4", torch.bfloat16: "<i2"}[dtype]
+
+    class _View:
+        pass
+    v = _View()
+    v.__cuda_array_interface__ = {"shape": tuple(int(n) for n in shape), "typestr": typestr, "data": (int(ptr), False),
+                                  "version": 2, "strides": None}
+    t = torch.as_tensor(v, device=device)
+    return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t
+
+
 class PeerComm:
     """Peer transport across processes: allocates this rank's mailbox and maps every other rank's through
     CUDA IPC (handles swapped once over torch.distributed).  After `connect` no collective is issued."""
@@ -168,7 +181,36 @@ class PeerComm:
                                     + (f" ({error})" if error else " (another rank failed)"))
         return self.mailbox, self.peer_ptrs
 
+    def map_neighbours(self, box: "Mailbox", device) -> Tuple[int, int]:
+        """Collective.  Shares one more peer-visible buffer of every rank (its slab of the vector field) and maps the two
+        Z-neighbours' buffers into this process: (pointer to rank-1's buffer or 0, pointer to rank+1's buffer or 0)."""
+        mine = torch.frombuffer(bytearray(box.handle()), dtype=torch.uint8).to(device)
+        every = torch.empty(self.world * L.PEER_HANDLE_BYTES, dtype=torch.uint8, device=device)
+        self.dist.all_gather_into_tensor(every, mine, group=self.group)
+        handles = every.cpu().numpy().tobytes()
+        ptrs, error = [0, 0], ""
+        with torch.cuda.device(device):
+            for k, r in enumerate((self.rank - 1, self.rank + 1)):
+                if r < 0 or r >= self.world:
+                    continue
+                out = ctypes.c_void_p()
+                rc = self.lib.skb_peer_open(handles[r * L.PEER_HANDLE_BYTES:(r + 1) * L.PEER_HANDLE_BYTES], ctypes.byref(out))
+                if rc != 0:
+                    error = f"cannot map rank {r}'s vector slab: {self.lib.skb_last_error().decode()}"
+                    break
+                ptrs[k] = int(out.value)
+                self._opened.append(int(out.value))
+        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            raise L.SkootsB200Error("the neighbours' vector slabs cannot be mapped" + (f" ({error})" if error else " (another rank failed)"))
+        self._boxes = getattr(self, "_boxes", []) + [box]
+        return ptrs[0], ptrs[1]
+
     def _release(self) -> None:
+        for box in getattr(self, "_boxes", []):
+            box.free()
+        self._boxes = []
         if self._opened:
             with torch.cuda.device(self.mailbox.device if self.mailbox else torch.cuda.current_device()):
                 for p in self._opened:
@@ -270,6 +312,12 @@ class ShardedAssembler:
         self.meta = mk(2)  # [n_components, status]
         self.out = torch.empty((X, Y, self.Zl), dtype=out_dtype, device=self.dev)
         self._vec_dtype = None  # vector halos are allocated when the field's dtype is known (load / run_host)
+        # N > 1 over the peer transport: the slab of the vector field lives in peer-visible memory and the two Z-neighbours'
+        # slabs are mapped into this process; the few hops that cross a face read the neighbour GPU's memory over NVLink
+        # directly — no vector planes are exchanged (the NCCL transport swaps packed copies of the faces every pass)
+        self.peer_vec = self.transport == "peer" and self.hops > 1 and world > 1
+        self._vec_box: Optional[Mailbox] = None
+        self.vdepth_lo = self.vdepth_hi = 0
         # stream/resolve split of the gather (pipeline.assemble_split): the slab's stream phase runs on the current
         # stream while the labelling chain AND both exchanges run on a high-priority side stream
         can_split = (X * Y * self.Zl) % 256 == 0
@@ -305,11 +353,38 @@ class ShardedAssembler:
         assert tuple(mask_slab.shape) == (X, Y, self.Zl) and tuple(vec_slab.shape) == (3, X, Y, self.Zl)
         L.require_cuda(mask_slab, vec_slab)
         self.mask = (mask_slab.view(torch.uint8) if mask_slab.dtype == torch.bool else mask_slab).contiguous()
-        self.vec = vec_slab.contiguous()
-        self._alloc_vector_halos(self.vec.dtype)
+        if self.peer_vec:
+            self._peer_vector_slab(vec_slab.dtype)
+            self.vec.copy_(vec_slab)
+            if self.comm is not None and hasattr(self.comm, "barrier"):
+                self.comm.barrier()  # every rank's slab is in place before anybody's walk reads it
+        else:
+            self.vec = vec_slab.contiguous()
+            self._alloc_vector_halos(self.vec.dtype)
+
+    def _peer_vector_slab(self, dtype) -> None:
+        """allocates this rank's vector slab in peer-visible memory (once per dtype) and maps the neighbours' slabs."""
+        if self._vec_box is not None and self._vec_dtype == dtype:
+            return
+        X, Y, _ = self.shape
+        self._vec_dtype = dtype
+        nbytes = 3 * X * Y * self.Zl * torch.empty(0, dtype=dtype).element_size()
+        self._vec_box = Mailbox(self.lib, nbytes, self.dev)
+        self.vec = _device_view(self._vec_box.ptr, (3, X, Y, self.Zl), dtype, self.dev)
+        self.graph = None
+        if self.comm is not None and hasattr(self.comm, "map_neighbours"):
+            lo, hi = self.comm.map_neighbours(self._vec_box, self.dev)
+            bounds = slab_bounds(self.shape[2], self.world)
+            self.attach_vector_peers(lo, bounds[self.rank - 1][1] - bounds[self.rank - 1][0] if self.rank > 0 else 0,
+                                     hi, bounds[self.rank + 1][1] - bounds[self.rank + 1][0] if self.rank < self.world - 1 else 0)
+
+    def attach_vector_peers(self, lo_ptr: int, lo_depth: int, hi_ptr: int, hi_depth: int) -> None:
+        """peer-vector mode: device pointers to the lower / upper neighbour's (3,X,Y,depth) vector slab (0 = none)."""
+        self.vhalo_lo, self.vhalo_hi = int(lo_ptr), int(hi_ptr)
+        self.vdepth_lo, self.vdepth_hi = int(lo_depth), int(hi_depth)
 
     def _alloc_vector_halos(self, dtype) -> None:
-        if self.hops == 1 or self.world == 1 or self._vec_dtype == dtype:
+        if self.hops == 1 or self.world == 1 or self._vec_dtype == dtype or self.peer_vec:
             return
         X, Y, _ = self.shape
         self._vec_dtype = dtype
@@ -329,7 +404,7 @@ class ShardedAssembler:
     def exchange_vector_halos(self) -> None:
         """N > 1: swap vh planes of the vector field with both Z-neighbours (my low face -> the lower rank's high halo, my
         high face -> the upper rank's low halo).  NCCL send/recv for both transports: 2 x 3 x X x Y x vh elements per face."""
-        if self.hops == 1 or self.world == 1:
+        if self.hops == 1 or self.world == 1 or self.peer_vec:
             return
         self.pack_vector_faces()
         d, ops = self.comm.dist, []
@@ -473,10 +548,20 @@ class ShardedAssembler:
             first, count = (0, X * Y * self.Zl) if voxel_range is None else (int(voxel_range[0]), int(voxel_range[1]))
             L.check(self.lib.skb_assemble_slab_ex(
                 self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, z0, self.Zl, L.f3(self.scale), self.hops, self.decay,
-                self._crop, self._overlap, L.ptr(self.vhalo_lo), L.ptr(self.vhalo_hi), self.vh, self.workspace.data_ptr(),
+                self._crop, self._overlap, self._vptr(self.vhalo_lo), self._vptr(self.vhalo_hi), self.vh, self.vdepth_lo, self.vdepth_hi,
+                self.workspace.data_ptr(),
                 L.ptr(self.halo_lo), L.ptr(self.halo_hi), self.halo, self.out.data_ptr(), L.dtype_code(self.out), first, count,
                 self.meta[1:2].data_ptr(), self._s()))
         return self.out
+
+    @staticmethod
+    def _vptr(h) -> int:
+        return 0 if h is None else (int(h) if isinstance(h, int) else h.data_ptr())
+
+    @property
+    def graphable(self) -> bool:
+        """a pass has no host step or NCCL call inside: N = 1, or N > 1 with the neighbours' vector slabs mapped"""
+        return self.transport == "peer" and (self.hops == 1 or self.peer_vec)
 
     def phase_merge_and_gather(self, timers=None) -> Tensor:
         self.phase_merge()
@@ -636,7 +721,11 @@ class ShardedAssembler:
             raise L.SkootsB200Error("run_host pipelines the fused slab gather; construct the assembler without split=True")
         if self.mask is None or self.mask.dtype != torch.uint8 or tuple(self.mask.shape) != (X, Y, self.Zl):
             self.mask = torch.empty((X, Y, self.Zl), dtype=torch.uint8, device=self.dev)
-        if self.vec is None or self.vec.dtype != vec_host.dtype:
+        if self.peer_vec:
+            self._peer_vector_slab(vec_host.dtype)
+            torch.cuda.synchronize(self.dev)
+            self.comm.barrier()  # nobody's walks of the previous pass still read the slab this upload overwrites
+        elif self.vec is None or self.vec.dtype != vec_host.dtype:
             self.vec = torch.empty((3, X, Y, self.Zl), dtype=vec_host.dtype, device=self.dev)
         self._alloc_vector_halos(self.vec.dtype)
         if out_host.dtype != self.out.dtype:
@@ -669,7 +758,10 @@ class ShardedAssembler:
         if self.transport != "peer":
             self.comm.all_gather(self.gathered, self.exch)
         self.phase_merge()
-        if self.hops > 1:  # the walks read the neighbours' vectors: swap the faces once the field has landed (every rank
+        if self.hops > 1 and self.peer_vec:   # the walks read the neighbours' slabs in place: every upload must have landed
+            landed[-1].synchronize()
+            self.comm.barrier()
+        elif self.hops > 1:  # the walks read the neighbours' vectors: swap the faces once the field has landed (every rank
             main.wait_event(landed[-1])  # issues it at this point of its pass, after the chain's in-kernel waits)
             self.exchange_vector_halos()
         for (x0, x1), ev in zip(ranges, landed):
@@ -749,9 +841,13 @@ class LocalGroup:
         for r in self.ranks:
             z0, z1 = r.z_range
             r.load(mask[:, :, z0:z1].contiguous(), vec[:, :, :, z0:z1].contiguous())
+        if self.ranks[0].peer_vec:  # same process: the neighbours' slabs are ordinary device pointers
+            for i, r in enumerate(self.ranks):
+                lo, hi = (self.ranks[i - 1] if i > 0 else None), (self.ranks[i + 1] if i < self.world - 1 else None)
+                r.attach_vector_peers(lo.vec.data_ptr() if lo else 0, lo.Zl if lo else 0, hi.vec.data_ptr() if hi else 0, hi.Zl if hi else 0)
 
     def step(self) -> Tensor:
-        if self.ranks[0].hops > 1 and self.world > 1:  # stand-in for exchange_vector_halos(): plain copies
+        if self.ranks[0].hops > 1 and self.world > 1 and not self.ranks[0].peer_vec:  # stand-in for exchange_vector_halos()
             for r in self.ranks:
                 r.pack_vector_faces()
             for i, r in enumerate(self.ranks):

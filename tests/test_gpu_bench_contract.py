@@ -27,7 +27,7 @@ def test_bench_line_has_the_contract_keys():
         assert key in d, key
     assert d["unit"] == "voxels/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert d["value"] == pytest.approx(256 * 256 * 128 / (d["ms_per_step"] * 1e-3), rel=1e-6)
-    assert "workload" in d["config"] and "model" not in d["config"]
+    assert "workload" in d["config"] and "model" not in d["config"] and "components" in d["details"]
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
     assert r["traffic"] is None or r["traffic"] > 0

@@ -66,18 +66,33 @@ def _worker(rank: int, world: int, port: int, transport: str, shape):
             run.run_host(mask_h, vec_h, out_h, n_slabs=4)
             assert torch.equal(out_h, want.cpu().to(dt)), f"rank {rank}: host pass ({dt}) differs"
     dist.barrier()
-    # eval()'s configuration Z-sharded: crop grid, N = 6 hops, the vector halos travel over NCCL send/recv
+    # eval()'s configuration Z-sharded: crop grid, N = 6 hops.  NCCL transport: packed copies of the faces' vector planes
+    # travel by send/recv every pass; peer transport: the neighbours' vector slabs are mapped through CUDA IPC and the
+    # hops that cross a face read the other GPU's memory directly
     crop, ov = (48, 40, 50), (4, 4, 5)
     want_eval = assemble_instances(mask, vec, torch.tensor(scale), N=6, crop=crop, overlap=ov, out_dtype=torch.int16)[:, :, z0:z1].contiguous()
-    comm2 = run.comm if transport != "peer" else TorchDistComm()
+    comm2 = PeerComm() if transport == "peer" else run.comm
     ev = ShardedAssembler(shape, world, rank, dev, scale=scale, hops=6, crop=crop, overlap=ov, comm=comm2, out_dtype=torch.int16)
+    assert ev.peer_vec == (transport == "peer")
     ev.load(run.mask, run.vec)
     for _ in range(2):
         assert torch.equal(ev.step(), want_eval), f"rank {rank}: sharded eval-mode pass differs from the unsharded one"
+    if ev.graphable:
+        ok = torch.tensor([1 if ev.capture() else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        assert int(ok.item()) == 1
+        for _ in range(2):
+            ev.out.zero_()
+            assert torch.equal(ev.step(), want_eval), f"rank {rank}: replayed eval-mode graph differs"
     out_h = torch.empty(want_eval.shape, dtype=torch.int16).pin_memory()
-    ev.run_host(mask_h, vec_h, out_h)
-    assert torch.equal(out_h, want_eval.cpu()), f"rank {rank}: eval-mode host pass differs"
+    for _ in range(2):
+        out_h.fill_(-1)
+        ev.run_host(mask_h, vec_h, out_h)
+        assert torch.equal(out_h, want_eval.cpu()), f"rank {rank}: eval-mode host pass differs"
     dist.barrier()
+    if comm2 is not run.comm and hasattr(comm2, "close"):
+        ev.graph = None
+        comm2.close()
     if hasattr(run.comm, "close"):
         run.comm.close()
     dist.destroy_process_group()

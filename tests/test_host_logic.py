@@ -138,3 +138,41 @@ def test_patch_skoots_bug_compatible_binding():
         assert getattr(fn, "keywords", None) == {"reference_crops": True} and fn.__name__ == "efficient_flood_fill"
     finally:
         skoots_b200.patch.unpatch_skoots()
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """the entry points added in round 2 reject bad arguments with a code and a message; nothing is enqueued."""
+    import skoots_b200._lib as L
+    lib = L.load()
+    f3, i3 = L.f3((60, 60, 12)), L.i3((500, 500, 50))
+    # slab gather: NULL pointers, a slab that is not a multiple of 64 planes, a range that does not start on 256 voxels
+    assert lib.skb_assemble_slab_ex(None, 3, 8, 8, 128, 0, 64, f3, 1, 1.0, None, None, None, None, 0, 0, 0, None, None, None, 12, None, 2, 0, 4096,
+                                    None, None) == -1 and b"NULL" in lib.skb_last_error()
+    assert lib.skb_assemble_slab_ex(1, 3, 8, 8, 128, 0, 60, f3, 1, 1.0, None, None, None, None, 0, 0, 0, 1, None, None, 12, 16, 2, 0, 3840,
+                                    None, None) == -1 and b"multiples of 64" in lib.skb_last_error()
+    assert lib.skb_assemble_slab_ex(1, 3, 8, 8, 128, 0, 64, f3, 1, 1.0, None, None, None, None, 0, 0, 0, 1, None, None, 12, 16, 2, 100, 256,
+                                    None, None) == -1 and b"multiple of 256" in lib.skb_last_error()
+    # N > 1 on an inner slab needs the neighbours' vector planes
+    assert lib.skb_assemble_slab_ex(1, 3, 600, 600, 256, 64, 64, f3, 10, 1.0, i3, L.i3((50, 50, 5)), None, None, 0, 0, 0, 1, None, None, 64, 16, 1, 0,
+                                    600 * 600 * 64, None, None) == -1 and b"vector halos" in lib.skb_last_error()
+    assert lib.skb_assemble_planar(None, 3, 4, 64, 64, L.f3((60, 60)), None, None, 0, None, 2, None) == -1
+    assert lib.skb_bake_skeletons(None, 2, 1, 8, 8, 8, None, None, None, 0, None, 0, L.f3((1, 1, 1)), 1, None, None, None, None) == -1
+    assert lib.skb_elastic_resample(None, 2, 6, 6, L.f3((0.01, 0.05, 0.05)), None, None, 1, 8, 8, 8, None) == -1
+    assert lib.skb_elastic_points(1, 2, 6, 6, L.f3((0.01, 0.05, 0.05)), None, 1, 5, 8, 8, 8, None, None) == -1
+    assert lib.skb_shard_begin_pass(None, 2, 16, 16, 16, 64, None, None, None, None) == -1
+    assert lib.skb_shard_push(None, 8, 8, 64, 16, None, None, None, 2, 0, 16, 16, 16, None, None) == -1
+
+
+def test_compute_device_rules_without_a_gpu():
+    """host tensors are staged through the GPU: without a CUDA device that is an error, never a CPU computation."""
+    import skoots_b200._lib as L
+    from skoots_b200.lib.morphology import binary_dilation
+    from skoots_b200.validate import mask_iou
+    if torch.cuda.is_available():
+        pytest.skip("this test is about the box without a GPU")
+    with pytest.raises(L.SkootsB200Error, match="no CPU fallback"):
+        binary_dilation(torch.zeros((1, 1, 4, 4, 4)))
+    with pytest.raises(L.SkootsB200Error, match="no CPU fallback"):
+        mask_iou(torch.zeros((4, 4, 4), dtype=torch.int32), torch.zeros((4, 4, 4), dtype=torch.int32))
+    with pytest.raises(L.SkootsB200Error):
+        L.compute_device(torch.zeros(1), "not a tensor")

@@ -106,8 +106,7 @@ __global__ void __launch_bounds__(256) masked_mean27_kernel(const float* __restr
     const int z0 = zg * 4;
     const float* base = in + vol * (long long)X * Y * Z;
     const bool aligned4 = (Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15u) == 0);
-    float sum[4] = {0.f, 0.f, 0.f, 0.f};
-    int cnt[4] = {0, 0, 0, 0};  // entries > 0 of the window: counted in integers (one IADD3 per row and output)
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, cnt[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int dx = -1; dx <= 1; ++dx) {
 #pragma unroll
@@ -120,29 +119,28 @@ __global__ void __launch_bounds__(256) masked_mean27_kernel(const float* __restr
             } else {
                 load_row6(base + ((long long)xx * Y + yy) * Z, z0, Z, aligned4, v);
             }
-            int pos[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) pos[k] = v[k] > 0.f ? 1 : 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                for (int dz = 0; dz < 3; ++dz) sum[j] = __fadd_rn(sum[j], v[j + dz]);
-                cnt[j] += pos[j] + pos[j + 1] + pos[j + 2];
+                for (int dz = 0; dz < 3; ++dz) {
+                    sum[j] = __fadd_rn(sum[j], v[j + dz]);
+                    cnt[j] += v[j + dz] > 0.f ? 1.f : 0.f;
+                }
             }
         }
     }
     float* orow = out + vol * (long long)X * Y * Z + ((long long)x * Y + y) * Z;
     if (aligned4 && z0 + 4 <= Z && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
         float4 o;
-        o.x = __fdiv_rn(sum[0], (float)max(cnt[0], 1));
-        o.y = __fdiv_rn(sum[1], (float)max(cnt[1], 1));
-        o.z = __fdiv_rn(sum[2], (float)max(cnt[2], 1));
-        o.w = __fdiv_rn(sum[3], (float)max(cnt[3], 1));
+        o.x = __fdiv_rn(sum[0], cnt[0] == 0.f ? 1.f : cnt[0]);
+        o.y = __fdiv_rn(sum[1], cnt[1] == 0.f ? 1.f : cnt[1]);
+        o.z = __fdiv_rn(sum[2], cnt[2] == 0.f ? 1.f : cnt[2]);
+        o.w = __fdiv_rn(sum[3], cnt[3] == 0.f ? 1.f : cnt[3]);
         *reinterpret_cast<float4*>(orow + z0) = o;
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (z0 + j < Z) orow[z0 + j] = __fdiv_rn(sum[j], (float)max(cnt[j], 1));
+            if (z0 + j < Z) orow[z0 + j] = __fdiv_rn(sum[j], cnt[j] == 0.f ? 1.f : cnt[j]);
     }
 }
 

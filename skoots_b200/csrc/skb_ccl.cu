@@ -27,6 +27,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "skb_ccl.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -745,24 +747,41 @@ __global__ void __launch_bounds__(32 * BND_WARPS) ccl_boundary_kernel(CclView v,
 // K3: pointer jumping of tile roots; global roots -> bitmap + chunk histogram + list
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ccl_flatten_kernel(CclView v) {
-    unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int r = v.tile_roots[i];
-        int g = gfind(v.parent, r);
-        v.flat[i] = g;
-        if (g == r) {
-            int bit;
-            long long wi = word_of_voxel(v, r, &bit);
-            atomicOr(&v.rootbits[wi], 1ull << bit);
-            atomicAdd(&v.chunks[wi >> 6], 1);
-            // warp-aggregated append: one atomic per warp, slots handed out by ballot rank
-            unsigned m = __activemask();
-            int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(&v.hdr->n_global_roots, (unsigned)__popc(m));
-            base = __shfl_sync(m, base, leader);
-            v.groots[base + __popc(m & ((1u << lane) - 1u))] = r;
+    // The list of global roots is appended to through ONE counter.  Round 1 took one atomicAdd per warp that held a root:
+    // fine for the ~16 K roots of a skeleton volume, but a 64-slice 2-D stack has 1.3 M roots = ~41 K same-address atomics
+    // at ~20 ns each (the kernel took 0.36 ms).  Now a CTA gathers its warps' counts in shared memory and takes one global
+    // atomic per CTA and iteration.
+    __shared__ unsigned s_count, s_base;
+    const unsigned n = min(v.hdr->n_tile_roots, (unsigned)v.capacity);
+    const unsigned stride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {  // uniform per CTA: barriers inside
+        const unsigned i = i0 + threadIdx.x;
+        bool is_root = false;
+        int r = 0;
+        if (i < n) {
+            r = v.tile_roots[i];
+            const int g = gfind(v.parent, r);
+            v.flat[i] = g;
+            if (g == r) {
+                is_root = true;
+                int bit;
+                long long wi = word_of_voxel(v, r, &bit);
+                atomicOr(&v.rootbits[wi], 1ull << bit);
+                atomicAdd(&v.chunks[wi >> 6], 1);
+            }
         }
+        if (threadIdx.x == 0) s_count = 0u;
+        __syncthreads();
+        const unsigned m = __ballot_sync(0xffffffffu, is_root);
+        unsigned wbase = 0u;
+        if (lane == 0 && m) wbase = atomicAdd(&s_count, (unsigned)__popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) s_base = atomicAdd(&v.hdr->n_global_roots, s_count);
+        __syncthreads();
+        if (is_root) v.groots[s_base + wbase + __popc(m & ((1u << lane) - 1u))] = r;
+        __syncthreads();  // s_count / s_base are rewritten by the next iteration
     }
 }
 
@@ -788,6 +807,46 @@ __global__ void __launch_bounds__(1024) ccl_scan_top_kernel(CclView v) {
 __global__ void __launch_bounds__(256) ccl_rank_kernel(CclView v) {
     unsigned n = v.hdr->n_global_roots;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ccl_rank_root(v, v.groots[i]);
+}
+
+// Planar stacks (2-D mode) have a component per object cross-section — 1.3 M roots on a 64 x 4096 x 4096 stack — and the
+// per-root kernel above walks up to 63 words of the root bitmap for every one of them (0.17 ms, plus 0.04 ms to clear the
+// bitmap afterwards).  This form streams the bitmap instead: a warp takes one 64-word chunk (two words per lane, one
+// coalesced kilobyte), a warp scan of the popcounts gives every lane the rank of its first root, the label codes are
+// written from the bit positions, and the words are zeroed on the way out (the clear kernel's job).  Needs whole chunks
+// per plane (Y * ZW a multiple of 64), which also makes the per-plane restart of the numbering a chunk-table look-up.
+__global__ void __launch_bounds__(256) ccl_rank_stream_kernel(CclView v) {
+    const int lane = threadIdx.x & 31;
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long plane_chunks = ((long long)v.Y * v.ZW) >> 6;
+    const int label0 = v.hdr->label_base + 1;
+    for (long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < v.n_chunks; c += n_warps) {
+        ull* words = v.rootbits + (c << 6) + 2 * lane;
+        const uint4 q = *reinterpret_cast<const uint4*>(words);
+        const ull w0 = ((ull)q.y << 32) | q.x, w1 = ((ull)q.w << 32) | q.z;
+        if (!__any_sync(0xffffffffu, (w0 | w1) != 0ull)) continue;
+        const int cnt = __popcll(w0) + __popcll(w1);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (cnt == 0) continue;  // lanes without roots are done (no further warp-wide operations below)
+        int rank = v.chunks[c] + v.scan_tiles[c / SKB_SCAN_TILE] + incl - cnt;
+        if (!v.connect_x) {  // planar: numbering restarts in every x-plane (= a whole number of chunks)
+            const long long pc = (c / plane_chunks) * plane_chunks;
+            rank -= v.chunks[pc] + v.scan_tiles[pc / SKB_SCAN_TILE];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long wi = (c << 6) + 2 * lane + h;
+            const long long rowi = wi / v.ZW;
+            const int vbase = (int)(rowi * v.Z + (wi - rowi * v.ZW) * 64);
+            for (ull m = h ? w1 : w0; m; m &= m - 1) v.parent[vbase + (__ffsll((long long)m) - 1)] = -(label0 + rank++);
+        }
+        *reinterpret_cast<uint4*>(words) = make_uint4(0u, 0u, 0u, 0u);  // leaves the bitmap clean for the next pass
+    }
 }
 
 // leaves the root bitmap all-zero again (only the words the global roots touched), so the next pass over
@@ -858,6 +917,43 @@ __global__ void __launch_bounds__(256) ccl_dense_kernel(const ull* __restrict__ 
     } else {
         for (int j = 0; j < 8 && z + j < Z; ++j) out[vox + j] = (OutT)lab[j];
     }
+}
+
+// int32 labels, FLAT volumes: the same work with the lanes arranged so that EACH store instruction of a warp writes 512
+// contiguous bytes.  In the kernel above a lane owns 8 consecutive voxels = 32 bytes and writes them with two 16-byte
+// stores, so each instruction touches all 32 sectors of the warp's kilobyte but fills only half of each.  Here lane l owns
+// the voxels [4l, 4l+4) of the warp's first 128 voxels and of its second 128 (two nibbles of the bit mask).
+__global__ void __launch_bounds__(256) ccl_dense32_kernel(const unsigned char* __restrict__ bits, const int* __restrict__ parent,
+                                                         unsigned n_groups, int* __restrict__ out) {
+    const unsigned gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;  // n_groups is a multiple of 32 (V % 256 == 0): whole warps leave together
+    const unsigned lane = threadIdx.x & 31u, wbase = gi - lane;  // wbase = first byte of the warp's 32 bytes of bit mask
+    const unsigned ba = __ldg(bits + wbase + (lane >> 1)), bb = __ldg(bits + wbase + 16u + (lane >> 1));
+    const unsigned sh = (lane & 1u) * 4u;
+    const unsigned nib[2] = {(ba >> sh) & 0xFu, (bb >> sh) & 0xFu};
+    const size_t vox[2] = {(size_t)wbase * 8 + 4 * lane, (size_t)wbase * 8 + 128 + 4 * lane};
+    unsigned lab[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lab[h][j] = 0u;
+    if (nib[0] | nib[1]) {
+        int p1[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p1[h][j] = ((nib[h] >> j) & 1u) ? __ldg(parent + vox[h] + j) : -1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!((nib[h] >> j) & 1u)) continue;
+                const int p2 = p1[h][j] < 0 ? p1[h][j] : __ldg(parent + p1[h][j]);
+                lab[h][j] = (unsigned)(-p2);
+            }
+    }
+    skb_st_stream16(out + vox[0], make_uint4(lab[0][0], lab[0][1], lab[0][2], lab[0][3]));
+    skb_st_stream16(out + vox[1], make_uint4(lab[1][0], lab[1][1], lab[1][2], lab[1][3]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -974,8 +1070,12 @@ extern "C" int skb_ccl_label_sparse(const void* mask, int mask_dtype, int64_t X,
     ccl_flatten_kernel<<<list_grid, 256, 0, st>>>(v);
     ccl_scan_tiles_kernel<<<(unsigned)L.n_scan_tiles, 1024, 0, st>>>(v);
     ccl_scan_top_kernel<<<1, 1024, 0, st>>>(v);
-    ccl_rank_kernel<<<list_grid, 256, 0, st>>>(v);
-    ccl_clear_rootbits_kernel<<<list_grid, 256, 0, st>>>(v);
+    if (planar && ((long long)L.Y * L.ZW) % 64 == 0 && L.n_words % 64 == 0) {
+        ccl_rank_stream_kernel<<<148 * 8, 256, 0, st>>>(v);  // many small components: stream the root bitmap (and clear it)
+    } else {
+        ccl_rank_kernel<<<list_grid, 256, 0, st>>>(v);
+        ccl_clear_rootbits_kernel<<<list_grid, 256, 0, st>>>(v);
+    }
     ccl_publish_kernel<<<list_grid, 256, 0, st>>>(v);
     SKB_LAUNCH_CHECK("ccl merge kernels");
     return SKB_OK;
@@ -1004,7 +1104,9 @@ extern "C" int skb_ccl_write_dense(const void* workspace, int64_t X, int64_t Y, 
         if (flat) ccl_dense_kernel<int16_t, true><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
         else ccl_dense_kernel<int16_t, false><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int16_t*>(out), vec_ok);
     } else {
-        if (flat) ccl_dense_kernel<int32_t, true><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
+        if (flat && (X * Y * Z) % 256 == 0 && !getenv("SKB_DENSE_OLD"))
+            ccl_dense32_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(bits), parent, groups, static_cast<int32_t*>(out));
+        else if (flat) ccl_dense_kernel<int32_t, true><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
         else ccl_dense_kernel<int32_t, false><<<nb, 256, 0, st>>>(bits, parent, (int)Z, L.ZW, Z8, groups, static_cast<int32_t*>(out), vec_ok);
     }
     SKB_LAUNCH_CHECK("ccl_dense_kernel");

@@ -218,26 +218,48 @@ __global__ void __launch_bounds__(256) tile_epilogue_kernel(EpiParams P, int bz,
     __syncthreads();
     const int n_out = EPI_BX * EPI_BY * bz;
     const long long V = (long long)P.X * P.Y * P.Z;
-    for (int i = threadIdx.x; i < n_out; i += 256) {
-        const int z = i % bz, q = i / bz, y = q % EPI_BY, x = q / EPI_BY;
-        const int lx = lx0 + x, ly = ly0 + y, lz = lz0 + z;
-        if (lx >= P.mx + ix || ly >= P.my + iy || lz >= P.mz + iz) continue;
-        const float* c0 = A + (x * EPI_BY + y) * bz + z;
-        float m = c0[0];
+    // Outputs in batches of EPI_BATCH per thread: the batch's global loads (probability + three vector channels) are all
+    // issued before anything is stored — one output per iteration left this loop waiting on a load round trip per output
+    // (10 dependent round trips per thread, about half of the kernel's time).
+    constexpr int EPI_BATCH = 5;
+    for (int i0 = threadIdx.x; i0 < n_out; i0 += 256 * EPI_BATCH) {
+        float pv[EPI_BATCH], vv[EPI_BATCH][3], mm[EPI_BATCH];
+        long long gat[EPI_BATCH];
+        bool ok[EPI_BATCH];
 #pragma unroll
-        for (int d = 1; d <= 6; ++d) m = fmaxf(m, c0[d * EPI_BY * bz]);
-        // zero joins the max only where the window of one of the three zero-padded dilations leaves the tile
-        if (lx <= 2 || lx >= P.tx - 3 || ly <= 2 || ly >= P.ty - 3 || lz == 0 || lz == P.tz - 1) m = fmaxf(m, 0.f);
-        const long long at = ((long long)lx * P.ty + ly) * P.tz + lz;
-        const long long gat = ((long long)(P.ox + lx) * P.Y + (P.oy + ly)) * P.Z + (P.oz + lz);
-        P.skel[gat] = m > P.thr ? 1 : 0;
-        // vectors: v * (prob > thr) computed in the network dtype, then .half()  (eval.py:149,175)
-        const float keep = epi_load<T>(prob, at) > P.thr ? 1.f : 0.f;
+        for (int u = 0; u < EPI_BATCH; ++u) {
+            const int i = i0 + 256 * u;
+            const int z = i % bz, q = i / bz, y = q % EPI_BY, x = q / EPI_BY;
+            const int lx = lx0 + x, ly = ly0 + y, lz = lz0 + z;
+            ok[u] = i < n_out && lx < P.mx + ix && ly < P.my + iy && lz < P.mz + iz;
+            pv[u] = 0.f; vv[u][0] = vv[u][1] = vv[u][2] = 0.f; mm[u] = 0.f; gat[u] = 0;
+            if (ok[u]) {
+                const long long at = ((long long)lx * P.ty + ly) * P.tz + lz;
+                pv[u] = epi_load<T>(prob, at);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v = epi_load<T>(P.unet, c * plane + at) * keep;
-            v = skb_to_float<T>(skb_from_float<T>(v));  // the product is rounded to the network dtype first
-            P.vectors[c * V + gat] = __float2half_rn(v);
+                for (int c = 0; c < 3; ++c) vv[u][c] = epi_load<T>(P.unet, c * plane + at);
+                const float* c0 = A + (x * EPI_BY + y) * bz + z;
+                float m = c0[0];
+#pragma unroll
+                for (int d = 1; d <= 6; ++d) m = fmaxf(m, c0[d * EPI_BY * bz]);
+                // zero joins the max only where the window of one of the three zero-padded dilations leaves the tile
+                if (lx <= 2 || lx >= P.tx - 3 || ly <= 2 || ly >= P.ty - 3 || lz == 0 || lz == P.tz - 1) m = fmaxf(m, 0.f);
+                mm[u] = m;
+                gat[u] = ((long long)(P.ox + lx) * P.Y + (P.oy + ly)) * P.Z + (P.oz + lz);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EPI_BATCH; ++u) {
+            if (!ok[u]) continue;
+            P.skel[gat[u]] = mm[u] > P.thr ? 1 : 0;
+            // vectors: v * (prob > thr) computed in the network dtype, then .half()  (eval.py:149,175)
+            const float keep = pv[u] > P.thr ? 1.f : 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = vv[u][c] * keep;
+                v = skb_to_float<T>(skb_from_float<T>(v));  // the product is rounded to the network dtype first
+                P.vectors[c * V + gat[u]] = __float2half_rn(v);
+            }
         }
     }
 }

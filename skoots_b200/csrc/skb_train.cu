@@ -503,12 +503,26 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
 
     // A. region voxels -> slot of their object in the CTA's id list (-1 background, <= -2: id index -2-v, list full)
     int any_fg = 0;
-    for (int i = threadIdx.x; i < RN; i += 256) {
-        const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
-        const int gx = x0 + rx, gy = y0 + ry, gz = z0 + rz;
-        int slot = -1;
-        if (gx >= 0 && gx < P.X && gy >= 0 && gy < P.Y && gz >= 0 && gz < P.Z) {
-            const int id = (int)mask[((long long)gx * P.Y + gy) * P.Z + gz];
+    constexpr int BAKE_A_BATCH = 4;  // mask loads in flight per thread (one per iteration left ~9 dependent round trips)
+    for (int i0 = threadIdx.x; i0 < RN; i0 += 256 * BAKE_A_BATCH) {
+        int ids_[BAKE_A_BATCH];
+#pragma unroll
+        for (int u = 0; u < BAKE_A_BATCH; ++u) {
+            const int i = i0 + 256 * u;
+            ids_[u] = 0;
+            if (i < RN) {
+                const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
+                const int gx = x0 + rx, gy = y0 + ry, gz = z0 + rz;
+                if (gx >= 0 && gx < P.X && gy >= 0 && gy < P.Y && gz >= 0 && gz < P.Z)
+                    ids_[u] = (int)mask[((long long)gx * P.Y + gy) * P.Z + gz];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BAKE_A_BATCH; ++u) {
+            const int i = i0 + 256 * u;
+            if (i >= RN) break;
+            const int id = ids_[u];
+            int slot = -1;
             if (id != 0) {
                 // a tile sees one to three objects: most voxels find their id among the ones the CTA has already looked
                 // up (shared memory) and skip the binary search through the id table (five dependent global loads)
@@ -543,8 +557,8 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
                     }
                 }
             }
+            s_slot[i] = slot;
         }
-        s_slot[i] = slot;
     }
     // most tiles of an instance mask hold no object at all (and neither does their halo): their output is zero
     if (!__syncthreads_or(any_fg)) {

@@ -376,8 +376,10 @@ def run_b200(args):
             if timers is not None:
                 timers[1].record()
             return out
-        # init, pack, tile, boundary, flatten, scan x2, rank, clear, publish, gather (split: stream + resolve) (+memsets)
-        launches_per_step = 12 if split else 11
+        # init, pack, tile, boundary, flatten, scan x2, rank, clear, publish, gather (split: stream + resolve) (+memsets);
+        # large whole-volume N = 1 passes add the density probe and the second gather instantiation (one of the two returns at once)
+        probed = (not split) and args.hops == 1 and args.mode == "whole" and V // 256 >= 65536 and Z % 64 == 0
+        launches_per_step = 12 if split else (13 if probed else 11)
 
     def barrier():
         if world > 1:

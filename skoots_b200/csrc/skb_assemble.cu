@@ -15,6 +15,7 @@
 // tile kernel (1/8 B per voxel, L2-resident over the +-scale window) and, only for targets
 // that are foreground, the sparse parent array.  A zero vector (background, ~95 % of a volume)
 // short-cuts to "label of myself", which is decided from one byte of the bit mask.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "skb_common.cuh"
@@ -29,6 +30,9 @@ struct AsmParams {
     const ull* halo_hi;
     int label_halo;         // slab mode: how many planes beyond each face the halo words really describe (0 = not checked)
     unsigned* status;       // slab mode: SKB_STATUS_HALO_RANGE is OR-ed in when a target lies beyond them (may be NULL)
+    const unsigned* density;  // probe result: sampled voxels that carry a vector (NULL: no probe, the sparse kernel runs)
+    unsigned dense_from;      // the dense kernel instantiation runs when *density >= dense_from, the sparse one otherwise
+    int dense_work;           // dense instantiation: work items of a chunk from which every lane resolves its own voxels
     int planar;             // 2-D mode: the volume is a stack (X = slices, Y, Z = image axes) and `vec` is (slices, 2, Y, Z):
     long long plane;        //   two channels per slice, `plane` = Y * Z elements each; the slice axis never moves
     const void* vhalo_lo;   // slab mode, N > 1: where hops that leave the slab inside their crop read the Z-neighbours' vectors:
@@ -248,13 +252,56 @@ __device__ __forceinline__ unsigned nonzero_bits(const Raw8<VecT>& a, const Raw8
     return work;
 }
 
-// Measured and NOT adopted (round 2): a per-lane form for DENSE chunks.  The density sweep (bench.py extras) shows the
-// path at 0.24 of its roofline when half of the voxels carry a vector (four queue rounds per chunk) against 0.81 on the
-// sparse headline volume, so chunks with >= 48 work items were handed to resolve_group (each lane resolves its own 8
-// voxels with staged, unconditional loads).  Inlined, it pushed the kernel over its 64-register budget (spills);
-// out of line, the call's stack frame did the same to every chunk's path: the headline gather went from 3.61 to 4.60 ms
-// while the 50 % case only improved from 1.89 to 1.76 ms per 268 Mvox.  The dense regime needs its own kernel
-// instantiation chosen per launch, not a branch in this one.
+// DENSE chunks.  The density sweep (bench.py extras) showed the path at 0.24 of its roofline when half of the voxels carry a
+// vector against 0.81 on the sparse headline volume: every chunk then takes four rounds through the warp queue (~750
+// warp-instructions, three dependent loads per round).  For such chunks it is cheaper to let every lane resolve ITS OWN 8
+// voxels, stage by stage with unconditional loads (a voxel without work reads index 0): 8 independent loads in flight
+// per lane and stage, no shared-memory traffic, one index division per lane.  A first attempt as a branch inside the one
+// kernel cost the SPARSE path its registers (inlined: spills; out of line: a stack frame per chunk — the headline gather
+// went from 3.61 to 4.60 ms), so this lives in a second instantiation of the kernel (DENSE = true, 3 CTAs per SM, more
+// registers); a probe samples the field's density on the device and both instantiations are launched: the one the probe
+// did not pick returns at once (no host decision, no synchronisation).
+template <typename VecT>
+__device__ __forceinline__ void resolve_own8(const AsmParams& P, const Raw8<VecT>& a, const Raw8<VecT>& b, const Raw8<VecT>& c,
+                                             unsigned work, long long i0, unsigned (&lab)[8]) {
+    const unsigned q = (unsigned)i0 / (unsigned)P.Zl;
+    const int z0 = (int)((unsigned)i0 - q * (unsigned)P.Zl) + P.z_off;  // the 8 voxels share a row (Zl % 8 == 0)
+    const int x = (int)(q / (unsigned)P.Y), y = (int)(q - (unsigned)x * (unsigned)P.Y);
+    const float fx = (float)x, fy = (float)y;
+    const ull* wp[8];
+    int tv[8], tb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float ex = __fadd_rn(fx, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(a.w, j)), P.s[0]));
+        const float ey = __fadd_rn(fy, __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(b.w, j)), P.s[1]));
+        const float ez = __fadd_rn((float)(z0 + j), __fmul_rn(raw_to_float<VecT>(raw_elem<VecT>(c.w, j)), P.s[2]));
+        const int tx = clamp_index(ex, P.X), ty = clamp_index(ey, P.Y), tz = clamp_index(ez, P.Z);
+        const long long rowi = (long long)tx * P.Y + ty;
+        const bool have = ((work >> j) & 1u) != 0u;
+        wp[j] = have ? P.bits + rowi * P.ZW + (tz >> 6) : P.bits;
+        tv[j] = have ? (int)(rowi * P.Z + tz) : -1;
+        tb[j] = tz & 63;
+    }
+    ull ww[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ww[j] = __ldg(wp[j]);
+    int p1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (!((ww[j] >> tb[j]) & 1ull)) tv[j] = -1;
+        p1[j] = __ldg(P.parent + (tv[j] < 0 ? 0 : tv[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int p2 = __ldg(P.parent + ((tv[j] < 0 || p1[j] < 0) ? 0 : p1[j]));  // parent[0] itself may be uninitialised
+        const int code = p1[j] < 0 ? p1[j] : p2;
+        lab[j] = tv[j] < 0 ? 0u : (unsigned)(-code);
+    }
+}
+
+// work items of a 256-voxel chunk from which the per-lane form is taken.  Measured on 1024x1024x256 (whole pass, ms) for
+// thresholds 16 / 24 / 40 / 64 / never: 25 % dense 1.36 / 1.35 / 1.33 / 1.32 / 1.50, 51 % dense 1.40 / 1.39 / 1.39 / 1.39 / 2.07
+constexpr int ASM_DENSE_WORK = 48;
 
 // What one lane holds for its 8 voxels between the load and the processing of a 256-voxel chunk.
 template <typename VecT> struct ChunkRegs {
@@ -325,7 +372,7 @@ __device__ __forceinline__ ChunkRegs<VecT> load_chunk(const AsmParams& P, long l
     return c;
 }
 
-template <typename VecT, typename OutT, bool FULL>
+template <typename VecT, typename OutT, bool FULL, bool DENSE = false>
 __device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkRegs<VecT>& c, OutT* __restrict__ out,
                                               long long V, long long warp_base,
                                               unsigned (*s_raw)[32][Raw8<VecT>::NW], int* s_res, unsigned char* s_queue) {
@@ -353,6 +400,9 @@ __device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkReg
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (DENSE && total >= P.dense_work) {  // warp-uniform; the dense instantiation runs whole-volume N = 1 passes only
+            if (work) resolve_own8<VecT>(P, c.r0, c.r1, c.r2, work, i0, lab);
+        } else {
         if (work) {
             int at = incl - cnt;
             for (unsigned m = work; m; m &= m - 1) s_queue[at++] = (unsigned char)((__ffs((int)m) - 1) * 32 + lane);
@@ -385,6 +435,7 @@ __device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkReg
             }
         }
         __syncwarp();  // the warp's shared-memory scratch is reused by its next chunk
+        }
     }
 
     if (FULL || nvalid == 8) {
@@ -405,12 +456,13 @@ __device__ __forceinline__ void process_chunk(const AsmParams& P, const ChunkReg
 // Main kernel: PERSISTENT warps over the full, aligned 256-voxel chunks [0, n_chunks).  A warp issues the
 // streaming loads of its next chunk before it starts on the current one, so a warp that is busy with
 // the latency-bound part (compaction, dependent label reads) still keeps 1.5 KB of loads in flight.
-template <typename VecT, typename OutT>
-__global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V,
-                                                                      unsigned chunk_begin, unsigned n_chunks) {
+template <typename VecT, typename OutT, bool DENSE>
+__global__ void __launch_bounds__(32 * ASM_WARPS, DENSE ? 3 : 4) assemble_kernel(AsmParams P, OutT* __restrict__ out, long long V,
+                                                                                  unsigned chunk_begin, unsigned n_chunks) {
     __shared__ unsigned s_raw[ASM_WARPS][3][32][Raw8<VecT>::NW];
     __shared__ int s_res[ASM_WARPS][256];
     __shared__ unsigned char s_queue[ASM_WARPS][256];
+    if (P.density && ((*P.density >= P.dense_from) != DENSE)) return;  // the probe picked the other instantiation
     const int warp = threadIdx.x >> 5;
     const unsigned stride = gridDim.x * ASM_WARPS;
     unsigned c = chunk_begin + blockIdx.x * ASM_WARPS + warp;  // chunks [chunk_begin, n_chunks)
@@ -420,7 +472,7 @@ __global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_kernel(AsmParams P
         const unsigned cn = c + stride;
         ChunkRegs<VecT> nxt = cur;
         if (cn < n_chunks) nxt = load_chunk<VecT, true>(P, V, (long long)cn * 256);
-        process_chunk<VecT, OutT, true>(P, cur, out, V, (long long)c * 256, s_raw[warp], s_res[warp], s_queue[warp]);
+        process_chunk<VecT, OutT, true, DENSE>(P, cur, out, V, (long long)c * 256, s_raw[warp], s_res[warp], s_queue[warp]);
         if (cn >= n_chunks) break;
         c = cn;
         cur = nxt;
@@ -629,6 +681,24 @@ __global__ void __launch_bounds__(32 * ASM_WARPS, 4) assemble_tma_kernel(AsmPara
         if (nx >= n_chunks) break;
         c = (unsigned)nx;
     }
+}
+
+// Density probe: every thread looks at one 8-voxel group (three 16-byte loads), groups spread evenly over the range; the
+// number of sampled voxels that carry a vector is added to *count (zeroed by the host-side memset before the launch).
+constexpr unsigned ASM_PROBE_GROUPS = 16384;  // 131 072 sampled voxels
+template <typename VecT>
+__global__ void __launch_bounds__(256) assemble_probe_kernel(AsmParams P, unsigned chunk_begin, unsigned n_chunks, unsigned* count) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n = 0;
+    if (g < ASM_PROBE_GROUPS) {
+        const unsigned long long groups = (unsigned long long)(n_chunks - chunk_begin) * 32ull;
+        const long long i0 = ((long long)chunk_begin * 32 + (long long)(groups * g / ASM_PROBE_GROUPS)) * 8;
+        const Raw8<VecT> a = load_raw8<VecT, true>(P.vec, i0, 8), b = load_raw8<VecT, true>(P.vec, i0 + P.cstride, 8),
+                         c = load_raw8<VecT, true>(P.vec, i0 + 2 * P.cstride, 8);
+        n = (unsigned)__popc(nonzero_bits<VecT>(a, b, c));
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
 }
 
 // Everything the main kernel does not cover: the ragged last chunk, or all chunks of an unaligned field.
@@ -954,7 +1024,26 @@ static void launch_assemble_t(const AsmParams& P, OutT* out, long long v_begin, 
             cudaFuncSetAttribute(assemble_tma_kernel<VecT, OutT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             assemble_tma_kernel<VecT, OutT, false><<<(unsigned)blocks, 32 * ASM_WARPS, smem, st>>>(P, out, (unsigned)c_begin, (unsigned)c_end);
         } else {
-            assemble_kernel<VecT, OutT><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(P, out, v_end, (unsigned)c_begin, (unsigned)c_end);
+            // large whole-volume N = 1 passes over the sparse labels: probe the field's density on the device and launch
+            // both instantiations (the one not picked returns at once); everything else takes the sparse one
+            AsmParams Q = P;
+            const bool probe = eligible && P.N == 1 && P.single_crop && P.halo_lo == nullptr && P.halo_hi == nullptr &&
+                               P.z_off == 0 && P.Zl == P.Z && P.density != nullptr && c_end - c_begin >= 65536 &&
+                               !getenv("SKB_NO_DENSE");
+            if (probe) {
+                unsigned* cnt = const_cast<unsigned*>(P.density);
+                cudaMemsetAsync(cnt, 0, sizeof(unsigned), st);
+                assemble_probe_kernel<VecT><<<ASM_PROBE_GROUPS / 256, 256, 0, st>>>(P, (unsigned)c_begin, (unsigned)c_end, cnt);
+                Q.dense_from = ASM_PROBE_GROUPS * 8u / 12u;  // >= ~8 % of the sampled voxels carry a vector
+                const char* dw = getenv("SKB_DENSE_WORK");     // measurements only
+                Q.dense_work = dw ? atoi(dw) : ASM_DENSE_WORK;
+                long long dblocks = (c_end - c_begin + ASM_WARPS - 1) / ASM_WARPS;
+                if (dblocks > 148 * 3) dblocks = 148 * 3;
+                assemble_kernel<VecT, OutT, true><<<(unsigned)dblocks, 32 * ASM_WARPS, 0, st>>>(Q, out, v_end, (unsigned)c_begin, (unsigned)c_end);
+            } else {
+                Q.density = nullptr;
+            }
+            assemble_kernel<VecT, OutT, false><<<(unsigned)blocks, 32 * ASM_WARPS, 0, st>>>(Q, out, v_end, (unsigned)c_begin, (unsigned)c_end);
         }
     }
     const long long first = c_end * 256;
@@ -1022,6 +1111,8 @@ extern "C" int skb_assemble_range(const void* vec, int vec_dtype, int64_t X, int
         P.parent = reinterpret_cast<const int*>(base + L.off_parent);
         P.ZW = L.ZW;
         P.flat_bits = (Z % 64 == 0) ? 1 : 0;
+        // the density probe's counter: a reserved word of the workspace header (the labelling does not touch it again)
+        P.density = reinterpret_cast<const unsigned*>(base + offsetof(SkbCclHeader, reserved));
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long v0 = first_voxel, v1 = first_voxel + n_voxels;

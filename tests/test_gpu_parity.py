@@ -1,5 +1,7 @@
 """GPU: CUDA path vs the CPU oracle on seeded synthetic inputs (sizes the oracle finishes in
 seconds), edge cases, and size-independent properties on large volumes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -500,3 +502,23 @@ def test_graphed_small_volume_assembler():
             assert torch.equal(got.cpu(), want), (kw, seed)
         host = run(tv.skeleton, tv.vectors)            # host tensors are copied straight into the static buffers
         assert torch.equal(host.cpu(), want)
+
+
+@pytest.mark.parametrize("radius,tubes", [(4.0, 300), (9.0, 900), (14.0, 1500)])
+def test_density_probe_picks_an_instantiation_and_both_are_exact(radius, tubes):
+    """large whole-volume N = 1 passes probe the field's density on the device and run the sparse or the dense
+    instantiation of the gather (the other returns at once): same labels either way, equal to the oracle, from ~1 % to
+    ~60 % of the voxels carrying a vector.  512 x 512 x 64 = 65 536 chunks: the smallest volume that probes."""
+    from skoots_b200.pipeline import assemble_instances
+    shape = (512, 512, 64)
+    tv = make_tube_volume(shape, tubes, seed=2, radius=radius, want_mask=False, want_skeleton_dict=False)
+    scale = torch.tensor((60, 60, 12))
+    want = orc.postprocess(tv.skeleton, tv.vectors, scale, N=1)
+    got = assemble_instances(tv.skeleton.to(DEV), tv.vectors.to(DEV), scale, N=1)
+    assert torch.equal(got.cpu(), want), (radius, float((tv.vectors != 0).any(0).float().mean()))
+    os.environ["SKB_NO_DENSE"] = "1"
+    try:
+        again = assemble_instances(tv.skeleton.to(DEV), tv.vectors.to(DEV), scale, N=1)
+    finally:
+        del os.environ["SKB_NO_DENSE"]
+    assert torch.equal(again, got)

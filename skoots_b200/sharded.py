@@ -410,6 +410,30 @@ class ShardedAssembler:
         # the same routing as the boundary runs (tests/test_sharded_gloo.py): my low face -> rank-1's high halo, ...
         self.comm.neighbour_exchange(self.vsend_lo, self.vsend_hi, self.vhalo_lo, self.vhalo_hi)
 
+    def _s(self):
+        return L.stream_ptr(self.dev)
+
+    def _chain(self):
+        """context of the labelling chain: the high-priority side stream when the gather is split."""
+        if not self.split:
+            return contextlib.nullcontext()
+        from .pipeline import chain_stream
+        return torch.cuda.stream(chain_stream(self.dev))
+
+    def _label_local(self, phase: int) -> None:
+        X, Y, Z = self.shape
+        # the status word is sticky across passes (graph replays included): check_status() reads and clears it
+        flags = phase | L.CCL_KEEP_STATUS | (L.CCL_WORKSPACE_CLEAN if self._clean and phase != L.CCL_PHASE_LABEL else 0)
+        L.check(self.lib.skb_shard_label_local(self.mask.data_ptr(), L.dtype_code(self.mask), X, Y, Z, self.z_range[0], self.Zl,
+                                               self.capacity, self.workspace.data_ptr(), self.workspace.numel(),
+                                               self.meta[1:2].data_ptr(), flags, self._s()))
+
+    def _stream_phase(self) -> None:
+        X, Y, Z = self.shape
+        L.check(self.lib.skb_assemble_stream(self.vec.data_ptr(), L.dtype_code(self.vec), X, Y, Z, self.z_range[0], self.Zl,
+                                             self.workspace.data_ptr(), self.flags.data_ptr(), self.out.data_ptr(),
+                                             L.dtype_code(self.out), self.stream_ctas, self._s()))
+
     # ---- phases ------------------------------------------------------------------------------------
     def phase_local(self) -> None:
         X, Y, Z = self.shape

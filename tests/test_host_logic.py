@@ -176,3 +176,16 @@ def test_compute_device_rules_without_a_gpu():
         mask_iou(torch.zeros((4, 4, 4), dtype=torch.int32), torch.zeros((4, 4, 4), dtype=torch.int32))
     with pytest.raises(L.SkootsB200Error):
         L.compute_device(torch.zeros(1), "not a tensor")
+
+
+@pytest.mark.parametrize("module", ["sharded", "pipeline", "_lib", "validate", "patch"])
+def test_every_private_method_a_class_calls_is_defined(module):
+    """the sharded driver only runs on a GPU box: catch a method lost in an edit here, where there is none."""
+    import ast
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "skoots_b200", module + ".py")
+    src = open(path).read()
+    for cls in [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef)]:
+        defined = {f.name for f in ast.walk(cls) if isinstance(f, (ast.FunctionDef, ast.ClassDef))}
+        assigned = set(re.findall(r"self\.(\w+)\s*=", ast.get_source_segment(src, cls)))
+        called = set(re.findall(r"self\.(_\w+)\(", ast.get_source_segment(src, cls)))
+        assert not (called - defined - assigned), (module, cls.name, sorted(called - defined - assigned))

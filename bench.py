@@ -592,8 +592,18 @@ def run_b200(args):
         os._exit(0)  # past a completed teardown: skips interpreter-exit destructors of CUDA-IPC mappings that are already closed
 
 
+def json_only_stdout():
+    """The contract is ONE JSON line on stdout: anything a library printf()s to file descriptor 1 (NCCL's version banner
+    under NCCL_DEBUG=VERSION/WARN) is sent to stderr, and Python's stdout keeps the original descriptor."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w", buffering=1)
+
+
 def main():
     args = parse()
+    json_only_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

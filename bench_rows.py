@@ -183,7 +183,7 @@ def main():
 
     def bake_kernel_only():
         L_.check(L_.load().skb_bake_skeletons(masks_b.data_ptr(), L_.dtype_code(masks_b), B, 300, 300, 20, ids_t.data_ptr(), begin_t.data_ptr(),
-                                              off_t.data_ptr(), n_ids, pts_t.data_ptr(), n_pts, L_.f3(an), 1, out_b.data_ptr(), 0,
+                                              off_t.data_ptr(), n_ids, pts_t.data_ptr(), n_pts, L_.f3(an), 1, 0, out_b.data_ptr(), 0,
                                               st_b.data_ptr(), L_.stream_ptr(DEV)))
     kern_ms = gpu_ms(bake_kernel_only, iters=10)
     rows.append(row("a8 bake_skeletons_batch (+average), ONE launch for the batch", "C4 8 x 300x300x20, 20 ids each",

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SKB_VERSION 200
+#define SKB_VERSION 201
 
 /* element types */
 enum { SKB_U8 = 0, SKB_I16 = 1, SKB_I32 = 2, SKB_F16 = 3, SKB_BF16 = 4, SKB_F32 = 5 };
@@ -208,12 +208,19 @@ int skb_vec_prob(const void* vec, int vec_dtype, const void* baked, int baked_dt
  *   field never reaches HBM.  distance (B,X,Y,Z) f32 optional.  *status |= SKB_STATUS_MISSING_ID when a mask id
  *   has no skeleton (the reference raises KeyError, skeleton.py:422); the caller zeroes *status and may read it
  *   once per batch.
+ *   triton_block (device, B ints) != NULL selects the semantics of the reference's Triton kernel instead
+ *   (skeleton.py:51-251, what bake_skeleton dispatches for a CUDA mask, :505-512): entry b = the SKEL_BLOCK_SIZE
+ *   of its launch (next power of two of the sample's longest skeleton, :361; 0 = no points: zeros).  Differences
+ *   from the CPU path: anisotropy weighs the squared differences; lanes past a skeleton's length act as a point
+ *   at the origin; ties take the per-axis maximum; an id without a skeleton gives zeros, no error; baked and
+ *   distance are fp16 values (stored here as f32).  Pinned for integer-valued coordinates and anisotropy
+ *   (tests/golden/bake_triton.npz, generated by the reference on a B200).
  * ------------------------------------------------------------------------------------------- */
 #define SKB_STATUS_MISSING_ID 2u
 int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
                        const int32_t* ids, const int32_t* id_begin, const int32_t* offsets, int n_ids,
                        const float* points_xyzw, int n_points, const float anisotropy[3], int average,
-                       float* baked, float* distance, uint32_t* status, void* stream);
+                       const int32_t* triton_block, float* baked, float* distance, uint32_t* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a9  skeleton_to_mask                                         skoots/lib/skeleton.py:531-593

@@ -407,6 +407,45 @@ def bake_skeleton(masks: torch.Tensor, skeletons: Dict[int, torch.Tensor], aniso
     return baked
 
 
+def bake_skeleton_triton(masks: torch.Tensor, skeletons: Dict[int, torch.Tensor], anisotropy=(1.0, 1.0, 1.0),
+                         average: bool = True):
+    """What the reference's TRITON kernel returns for a CUDA mask (skeleton.py:51-367 via :505-512), restated on the CPU:
+    dist = sum_c (s_c - v_c)^2 * a_c (:208-212); the skeleton row is loaded SKEL_BLOCK_SIZE wide (:204-206, block =
+    next power of two of the longest skeleton, :361) and the lanes past its length hold zeros, i.e. a phantom point at
+    the origin; each coordinate = max over the tied lanes and over 0 from the untied ones (:219-221); an id without a
+    skeleton uses index 0 with length 0 (:176,:187) -> zeros; fp16 stores.  Returns (baked, distance): baked (3,X,Y,Z)
+    fp16, or fp32 after the averaging (:519-523); distance (1,X,Y,Z) fp16 (exact sqrt here, tl.sqrt on the device: the
+    fp16 value may differ by one ulp).  PINNED by tests/golden/bake_triton.npz (reference outputs from a B200) for
+    integer-valued coordinates and anisotropy."""
+    vol = (masks.squeeze(0) if masks.ndim == 4 else masks).numpy()
+    X, Y, Z = vol.shape
+    baked = np.zeros((3, X, Y, Z), dtype=np.float32)
+    dist = np.zeros((1, X, Y, Z), dtype=np.float32)
+    longest = max((int(v.shape[0]) for v in skeletons.values()), default=0)
+    if longest == 0:
+        return torch.zeros((3, X, Y, Z), dtype=torch.float16), torch.zeros((3, X, Y, Z), dtype=torch.float16)
+    block = 1 if longest == 0 else 2 ** (longest - 1).bit_length()
+    an = np.asarray(anisotropy, dtype=np.float32)
+    for k in np.unique(vol).tolist():
+        if k == 0:
+            continue
+        where = np.argwhere(vol == k)
+        pts = skeletons[int(k)].float().numpy().reshape(-1, 3) if int(k) in skeletons else np.zeros((0, 3), np.float32)
+        lanes = np.zeros((block, 3), dtype=np.float32)
+        lanes[:len(pts)] = pts
+        e = lanes[:, None, :] - where[None, :, :].astype(np.float32)
+        d2 = ((e[..., 0] * e[..., 0]) * an[0] + (e[..., 1] * e[..., 1]) * an[1]) + (e[..., 2] * e[..., 2]) * an[2]
+        tied = d2 == d2.min(axis=0, keepdims=True)
+        close = np.where(tied[..., None], lanes[:, None, :], np.float32(0)).max(axis=0)
+        baked[:, where[:, 0], where[:, 1], where[:, 2]] = close.T
+        dist[0, where[:, 0], where[:, 1], where[:, 2]] = np.sqrt(d2.min(axis=0))
+    baked_t = torch.from_numpy(baked).to(torch.float16)
+    dist_t = torch.from_numpy(dist).to(torch.float16)
+    if average:
+        return average_baked_skeletons(baked_t[None].float())[0], dist_t
+    return baked_t, dist_t
+
+
 # --------------------------------------------------------------------------------------
 # a9: skeleton -> mask                 skoots/lib/skeleton.py:531-593, utils.py:421-438
 # --------------------------------------------------------------------------------------

@@ -61,7 +61,7 @@ SIGNATURES = {
     "skb_embed_prob_bwd": (_c_int, [_c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_i64, _c_int, _c_i64, _c_f3, ctypes.c_float, _c_vp, _c_vp, _c_vp]),
     "skb_vec_prob": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_int, _c_i64, _c_i64, _c_i64, _c_f3, _c_f3, ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_bake_skeletons": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_f3, _c_int,
-                                    _c_vp, _c_vp, _c_vp, _c_vp]),
+                                    _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "skb_stamp_disks": (_c_int, [_c_vp, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp]),
     "skb_shard_label_local": (_c_int, [_c_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_vp, _c_sz, _c_vp, _c_int, _c_vp]),
     "skb_shard_emit_runs": (_c_int, [_c_vp, _c_i64, _c_i64, _c_i64, _c_i64, _c_i64, _c_int, _c_i64, _c_vp, _c_i64, _c_vp, _c_vp]),

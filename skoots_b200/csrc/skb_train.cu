@@ -12,6 +12,7 @@
 //                             per id, cp.async.bulk + mbarrier); the search is an fp32 min-reduction per
 //                             voxel — no tensor cores, by design.  One launch per batch.
 //   skb_stamp_disks           skoots/lib/skeleton.py:531-593 (skeleton_to_mask)
+#include <climits>
 #include <initializer_list>
 
 #include "skb_common.cuh"
@@ -440,8 +441,43 @@ struct BakeParams {
     const int* offsets;    // (n_ids + 1) prefix of point counts, global over the batch
     const float* points;   // (n_points, 4) xyz + pad, 16-byte rows
     unsigned* status;      // SKB_STATUS_MISSING_ID: a mask id has no skeleton (the reference raises KeyError)
+    const int* tri_block;  // NULL: CPU/torch semantics.  Else per sample the SKEL_BLOCK_SIZE of the reference's Triton launch
+                           // (skeleton.py:361): the semantics of _min_skeleton_kernel, see bake_nearest_triton below
     long long V;           // voxels per sample
 };
+
+constexpr int BAKE_MISSING = INT_MIN;  // slot of a voxel whose id has no skeleton, Triton semantics only (no error there)
+
+// What the reference's Triton kernel computes for one voxel (skeleton.py:171-251), which is NOT what its CPU path does:
+//   * the anisotropy weighs the SQUARED differences (dist = sum_c (s_c - v_c)^2 * a_c), :208-212;
+//   * the skeleton row is loaded SKEL_BLOCK_SIZE wide with a mask and no `other` (:204-206): lanes past the skeleton's
+//     length hold zeros (Triton's PTX clears the destination of a predicated load), i.e. a phantom point at the origin
+//     competes whenever the skeleton is shorter than the block — a voxel nearer to (0,0,0) than to its skeleton gets 0;
+//   * ties: each coordinate is the MAXIMUM over the tied lanes, and over 0 from the lanes that are not tied (:219-221);
+//   * an id without a skeleton silently uses index 0 with length 0 (:176,:187): all lanes phantom, result 0;
+//   * baked and distance are stored as fp16 (:225-251); the distance is sqrt(min dist) (tl.sqrt is the approximate
+//     square root: the fp16 result can differ by one ulp).
+// Sums are taken in the written order without contraction; the reference's compiler may contract them into FMAs, which
+// cannot matter while coordinates and anisotropy are integer-valued (the products are exact) — the pinned domain.
+__device__ __forceinline__ void bake_nearest_triton(const float4* src, int cnt, int block, float fx, float fy, float fz,
+                                                    const float (&an)[3], float& bx, float& by, float& bz, float& best) {
+    int ties = 0;
+    bx = by = bz = 0.f;
+    best = INFINITY;
+    for (int k = 0; k <= cnt; ++k) {
+        if (k == cnt && cnt >= block) break;     // the block is full: no phantom lanes
+        const float4 p = k < cnt ? src[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float ex = __fsub_rn(p.x, fx), ey = __fsub_rn(p.y, fy), ez = __fsub_rn(p.z, fz);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(ex, ex), an[0]), __fmul_rn(__fmul_rn(ey, ey), an[1])),
+                                   __fmul_rn(__fmul_rn(ez, ez), an[2]));
+        const int lanes = k < cnt ? 1 : block - cnt;
+        if (d2 < best) { best = d2; bx = p.x; by = p.y; bz = p.z; ties = lanes; }
+        else if (d2 == best) { bx = fmaxf(bx, p.x); by = fmaxf(by, p.y); bz = fmaxf(bz, p.z); ties += lanes; }
+    }
+    if (ties < block) { bx = fmaxf(bx, 0.f); by = fmaxf(by, 0.f); bz = fmaxf(bz, 0.f); }
+    bx = __half2float(__float2half_rn(bx)); by = __half2float(__float2half_rn(by)); bz = __half2float(__float2half_rn(bz));
+    best = __half2float(__float2half_rn(sqrtf(best)));
+}
 
 template <typename MT>
 __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ masks, float* __restrict__ baked,
@@ -541,7 +577,8 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
                         if (v < id) a = m + 1; else e = m - 1;
                     }
                     if (found < 0) {
-                        atomicOr(P.status, SKB_STATUS_MISSING_ID);
+                        if (P.tri_block) { slot = BAKE_MISSING; any_fg = 1; }
+                        else atomicOr(P.status, SKB_STATUS_MISSING_ID);
                     } else {
                         any_fg = 1;
                         slot = -2 - found;
@@ -612,15 +649,22 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
             const int rz = i % RZ, q = i / RZ, ry = q % RY, rx = q / RY;
             const float ax = __fmul_rn(P.an[0], (float)(x0 + rx)), ay = __fmul_rn(P.an[1], (float)(y0 + ry)),
                         az = __fmul_rn(P.an[2], (float)(z0 + rz));
-            int lo, cnt;
-            const float4* src;
+            int lo = 0, cnt = 0;
+            const float4* src = gpts;
             if (slot >= 0) {
                 lo = s_lo[slot]; cnt = s_cnt[slot];
                 src = s_at[slot] >= 0 ? s_arena + s_at[slot] : gpts + lo;
-            } else {
+            } else if (slot != BAKE_MISSING) {
                 const int f = -2 - slot;
                 lo = __ldg(P.offsets + f); cnt = __ldg(P.offsets + f + 1) - lo;
                 src = gpts + lo;
+            }
+            if (P.tri_block) {
+                const int block = __ldg(P.tri_block + b);
+                if (block > 0)
+                    bake_nearest_triton(src, cnt, block, (float)(x0 + rx), (float)(y0 + ry), (float)(z0 + rz), P.an, bx, by, bz, best);
+                cnt = 0;
+                if (block <= 0) best = 0.f;
             }
             for (int k = 0; k < cnt; ++k) {
                 const float4 p = src[k];
@@ -631,7 +675,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
                 const float d = sqrtf(d2);
                 if (d < best) { best = d; bx = p.x; by = p.y; bz = p.z; }
             }
-            if (cnt <= 0) best = 0.f;
+            if (cnt <= 0 && !P.tri_block) best = 0.f;
         } else {
             best = 0.f;
         }
@@ -688,7 +732,7 @@ __global__ void __launch_bounds__(256) bake_tile_kernel(const MT* __restrict__ m
 extern "C" int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, int64_t X, int64_t Y, int64_t Z,
                                   const int32_t* ids, const int32_t* id_begin, const int32_t* offsets, int n_ids,
                                   const float* points_xyzw, int n_points, const float anisotropy[3], int average,
-                                  float* baked, float* distance, uint32_t* status, void* stream) {
+                                  const int32_t* triton_block, float* baked, float* distance, uint32_t* status, void* stream) {
     int rc = skb_check_volume(X, Y, Z, "skb_bake_skeletons");
     if (rc) return rc;
     SKB_REQUIRE(masks && baked && status && anisotropy && id_begin && B >= 1 && B <= 65535 && n_ids >= 0 && n_points >= 0,
@@ -705,6 +749,7 @@ extern "C" int skb_bake_skeletons(const void* masks, int mask_dtype, int64_t B, 
     P.tiles_z = (int)((Z + P.TZ - 1) / P.TZ);
     P.an[0] = anisotropy[0]; P.an[1] = anisotropy[1]; P.an[2] = anisotropy[2];
     P.ids = ids; P.id_begin = id_begin; P.offsets = offsets; P.points = points_xyzw; P.status = status;
+    P.tri_block = triton_block;
     P.V = X * Y * Z;
     const long long tiles = (long long)tiles_x * P.tiles_y * P.tiles_z;
     SKB_REQUIRE(tiles < (1LL << 31), "skb_bake_skeletons: too many tiles");

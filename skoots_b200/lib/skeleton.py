@@ -105,12 +105,18 @@ def _pack_batch(skeletons_list, device):
     return table_d[:n_ids], table_d[n_ids:n_ids + len(begin)], table_d[n_ids + len(begin):], pts, n_ids, n_pts
 
 
+def _next_power_of_2(x: int) -> int:
+    return 1 if x == 0 else 2 ** (x - 1).bit_length()
+
+
 def bake_skeletons_batch(masks, skeletons_list, anisotropy: Tuple[float, float, float] = (1.0, 1.0, 1.0), average: bool = True,
-                         return_distance: bool = False, check: bool = True):
+                         return_distance: bool = False, check: bool = True, triton_compat: bool = False):
     """`bake_skeleton` for a whole batch in ONE launch: masks (B,X,Y,Z) tensor (or a list of (X,Y,Z) / (1,X,Y,Z) tensors of
     one shape), skeletons_list = one `Dict[int, Tensor[M,3]]` per sample.  Returns (B,3,X,Y,Z) fp32 (and (B,1,X,Y,Z)
     distances).  The status word is read ONCE for the batch (check=False: not at all; the caller owns the check).
-    Semantics per sample = the reference's CPU path (skeleton.py:370-445) followed by average_baked_skeletons."""
+    Semantics per sample = the reference's CPU path (skeleton.py:370-445) followed by average_baked_skeletons;
+    triton_compat=True = the reference's Triton kernel instead (skeleton.py:51-367, what it runs for CUDA masks): values
+    are fp16-representable, a missing id gives zeros and raises nothing."""
     if not isinstance(masks, torch.Tensor):
         masks = torch.stack([m.squeeze(0) if m.ndim == 4 else m for m in masks])
     dev = L.require_cuda(masks)
@@ -119,14 +125,18 @@ def bake_skeletons_batch(masks, skeletons_list, anisotropy: Tuple[float, float, 
     m = m.contiguous()
     B, X, Y, Z = m.shape
     ids, begin, offsets, pts, n_ids, n_pts = _pack_batch(skeletons_list, dev)
+    blocks = None
+    if triton_compat:  # SKEL_BLOCK_SIZE of the reference's launch per sample (skeleton.py:302,361); 0 = it returns zeros (:304)
+        longest = [max((int(v.shape[0]) for v in sk.values()), default=0) for sk in skeletons_list]
+        blocks = torch.tensor([_next_power_of_2(n) if n else 0 for n in longest], dtype=torch.int32).to(dev, non_blocking=True)
     baked = torch.empty((B, 3, X, Y, Z), dtype=torch.float32, device=dev)
     dist = torch.empty((B, 1, X, Y, Z), dtype=torch.float32, device=dev) if return_distance else None
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.check(L.load().skb_bake_skeletons(m.data_ptr(), L.dtype_code(m), B, X, Y, Z, ids.data_ptr(), begin.data_ptr(),
                                             offsets.data_ptr(), n_ids, pts.data_ptr(), n_pts, L.f3(anisotropy), int(bool(average)),
-                                            baked.data_ptr(), L.ptr(dist), status.data_ptr(), L.stream_ptr(dev)))
-    if check and int(status.item()) & L.STATUS_MISSING_ID:
+                                            L.ptr(blocks), baked.data_ptr(), L.ptr(dist), status.data_ptr(), L.stream_ptr(dev)))
+    if check and not triton_compat and int(status.item()) & L.STATUS_MISSING_ID:
         for b in range(B):
             present = set(torch.unique(m[b]).tolist()) - {0}
             missing = sorted(present - set(int(k) for k in skeletons_list[b]))
@@ -137,25 +147,37 @@ def bake_skeletons_batch(masks, skeletons_list, anisotropy: Tuple[float, float, 
 
 
 def bake_skeleton(masks: Tensor, skeletons: Dict[int, Tensor], anisotropy: Tuple[float, float, float] = (1.0, 1.0, 1.0),
-                  average: bool = True, device: str = "cpu", return_distance: bool = False):
+                  average: bool = True, device: str = "cpu", return_distance: bool = False, triton_compat=False):
     """Drop-in for skoots.lib.skeleton.bake_skeleton (:448-528) with the CPU/torch semantics
     (anisotropy scales coordinates, first minimum wins, fp32 out — SURVEY A.5).  `device` is
     accepted and ignored like the reference's positional mix-up (:507); the work runs on
     masks.device (host tensors are staged through the GPU).  return_distance=True also returns the (1,X,Y,Z)
     distance.  One kernel launch (nearest point + the masked 27-mean fused) and one status read — the reference raises
     KeyError synchronously for a mask id without a skeleton (:422), so does this; `bake_skeletons_batch` does a whole
-    batch with one launch and one read."""
+    batch with one launch and one read.
+
+    triton_compat: the reference answers a CUDA mask with its Triton kernel (:505-512), whose results differ from its CPU
+    path (see skb_train.cu, bake_nearest_triton).  True = those semantics (fp16 baked when average=False, fp16 distance,
+    no KeyError); "auto" = the reference's own dispatch (Triton semantics for CUDA masks, CPU semantics for host
+    tensors) — what `patch_skoots(bug_compatible=True)` binds; False (default) = the CPU semantics everywhere."""
     dev, staged = L.compute_device(masks)
+    if triton_compat == "auto":
+        triton_compat = not staged
     if staged:
-        return L.stage_out(bake_skeleton(L.stage_in(masks, dev), skeletons, anisotropy, average, device, return_distance), True)
+        return L.stage_out(bake_skeleton(L.stage_in(masks, dev), skeletons, anisotropy, average, device, return_distance,
+                                         triton_compat), True)
     if -1 in skeletons:
         x, y, z = masks.shape[-3:]
         return torch.zeros((3, x, y, z), device=dev, dtype=torch.float16)
     if masks.ndim == 4 and masks.shape[0] == 1:
         masks = masks.squeeze(0)
     assert masks.ndim == 3, f"masks must be 3d with no batch. not {masks.shape=}"
-    out = bake_skeletons_batch(masks.unsqueeze(0), [skeletons], anisotropy, average, return_distance)
-    return (out[0][0], out[1][0]) if return_distance else out[0]
+    out = bake_skeletons_batch(masks.unsqueeze(0), [skeletons], anisotropy, average, return_distance, triton_compat=bool(triton_compat))
+    baked, dist = (out[0][0], out[1][0]) if return_distance else (out[0], None)
+    if triton_compat:  # the Triton launcher's dtypes (:287-293): fp16, widened only by the averaging (:519-523)
+        baked = baked if average else baked.to(torch.float16)
+        dist = None if dist is None else dist.to(torch.float16)
+    return (baked, dist) if return_distance else baked
 
 
 def skeleton_to_mask(skeletons: Dict[int, Tensor], shape: Tuple[int, int, int], device=None, radius: int = 7,

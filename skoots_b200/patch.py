@@ -60,16 +60,30 @@ def _bug_compatible_flood_fill():
     return bound
 
 
+def _bug_compatible_bake_skeleton():
+    """`bake_skeleton` with the reference's own dispatch: the semantics of its Triton kernel for CUDA masks
+    (skeleton.py:505-512), of its CPU path for host tensors."""
+    import functools
+
+    from skoots_b200.lib.skeleton import bake_skeleton
+    bound = functools.partial(bake_skeleton, triton_compat="auto")
+    functools.update_wrapper(bound, bake_skeleton)
+    return bound
+
+
 def patch_skoots(bug_compatible: bool = False) -> List[Tuple[str, str]]:
     """Returns the (module, attribute) pairs that were rebound. Idempotent.
 
     bug_compatible=False (default) binds the exact connected-component labelling: identical to the reference on any
     volume that fits one of its 1000x1000x200 flood-fill crops, and the same partition minus the reference's spurious
     seam merges on larger ones.  bug_compatible=True binds `efficient_flood_fill(..., reference_crops=True)` instead:
-    the reference's own result bit for bit on every volume, quirks included (north_star's "bit-exact to the reference")."""
+    the reference's own result bit for bit on every volume, quirks included (north_star's "bit-exact to the reference"),
+    and `bake_skeleton(..., triton_compat="auto")`: CUDA masks get what the reference's Triton kernel returns (fp16,
+    anisotropy on the squared differences, per-axis maximum on ties, phantom origin point), host masks its CPU result."""
     done: List[Tuple[str, str]] = []
     originals = {}
-    special = {("skoots.lib.flood_fill", "efficient_flood_fill"): _bug_compatible_flood_fill()} if bug_compatible else {}
+    special = {("skoots.lib.flood_fill", "efficient_flood_fill"): _bug_compatible_flood_fill(),
+               ("skoots.lib.skeleton", "bake_skeleton"): _bug_compatible_bake_skeleton()} if bug_compatible else {}
     for (mod_name, attr), (new_mod, new_attr) in _TARGETS.items():
         try:
             mod = importlib.import_module(mod_name)

@@ -23,7 +23,7 @@ def cu(a, dtype=None):
 
 def test_library_loaded_is_in_tree():
     import skoots_b200._lib as L
-    assert L.load().skb_version() == 200
+    assert L.load().skb_version() == 201
     assert L.LIB_PATH.endswith("skoots_b200/libskoots_b200.so")
 
 
@@ -172,6 +172,37 @@ def test_bake_skeleton():
     with pytest.raises(KeyError):
         bake_skeleton(mask, {k: v for k, v in list(sk.items())[1:]})
     assert bake_skeleton(mask, {-1: sk[next(iter(sk))]}).dtype == torch.float16
+
+
+@pytest.mark.parametrize("name", ("blobs", "aniso", "missing", "crop"))
+def test_bake_skeleton_triton_compat_against_reference_fixture(name):
+    """a8 with the semantics of the reference's own GPU kernel (triton_compat=True): bit-equal to what the unmodified
+    reference's Triton launch returned on a B200 (tests/golden/bake_triton.npz) — raw fp16 points, fp16 distances,
+    and the averaged field; one call per sample and the batch call."""
+    from test_oracle_golden import triton_case
+    from skoots_b200.lib.skeleton import bake_skeleton, bake_skeletons_batch
+    fx = load_golden("bake_triton")
+    mask, sk, an = triton_case(fx, name)
+    mask = mask.to(DEV)
+    skd = {k: v.to(DEV).float() for k, v in sk.items()}
+    raw, dist = bake_skeleton(mask, skd, an, average=False, return_distance=True, triton_compat=True)
+    assert raw.dtype == torch.float16 and dist.dtype == torch.float16 and dist.shape == (1,) + tuple(mask.shape)
+    assert np.array_equal(raw.cpu().numpy(), fx[f"{name}_raw"])
+    ulp = np.abs(dist.cpu().numpy().view(np.int16).astype(np.int32) - fx[f"{name}_dist"].view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1
+    avg = bake_skeleton(mask, skd, an, average=True, triton_compat="auto")   # a CUDA mask: the reference dispatches Triton
+    assert avg.dtype == torch.float32
+    np.testing.assert_allclose(avg.cpu().numpy(), fx[f"{name}_avg"], rtol=1e-5, atol=1e-6)
+    both = bake_skeletons_batch(torch.stack([mask, mask.flip(0)]), [skd, skd], an, average=False, triton_compat=True)
+    assert np.array_equal(both[0].cpu().numpy(), fx[f"{name}_raw"].astype(np.float32))
+    # host tensors under "auto" keep the CPU semantics (and its KeyError for the id without a skeleton)
+    if name == "missing":
+        with pytest.raises(KeyError):
+            bake_skeleton(mask.cpu(), sk, an, average=False, triton_compat="auto")
+    else:
+        host = bake_skeleton(mask.cpu(), sk, an, average=False, triton_compat="auto")
+        want = orc.bake_skeleton(mask.cpu(), sk, an, average=False)
+        assert host.dtype == torch.float32 and torch.equal(host, want)
 
 
 def test_average_baked():

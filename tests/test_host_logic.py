@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/skoots_b200.h but not exported"
     assert declared == set(L.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert L.load().skb_version() == 200
+    assert L.load().skb_version() == 201
 
 
 def test_argument_errors_do_not_need_a_gpu():
@@ -136,6 +136,9 @@ def test_patch_skoots_bug_compatible_binding():
         skoots_b200.patch.patch_skoots(bug_compatible=True)
         fn = skoots.lib.flood_fill.efficient_flood_fill
         assert getattr(fn, "keywords", None) == {"reference_crops": True} and fn.__name__ == "efficient_flood_fill"
+        import skoots.lib.skeleton
+        bake = skoots.lib.skeleton.bake_skeleton  # the reference's own dispatch: Triton semantics for CUDA masks
+        assert getattr(bake, "keywords", None) == {"triton_compat": "auto"} and bake.__name__ == "bake_skeleton"
     finally:
         skoots_b200.patch.unpatch_skoots()
 
@@ -156,7 +159,7 @@ def test_round2_entry_points_validate_arguments_without_a_gpu():
     assert lib.skb_assemble_slab_ex(1, 3, 600, 600, 256, 64, 64, f3, 10, 1.0, i3, L.i3((50, 50, 5)), None, None, 0, 0, 0, 1, None, None, 64, 16, 1, 0,
                                     600 * 600 * 64, None, None) == -1 and b"vector halos" in lib.skb_last_error()
     assert lib.skb_assemble_planar(None, 3, 4, 64, 64, L.f3((60, 60)), None, None, 0, None, 2, None) == -1
-    assert lib.skb_bake_skeletons(None, 2, 1, 8, 8, 8, None, None, None, 0, None, 0, L.f3((1, 1, 1)), 1, None, None, None, None) == -1
+    assert lib.skb_bake_skeletons(None, 2, 1, 8, 8, 8, None, None, None, 0, None, 0, L.f3((1, 1, 1)), 1, None, None, None, None, None) == -1
     assert lib.skb_elastic_resample(None, 2, 6, 6, L.f3((0.01, 0.05, 0.05)), None, None, 1, 8, 8, 8, None) == -1
     assert lib.skb_elastic_points(1, 2, 6, 6, L.f3((0.01, 0.05, 0.05)), None, 1, 5, 8, 8, 8, None, None) == -1
     assert lib.skb_shard_begin_pass(None, 2, 16, 16, 16, 64, None, None, None, None) == -1

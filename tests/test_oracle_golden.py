@@ -202,3 +202,32 @@ def test_elastic_deform_against_reference_fixture():
         assert np.array_equal(img.numpy(), fx[f"{tag}_out_image"]) and np.array_equal(mask.numpy(), fx[f"{tag}_out_mask"])
         assert np.array_equal(new[1].numpy(), fx[f"{tag}_out_sk1"]) and np.array_equal(new[2].numpy(), fx[f"{tag}_out_sk2"])
         assert np.array_equal(new[2].numpy()[2:4], fx[f"{tag}_sk2"][2:4])   # points outside the volume are left alone
+
+
+TRITON_CASES = ("blobs", "aniso", "missing", "crop")
+
+
+def triton_case(fx, name):
+    sk, at = {}, 0
+    for k, n in zip(fx[f"{name}_ids"].tolist(), fx[f"{name}_lens"].tolist()):
+        sk[int(k)] = torch.from_numpy(fx[f"{name}_pts"][at:at + n].copy())
+        at += n
+    return torch.from_numpy(fx[f"{name}_mask"]), sk, tuple(float(v) for v in fx[f"{name}_anisotropy"])
+
+
+@pytest.mark.parametrize("name", TRITON_CASES)
+def test_bake_skeleton_triton_semantics_against_reference_fixture(name):
+    """a8, the GPU half of the reference: the restatement of what its Triton kernel returns (fp16, anisotropy on the
+    squared differences, phantom origin lanes, per-axis maximum on ties, zeros for an id without a skeleton) against
+    tests/golden/bake_triton.npz — outputs of the unmodified reference on a B200 (oracle/gen_golden_triton.py)."""
+    fx = load_golden("bake_triton")
+    mask, sk, an = triton_case(fx, name)
+    raw, dist = orc.bake_skeleton_triton(mask, sk, an, average=False)
+    assert raw.dtype == torch.float16 and np.array_equal(raw.numpy(), fx[f"{name}_raw"])
+    ulp = np.abs(dist.numpy().view(np.int16).astype(np.int32) - fx[f"{name}_dist"].view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1                                    # tl.sqrt is the approximate square root
+    avg, _ = orc.bake_skeleton_triton(mask, sk, an, average=True)
+    np.testing.assert_allclose(avg.numpy(), fx[f"{name}_avg"], rtol=1e-5, atol=1e-6)
+    # and the fixture really exercises what sets the Triton kernel apart from the CPU path
+    cpu = orc.bake_skeleton(mask, {**{int(k): torch.zeros((1, 3)) for k in np.unique(mask.numpy()) if k}, **sk}, an, average=False)
+    assert ((raw.float() != cpu).any(0) & (mask != 0)).sum() > 100

@@ -113,22 +113,33 @@ def write_dense(sparse: SparseLabels, out: Tensor) -> Tensor:
 REFERENCE_CROP = (1000, 1000, 200)  # skoots/lib/flood_fill.py:28
 
 
-def _adjacent_by_sum_product(p0, p1):
-    """get_adjacent_labels, flood_fill.py:237-261, on two seam planes (host int16 arrays): labels (a, b) count as
+def _wrap16(v: Tensor) -> Tensor:
+    """int32 -> the value int16 arithmetic would have produced (two's complement wrap), still int32."""
+    return torch.remainder(v + 32768, 65536) - 32768
+
+
+def _adjacent_by_sum_product(p0: Tensor, p1: Tensor):
+    """get_adjacent_labels, flood_fill.py:237-261, on two seam planes (device int16 tensors): labels (a, b) count as
     touching when a+b and a*b (int16 arithmetic) both occur among the element-wise sums / products of the planes.
-    Host logic on two 2-D slices; the reference's double Python loop over the label pairs is one outer sum / product
-    and two membership tests here (same pairs, same order: a ascending, then b ascending)."""
-    import numpy as np
-    p0, p1 = p0.astype(np.int16), p1.astype(np.int16)
-    with np.errstate(over="ignore"):
-        sums, prods = np.unique(p0 + p1), np.unique(p0 * p1)
-        a, b = np.unique(p0), np.unique(p1)
-        a, b = a[a != 0], b[b != 0]
-        if a.size == 0 or b.size == 0:
-            return []
-        hit = np.isin((a[:, None] + b[None, :]).astype(np.int16), sums) & np.isin((a[:, None] * b[None, :]).astype(np.int16), prods)
-    ia, ib = np.nonzero(hit)
-    return list(zip(a[ia].astype(int).tolist(), b[ib].astype(int).tolist()))
+    On the device: the sums, products and labels that occur are marked in 65 536-entry presence tables (one scatter
+    each), the reference's double Python loop over the label pairs is one outer sum / product looked up in them.  One
+    small D2H read (the pairs), same pairs in the same order: a ascending, then b ascending."""
+    a32, b32 = p0.reshape(-1).to(torch.int32), p1.reshape(-1).to(torch.int32)
+
+    def present(values):
+        table = torch.zeros(65536, dtype=torch.bool, device=values.device)
+        table[(values + 32768).long()] = True
+        return table
+
+    sums, prods = present(_wrap16(a32 + b32)), present(_wrap16(a32 * b32))
+    a = (present(a32).nonzero().squeeze(1) - 32768).to(torch.int32)
+    b = (present(b32).nonzero().squeeze(1) - 32768).to(torch.int32)
+    a, b = a[a != 0], b[b != 0]
+    if a.numel() == 0 or b.numel() == 0:
+        return []
+    hit = sums[(_wrap16(a[:, None] + b[None, :]) + 32768).long()] & prods[(_wrap16(a[:, None] * b[None, :]) + 32768).long()]
+    ia, ib = hit.nonzero(as_tuple=True)
+    return list(zip(a[ia].tolist(), b[ib].tolist()))
 
 
 def _flood_fill_reference_crops(vol: Tensor, crop=REFERENCE_CROP) -> Tensor:
@@ -136,8 +147,8 @@ def _flood_fill_reference_crops(vol: Tensor, crop=REFERENCE_CROP) -> Tensor:
     volumes larger than one 1000x1000x200 crop: every crop is labelled on its own (numbering continues from the
     previous crop's maximum — and restarts after an empty crop, :140), labels that meet at a crop seam are found
     with the sum/product test and every group of them is replaced by its last-visited member.  The per-crop
-    labelling and the replacement run on the GPU; the seam test and the graph walk are host logic on two planes
-    per seam.  Bit-identical to the reference on its own fixture (tests/golden/flood_multicrop.npz)."""
+    labelling, the seam test and the replacement run on the GPU; only the walk over the (small) label graph is host
+    logic.  Bit-identical to the reference on its own fixture (tests/golden/flood_multicrop.npz)."""
     import numpy as np
     from .cropper import _origins
     X, Y, Z = vol.shape
@@ -164,9 +175,7 @@ def _flood_fill_reference_crops(vol: Tensor, crop=REFERENCE_CROP) -> Tensor:
     for ax in range(3):
         for o in seams[ax]:
             if o > 0:
-                p0 = vol.select(ax, o).cpu().numpy()
-                p1 = vol.select(ax, o - 1).cpu().numpy()
-                pairs.extend(_adjacent_by_sum_product(p0, p1))
+                pairs.extend(_adjacent_by_sum_product(vol.select(ax, o), vol.select(ax, o - 1)))
     graph = {}
     for a, b in pairs:
         graph.setdefault(a, []).append(b)

@@ -192,3 +192,18 @@ def test_every_private_method_a_class_calls_is_defined(module):
         assigned = set(re.findall(r"self\.(\w+)\s*=", ast.get_source_segment(src, cls)))
         called = set(re.findall(r"self\.(_\w+)\(", ast.get_source_segment(src, cls)))
         assert not (called - defined - assigned), (module, cls.name, sorted(called - defined - assigned))
+
+
+def test_seam_test_of_the_reference_crops_path_equals_the_oracles():
+    """row f3: the sum/product seam test (flood_fill.py:237-261) as presence-table lookups (device-agnostic torch) returns
+    the oracle's pairs in the oracle's order, int16 wrap-around of large labels included."""
+    import numpy as np
+    from skoots_b200.lib.flood_fill import _adjacent_by_sum_product
+    rng = np.random.default_rng(0)
+    for trial in range(12):
+        hi = (5, 200, 3000, 32767)[trial % 4]
+        p0 = (rng.integers(0, hi + 1, size=(40, 50)) * (rng.random((40, 50)) < 0.3)).astype(np.int16)
+        p1 = (rng.integers(0, hi + 1, size=(40, 50)) * (rng.random((40, 50)) < 0.3)).astype(np.int16)
+        want = [(int(a), int(b)) for a, b in orc._adjacent_by_sum_product(p0, p1)]
+        assert _adjacent_by_sum_product(torch.from_numpy(p0), torch.from_numpy(p1)) == want
+    assert _adjacent_by_sum_product(torch.zeros((4, 4), dtype=torch.int16), torch.ones((4, 4), dtype=torch.int16)) == []

@@ -428,6 +428,35 @@ def test_bake_many_ids_per_tile_and_long_skeletons():
     assert torch.equal(got[0].cpu(), want)
 
 
+def test_bake_triton_compat_on_the_table_fallback_paths():
+    """the Triton-kernel semantics (pinned by tests/golden/bake_triton.npz through the oracle's restatement) on the paths
+    the fixture does not reach: more ids per tile than the shared-memory list, a skeleton longer than the arena (the
+    2048-lane block is full: no phantom point for it, one for everybody else), an empty skeleton (all lanes phantom),
+    ids without a skeleton, and the averaged output of a batch of two."""
+    from skoots_b200.lib.skeleton import bake_skeletons_batch
+    g = torch.Generator().manual_seed(9)
+    shape = (24, 24, 20)
+    mask = torch.randint(0, 120, shape, generator=g, dtype=torch.int32)
+    sk = {k: torch.randint(0, 24, (int(torch.randint(1, 6, (1,), generator=g)), 3), generator=g).float() for k in range(1, 110)}
+    sk[7] = torch.randint(0, 24, (2048, 3), generator=g).float()
+    sk[8] = torch.zeros((0, 3))
+    an = (1.0, 2.0, 3.0)
+    skd = {k: v.to(DEV) for k, v in sk.items()}
+    got, dist = bake_skeletons_batch(torch.stack([mask, mask.flip(1)]).to(DEV), [skd, skd], an, average=False, return_distance=True,
+                                     triton_compat=True)
+    for b, m in enumerate((mask, mask.flip(1))):
+        want, wdist = orc.bake_skeleton_triton(m, sk, an, average=False)
+        assert torch.equal(got[b].cpu(), want.float()), b
+        ulp = (dist[b].cpu().to(torch.float16).view(torch.int16).int() - wdist.view(torch.int16).int()).abs().max()
+        assert int(ulp) <= 1
+    avg = bake_skeletons_batch(mask[None].to(DEV), [skd], an, average=True, triton_compat=True)
+    want_avg, _ = orc.bake_skeleton_triton(mask, sk, an, average=True)
+    torch.testing.assert_close(avg[0].cpu(), want_avg, rtol=1e-5, atol=1e-6)
+    # no skeleton has a point: the reference returns zeros before launching anything (skeleton.py:304-305)
+    none = bake_skeletons_batch(mask[None].to(DEV), [{1: torch.zeros((0, 3), device=DEV)}], an, average=False, triton_compat=True)
+    assert not none.any()
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16, torch.float32])
 def test_vectorised_kernels_on_rows_that_are_not_multiples_of_8(dt):
     """Z = 20 (the training crop): an 8-element group runs over row ends; the 16-byte kernels must give what the

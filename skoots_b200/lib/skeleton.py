@@ -194,7 +194,9 @@ def skeleton_to_mask(skeletons: Dict[int, Tensor], shape: Tuple[int, int, int], 
         return skeleton_to_mask({k: L.stage_in(v, dev) for k, v in skeletons.items()}, shape, device, radius, flank_radius).cpu()
     X, Y, Z = (int(s) for s in shape)
     out = torch.zeros((X, Y, Z), dtype=torch.float32, device=dev)
-    pts = torch.cat([v.to(device=dev, dtype=torch.float32).reshape(-1, 3) for v in skeletons.values()], 0).contiguous()
+    vals = list(skeletons.values())
+    ready = all(v.device == dev and v.dtype == torch.float32 and v.ndim == 2 for v in vals)  # the usual case: one cat, no per-tensor work
+    pts = torch.cat(vals if ready else [v.to(device=dev, dtype=torch.float32).reshape(-1, 3) for v in vals], 0).contiguous()
     key = ("i32", str(dev), int(radius), int(flank_radius))
     off = _DISK_CACHE.get(key)
     if off is None:  # (S,3) int32 form of the cached stamp, built once per (device, radius, flank)

@@ -231,3 +231,17 @@ def test_bake_skeleton_triton_semantics_against_reference_fixture(name):
     # and the fixture really exercises what sets the Triton kernel apart from the CPU path
     cpu = orc.bake_skeleton(mask, {**{int(k): torch.zeros((1, 3)) for k in np.unique(mask.numpy()) if k}, **sk}, an, average=False)
     assert ((raw.float() != cpu).any(0) & (mask != 0)).sum() > 100
+
+
+def test_bake_triton_fixture_inputs_come_from_the_committed_generator():
+    """the inputs stored in tests/golden/bake_triton.npz are exactly what oracle/gen_golden_triton.py's seeded cases()
+    produce (the outputs next to them were computed by the reference on a B200 from those)."""
+    import gen_golden_triton as gen
+    fx = load_golden("bake_triton")
+    made = gen.cases()
+    assert tuple(made) == TRITON_CASES
+    for name, (mask, sk, an) in made.items():
+        ids, lens, pts = gen.pack_skeletons(sk)
+        assert np.array_equal(mask, fx[f"{name}_mask"]) and np.array_equal(ids, fx[f"{name}_ids"])
+        assert np.array_equal(lens, fx[f"{name}_lens"]) and np.array_equal(pts, fx[f"{name}_pts"])
+        assert np.allclose(np.asarray(an, np.float32), fx[f"{name}_anisotropy"])

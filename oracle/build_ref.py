@@ -13,7 +13,6 @@ product source) but not gpurun-ignored, so it rides along with the snapshot exac
 import hashlib
 import os
 import shutil
-import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCE = os.environ.get("SKOOTS_REFERENCE_SOURCE", "/root/reference")

@@ -21,7 +21,6 @@ reference (which is itself torch-on-CPU) would.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Iterator, List, Sequence, Tuple
 
 import numpy as np

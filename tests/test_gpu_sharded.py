@@ -1,6 +1,5 @@
 """GPU: the Z-sharded pass (all ranks emulated in one process on one GPU, collectives replaced by
 copies) must be bit-identical to the unsharded pass — same labels, same numbering."""
-import numpy as np
 import pytest
 import torch
 

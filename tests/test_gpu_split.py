@@ -1,6 +1,5 @@
 """GPU: the stream/resolve split of the N = 1 gather (run next to the labelling chain on two streams) must
 write exactly what the fused gather after the labelling writes — and what the CPU oracle computes."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,5 @@
 """CPU: the full-volume-vs-sample comparison bench.py reports as `parity.sample_vs_oracle` (oracle/sample_check.py):
 accepts a correct full-volume result, including components cut by the sample box, and rejects corrupted ones."""
-import numpy as np
 import torch
 
 import sample_check

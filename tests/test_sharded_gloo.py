@@ -60,3 +60,18 @@ def test_comm_routing_gloo(world):
             assert lo == ([10 * (r - 1) + 2] * 12 if r > 0 else [-1] * 12)        # lower neighbour's send_hi
             assert hi == ([10 * (r + 1) + 1] * 12 if r < world - 1 else [-1] * 12)  # upper neighbour's send_lo
             assert gathered == [v + 100 * q for q in range(world) for v in range(5)]
+
+
+@pytest.mark.parametrize("shape,Zl,n", [((2048, 2048, 512), 64, 8), ((7, 5, 128), 64, 8), ((1, 3, 64), 64, 8), ((33, 17, 192), 128, 4),
+                                        ((100, 9, 64), 64, 16), ((5, 1, 64), 64, 3)])
+def test_host_pipeline_ranges_cover_the_slab_and_start_on_gather_boundaries(shape, Zl, n):
+    """run_host's X-ranges: contiguous, covering [0, X), each starting on a multiple of 256 slab voxels (what
+    skb_assemble_slab_ex accepts as the start of a range), whatever the shape."""
+    import types
+    from skoots_b200.sharded import ShardedAssembler
+    ranges = ShardedAssembler._host_plan(types.SimpleNamespace(shape=shape, Zl=Zl), n)
+    X, Y, _ = shape
+    assert ranges and ranges[0][0] == 0 and ranges[-1][1] == X
+    assert all(a1 == b0 for (_, a1), (b0, _) in zip(ranges[:-1], ranges[1:]))
+    assert all(x1 > x0 and (x0 * Y * Zl) % 256 == 0 for x0, x1 in ranges)
+    assert len(ranges) <= n

@@ -14,6 +14,11 @@ so this oracle is pinned by (1) the reference's two `__main__` known answers
 `scipy.ndimage.label` (scipy 1.18.1 in this image; requirement >=1.10.1,
 requirements.txt:36) is the third-party CCL the reference calls (flood_fill.py:135); it is
 installed here and on the GPU box and is used as-is.
+`bake_skeleton_triton` (the semantics of the reference's Triton kernel) is pinned by outputs of the
+unmodified reference's Triton launch on a B200 (`oracle/gen_golden_triton.py` -> tests/golden/bake_triton.npz).
+PARITY UNPINNED for two restatements, because the reference code cannot run in this image:
+`renumber` (fastremap is absent) and the skeleton-point half of `elastic_deform` (the reference's
+`_elastic_on_skeletons` raises under torch 2.11, see oracle/gen_golden_elastic.py).
 
 Each function cites the reference lines it restates. torch CPU ops are used for the bulk
 element-wise work so that the timed CPU baseline uses all host threads exactly as the

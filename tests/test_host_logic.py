@@ -207,3 +207,24 @@ def test_seam_test_of_the_reference_crops_path_equals_the_oracles():
         want = [(int(a), int(b)) for a, b in orc._adjacent_by_sum_product(p0, p1)]
         assert _adjacent_by_sum_product(torch.from_numpy(p0), torch.from_numpy(p1)) == want
     assert _adjacent_by_sum_product(torch.zeros((4, 4), dtype=torch.int16), torch.ones((4, 4), dtype=torch.int16)) == []
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/skoots_b200.h compiles as C99 (-pedantic), and a plain C program links against
+    the shared library and uses its host-side entry points (examples/c_abi_check.c; no GPU needed)."""
+    import shutil
+    import subprocess
+    import skoots_b200._lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "skoots_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    L.load()
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = str(tmp_path / "c_abi_check")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_abi_check.c"), "-L", libdir, "-lskoots_b200", f"-Wl,-rpath,{libdir}", "-o", exe],
+                   check=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and "NULL argument -> -1" in run.stdout, run.stdout + run.stderr

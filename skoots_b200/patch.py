@@ -23,6 +23,9 @@ _TARGETS = {
     ("skoots.lib.morphology", "binary_dilation_2d"): ("skoots_b200.lib.morphology", "binary_dilation_2d"),
     ("skoots.lib.morphology", "binary_erosion"): ("skoots_b200.lib.morphology", "binary_erosion"),
     ("skoots.lib.embedding_to_prob", "baked_embed_to_prob"): ("skoots_b200.lib.embedding_to_prob", "baked_embed_to_prob"),
+    # the crop grid (host index arithmetic; same yields, raises where the reference would loop forever — SURVEY B#16)
+    ("skoots.lib.cropper", "crops"): ("skoots_b200.lib.cropper", "crops"),
+    ("skoots.lib.cropper", "get_total_num_crops"): ("skoots_b200.lib.cropper", "get_total_num_crops"),
     # row f2: the validation metrics (skoots/validate/lib.py:170-275), bound by name in skoots/validate/__main__.py:9-13
     ("skoots.validate.lib", "mask_iou"): ("skoots_b200.validate", "mask_iou"),
     ("skoots.validate.lib", "mask_dice"): ("skoots_b200.validate", "mask_dice"),
@@ -31,7 +34,7 @@ _TARGETS = {
 
 # modules holding `from ... import name` copies (SURVEY.md §8b "bound at")
 _CALLERS = (
-    "skoots.lib.eval", "skoots.train.engine", "skoots.train.merged_transform", "skoots.train.loss",
+    "skoots.lib.eval", "skoots.lib.flood_fill", "skoots.train.engine", "skoots.train.merged_transform", "skoots.train.loss",
     "skoots.experimental.sparse_engine", "skoots.experimental.eval", "skoots.experimental.sparse_loss",
     "skoots.experimental.sparse_transforms", "skoots.experimental.modifiers", "skoots.validate.__main__",
 )

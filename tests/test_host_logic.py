@@ -119,9 +119,15 @@ def test_patch_skoots_rebinds_reference_modules():
         import skoots.validate.lib
         assert ("skoots.validate.lib", "mask_iou") in done
         assert skoots.validate.lib.mask_iou.__module__ == "skoots_b200.validate"
+        # the crop grid: the defining module and the by-name copy inside the reference's flood fill (flood_fill.py:10)
+        import skoots.lib.cropper
+        assert skoots.lib.cropper.crops.__module__ == "skoots_b200.lib.cropper"
+        assert skoots.lib.flood_fill.crops.__module__ == "skoots_b200.lib.cropper"
+        assert ("skoots.lib.flood_fill", "crops") in done
     finally:
         skoots_b200.patch.unpatch_skoots()
     assert skoots.lib.flood_fill.efficient_flood_fill is before
+    assert skoots.lib.flood_fill.crops.__module__ == "skoots.lib.cropper"
 
 
 def test_patch_skoots_bug_compatible_binding():

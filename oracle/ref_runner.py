@@ -46,10 +46,15 @@ def load():
         from skoots.lib.skeleton import index_skeleton_by_embed
         from skoots.lib.vector_to_embedding import vector_to_embedding
 
+        for fn in (crops, efficient_flood_fill, index_skeleton_by_embed, vector_to_embedding):
+            # the checker must be the reference itself: never the product's functions left bound by patch_skoots()
+            assert getattr(fn, "__module__", "").startswith("skoots."), f"{fn} is not the reference's own function"
+
         class NS:
             pass
-        _ns = NS()
-        _ns.crops, _ns.flood, _ns.index, _ns.v2e = crops, efficient_flood_fill, index_skeleton_by_embed, vector_to_embedding
+        ns = NS()
+        ns.crops, ns.flood, ns.index, ns.v2e = crops, efficient_flood_fill, index_skeleton_by_embed, vector_to_embedding
+        _ns = ns
     return _ns
 
 

@@ -464,9 +464,10 @@ def run_b200(args):
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 5))
         if world == 1:
-            host_mask = torch.empty(shape, dtype=torch.uint8).pin_memory()
-            host_vec = torch.empty((3,) + shape, dtype=torch.float16).pin_memory()
-            host_out = torch.empty(shape, dtype=e2e_dtype).pin_memory()
+            with L_.numa_local(dev) as numa:  # pinned pages on the GPU's own NUMA node (matters when 8 GPUs copy at once)
+                host_mask = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                host_vec = torch.empty((3,) + shape, dtype=torch.float16).pin_memory()
+                host_out = torch.empty(shape, dtype=e2e_dtype).pin_memory()
             host_mask.copy_(mask)
             host_vec.copy_(vec)
             runner_h = HostAssembler(shape, dev, out_dtype=e2e_dtype)
@@ -480,7 +481,8 @@ def run_b200(args):
             h2d, d2h = host_mask.numel() + host_vec.numel() * 2, host_out.numel() * host_out.element_size()
             e2e = {"value": V / dt, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": dt * 1e3, "steps": e2e_steps, "out_dtype": str(e2e_dtype).replace("torch.", ""),
-                   "pcie_GBps_per_rank": [round((h2d + d2h) / dt / 1e9, 1)], "api": "skoots_b200.pipeline.HostAssembler"}
+                   "pcie_GBps_per_rank": [round((h2d + d2h) / dt / 1e9, 1)], "numa_rank0": numa,
+                   "api": "skoots_b200.pipeline.HostAssembler"}
             same = True
             for x0 in range(0, X, max(1, X // 8)):  # compare on the device, piece by piece
                 x1 = min(X, x0 + max(1, X // 8))

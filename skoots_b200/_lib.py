@@ -8,6 +8,7 @@ the current CUDA device (`compute_device` / `stage_in` / `stage_out`): H2D, the 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from typing import Sequence
@@ -211,3 +212,47 @@ def i3(values: Sequence[int]):
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def _nvml_handle(device):
+    """NVML handle of a torch CUDA device (logical index -> physical GPU through its UUID or PCI address)."""
+    import pynvml
+    pynvml.nvmlInit()
+    props = torch.cuda.get_device_properties(device)
+    try:
+        return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+    except Exception:
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+
+
+@contextlib.contextmanager
+def numa_local(device):
+    """While active, the calling thread runs only on the CPUs that NVML reports as local to `device`, so that pinned host
+    memory allocated inside (cudaHostAlloc places its pages at allocation time, on the node of the allocating thread) lands
+    on the GPU's own NUMA node and its DMA does not cross the socket interconnect — what limits the uploads when all
+    eight GPUs of a box copy at once (profiles/r02_h2d_probe_g8.json).  Best effort: without NVML, a topology or the
+    permission it changes nothing.  Yields a dict describing what happened; the previous affinity is restored on exit."""
+    info = {"bound": False}
+    previous = None
+    try:
+        pynvml, handle = _nvml_handle(device)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(allowed) + 64) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+        try:
+            info["node"] = int(pynvml.nvmlDeviceGetNumaNodeId(handle))
+        except Exception:
+            pass
+        info["local_cpus"], info["allowed_cpus"] = len(local), len(allowed)
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            previous = allowed
+            info["bound"] = True
+    except Exception as exc:  # no NVML / no topology / not permitted: the allocation simply stays where the OS puts it
+        info["why"] = repr(exc)[:120]
+    try:
+        yield info
+    finally:
+        if previous is not None:
+            os.sched_setaffinity(0, previous)

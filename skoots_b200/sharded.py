@@ -776,11 +776,12 @@ class ShardedAssembler:
         pinned HOST memory; returns the e2e record of bench.py plus this rank's PCIe rates."""
         import time
         X, Y, Z = self.shape
-        if mask_host is None:
-            mask_host = self.mask.cpu().pin_memory()
-            vec_host = self.vec.cpu().pin_memory()
-        if out_host is None:
-            out_host = torch.empty((X, Y, self.Zl), dtype=out_dtype or self.out.dtype).pin_memory()
+        with L.numa_local(self.dev) as numa:  # this rank's pinned buffers on its GPU's NUMA node
+            if mask_host is None:
+                mask_host = self.mask.cpu().pin_memory()
+                vec_host = self.vec.cpu().pin_memory()
+            if out_host is None:
+                out_host = torch.empty((X, Y, self.Zl), dtype=out_dtype or self.out.dtype).pin_memory()
         self.run_host(mask_host, vec_host, out_host, n_slabs)
         self.comm.barrier()
         torch.cuda.synchronize(self.dev)
@@ -804,7 +805,7 @@ class ShardedAssembler:
         return {"value": X * Y * Z / dt, "unit": "voxels/s", "h2d_bytes_per_step": h2d * self.world,
                 "d2h_bytes_per_step": d2h * self.world, "ms_per_step": dt * 1e3, "steps": steps,
                 "out_dtype": str(out_host.dtype).replace("torch.", ""),
-                "pcie_GBps_per_rank": [round(float(v), 1) for v in rates.tolist()],
+                "pcie_GBps_per_rank": [round(float(v), 1) for v in rates.tolist()], "numa_rank0": numa,
                 "pipeline": f"mask up -> labelling chain + exchanges while {len(self._host_plan(n_slabs))} X-ranges of the vectors "
                             "follow; each range gathered when landed, labels travel back meanwhile (3 streams)",
                 "api": "skoots_b200.sharded.ShardedAssembler.run_host"}

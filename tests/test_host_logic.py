@@ -234,3 +234,16 @@ def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
                    check=True)
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0 and "NULL argument -> -1" in run.stdout, run.stdout + run.stderr
+
+
+def test_numa_local_is_best_effort_and_restores_the_affinity():
+    """pinned buffers are allocated under `numa_local(device)`: without a GPU / NVML it must change nothing, say why,
+    and leave the thread's CPU affinity as it found it."""
+    import skoots_b200._lib as L
+    before = os.sched_getaffinity(0)
+    with L.numa_local("cuda:0") as info:
+        inside = os.sched_getaffinity(0)
+        assert info["bound"] in (False, True) and (info["bound"] or inside == before)
+    assert os.sched_getaffinity(0) == before
+    if not torch.cuda.is_available():
+        assert info["bound"] is False and "why" in info

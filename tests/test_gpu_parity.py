@@ -118,6 +118,19 @@ def test_ragged_shapes_unaligned_paths(shape):
         assert np.array_equal(got.cpu().numpy(), want.numpy()), N
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.float32])
+def test_vector_to_embedding_batch_hops_read_batch_zero(dt):
+    """B > 1 with N > 1: the reference's `take` over the flattened batch makes every element's hops read element 0's
+    vectors (vector_to_embedding.py:130; oracle pinned live by tests/test_oracle_vs_reference.py) — reproduced."""
+    from skoots_b200.lib.vector_to_embedding import vector_to_embedding
+    g = torch.Generator().manual_seed(77)
+    vec = ((torch.rand((3, 3, 9, 8, 7), generator=g) * 2 - 1) * 1.5).to(dt)
+    scale = torch.tensor((4, 3, 2))
+    for N, decay in ((1, 1.0), (3, 1.0), (5, 0.9)):
+        got = vector_to_embedding(scale, vec.to(DEV), N=N, decay=decay)
+        assert torch.equal(got.cpu(), orc.vector_to_embedding(scale, vec, N, decay)), (N, decay)
+
+
 def test_autograd_vector_to_embedding():
     from skoots_b200.lib.vector_to_embedding import vector_to_embedding
     v = (torch.rand((2, 3, 6, 5, 4), device=DEV) * 2 - 1).requires_grad_(True)

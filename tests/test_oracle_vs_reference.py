@@ -48,6 +48,16 @@ def test_vec2embed_random_fields(ref, seed):
         assert torch.equal(orc.vector_to_embedding(scale, vec, N, decay), ref.v2e(scale, vec, N, decay)), (shape, N, decay)
 
 
+def test_vec2embed_batch_quirk(ref):
+    """B > 1 with N > 1: the reference's `take` runs over the flattened (B,1,X,Y,Z) slice with per-volume indices, so
+    the hops of EVERY batch element read the vectors of element 0 (vector_to_embedding.py:130)."""
+    g = torch.Generator().manual_seed(77)
+    vec = ((torch.rand((3, 3, 9, 8, 7), generator=g) * 2 - 1) * 1.5).to(torch.float16)
+    scale = torch.tensor((4, 3, 2))
+    for N, decay in ((1, 1.0), (3, 1.0), (5, 0.9)):
+        assert torch.equal(orc.vector_to_embedding(scale, vec, N, decay), ref.v2e(scale, vec, N, decay)), (N, decay)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_flood_fill_random_masks(ref, seed):
     g = torch.Generator().manual_seed(100 + seed)
